@@ -1,0 +1,547 @@
+/* oracle/zigz_oracle.c — TEST INFRASTRUCTURE ONLY. See zigz_oracle.h.
+ *
+ * Each function follows the cited reference lines operation for operation
+ * (same loop order, same modular formulae, same allocation pattern where it
+ * matters for timing: per-round fresh array in partialEval, per-level arrays
+ * and full recomputation in Merkle open), so that it can double as the
+ * single-core "port" CPU baseline.
+ */
+#include "zigz_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ */
+/* Field(u64, p) — /root/reference/src/core/field.zig                   */
+/* ------------------------------------------------------------------ */
+uint64_t zo_f_init(uint64_t p, uint64_t v) { return v % p; } /* :36-38 */
+
+uint64_t zo_f_add(uint64_t p, uint64_t a, uint64_t b) { /* :73-88 */
+    uint64_t sum;
+    if (__builtin_add_overflow(a, b, &sum)) return sum % p; /* reference quirk kept: wrapped value mod p */
+    if (sum >= p) return sum - p;
+    return sum;
+}
+
+uint64_t zo_f_sub(uint64_t p, uint64_t a, uint64_t b) { /* :91-98 */
+    if (a >= b) return a - b;
+    return p - (b - a);
+}
+
+uint64_t zo_f_neg(uint64_t p, uint64_t a) { return a == 0 ? 0 : p - a; } /* :101-106 */
+
+uint64_t zo_f_mul(uint64_t p, uint64_t a, uint64_t b) { /* :112-147, the `bits <= 64` arm: u128 product % modulus */
+    unsigned __int128 prod = (unsigned __int128)a * (unsigned __int128)b;
+    return (uint64_t)(prod % (unsigned __int128)p);
+}
+
+uint64_t zo_f_pow(uint64_t p, uint64_t a, uint64_t e) { /* :204-225 */
+    if (e == 0) return 1;
+    if (e == 1) return a;
+    uint64_t result = 1, base = a;
+    while (e > 0) {
+        if (e & 1) result = zo_f_mul(p, result, base);
+        base = zo_f_mul(p, base, base);
+        e >>= 1;
+    }
+    return result;
+}
+
+int zo_f_inv(uint64_t p, uint64_t a, uint64_t *out) { /* :157-191 extended Euclid in i128 */
+    if (a == 0) return -1;
+    __int128 t = 0, new_t = 1, r = (__int128)p, new_r = (__int128)a;
+    while (new_r != 0) {
+        __int128 q = r / new_r; /* both positive: divFloor == trunc */
+        __int128 tmp = t;
+        t = new_t;
+        new_t = tmp - q * new_t;
+        tmp = r;
+        r = new_r;
+        new_r = tmp - q * new_r;
+    }
+    if (r > 1) return -1;
+    if (t < 0) t += (__int128)p;
+    *out = (uint64_t)t;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* Multilinear(F) — /root/reference/src/poly/multilinear.zig            */
+/* ------------------------------------------------------------------ */
+int zo_mle_check(uint64_t n, uint32_t *num_vars) { /* init :36-47 */
+    if (n == 0) return ZO_ERR_EMPTY_EVALUATIONS;
+    if (n & (n - 1)) return ZO_ERR_LENGTH_NOT_POW2;
+    if (num_vars) *num_vars = (uint32_t)__builtin_ctzll(n);
+    return ZO_OK;
+}
+
+uint64_t zo_mle_sum(uint64_t p, const uint64_t *e, uint64_t n) { /* :188-194 */
+    uint64_t sum = 0;
+    for (uint64_t i = 0; i < n; i++) sum = zo_f_add(p, sum, e[i]);
+    return sum;
+}
+
+int zo_mle_round_poly(uint64_t p, const uint64_t *e, uint64_t n, uint64_t out[2]) { /* :205-232 */
+    if (n < 2) return ZO_ERR_NO_VARIABLES;
+    uint64_t half = n / 2, s0 = 0, s1 = 0;
+    for (uint64_t i = 0; i < half; i++) {
+        s0 = zo_f_add(p, s0, e[i]);
+        s1 = zo_f_add(p, s1, e[i + half]);
+    }
+    out[0] = s0;
+    out[1] = zo_f_sub(p, s1, s0);
+    return ZO_OK;
+}
+
+int zo_mle_partial_eval(uint64_t p, const uint64_t *e, uint64_t n, uint64_t r, uint64_t *out) { /* :154-180 */
+    if (n < 2) return ZO_ERR_NO_VARIABLES;
+    uint64_t new_len = n / 2;
+    for (uint64_t i = 0; i < new_len; i++) {
+        uint64_t at0 = e[i], at1 = e[i + new_len];
+        uint64_t one_minus_r = zo_f_sub(p, 1 % p, r);
+        out[i] = zo_f_add(p, zo_f_mul(p, one_minus_r, at0), zo_f_mul(p, r, at1));
+    }
+    return ZO_OK;
+}
+
+int zo_mle_eval(uint64_t p, const uint64_t *e, uint64_t n, const uint64_t *point, uint32_t npoint, uint64_t *out) { /* :110-144 */
+    uint32_t v;
+    int rc = zo_mle_check(n, &v);
+    if (rc) return rc;
+    if (npoint != v) return ZO_ERR_WRONG_NUM_VARS;
+    uint64_t(*basis)[2] = malloc(sizeof(uint64_t[2]) * (v ? v : 1));
+    if (!basis) return ZO_ERR_OOM;
+    for (uint32_t i = 0; i < v; i++) {
+        basis[i][0] = zo_f_sub(p, 1 % p, point[i]);
+        basis[i][1] = point[i];
+    }
+    uint64_t result = 0;
+    for (uint64_t idx = 0; idx < n; idx++) {
+        uint64_t term = e[idx], index = idx;
+        for (uint32_t k = 0; k < v; k++) { /* LSB-first: point[k] <-> bit k */
+            term = zo_f_mul(p, term, basis[k][index & 1]);
+            index >>= 1;
+        }
+        result = zo_f_add(p, result, term);
+    }
+    free(basis);
+    *out = result;
+    return ZO_OK;
+}
+
+void zo_mle_add(uint64_t p, const uint64_t *a, const uint64_t *b, uint64_t n, uint64_t *out) { /* :235-250 */
+    for (uint64_t i = 0; i < n; i++) out[i] = zo_f_add(p, a[i], b[i]);
+}
+
+void zo_mle_scalar_mul(uint64_t p, const uint64_t *a, uint64_t s, uint64_t n, uint64_t *out) { /* :253-264 */
+    for (uint64_t i = 0; i < n; i++) out[i] = zo_f_mul(p, a[i], s);
+}
+
+/* ------------------------------------------------------------------ */
+/* hash.zig                                                            */
+/* ------------------------------------------------------------------ */
+static void le64(uint64_t v, uint8_t out[8]) {
+    for (int i = 0; i < 8; i++) out[i] = (uint8_t)(v >> (8 * i));
+}
+
+void zo_transcript_init(zo_transcript *t) { zo_sha3_256_init(&t->h); } /* :261-276 */
+
+void zo_transcript_append_field(zo_transcript *t, uint64_t value) { /* :279-283 */
+    uint8_t b[8];
+    le64(value, b);
+    zo_sha3_256_update(&t->h, b, 8);
+}
+
+void zo_transcript_append_bytes(zo_transcript *t, const void *d, size_t n) { zo_sha3_256_update(&t->h, d, n); } /* :293-295 */
+
+uint64_t zo_transcript_challenge(zo_transcript *t, uint64_t p) { /* :301-316 */
+    uint8_t digest[32];
+    zo_sha3_256_peek(&t->h, digest); /* clone + final */
+    uint64_t value = 0;              /* digestToFieldElement :228-242: first 8 bytes LE, then F.init */
+    for (int i = 0; i < 8; i++) value |= (uint64_t)digest[i] << (8 * i);
+    uint64_t result = zo_f_init(p, value);
+    zo_sha3_256_update(&t->h, digest, 32); /* transcript absorbs its own digest */
+    return result;
+}
+
+void zo_hash_field_element(uint64_t value, uint8_t out[32]) { /* :135-147 */
+    uint8_t b[8];
+    le64(value, b);
+    zo_sha3_256_oneshot(b, 8, out);
+}
+
+void zo_merge_hashes(const uint8_t l[32], const uint8_t r[32], uint8_t out[32]) { /* :187-195 */
+    uint8_t b[64];
+    memcpy(b, l, 32);
+    memcpy(b + 32, r, 32);
+    zo_sha3_256_oneshot(b, 64, out);
+}
+
+/* ------------------------------------------------------------------ */
+/* Sumcheck                                                            */
+/* ------------------------------------------------------------------ */
+uint64_t zo_eval_univariate(uint64_t p, const uint64_t *c, uint32_t n, uint64_t x) { /* sumcheck_protocol.zig:113-123 */
+    if (n == 0) return 0;
+    uint64_t result = c[n - 1];
+    for (uint32_t i = n - 1; i > 0; i--) result = zo_f_add(p, zo_f_mul(p, result, x), c[i - 1]);
+    return result;
+}
+
+int zo_sumcheck_prove(uint64_t p, const uint64_t *evals, uint64_t n, uint64_t *round_polys, uint64_t *final_point,
+                      uint64_t *final_eval, uint64_t *claimed_sum) { /* sumcheck_prover.zig:26-91 */
+    uint32_t v;
+    int rc = zo_mle_check(n, &v);
+    if (rc) return rc;
+    if (v == 0) return ZO_ERR_NO_VARIABLES;
+    uint64_t claim = zo_mle_sum(p, evals, n); /* :40 */
+    if (claimed_sum) *claimed_sum = claim;
+    zo_transcript tr;
+    zo_transcript_init(&tr); /* State.init sumcheck_protocol.zig:149-164 */
+    uint64_t *cur = malloc(n * sizeof(uint64_t)); /* Multilinear.init dupes :47 */
+    if (!cur) return ZO_ERR_OOM;
+    memcpy(cur, evals, n * sizeof(uint64_t));
+    uint64_t len = n;
+    for (uint32_t round = 0; round < v; round++) { /* :50-77 */
+        uint64_t coeffs[2];
+        zo_mle_round_poly(p, cur, len, coeffs);
+        round_polys[2 * round] = coeffs[0];
+        round_polys[2 * round + 1] = coeffs[1];
+        zo_transcript_append_field(&tr, coeffs[0]); /* generateChallenge sumcheck_protocol.zig:176-184 */
+        zo_transcript_append_field(&tr, coeffs[1]);
+        uint64_t r = zo_transcript_challenge(&tr, p);
+        claim = zo_eval_univariate(p, coeffs, 2, r); /* :63-70, value unused by the output */
+        final_point[round] = r;
+        uint64_t *next = malloc((len / 2) * sizeof(uint64_t)); /* partialEval allocates :162 */
+        if (!next) { free(cur); return ZO_ERR_OOM; }
+        zo_mle_partial_eval(p, cur, len, r, next);
+        free(cur);
+        cur = next;
+        len /= 2;
+    }
+    *final_eval = cur[0]; /* :88 */
+    free(cur);
+    (void)claim;
+    return ZO_OK;
+}
+
+int zo_sumcheck_prove_interactive(uint64_t p, const uint64_t *evals, uint64_t n, const uint64_t *challenges,
+                                  uint32_t n_challenges, uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval) {
+    /* sumcheck_prover.zig:97-144 */
+    uint32_t v;
+    int rc = zo_mle_check(n, &v);
+    if (rc) return rc;
+    if (v == 0) return ZO_ERR_NO_VARIABLES;
+    if (n_challenges != v) return ZO_ERR_WRONG_NUM_CHALLENGES;
+    uint64_t *cur = malloc(n * sizeof(uint64_t));
+    if (!cur) return ZO_ERR_OOM;
+    memcpy(cur, evals, n * sizeof(uint64_t));
+    uint64_t len = n;
+    for (uint32_t round = 0; round < v; round++) {
+        zo_mle_round_poly(p, cur, len, &round_polys[2 * round]);
+        uint64_t *next = malloc((len / 2) * sizeof(uint64_t));
+        if (!next) { free(cur); return ZO_ERR_OOM; }
+        zo_mle_partial_eval(p, cur, len, challenges[round], next);
+        free(cur);
+        cur = next;
+        len /= 2;
+    }
+    for (uint32_t i = 0; i < v; i++) final_point[i] = challenges[i];
+    *final_eval = cur[0];
+    free(cur);
+    return ZO_OK;
+}
+
+void zo_sumcheck_proof_to_bytes(uint32_t v, const uint64_t *round_polys, const uint64_t *final_point, uint64_t final_eval,
+                                uint8_t *out) { /* sumcheck_protocol.zig:76-109 */
+    size_t off = 0;
+    le64(v, out + off); off += 8;
+    for (uint32_t i = 0; i < 2 * v; i++) { le64(round_polys[i], out + off); off += 8; }
+    for (uint32_t i = 0; i < v; i++) { le64(final_point[i], out + off); off += 8; }
+    le64(final_eval, out + off);
+}
+
+int zo_sumcheck_verify_rounds(uint64_t p, uint32_t v, uint32_t ncoef, const uint64_t *round_polys, uint64_t claimed_sum,
+                              int *is_valid, uint64_t *final_claim) { /* sumcheck_verifier.zig:172-202 */
+    zo_transcript tr;
+    zo_transcript_init(&tr);
+    uint64_t claim = claimed_sum;
+    for (uint32_t round = 0; round < v; round++) {
+        const uint64_t *rp = round_polys + (size_t)round * ncoef;
+        uint64_t e0 = zo_eval_univariate(p, rp, ncoef, 0);
+        uint64_t e1 = zo_eval_univariate(p, rp, ncoef, 1 % p);
+        if (zo_f_add(p, e0, e1) != claim) {
+            *is_valid = 0;
+            *final_claim = 0;
+            return ZO_OK;
+        }
+        for (uint32_t k = 0; k < ncoef; k++) zo_transcript_append_field(&tr, rp[k]);
+        uint64_t r = zo_transcript_challenge(&tr, p);
+        claim = zo_eval_univariate(p, rp, ncoef, r);
+    }
+    *is_valid = 1;
+    *final_claim = claim;
+    return ZO_OK;
+}
+
+/* ---- extension: product of d multilinears (no reference behaviour for d > 1) ---- */
+int zo_prodcheck_prove(uint64_t p, const uint64_t *const *polys, uint32_t d, uint64_t n, uint64_t *round_polys,
+                       uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum) {
+    uint32_t v;
+    int rc = zo_mle_check(n, &v);
+    if (rc) return rc;
+    if (v == 0 || d == 0 || d > 3) return ZO_ERR_NO_VARIABLES;
+    uint64_t *cur[3] = {0, 0, 0};
+    for (uint32_t k = 0; k < d; k++) {
+        cur[k] = malloc(n * sizeof(uint64_t));
+        if (!cur[k]) return ZO_ERR_OOM;
+        memcpy(cur[k], polys[k], n * sizeof(uint64_t));
+    }
+    if (claimed_sum) {
+        uint64_t s = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            uint64_t t = cur[0][i];
+            for (uint32_t k = 1; k < d; k++) t = zo_f_mul(p, t, cur[k][i]);
+            s = zo_f_add(p, s, t);
+        }
+        *claimed_sum = s;
+    }
+    zo_transcript tr;
+    zo_transcript_init(&tr);
+    uint64_t len = n;
+    for (uint32_t round = 0; round < v; round++) {
+        uint64_t half = len / 2;
+        uint64_t acc[4] = {0, 0, 0, 0};
+        for (uint64_t i = 0; i < half; i++) {
+            /* g_i(X) = prod_k (lo_k + (hi_k - lo_k) X), coefficient form */
+            uint64_t c[4] = {1 % p, 0, 0, 0};
+            for (uint32_t k = 0; k < d; k++) {
+                uint64_t lo = cur[k][i], df = zo_f_sub(p, cur[k][i + half], lo);
+                uint64_t nc[4] = {0, 0, 0, 0};
+                for (uint32_t j = 0; j <= k; j++) {
+                    nc[j] = zo_f_add(p, nc[j], zo_f_mul(p, c[j], lo));
+                    nc[j + 1] = zo_f_add(p, nc[j + 1], zo_f_mul(p, c[j], df));
+                }
+                memcpy(c, nc, sizeof(c));
+            }
+            for (uint32_t j = 0; j <= d; j++) acc[j] = zo_f_add(p, acc[j], c[j]);
+        }
+        for (uint32_t j = 0; j <= d; j++) {
+            round_polys[(size_t)round * (d + 1) + j] = acc[j];
+            zo_transcript_append_field(&tr, acc[j]);
+        }
+        uint64_t r = zo_transcript_challenge(&tr, p);
+        final_point[round] = r;
+        for (uint32_t k = 0; k < d; k++) {
+            uint64_t *next = malloc(half * sizeof(uint64_t));
+            if (!next) return ZO_ERR_OOM;
+            zo_mle_partial_eval(p, cur[k], len, r, next);
+            free(cur[k]);
+            cur[k] = next;
+        }
+        len = half;
+    }
+    for (uint32_t k = 0; k < d; k++) {
+        final_evals[k] = cur[k][0];
+        free(cur[k]);
+    }
+    return ZO_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* SimpleMerkleTree — /root/reference/src/commitments/merkle_tree.zig   */
+/* ------------------------------------------------------------------ */
+uint64_t zo_ceil_pow2(uint64_t n) {
+    uint64_t r = 1;
+    while (r < n) r <<= 1;
+    return r;
+}
+
+static int compute_root(const uint8_t *hashes, uint64_t count, uint8_t root[32]) { /* computeRoot :380-400 */
+    if (count == 1) {
+        memcpy(root, hashes, 32);
+        return ZO_OK;
+    }
+    uint8_t *cur = malloc(count * 32);
+    if (!cur) return ZO_ERR_OOM;
+    memcpy(cur, hashes, count * 32);
+    while (count > 1) {
+        uint64_t next_size = count / 2;
+        uint8_t *next = malloc(next_size * 32);
+        if (!next) { free(cur); return ZO_ERR_OOM; }
+        for (uint64_t i = 0; i < next_size; i++) zo_merge_hashes(cur + 64 * i, cur + 64 * i + 32, next + 32 * i);
+        free(cur);
+        cur = next;
+        count = next_size;
+    }
+    memcpy(root, cur, 32);
+    free(cur);
+    return ZO_OK;
+}
+
+int zo_merkle_build(const uint64_t *values, uint64_t n, uint8_t *leaf_hashes, uint8_t root[32], uint32_t *height) { /* :283-318 */
+    if (n == 0) return ZO_ERR_EMPTY_VALUES;
+    uint64_t padded = zo_ceil_pow2(n);
+    if (height) *height = (uint32_t)__builtin_ctzll(padded);
+    uint8_t *lh = leaf_hashes ? leaf_hashes : malloc(padded * 32);
+    if (!lh) return ZO_ERR_OOM;
+    for (uint64_t i = 0; i < n; i++) zo_hash_field_element(values[i], lh + 32 * i);
+    uint8_t zero_hash[32];
+    zo_hash_field_element(0, zero_hash);
+    for (uint64_t i = n; i < padded; i++) memcpy(lh + 32 * i, zero_hash, 32);
+    int rc = compute_root(lh, padded, root);
+    if (!leaf_hashes) free(lh);
+    return rc;
+}
+
+int zo_merkle_open(const uint64_t *values, uint64_t n, const uint8_t *leaf_hashes, uint64_t index, uint8_t *siblings,
+                   uint8_t *dirs, uint64_t *value) { /* :324-360 */
+    if (index >= n) return ZO_ERR_INDEX_OUT_OF_BOUNDS;
+    uint64_t count = zo_ceil_pow2(n);
+    uint32_t height = (uint32_t)__builtin_ctzll(count);
+    uint64_t cur_index = index;
+    uint8_t *cur = malloc(count * 32);
+    if (!cur) return ZO_ERR_OOM;
+    memcpy(cur, leaf_hashes, count * 32);
+    for (uint32_t level = 0; level < height; level++) {
+        int is_right = (cur_index % 2) == 1;
+        uint64_t sib = is_right ? cur_index - 1 : cur_index + 1;
+        memcpy(siblings + 32 * level, cur + 32 * sib, 32);
+        dirs[level] = (uint8_t)is_right;
+        uint64_t next_size = count / 2;
+        uint8_t *next = malloc(next_size * 32);
+        if (!next) { free(cur); return ZO_ERR_OOM; }
+        for (uint64_t i = 0; i < next_size; i++) zo_merge_hashes(cur + 64 * i, cur + 64 * i + 32, next + 32 * i);
+        free(cur);
+        cur = next;
+        count = next_size;
+        cur_index /= 2;
+    }
+    free(cur);
+    if (value) *value = values[index];
+    return ZO_OK;
+}
+
+int zo_merkle_verify(const uint8_t root[32], uint64_t value, const uint8_t *siblings, const uint8_t *dirs, uint32_t height) {
+    /* :362-373 */
+    uint8_t cur[32], nxt[32];
+    zo_hash_field_element(value, cur);
+    for (uint32_t l = 0; l < height; l++) {
+        if (dirs[l]) zo_merge_hashes(siblings + 32 * l, cur, nxt);
+        else zo_merge_hashes(cur, siblings + 32 * l, nxt);
+        memcpy(cur, nxt, 32);
+    }
+    return memcmp(cur, root, 32) == 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* CommitmentScheme — polynomial_commit.zig                            */
+/* ------------------------------------------------------------------ */
+uint64_t zo_point_to_index(const uint64_t *point, uint32_t npoint) { /* :178-183 */
+    if (npoint == 0) return 0;
+    return point[0] % ((uint64_t)1 << npoint);
+}
+
+int zo_commit_open(uint64_t p, const uint64_t *evals, uint64_t n, const uint8_t *leaf_hashes, const uint64_t *point,
+                   uint32_t npoint, uint64_t *value, uint64_t *leaf_index, uint64_t *leaf_value, uint8_t *siblings,
+                   uint8_t *dirs) { /* open :86-115 */
+    uint32_t v;
+    int rc = zo_mle_check(n, &v);
+    if (rc) return rc;
+    if (npoint != v) return ZO_ERR_POINT_DIM_MISMATCH;
+    rc = zo_mle_eval(p, evals, n, point, npoint, value);
+    if (rc) return rc;
+    uint64_t index = zo_point_to_index(point, npoint);
+    *leaf_index = index;
+    return zo_merkle_open(evals, n, leaf_hashes, index, siblings, dirs, leaf_value);
+}
+
+/* ------------------------------------------------------------------ */
+/* Lasso — lasso_prover.zig, table_builder.zig                          */
+/* ------------------------------------------------------------------ */
+uint64_t zo_lasso_hash_row(uint64_t p, const uint64_t *row, uint32_t arity) { /* hashEntry/hashQuery :208-239 */
+    uint64_t h = 0;
+    for (uint32_t k = 0; k < arity; k++) {
+        h ^= row[k];
+        uint8_t b[8];
+        le64(h, b);
+        h = zo_xxh3_64_small(b, 8, 0);
+    }
+    return zo_f_init(p, h % p);
+}
+
+void zo_lasso_commit_poly(const uint64_t *evals, uint64_t n, uint8_t out[32]) { /* commitToPolynomial :242-252 */
+    zo_sha3_256 c;
+    zo_sha3_256_init(&c);
+    for (uint64_t i = 0; i < n; i++) {
+        uint8_t b[8];
+        le64(evals[i], b);
+        zo_sha3_256_update(&c, b, 8);
+    }
+    zo_sha3_256_peek(&c, out);
+}
+
+void zo_build_table(uint64_t p, int op, uint32_t bits, uint64_t *rows) { /* table_builder.zig:126-213 */
+    uint64_t max_val = (uint64_t)1 << bits, idx = 0;
+    for (uint64_t a = 0; a < max_val; a++)
+        for (uint64_t b = 0; b < max_val; b++) {
+            uint64_t r = op == ZO_TABLE_ADD ? (a + b) % max_val : op == ZO_TABLE_XOR ? (a ^ b) : (a & b);
+            rows[3 * idx] = zo_f_init(p, a);
+            rows[3 * idx + 1] = zo_f_init(p, b);
+            rows[3 * idx + 2] = zo_f_init(p, r);
+            idx++;
+        }
+}
+
+int zo_lasso_prove(uint64_t p, const uint64_t *table_rows, uint64_t n_table, const uint64_t *query_rows, uint64_t n_queries,
+                   uint32_t arity, uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars,
+                   uint8_t query_commitment[32], uint8_t table_commitment[32]) { /* prove :103-173 */
+    if (n_queries == 0) return ZO_ERR_NO_QUERIES;
+    uint64_t *table_evals = malloc((n_table ? n_table : 1) * sizeof(uint64_t));
+    if (!table_evals) return ZO_ERR_OOM;
+    for (uint64_t i = 0; i < n_table; i++) table_evals[i] = zo_lasso_hash_row(p, table_rows + (size_t)i * arity, arity);
+    int rc = zo_mle_check(n_table, NULL); /* Multilinear.init(table_evals) :124 */
+    if (rc) { free(table_evals); return rc; }
+    uint64_t padded = zo_ceil_pow2(n_queries);
+    uint64_t *query_evals = malloc(padded * sizeof(uint64_t));
+    if (!query_evals) { free(table_evals); return ZO_ERR_OOM; }
+    for (uint64_t j = 0; j < n_queries; j++) query_evals[j] = zo_lasso_hash_row(p, query_rows + (size_t)j * arity, arity);
+    for (uint64_t j = n_queries; j < padded; j++) query_evals[j] = 0; /* :140-142 */
+    (void)zo_mle_sum(p, query_evals, padded);                          /* :154, result discarded */
+    uint32_t v = (uint32_t)__builtin_ctzll(padded);
+    if (num_vars) *num_vars = v;
+    rc = zo_sumcheck_prove(p, query_evals, padded, round_polys, final_point, final_eval, NULL); /* :160 */
+    if (rc == ZO_OK) {
+        zo_lasso_commit_poly(query_evals, padded, query_commitment); /* :163 */
+        zo_lasso_commit_poly(table_evals, n_table, table_commitment); /* :164 */
+    }
+    free(query_evals);
+    free(table_evals);
+    return rc;
+}
+
+int zo_lasso_prove_with_mapping(uint64_t p, const uint64_t *table_rows, uint64_t n_table, const uint64_t *query_rows,
+                                uint64_t n_queries, const uint64_t *mapping, uint64_t n_mapping, uint32_t arity,
+                                uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars,
+                                uint8_t query_commitment[32], uint8_t table_commitment[32]) { /* :179-205 */
+    if (n_queries != n_mapping) return ZO_ERR_MAPPING_LEN_MISMATCH;
+    for (uint64_t j = 0; j < n_queries; j++) {
+        if (mapping[j] >= n_table) return ZO_ERR_INVALID_MAPPING;
+        if (memcmp(query_rows + (size_t)j * arity, table_rows + (size_t)mapping[j] * arity, arity * sizeof(uint64_t)) != 0)
+            return ZO_ERR_QUERY_TABLE_MISMATCH; /* entriesMatch :255-268 */
+    }
+    return zo_lasso_prove(p, table_rows, n_table, query_rows, n_queries, arity, round_polys, final_point, final_eval, num_vars,
+                          query_commitment, table_commitment);
+}
+
+/* ------------------------------------------------------------------ */
+/* synthetic inputs                                                    */
+/* ------------------------------------------------------------------ */
+uint64_t zo_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+void zo_fill_synthetic(uint64_t p, uint64_t seed, uint64_t start, uint64_t n, uint64_t *out) {
+    for (uint64_t i = 0; i < n; i++) out[i] = zo_splitmix64(seed + start + i) % p;
+}
