@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of zigz on B200, measured as BASELINE.json asks.
+
+Headline workload (config C5 of BASELINE.json, per GPU): degree-3 product sumcheck over three 2^LOG2N-entry BabyBear
+multilinears (synthetic, counter-based), round polynomials in coefficient form, Fiat-Shamir transcript on the host.
+A "step" is one complete prove (all LOG2N + log2(N_GPUS) rounds).  metric = field elements of the hypercube per
+second, whole job.  N GPUs => the hypercube is N times larger (weak scaling), cyclically sharded, per-round partial
+sums all-reduced (NCCL) — see DESIGN.md §multi-GPU.
+
+  value : inputs resident in HBM when the clock starts (device events, max over ranks)
+  e2e   : the same prove through the C ABI from HOST u64 buffers (pinned): H2D of the three tables inside the timed
+          region, proof (round polys, point, evaluations) back on the host
+  extras: the other BASELINE configs as secondary numbers (d=1 sumcheck 2^20, Lasso 2^22, Merkle 2^26)
+
+`--impl reference` times the CPU restatement of the reference (oracle/, single thread like the reference) on a bounded
+sample of the same workload.  Nothing here reads /root/reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SEED = 0x5A49475A
+METRIC = "babybear_sumcheck_melem_per_s"
+UNIT = "Melem/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+        # clocks under load = upper half of the samples (idle samples before/after the region drag the median down)
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return rank, world, local, dist
+    return 0, 1, 0, None
+
+
+def barrier(dist):
+    if dist is not None:
+        dist.barrier()
+
+
+def max_over_ranks(dist, x, local):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    from oracle import pyoracle as po
+    BB = po.BABYBEAR_P
+    lg = args.ref_log2n
+    n = 1 << lg
+    es = [po.fill_synthetic(BB, SEED + k, 0, n) for k in range(3)]
+    for _ in range(args.warmup):
+        po.prodcheck_prove(BB, [e[: n >> 4] for e in es])  # warm caches / page in; small
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        po.prodcheck_prove(BB, es)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n / dt / 1e6
+    sample = f"degree-3 product sumcheck over three 2^{lg}-entry tables per step (same generator, same algorithm; the 2^{args.log2n} job is out of reach for one CPU thread in minutes)"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 (canonical BabyBear, u128 % reduction like the reference)", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world):
+    return {"workload": f"C5: degree-3 product sumcheck, three 2^{args.log2n}-entry BabyBear MLEs per GPU"
+                        f" (2^{args.log2n + (world - 1).bit_length()} total), coefficient-form round polys, host SHA3 transcript",
+            "log2_n_per_gpu": args.log2n, "degree": 3, "sharding": "cyclic (rank = low index bits)" if world > 1 else "none",
+            "l2": "inputs (12.9 GB at 2^30) are far larger than the 126 MB L2; no flush needed", "seed": SEED}
+
+
+# ----------------------------------------------------------------------------- our arm (GPU)
+def run_ours(args):
+    rank, world, local, dist = dist_setup(args.gpus)
+    import zigz_b200 as z
+    BB = z.BABYBEAR_P
+    ctx = z.Context(local)
+    n = 1 << args.log2n
+    d = 3
+    if world > 1:
+        from zigz_b200 import sharded
+        comm = sharded.Comm(ctx, dist, rank, world)
+    else:
+        comm = None
+
+    def make_polys():
+        # cyclic shard: local element j is global index rank + world*j
+        return [z.Multilinear.synthetic(ctx, SEED + k, n, start=rank, stride=world) for k in range(d)]
+
+    def prove(polys):
+        if comm is None:
+            return z.ProductSumcheckProver.prove(polys)
+        return comm.prodcheck_prove(polys)
+
+    polys = make_polys()
+    for _ in range(args.warmup):
+        pr = prove(polys)
+    # ---- value: device-resident inputs, device events, max over ranks
+    sampler = ClockSampler(local)
+    ctx.profile(True)
+    launches0 = ctx.kernel_launches
+    barrier(dist)
+    ctx.sync()
+    sampler.start()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        pr = prove(polys)
+    ms = ctx.timer_stop()
+    barrier(dist)
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches - launches0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    ms = max_over_ranks(dist, ms, local)
+    ms_per_step = ms / args.steps
+    total_elems = n * world
+    value = total_elems / (ms_per_step * 1e-3) / 1e6
+
+    # roofline of the dominant kernel family, from the events recorded live in the timed region
+    peak, peak_src = peaks()
+    dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0, 0))
+    dom_name, (dom_cnt, dom_ms, dom_bytes) = dom
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else 0.0
+    kernel_ms = sum(v[1] for v in prof.values())
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                "launches": dom_cnt, "avg_launch_ms": dom_ms / dom_cnt if dom_cnt else None,
+                "algorithmic_bytes_per_step": dom_bytes // max(args.steps, 1),
+                "kernel_share_of_step": dom_ms / ms if ms else None, "all_kernels_share_of_step": kernel_ms / ms if ms else None,
+                "whole_prove_frac": (48.0 * n) / (ms_per_step * 1e-3) / 1e9 / peak}
+    by_kernel = {k: {"launches": v[0], "ms": round(v[1], 4), "GBps": round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] else None}
+                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+
+    # ---- e2e: host u64 buffers -> C ABI -> proof on the host
+    e2e = None
+    if not args.skip_e2e:
+        e2e = run_e2e(args, z, ctx, comm, dist, local, rank, world, polys)
+    for p in polys:
+        p.deinit()
+
+    extras = None
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_extras:
+        extras = run_extras(args, z, ctx, peak)
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = cpu_baseline(args)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32 (canonical BabyBear in registers; u64 accumulators)", "data": "synthetic",
+                "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "kernels": by_kernel}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if extras:
+            line["extras"] = extras
+        print(json.dumps(line))
+    barrier(dist)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, z, ctx, comm, dist, local, rank, world, polys):
+    """Same prove, inputs in pinned HOST memory as the reference's u64 field elements."""
+    n = 1 << args.log2n
+    host = []
+    for p in polys:  # untimed: materialise this rank's shard on the host
+        h = ctx.pinned(n, np.uint64)
+        ctx.check(z.lib().zb_mle_download(ctx.handle, p.handle, h.ctypes.data_as(z.api.P64), n))
+        host.append(h)
+
+    def step():
+        ms_ = [z.Multilinear.init(ctx, h) for h in host]
+        pr = z.ProductSumcheckProver.prove(ms_, consume=True) if comm is None else comm.prodcheck_prove(ms_, consume=True)
+        for m in ms_:
+            m.deinit()
+        return pr
+
+    step()  # warm-up (allocator cache, page tables)
+    steps = max(1, min(args.steps, args.e2e_steps))
+    barrier(dist)
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pr = step()
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    dt = max_over_ranks(dist, dt, local)
+    v = pr.num_vars
+    d2h = (v * 4 + v + 3) * 8
+    return {"value": n * world / (dt / steps) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 3 * n * 8 * world,
+            "d2h_bytes_per_step": d2h * world, "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "api": "zb_mle_upload x3 + zh_prodcheck_prove_consume (include/zigz_b200.h, zigz_host.h)"}
+
+
+def timed(ctx, fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(reps):
+        fn()
+    return ctx.timer_stop() / reps
+
+
+def run_extras(args, z, ctx, peak):
+    """Secondary numbers for the other BASELINE configs (single GPU)."""
+    out = {}
+    # C1: d=1 sumcheck over 2^20 (the reference's own API, SumcheckProver.prove)
+    p20 = z.Multilinear.synthetic(ctx, SEED, 1 << 20)
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(3):
+        z.SumcheckProver.prove(p20)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        z.SumcheckProver.prove(p20)
+    dt = (time.perf_counter() - t0) / reps
+    out["C1_sumcheck_d1_2^20"] = {"ms": dt * 1e3, "melem_per_s": (1 << 20) / dt / 1e6, "note": "latency-bound: 20 host round trips"}
+    p20.deinit()
+    # d=1 sumcheck over 2^28: HBM-bound regime of the reference's own prover
+    lg = min(28, args.log2n)
+    pb = z.Multilinear.synthetic(ctx, SEED, 1 << lg)
+    ms = timed(ctx, lambda: z.SumcheckProver.prove(pb), 5)
+    out[f"sumcheck_d1_2^{lg}"] = {"ms": ms, "melem_per_s": (1 << lg) / ms / 1e3, "hbm_frac_16B_per_elem": 16.0 * (1 << lg) / (ms * 1e-3) / 1e9 / peak}
+    # MLE eval at 2^lg
+    pt = np.arange(1, lg + 1, dtype=np.uint64) * 7919 % z.BABYBEAR_P
+    ms = timed(ctx, lambda: pb.eval(pt), 5)
+    out[f"mle_eval_2^{lg}"] = {"ms": ms, "hbm_frac_4B_per_elem": 4.0 * (1 << lg) / (ms * 1e-3) / 1e9 / peak}
+    pb.deinit()
+    # C3: Merkle commitment of a 2^26-entry witness polynomial + 16 openings
+    lgm = min(26, args.log2n)
+    pm = z.Multilinear.synthetic(ctx, SEED + 9, 1 << lgm)
+    trees = []
+
+    def commit():
+        com, tree = z.CommitmentScheme.commit(pm)
+        trees.append(tree)
+        while len(trees) > 1:
+            trees.pop(0).deinit()
+    ms = timed(ctx, commit, 3, warm=1)
+    hashes = 2 * (1 << lgm) - 1
+    t0 = time.perf_counter()
+    for i in range(16):
+        trees[-1].open((i * 2654435761) % (1 << lgm))
+    open_ms = (time.perf_counter() - t0) / 16 * 1e3
+    out[f"C3_merkle_commit_2^{lgm}"] = {"ms": ms, "keccak_per_s": hashes / (ms * 1e-3), "hbm_frac_68B_per_leaf": 68.0 * (1 << lgm) / (ms * 1e-3) / 1e9 / peak,
+                                         "open_ms": open_ms}
+    trees.pop().deinit()
+    pm.deinit()
+    # C2: Lasso over the 8-bit ADD/AND/XOR subtables, 2^22 lookups each (host rows -> proof)
+    lgq = min(22, args.log2n)
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, size=1 << lgq, dtype=np.uint64)
+    b = rng.integers(0, 256, size=1 << lgq, dtype=np.uint64)
+    res = {}
+    for name, code, f in (("add", z.TABLE_ADD, lambda x, y: (x + y) & 255), ("and", z.TABLE_AND, lambda x, y: x & y),
+                          ("xor", z.TABLE_XOR, lambda x, y: x ^ y)):
+        q = np.ascontiguousarray(np.stack([a, b, f(a, b)], axis=1))
+        z.LassoProver.prove_builtin(ctx, code, 8, q[:1024])
+        t0 = time.perf_counter()
+        z.LassoProver.prove_builtin(ctx, code, 8, q)
+        res[name] = (time.perf_counter() - t0) * 1e3
+    out[f"C2_lasso_2^{lgq}_lookups"] = {"ms_per_table": res, "note": "dominated by the two flat SHA3 commitments, one sequential host sponge (lasso_prover.zig:242-252)"}
+    return out
+
+
+def cpu_baseline(args):
+    """The oracle (single-threaded restatement of the reference) on a bounded sample of the same workload."""
+    from oracle import pyoracle as po
+    BB = po.BABYBEAR_P
+    lg = args.cpu_log2n
+    n = 1 << lg
+    es = [po.fill_synthetic(BB, SEED + k, 0, n) for k in range(3)]
+    t0 = time.perf_counter()
+    po.prodcheck_prove(BB, es)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
+            "sample": f"one degree-3 product sumcheck over three 2^{lg}-entry tables (same generator and algorithm as the GPU job, "
+                      f"1/{1 << (args.log2n - lg)} of its size); the reference is single-threaded, so is the port",
+            "host_cores_available": os.cpu_count()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2n", type=int, default=30, help="log2 of the per-GPU table length")
+    ap.add_argument("--cpu-log2n", type=int, default=26)
+    ap.add_argument("--ref-log2n", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

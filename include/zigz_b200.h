@@ -1,0 +1,149 @@
+/* zigz_b200.h — C ABI of the B200 device layer for the zigz proving hot path.
+ *
+ * The reference (ch4r10t33r/zigz) has no FFI surface: callers use comptime-generic
+ * Zig types (src/lib.zig:9-17). Each entry point below replaces the body of the
+ * reference function cited next to it; a Zig host binds them with `extern fn`
+ * (see INTEGRATION.md). Plain pointers and sizes only; no torch / CUDA types.
+ *
+ * Conventions
+ *   - field elements cross the boundary as the reference's `struct { value: u64 }`
+ *     (src/core/field.zig:26-27): canonical BabyBear values in [0, p), 8-byte LE.
+ *     On the device they are stored as canonical u32.
+ *   - every call returns int32 status: 0 = ok, negative = the reference's Zig error
+ *     (names below) or a device error. Nothing falls back to the CPU.
+ *   - one context per host thread and GPU; calls on a context are synchronous and
+ *     serialized, like the single-threaded reference.
+ *   - device objects are opaque 64-bit handles released explicitly.
+ */
+#ifndef ZIGZ_B200_H
+#define ZIGZ_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZB_BABYBEAR_P 2013265921u /* src/core/field_presets.zig:19 */
+
+typedef struct zb_ctx zb_ctx;
+typedef uint64_t zb_mle;  /* Multilinear(BabyBear) resident in HBM */
+typedef uint64_t zb_tree; /* SimpleMerkleTree(BabyBear, SHA3Hasher) resident in HBM, all levels retained */
+
+enum zb_status {
+    ZB_OK = 0,
+    ZB_ERR_EMPTY_EVALUATIONS = -1,     /* multilinear.zig:38 */
+    ZB_ERR_LENGTH_NOT_POW2 = -2,       /* multilinear.zig:43 */
+    ZB_ERR_WRONG_NUM_VARS = -3,        /* multilinear.zig:112 */
+    ZB_ERR_NO_VARIABLES = -4,          /* multilinear.zig:156,207; sumcheck_prover.zig:31 */
+    ZB_ERR_EMPTY_VALUES = -5,          /* merkle_tree.zig:284 */
+    ZB_ERR_INDEX_OUT_OF_BOUNDS = -6,   /* merkle_tree.zig:325 */
+    ZB_ERR_POINT_DIM_MISMATCH = -7,    /* polynomial_commit.zig:93 */
+    ZB_ERR_NO_QUERIES = -8,            /* lasso_prover.zig:109 */
+    ZB_ERR_MAPPING_LEN_MISMATCH = -9,  /* lasso_prover.zig:186 */
+    ZB_ERR_INVALID_MAPPING = -10,      /* lasso_prover.zig:192 */
+    ZB_ERR_QUERY_TABLE_MISMATCH = -11, /* lasso_prover.zig:199 */
+    ZB_ERR_WRONG_NUM_CHALLENGES = -12, /* sumcheck_prover.zig:105 */
+    ZB_ERR_DIFFERENT_NUM_VARS = -13,   /* multilinear.zig:237 */
+    ZB_ERR_NOT_CANONICAL = -20,        /* an input element was >= p (reference asserts val < MODULUS, field.zig:43) */
+    ZB_ERR_BAD_HANDLE = -21,
+    ZB_ERR_BAD_ARGUMENT = -22,
+    ZB_ERR_OOM = -100,                 /* error.OutOfMemory */
+    ZB_ERR_NO_DEVICE = -200,           /* no CUDA device / driver: there is no CPU fallback */
+    ZB_ERR_CUDA = -201,                /* see zb_last_error() */
+    ZB_ERR_TIMEOUT = -202
+};
+
+/* ---- context ---- */
+int32_t zb_ctx_create(int32_t device, zb_ctx **out);
+void zb_ctx_destroy(zb_ctx *ctx);
+const char *zb_last_error(zb_ctx *ctx);
+const char *zb_status_name(int32_t status);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t zb_kernel_launches(zb_ctx *ctx);
+/* pinned host memory for fast transfers (optional; any host pointer is accepted everywhere) */
+int32_t zb_host_alloc(zb_ctx *ctx, size_t bytes, void **out);
+int32_t zb_host_free(zb_ctx *ctx, void *p);
+int32_t zb_device_info(zb_ctx *ctx, int32_t *sm_count, uint64_t *total_mem, uint64_t *free_mem);
+/* raw stream handle (cudaStream_t) the context launches on: for CUDA-event timing by a harness */
+void *zb_stream(zb_ctx *ctx);
+int32_t zb_sync(zb_ctx *ctx);
+/* CUDA-event stopwatch on the context's stream (device time between the two calls, in milliseconds) */
+int32_t zb_timer_start(zb_ctx *ctx);
+int32_t zb_timer_stop(zb_ctx *ctx, float *ms);
+/* per-kernel accounting for the roofline: while enabled every launch is bracketed by CUDA events on the launching
+ * stream and accumulated by kernel family together with its ALGORITHMIC bytes (DESIGN.md gives the formula per kernel).
+ * enable(1) clears the table. */
+int32_t zb_profile_enable(zb_ctx *ctx, int32_t on);
+uint32_t zb_profile_count(zb_ctx *ctx);
+int32_t zb_profile_entry(zb_ctx *ctx, uint32_t i, char *name, uint32_t name_cap, uint64_t *launches, double *total_ms,
+                         uint64_t *algorithmic_bytes);
+
+/* ---- Multilinear(F): src/poly/multilinear.zig ---- */
+/* init :36-54 — copies `n` evaluations to the device; n must be a power of two, every value < p */
+int32_t zb_mle_upload(zb_ctx *ctx, const uint64_t *evals, uint64_t n, zb_mle *out);
+/* same, from canonical u32 host values (narrow host representation; optional fast path) */
+int32_t zb_mle_upload_u32(zb_ctx *ctx, const uint32_t *evals, uint64_t n, zb_mle *out);
+/* zero :57-70 / constant :73-86 */
+int32_t zb_mle_constant(zb_ctx *ctx, uint32_t num_vars, uint64_t value, zb_mle *out);
+/* synthetic input generated on the device: e[i] = splitmix64(seed + start + i*stride) mod p */
+int32_t zb_mle_synthetic(zb_ctx *ctx, uint64_t seed, uint64_t start, uint64_t stride, uint64_t n, zb_mle *out);
+int32_t zb_mle_clone(zb_ctx *ctx, zb_mle src, zb_mle *out);
+/* deinit :89-91 */
+int32_t zb_mle_free(zb_ctx *ctx, zb_mle m);
+int32_t zb_mle_len(zb_ctx *ctx, zb_mle m, uint64_t *n, uint32_t *num_vars);
+int32_t zb_mle_download(zb_ctx *ctx, zb_mle m, uint64_t *out, uint64_t n);
+/* evaluations [offset, offset + n) */
+int32_t zb_mle_download_range(zb_ctx *ctx, zb_mle m, uint64_t offset, uint64_t *out, uint64_t n);
+/* sumOverHypercube :188-194 */
+int32_t zb_mle_sum(zb_ctx *ctx, zb_mle m, uint64_t *out);
+/* roundPolynomial :205-232 — returns the two half sums (s0, s1) mod p; the host forms [s0, s1 - s0] */
+int32_t zb_mle_round_sums(zb_ctx *ctx, zb_mle m, uint64_t out_s0_s1[2]);
+/* partialEval :154-180 — new[i] = (1-r)*e[i] + r*e[i+n/2] (binds the TOP index bit). Returns a NEW polynomial.
+ * If next_s0_s1 != NULL the same kernel also produces the next round's half sums (for n/2 == 1 both slots hold
+ * the single remaining evaluation and 0). */
+int32_t zb_mle_partial_eval(zb_ctx *ctx, zb_mle m, uint64_t r, zb_mle *out, uint64_t next_s0_s1[2]);
+/* the same fold, in place: the handle keeps its identity and halves its length (no allocation in the round loop) */
+int32_t zb_mle_fold_inplace(zb_ctx *ctx, zb_mle m, uint64_t r, uint64_t next_s0_s1[2]);
+/* eval :110-144 — LSB-first: point[k] <-> index bit k. O(N) fold instead of the reference's O(N*v) loop; same value */
+int32_t zb_mle_eval(zb_ctx *ctx, zb_mle m, const uint64_t *point, uint32_t npoint, uint64_t *out);
+/* add :235-250 / scalarMul :253-264 */
+int32_t zb_mle_add(zb_ctx *ctx, zb_mle a, zb_mle b, zb_mle *out);
+int32_t zb_mle_scalar_mul(zb_ctx *ctx, zb_mle a, uint64_t scalar, zb_mle *out);
+
+/* ---- product sumcheck rounds (extension in reference conventions) ----
+ * g(X) = sum_i prod_k (lo_k[i] + (hi_k[i] - lo_k[i]) X) over the d (1..3) polynomials, MSB-first pairs (i, i+n/2).
+ * out_coeffs receives the d+1 COEFFICIENTS [a0..ad] (canonical). d == 1 equals roundPolynomial. */
+int32_t zb_prod_round_coeffs(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *out_coeffs);
+/* folds all d polynomials in place with r; if next_coeffs != NULL also returns the next round's coefficients.
+ * When the folded length is 1, next_coeffs[0..d) receives the d final evaluations instead. */
+int32_t zb_prod_fold_inplace(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, uint64_t *next_coeffs);
+/* the same fold out of place (partialEval semantics for all d polynomials): `out` receives d NEW handles */
+int32_t zb_prod_partial_eval(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, zb_mle *out, uint64_t *next_coeffs);
+
+/* ---- SimpleMerkleTree(F, SHA3Hasher): src/commitments/merkle_tree.zig:273-402 ---- */
+/* build :283-318 for `count` polynomials of equal length in one batch (CommitmentScheme.batchCommit,
+ * polynomial_commit.zig:132-157; Prover.generateCommitments, prover.zig:405-410). roots: count*32 bytes. */
+int32_t zb_merkle_build(zb_ctx *ctx, const zb_mle *polys, uint32_t count, zb_tree *trees, uint8_t *roots);
+/* build from host values of arbitrary length n >= 1 (pads to a power of two with hash(0), :303-306) */
+int32_t zb_merkle_build_values(zb_ctx *ctx, const uint64_t *values, uint64_t n, zb_tree *tree, uint8_t root[32]);
+int32_t zb_merkle_info(zb_ctx *ctx, zb_tree t, uint64_t *n_values, uint32_t *height, uint8_t root[32]);
+/* open :324-360 — siblings: height*32 bytes leaf->root, dirs[l] = (index >> l) & 1, leaf_value = values[index] */
+int32_t zb_merkle_open(zb_ctx *ctx, zb_tree t, uint64_t index, uint8_t *siblings, uint8_t *dirs, uint64_t *leaf_value);
+/* leaf_hashes copy-out (tests): padded*32 bytes */
+int32_t zb_merkle_leaf_hashes(zb_ctx *ctx, zb_tree t, uint8_t *out, uint64_t n_digests);
+int32_t zb_merkle_free(zb_ctx *ctx, zb_tree t);
+
+/* ---- Lasso: src/lookups/lasso_prover.zig:208-239, table_builder.zig:126-213 ---- */
+/* hashEntry / hashQuery over flattened rows (inputs || outputs), `arity` u64 each:
+ * h = 0; for x in row: h ^= x; h = XXH3_64(seed 0, le64(h)); eval = h % p. Rows beyond n_rows up to n_padded are zero
+ * (lasso_prover.zig:140-142). Result is a Multilinear of n_padded (power of two) evaluations. */
+int32_t zb_xxh3_rows(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, zb_mle *out);
+/* buildAddTable (op 0) / buildXorTable (1) / buildAndTable (2) hashed directly on the device:
+ * entry index = a * 2^bits + b -> hashEntry((a, b) -> op(a, b)) */
+int32_t zb_table_mle(zb_ctx *ctx, int32_t op, uint32_t bits, zb_mle *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZIGZ_B200_H */

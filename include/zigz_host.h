@@ -1,0 +1,107 @@
+/* zigz_host.h — C exports of the HOST side of the zigz proving hot path.
+ *
+ * The reference's host language is Zig; no Zig toolchain exists in the build image, so the host bodies that a
+ * Zig maintainer would keep (Fiat-Shamir transcript, the sumcheck round loop, proof assembly, the commitment
+ * scheme glue, the Lasso driver) are written in C++ ON TOP OF the device C ABI of zigz_b200.h — they call
+ * nothing but zb_* entry points — and are exported here with plain-C signatures so that tests (ctypes) and a Zig
+ * host can drive them. Function-for-function they mirror the reference API named beside each entry:
+ * same argument meaning, same outputs, same error names (enum zb_status).
+ *
+ * The transcript, the per-round challenge derivation and all proof bytes are produced on the host, exactly as in
+ * the reference; the device only ever sees evaluation tables, one challenge per round and digests.
+ */
+#ifndef ZIGZ_HOST_H
+#define ZIGZ_HOST_H
+#include "zigz_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- FiatShamirTranscript: src/core/hash.zig:255-324 (host-resident SHA3-256 sponge) ---- */
+typedef struct zh_transcript zh_transcript;
+zh_transcript *zh_transcript_new(void);                                         /* init :261-276 */
+zh_transcript *zh_transcript_clone(const zh_transcript *t);
+void zh_transcript_free(zh_transcript *t);
+void zh_transcript_append_field(zh_transcript *t, uint64_t value);              /* appendFieldElement :279-283 */
+void zh_transcript_append_fields(zh_transcript *t, const uint64_t *v, size_t n); /* appendFieldElements :286-290 */
+void zh_transcript_append_bytes(zh_transcript *t, const void *data, size_t n);  /* appendBytes :293-295 */
+uint64_t zh_transcript_challenge(zh_transcript *t);                             /* challenge(BabyBear) :301-316 */
+void zh_transcript_finalize(zh_transcript *t, uint8_t out[32]);                 /* finalize :319-323 */
+/* std.crypto.hash.sha3.Sha3_256 one-shot (hashBytesSHA3, hash.zig:150-160) */
+void zh_sha3_256(const void *data, size_t n, uint8_t out[32]);
+/* digestToFieldElement(BabyBear) hash.zig:228-242 */
+uint64_t zh_digest_to_field(const uint8_t digest[32]);
+
+/* ---- BabyBear = Field(u64, 2013265921): src/core/field.zig (host scalar ops used by the twin) ---- */
+uint64_t zh_f_add(uint64_t a, uint64_t b); /* :73-88 */
+uint64_t zh_f_sub(uint64_t a, uint64_t b); /* :91-98 */
+uint64_t zh_f_mul(uint64_t a, uint64_t b); /* :112-147 */
+/* evalUnivariateCoeffs: src/proofs/sumcheck_protocol.zig:113-123 */
+uint64_t zh_eval_univariate(const uint64_t *coeffs, uint32_t n, uint64_t x);
+
+/* ---- SumcheckProver(BabyBear): src/proofs/sumcheck_prover.zig ---- */
+/* prove :26-91. `poly` is left untouched (the reference copies it, :47). round_polys: v*2 coefficients [s0, s1-s0],
+ * final_point: v challenges, final_eval: current_poly.evaluations[0], claimed_sum: sumOverHypercube (:40).
+ * error.NoVariables when num_vars == 0. */
+int32_t zh_sumcheck_prove(zb_ctx *ctx, zb_mle poly, uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval,
+                          uint64_t *claimed_sum);
+/* proveInteractive :97-144 — error.WrongNumberOfChallenges when n_challenges != num_vars */
+int32_t zh_sumcheck_prove_interactive(zb_ctx *ctx, zb_mle poly, const uint64_t *challenges, uint32_t n_challenges,
+                                      uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval);
+/* SumcheckProof.toBytes: src/proofs/sumcheck_protocol.zig:76-109. out: (2 + 3v)*8 bytes; returns the byte count */
+size_t zh_sumcheck_proof_to_bytes(uint32_t num_vars, const uint64_t *round_polys, const uint64_t *final_point,
+                                  uint64_t final_eval, uint8_t *out);
+/* Product sumcheck of d (1..3) polynomials — extension in the reference's conventions:
+ * round polynomial in coefficient form [a0..ad], MSB-first binding, the transcript absorbs every coefficient as le64
+ * and then challenge(). d == 1 produces exactly zh_sumcheck_prove's output. round_polys: v*(d+1), final_evals: d.
+ * The inputs are left untouched. */
+int32_t zh_prodcheck_prove(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *round_polys, uint64_t *final_point,
+                           uint64_t *final_evals, uint64_t *claimed_sum);
+/* same, consuming the inputs (folded in place: no extra device memory; handles end with length 1) */
+int32_t zh_prodcheck_prove_consume(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *round_polys,
+                                   uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum);
+
+/* ---- CommitmentScheme(BabyBear, SHA3Hasher): src/commitments/polynomial_commit.zig ---- */
+/* commit :69-83 */
+int32_t zh_commit(zb_ctx *ctx, zb_mle poly, zb_tree *tree, uint8_t root[32], uint32_t *num_vars);
+/* batchCommit :132-157 */
+int32_t zh_batch_commit(zb_ctx *ctx, const zb_mle *polys, uint32_t count, zb_tree *trees, uint8_t *roots);
+/* open :86-115 — value = poly.eval(point), leaf_index = pointToIndex(point) (:178-183), Merkle path of that leaf.
+ * siblings: num_vars*32 bytes, dirs: num_vars bytes. error.PointDimensionMismatch when npoint != num_vars */
+int32_t zh_commit_open(zb_ctx *ctx, zb_mle poly, zb_tree tree, const uint64_t *point, uint32_t npoint, uint64_t *value,
+                       uint64_t *leaf_index, uint64_t *leaf_value, uint8_t *siblings, uint8_t *dirs);
+/* pointToIndex :178-183 */
+uint64_t zh_point_to_index(const uint64_t *point, uint32_t npoint);
+/* SimpleMerkleTree.verify: src/commitments/merkle_tree.zig:362-373 (host; O(height) hashes). returns 1 / 0 */
+int32_t zh_merkle_verify(const uint8_t root[32], uint64_t value, const uint8_t *siblings, const uint8_t *dirs, uint32_t height);
+/* CommitmentScheme.verify :118-129 : opening.value == proof.value is NOT checked there; only the path. returns 1 / 0 */
+int32_t zh_commit_verify(const uint8_t root[32], uint64_t leaf_value, const uint8_t *siblings, const uint8_t *dirs,
+                         uint32_t height);
+
+/* ---- LassoProver(BabyBear): src/lookups/lasso_prover.zig ---- */
+/* prove :103-173. Rows are flattened (inputs || outputs), `arity` u64 each (the reference's TableEntry / LookupQuery
+ * hold separately allocated slices, table_builder.zig:14-35, lasso_prover.zig:65-86).
+ * Outputs: the sumcheck proof of the zero-padded query polynomial (round_polys: v*2, final_point: v), num_vars = v,
+ * query_commitment / table_commitment = commitToPolynomial (:242-252, flat SHA3 over le64 evaluations, host).
+ * error.NoQueries, error.LengthNotPowerOfTwo (table), error.NoVariables (a single query => v = 0). */
+int32_t zh_lasso_prove(zb_ctx *ctx, const uint64_t *table_rows, uint64_t n_table, const uint64_t *query_rows,
+                       uint64_t n_queries, uint32_t arity, uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval,
+                       uint32_t *num_vars, uint8_t query_commitment[32], uint8_t table_commitment[32]);
+/* proveWithMapping :179-205 */
+int32_t zh_lasso_prove_with_mapping(zb_ctx *ctx, const uint64_t *table_rows, uint64_t n_table, const uint64_t *query_rows,
+                                    uint64_t n_queries, const uint64_t *mapping, uint64_t n_mapping, uint32_t arity,
+                                    uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars,
+                                    uint8_t query_commitment[32], uint8_t table_commitment[32]);
+/* the same proof for a table generated on the device (buildAddTable / buildXorTable / buildAndTable,
+ * table_builder.zig:126-213; op 0/1/2, `bits`-wide operands): no host table, no table upload */
+int32_t zh_lasso_prove_builtin(zb_ctx *ctx, int32_t op, uint32_t bits, const uint64_t *query_rows, uint64_t n_queries,
+                               uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars,
+                               uint8_t query_commitment[32], uint8_t table_commitment[32]);
+/* commitToPolynomial :242-252 of a device-resident polynomial */
+int32_t zh_lasso_commit_poly(zb_ctx *ctx, zb_mle poly, uint8_t out[32]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZIGZ_HOST_H */

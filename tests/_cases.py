@@ -1,0 +1,45 @@
+"""Shared helpers: rebuild the inputs the golden file describes (seeded synthetic data) and compare proofs."""
+import numpy as np
+
+BB = 2013265921
+MASK = (1 << 64) - 1
+
+
+def splitmix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & MASK
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & MASK
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & MASK
+    return x ^ (x >> 31)
+
+
+def synthetic(seed, n, p=BB, start=0, stride=1):
+    return np.array([splitmix64((seed + start + i * stride) & MASK) % p for i in range(n)], dtype=np.uint64)
+
+
+def sumcheck_case_evals(case):
+    if "evals" in case:
+        return np.array(case["evals"], np.uint64)
+    if case.get("pattern") == "i+1":
+        return np.arange(1, case["n"] + 1, dtype=np.uint64)
+    return synthetic(case["seed"], case["n"], case["p"])
+
+
+def lasso_queries(op, bits, n):
+    m = 1 << bits
+    f = {"add": lambda a, b: (a + b) % m, "xor": lambda a, b: a ^ b, "and": lambda a, b: a & b}[op]
+    rows = []
+    for j in range(n):
+        a, b = splitmix64(3 * j) & (m - 1), splitmix64(3 * j + 1) & (m - 1)
+        rows.append([a, b, f(a, b)])
+    return np.array(rows, np.uint64)
+
+
+def assert_sumcheck_equal(proof, gold, ncoef=2):
+    v = len(gold["final_point"])
+    assert proof.num_vars == v
+    assert np.asarray(proof.round_polys if hasattr(proof, "round_polys") else proof.round_polynomials)[:v].tolist() == gold["round_polys"]
+    assert np.asarray(proof.final_point)[:v].tolist() == gold["final_point"]
+    if "final_eval" in gold:
+        assert proof.final_eval == gold["final_eval"]
+    if "final_evals" in gold:
+        assert list(proof.final_evals) == gold["final_evals"]

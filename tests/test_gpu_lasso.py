@@ -1,0 +1,110 @@
+"""LassoProver on the GPU (XXH3 row hashing + sumcheck on the device, flat SHA3 commitments on the host)."""
+import numpy as np
+import pytest
+
+from _cases import BB, assert_sumcheck_equal, lasso_queries
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(pr, want):
+    assert pr.sumcheck_proof.num_vars == want.sumcheck.num_vars
+    assert pr.sumcheck_proof.round_polynomials.tolist() == want.sumcheck.round_polys.tolist()
+    assert pr.sumcheck_proof.final_point.tolist() == want.sumcheck.final_point.tolist()
+    assert pr.sumcheck_proof.final_eval == want.sumcheck.final_eval
+    assert pr.query_commitment == want.query_commitment and pr.table_commitment == want.table_commitment
+    assert pr.num_lookups == want.num_lookups
+
+
+def test_golden(zlib, ctx, golden):
+    g = golden["lasso"]
+    xor2 = zlib.build_xor_table(2)
+    c = g["xor2_queries"]
+    for pr in (zlib.LassoProver.prove(ctx, xor2, c["queries"]),
+               zlib.LassoProver.prove_with_mapping(ctx, xor2, c["queries"], c["mapping"])):
+        assert_sumcheck_equal(pr.sumcheck_proof, c["sumcheck"])
+        assert (pr.query_commitment.hex(), pr.table_commitment.hex()) == (c["query_commitment"], c["table_commitment"])
+        assert pr.num_lookups == 3
+    for op, build, code in (("add", zlib.build_add_table, zlib.TABLE_ADD), ("xor", zlib.build_xor_table, zlib.TABLE_XOR),
+                            ("and", zlib.build_and_table, zlib.TABLE_AND)):
+        c = g[f"{op}4_200"]
+        q = lasso_queries(op, 4, 200)
+        for pr in (zlib.LassoProver.prove(ctx, build(4), q), zlib.LassoProver.prove_builtin(ctx, code, 4, q)):
+            assert pr.sumcheck_proof.num_vars == 8
+            assert_sumcheck_equal(pr.sumcheck_proof, c["sumcheck"])
+            assert (pr.query_commitment.hex(), pr.table_commitment.hex()) == (c["query_commitment"], c["table_commitment"])
+
+
+def test_hash_rows_vs_oracle(zlib, ctx, po):
+    rng = np.random.default_rng(0)
+    L = zlib.lib()
+    import ctypes as C
+    for arity in (1, 2, 3, 5):
+        rows = rng.integers(0, BB, size=(1000, arity), dtype=np.uint64)
+        rows[0] = 0
+        rows[1] = BB - 1
+        h = C.c_uint64(0)
+        ctx.check(L.zb_xxh3_rows(ctx.handle, rows.ctypes.data_as(C.POINTER(C.c_uint64)), 1000, arity, 1024, C.byref(h)))
+        got = zlib.Multilinear(ctx, h.value).evaluations
+        want = [po.lasso_hash_row(BB, r) for r in rows] + [0] * 24  # zero padding lasso_prover.zig:140-142
+        assert got.tolist() == want
+    assert zlib.Multilinear(ctx, _table(zlib, ctx, 1, 4)).evaluations.tolist() == \
+        [po.lasso_hash_row(BB, r) for r in po.build_table(BB, po.TABLE_XOR, 4)]
+
+
+def _table(zlib, ctx, op, bits):
+    import ctypes as C
+    h = C.c_uint64(0)
+    ctx.check(zlib.lib().zb_table_mle(ctx.handle, op, bits, C.byref(h)))
+    return h.value
+
+
+@pytest.mark.parametrize("op", ["add", "xor", "and"])
+@pytest.mark.parametrize("nq", [2, 3, 1000, 4096, 3 * 1024])
+def test_prove_vs_oracle_8bit_tables(zlib, ctx, po, op, nq):
+    """RV64I ADD/AND/XOR 8-bit subtables (65536 entries, the XOR8 shape of table_decomposition.zig:130-164)."""
+    code = {"add": po.TABLE_ADD, "xor": po.TABLE_XOR, "and": po.TABLE_AND}[op]
+    table = po.build_table(BB, code, 8)
+    q = lasso_queries(op, 8, nq)
+    want = po.lasso_prove(BB, table, q)
+    _same(zlib.LassoProver.prove(ctx, table, q), want)
+    _same(zlib.LassoProver.prove_builtin(ctx, code, 8, q), want)
+    mapping = q[:, 0] * 256 + q[:, 1]
+    _same(zlib.LassoProver.prove_with_mapping(ctx, table, q, mapping), want)
+
+
+def test_errors(zlib, ctx):  # lasso_prover.zig:108-110, 186-201, 352-412
+    xor2 = zlib.build_xor_table(2)
+    with pytest.raises(zlib.ZigzError) as e:
+        zlib.LassoProver.prove(ctx, xor2, np.zeros((0, 3), np.uint64))
+    assert e.value.name == "NoQueries"
+    with pytest.raises(zlib.ZigzError) as e:  # one query pads to 2^0: SumcheckProver.prove -> NoVariables
+        zlib.LassoProver.prove_with_mapping(ctx, xor2, [[3, 2, 1]], [14])
+    assert e.value.name == "NoVariables"
+    q = [[3, 2, 1], [0, 0, 0]]
+    assert zlib.LassoProver.prove_with_mapping(ctx, xor2, q, [14, 0]).num_lookups == 2
+    for mapping, name in (([13, 0], "QueryTableMismatch"), ([16, 0], "InvalidMapping"), ([14], "MappingLengthMismatch")):
+        with pytest.raises(zlib.ZigzError) as e:
+            zlib.LassoProver.prove_with_mapping(ctx, xor2, q, mapping)
+        assert e.value.name == name
+    with pytest.raises(zlib.ZigzError) as e:  # Multilinear.init(table_evals): 15 entries
+        zlib.LassoProver.prove(ctx, xor2[:15], q)
+    assert e.value.name == "LengthNotPowerOfTwo"
+
+
+def test_full_size_lookup_properties(zlib, ctx, po):
+    """2^22 lookups (BASELINE config 2): commitments are checked against hashlib over the downloaded evaluations
+    is too slow for the oracle's sumcheck, so use structure: the proof of 2^22 queries that repeat a 2^12 block must
+    (a) pass the verifier's round checks and (b) have claimed sum = 2^10 * sum of the block's hashes."""
+    blk = lasso_queries("xor", 8, 1 << 12)
+    q = np.tile(blk, (1 << 10, 1))
+    pr = zlib.LassoProver.prove_builtin(ctx, zlib.TABLE_XOR, 8, q)
+    assert pr.sumcheck_proof.num_vars == 22
+    block_sum = sum(po.lasso_hash_row(BB, r) for r in blk) % BB
+    rp = pr.sumcheck_proof.round_polynomials
+    claimed = (2 * int(rp[0][0]) + int(rp[0][1])) % BB
+    assert claimed == block_sum * (1 << 10) % BB
+    ok, final_claim = po.sumcheck_verify_rounds(BB, rp, claimed)
+    assert ok and final_claim == pr.sumcheck_proof.final_eval
+    want_small = po.lasso_prove(BB, po.build_table(BB, po.TABLE_XOR, 8), blk)
+    assert pr.table_commitment == want_small.table_commitment

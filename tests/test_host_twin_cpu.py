@@ -1,0 +1,92 @@
+"""Host twin (C++ FiatShamirTranscript / SHA3 / field / verify / serialisation) against the oracle and the golden
+vectors. These run on the CPU box: none of them touches the device ABI."""
+import hashlib
+import random
+
+import numpy as np
+
+from _cases import BB
+
+
+def test_sha3_host_vs_hashlib(zlib):
+    rng = random.Random(5)
+    for n in list(range(0, 300)) + [136 * 5, 136 * 5 + 3, 8 * 17 * 9, 5000]:
+        data = bytes(rng.getrandbits(8) for _ in range(n))
+        assert zlib.sha3_256(data) == hashlib.sha3_256(data).digest(), n
+
+
+def test_transcript_vs_golden_and_oracle(zlib, po, golden):
+    t = zlib.FiatShamirTranscript()
+    assert [t.challenge() for _ in range(3)] == golden["transcript_first_challenges"]
+    t = zlib.FiatShamirTranscript()
+    t.append_bytes(b"SUMCHECK_BEGIN")
+    t.append_field_element(12345)
+    assert [t.challenge(), t.challenge()] == golden["transcript_mixed"]
+    # long mixed stream, misaligned appends, against the oracle
+    rng = random.Random(9)
+    a, b = zlib.FiatShamirTranscript(), po.Transcript()
+    for step in range(400):
+        k = rng.randrange(4)
+        if k == 0:
+            v = rng.randrange(BB)
+            a.append_field_element(v)
+            b.append_field(v)
+        elif k == 1:
+            data = bytes(rng.getrandbits(8) for _ in range(rng.randrange(0, 70)))
+            a.append_bytes(data)
+            b.append_bytes(data)
+        elif k == 2:
+            vs = [rng.randrange(BB) for _ in range(rng.randrange(1, 40))]
+            a.append_field_elements(vs)
+            for v in vs:
+                b.append_field(v)
+        else:
+            assert a.challenge() == b.challenge(BB), step
+
+
+def test_field_and_horner(zlib, po):
+    L = zlib.lib()
+    rng = random.Random(3)
+    for _ in range(2000):
+        x, y = rng.randrange(BB), rng.randrange(BB)
+        assert L.zh_f_add(x, y) == po.lib().zo_f_add(BB, x, y)
+        assert L.zh_f_sub(x, y) == po.lib().zo_f_sub(BB, x, y)
+        assert L.zh_f_mul(x, y) == po.lib().zo_f_mul(BB, x, y)
+    assert [zlib.eval_univariate_coeffs([3, 5], x) for x in (0, 1, 2)] == [3, 8, 13]  # sumcheck_protocol.zig:219-236
+    for _ in range(200):
+        c = [rng.randrange(BB) for _ in range(rng.randrange(1, 5))]
+        x = rng.randrange(BB)
+        assert zlib.eval_univariate_coeffs(c, x) == po.eval_univariate(BB, c, x)
+
+
+def test_proof_to_bytes(zlib, po, golden):
+    case = golden["sumcheck"]["bb_1to8"]
+    pr = zlib.SumcheckProof(3, np.array(case["round_polys"], np.uint64), np.array(case["final_point"], np.uint64),
+                            case["final_eval"])
+    b = pr.to_bytes()
+    assert len(b) == (2 + 3 * 3) * 8
+    assert hashlib.sha3_256(b).hexdigest() == case["to_bytes_sha3"]
+
+
+def test_merkle_verify_host(zlib, po, golden):
+    for name, case in golden["merkle"].items():
+        root = bytes.fromhex(case["root"])
+        for idx, o in case["opens"].items():
+            sib = np.array([list(bytes.fromhex(s)) for s in o["siblings"]], np.uint8).reshape(-1, 32)
+            proof = zlib.MerkleOpeningProof(o["value"], int(idx), zlib.MerklePath(sib, np.array(o["dirs"], np.uint8)))
+            assert zlib.SimpleMerkleTree.verify(root, proof), name
+            bad = zlib.MerkleOpeningProof((o["value"] + 1) % BB, int(idx), proof.path)
+            assert not zlib.SimpleMerkleTree.verify(root, bad)
+
+
+def test_point_to_index(zlib):
+    assert zlib.CommitmentScheme.point_to_index([]) == 0
+    assert zlib.CommitmentScheme.point_to_index([13, 5, 6]) == 5
+    assert zlib.CommitmentScheme.point_to_index([BB - 1] * 20) == (BB - 1) % (1 << 20)
+
+
+def test_table_builders_match_oracle(zlib, po):
+    for bits in (2, 4):
+        assert np.array_equal(zlib.build_add_table(bits), po.build_table(BB, po.TABLE_ADD, bits))
+        assert np.array_equal(zlib.build_xor_table(bits), po.build_table(BB, po.TABLE_XOR, bits))
+        assert np.array_equal(zlib.build_and_table(bits), po.build_table(BB, po.TABLE_AND, bits))

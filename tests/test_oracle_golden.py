@@ -1,0 +1,93 @@
+"""The C oracle against the committed golden vectors (tests/golden/zigz_golden.json, produced by the independent
+pure-Python restatement tests/golden/make_golden.py)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from _cases import BB, assert_sumcheck_equal, lasso_queries, sumcheck_case_evals, synthetic
+
+
+def test_transcript(po, golden):
+    t = po.Transcript()
+    assert [t.challenge(BB) for _ in range(3)] == golden["transcript_first_challenges"]
+    t = po.Transcript()
+    t.append_bytes(b"SUMCHECK_BEGIN")
+    t.append_field(12345)
+    assert [t.challenge(BB), t.challenge(BB)] == golden["transcript_mixed"]
+    assert po.hash_leaf(0).hex() == golden["sha3_leaf_0"]
+    assert po.hash_leaf(BB - 1).hex() == golden["sha3_leaf_p_minus_1"]
+
+
+def test_synthetic_generator_matches(po):
+    assert po.fill_synthetic(BB, 0x5A49475A, 3, 50).tolist() == synthetic(0x5A49475A, 50, start=3).tolist()
+
+
+def test_sumcheck(po, golden):
+    for name, case in golden["sumcheck"].items():
+        e = sumcheck_case_evals(case)
+        if "challenges" in case:
+            pr = po.sumcheck_prove_interactive(case["p"], e, case["challenges"])
+        else:
+            pr = po.sumcheck_prove(case["p"], e)
+            assert pr.claimed_sum == case["claimed_sum"], name
+        assert_sumcheck_equal(pr, case)
+        if case["p"] == BB or True:
+            assert hashlib.sha3_256(pr.to_bytes()).hexdigest() == case["to_bytes_sha3"], name
+
+
+def test_prodcheck(po, golden):
+    for name, case in golden["prodcheck"].items():
+        polys = [synthetic(case["seed"] + k, case["n"]) for k in range(case["d"])]
+        pr = po.prodcheck_prove(BB, polys)
+        assert pr.claimed_sum == case["claimed_sum"], name
+        assert_sumcheck_equal(pr, case)
+    # d == 1 must be bit-identical to the reference sumcheck
+    e = synthetic(0x5A49475A, 256)
+    a, b = po.prodcheck_prove(BB, [e]), po.sumcheck_prove(BB, e)
+    assert a.round_polys.tolist() == b.round_polys.tolist() and a.final_point.tolist() == b.final_point.tolist()
+    assert a.final_evals[0] == b.final_eval
+
+
+def test_eval(po, golden):
+    for name, case in golden["eval"].items():
+        if "seed" not in case:
+            continue
+        e = synthetic(case["seed"], case["n"])
+        assert po.mle_eval(BB, e, case["point"]) == case["value"], name
+    assert [po.mle_eval(17, [0, 1], [2]), po.mle_eval(17, [0, 1], [5])] == golden["eval"]["f17_x_at_2_5"]["values"]
+
+
+def _merkle_values(case):
+    return np.array(case["values"], np.uint64) if case["values"] else synthetic(case["seed"], case["n"])
+
+
+def test_merkle(po, golden):
+    for name, case in golden["merkle"].items():
+        t = po.merkle_build(_merkle_values(case))
+        assert t.root.hex() == case["root"], name
+        assert t.height == case["height"]
+        assert t.leaf_hashes[0].tobytes().hex() == case["leaf0"]
+        for idx, o in case["opens"].items():
+            v, sib, dirs = po.merkle_open(t, int(idx))
+            assert v == o["value"] and dirs.tolist() == o["dirs"]
+            assert [s.tobytes().hex() for s in sib] == o["siblings"]
+            assert po.merkle_verify(t.root, v, sib, dirs)
+
+
+def test_lasso(po, golden):
+    g = golden["lasso"]
+    assert po.lasso_hash_row(BB, [1, 2, 3]) == g["hash_entry_1_2_3"]
+    assert po.lasso_commit_poly([1, 2, 3, 4]).hex() == g["flat_commit_1234"]
+    xor2 = po.build_table(BB, po.TABLE_XOR, 2)
+    c = g["xor2_queries"]
+    for mapping in (None, c["mapping"]):
+        pr = po.lasso_prove(BB, xor2, c["queries"], mapping=mapping)
+        assert_sumcheck_equal(pr.sumcheck, c["sumcheck"])
+        assert (pr.query_commitment.hex(), pr.table_commitment.hex()) == (c["query_commitment"], c["table_commitment"])
+    for op, code in (("add", po.TABLE_ADD), ("xor", po.TABLE_XOR), ("and", po.TABLE_AND)):
+        c = g[f"{op}4_200"]
+        pr = po.lasso_prove(BB, po.build_table(BB, code, 4), lasso_queries(op, 4, 200))
+        assert pr.sumcheck.num_vars == c["num_vars"] == 8
+        assert_sumcheck_equal(pr.sumcheck, c["sumcheck"])
+        assert (pr.query_commitment.hex(), pr.table_commitment.hex()) == (c["query_commitment"], c["table_commitment"])

@@ -1,0 +1,51 @@
+// BabyBear arithmetic in registers (p = 2^31 - 2^27 + 1), canonical u32 in / canonical u32 out.
+// Replaces Field(u64, 2013265921).{add,sub,mul} — /root/reference/src/core/field.zig:73-147.
+// The reference multiplies with a u128 `%`; any exact modular product gives the same canonical value,
+// so the device uses Shoup (fixed multiplier) and Montgomery (general) reductions on the 32-bit IMAD pipe.
+#pragma once
+#include <cstdint>
+
+namespace bb {
+
+constexpr uint32_t P = 2013265921u;        // 0x78000001
+constexpr uint32_t P_NEG_INV = 2013265919u; // -P^{-1} mod 2^32  (P * 0x88000001 == 1 mod 2^32)
+constexpr uint32_t R_MOD_P = 268435454u;   // 2^32 mod P
+constexpr uint32_t R2_MOD_P = 1172168163u; // 2^64 mod P
+
+__host__ __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
+    uint32_t s = a + b;
+    return s >= P ? s - P : s;
+}
+__host__ __device__ __forceinline__ uint32_t sub(uint32_t a, uint32_t b) {
+    uint32_t d = a - b;
+    return a < b ? d + P : d;
+}
+__host__ __device__ __forceinline__ uint32_t reduce64(uint64_t x) { return (uint32_t)(x % P); }
+
+// Shoup precomputation for a fixed multiplier w < P: w' = floor(w * 2^32 / P)
+__host__ __device__ __forceinline__ uint32_t shoup_pre(uint32_t w) { return (uint32_t)(((uint64_t)w << 32) / P); }
+
+// x * w mod P for any x < 2^32, w < P with w' = shoup_pre(w); 1 mulhi + 2 mullo
+__device__ __forceinline__ uint32_t mul_shoup(uint32_t x, uint32_t w, uint32_t wp) {
+    uint32_t q = __umulhi(x, wp);
+    uint32_t t = x * w - q * P; // in [0, 2P) and 2P < 2^32
+    return t >= P ? t - P : t;
+}
+
+// Montgomery product a*b*2^-32 mod P, canonical output, for a*b < P*2^32
+__device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b) {
+    uint64_t t = (uint64_t)a * b;
+    uint32_t m = (uint32_t)t * P_NEG_INV;
+    uint32_t u = (uint32_t)((t + (uint64_t)m * P) >> 32); // [0, 2P)
+    return u >= P ? u - P : u;
+}
+
+// plain a*b mod P via two Montgomery steps is wasteful; for a one-off product use this
+__host__ __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) % P); }
+
+// linear interpolation lo + r*(hi - lo): the fold of multilinear.zig:166-173 with one modmul
+__device__ __forceinline__ uint32_t lerp(uint32_t lo, uint32_t hi, uint32_t r, uint32_t rp) {
+    return add(lo, mul_shoup(sub(hi, lo), r, rp));
+}
+
+} // namespace bb

@@ -1,0 +1,1088 @@
+// Context layer: implements the C ABI of include/zigz_b200.h on top of the kernels (kernels.h).
+// Owns the stream, a caching device allocator (no cudaMalloc inside the sumcheck round loop), the
+// host-mapped completion mailbox, and the handle tables. There is no CPU fallback anywhere:
+// without a CUDA device zb_ctx_create fails with ZB_ERR_NO_DEVICE.
+#include "../../include/zigz_b200.h"
+#include "bb.cuh"
+#include "kernels.h"
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace zk;
+
+namespace {
+
+struct DevBuf {
+    struct zb_ctx *ctx;
+    void *ptr;
+    size_t bytes;
+    DevBuf(zb_ctx *c, void *p, size_t b) : ctx(c), ptr(p), bytes(b) {}
+    ~DevBuf();
+};
+using BufRef = std::shared_ptr<DevBuf>;
+
+struct Mle {
+    BufRef buf;
+    uint64_t n;
+    uint32_t *d() const { return (uint32_t *)buf->ptr; }
+};
+
+struct Tree {
+    BufRef values;      // u32 values (shared with the Multilinear it was built from)
+    uint64_t n_values;  // unpadded
+    uint64_t padded;
+    uint32_t height;
+    BufRef store;       // all levels
+    uint8_t root[32];
+};
+
+constexpr size_t BULK_OFFSET = 256;          // bytes into the mapped mailbox page
+constexpr size_t BULK_BYTES = 64 * 32 * 2;   // 64 digests for paths / roots (x2 slack)
+constexpr size_t STAGE_ELEMS = 32ull << 20;  // upload staging chunk (u64 elements)
+
+} // namespace
+
+struct zb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    // mailbox
+    unsigned long long *h_mail = nullptr; // mapped pinned
+    unsigned long long *d_mail = nullptr; // device alias
+    unsigned long long *d_acc = nullptr;
+    unsigned int *d_ticket = nullptr;
+    unsigned int *d_err = nullptr;
+    unsigned long long seq = 0;
+    uint64_t launches = 0;
+    // allocator cache
+    std::multimap<size_t, void *> free_blocks;
+    size_t cached_bytes = 0;
+    // handles
+    std::unordered_map<uint64_t, Mle> mles;
+    std::unordered_map<uint64_t, Tree> trees;
+    uint64_t next_handle = 1;
+    std::string last_error;
+    // stopwatch + per-kernel accounting
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool profiling = false;
+    struct ProfEntry {
+        std::string name;
+        uint64_t launches = 0;
+        double ms = 0;
+        uint64_t bytes = 0;
+    };
+    struct ProfPending {
+        cudaEvent_t a, b;
+        uint32_t entry;
+    };
+    std::vector<ProfEntry> prof;
+    std::vector<ProfPending> prof_pending;
+    std::vector<cudaEvent_t> event_pool;
+
+    Mailbox mailbox() {
+        Mailbox m;
+        m.acc = d_acc;
+        m.ticket = d_ticket;
+        m.mail = d_mail;
+        m.seq = ++seq;
+        return m;
+    }
+    uint8_t *h_bulk() { return (uint8_t *)h_mail + BULK_OFFSET; }
+    uint8_t *d_bulk() { return (uint8_t *)d_mail + BULK_OFFSET; }
+};
+
+namespace {
+
+int32_t cuda_fail(zb_ctx *c, cudaError_t e, const char *what) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    if (c) c->last_error = buf;
+    return e == cudaErrorMemoryAllocation ? ZB_ERR_OOM : ZB_ERR_CUDA;
+}
+#define CK(call)                                               \
+    do {                                                       \
+        cudaError_t _e = (call);                               \
+        if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call); \
+    } while (0)
+
+size_t round_size(size_t b) {
+    if (b < 512) return 512;
+    // round to 1/8 of the leading power of two so the cache reuses blocks across rounds
+    size_t p = 1;
+    while (p < b) p <<= 1;
+    size_t step = p / 16;
+    return (b + step - 1) / step * step;
+}
+
+void release_cache(zb_ctx *c) {
+    for (auto &kv : c->free_blocks) cudaFree(kv.second);
+    c->free_blocks.clear();
+    c->cached_bytes = 0;
+}
+
+int32_t dev_alloc(zb_ctx *ctx, size_t bytes, BufRef *out) {
+    size_t want = round_size(bytes);
+    auto it = ctx->free_blocks.lower_bound(want);
+    if (it != ctx->free_blocks.end() && it->first <= want + want / 4) {
+        void *p = it->second;
+        size_t sz = it->first;
+        ctx->free_blocks.erase(it);
+        ctx->cached_bytes -= sz;
+        *out = std::make_shared<DevBuf>(ctx, p, sz);
+        return ZB_OK;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        release_cache(ctx);
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
+    *out = std::make_shared<DevBuf>(ctx, p, want);
+    return ZB_OK;
+}
+
+} // namespace
+
+DevBuf::~DevBuf() {
+    // all work on a context is stream-ordered and every API call drains the stream before returning,
+    // so a block can be recycled as soon as its last owner drops it
+    if (ctx && ptr) {
+        ctx->free_blocks.emplace(bytes, ptr);
+        ctx->cached_bytes += bytes;
+    }
+}
+
+namespace {
+
+// Wait for the mailbox sequence number published by the last CTA of the most recent launch.
+int32_t wait_mail(zb_ctx *ctx, unsigned long long seq) {
+    volatile unsigned long long *flag = ctx->h_mail + MAIL_WORDS;
+    auto t0 = std::chrono::steady_clock::now();
+    uint64_t spins = 0;
+    while (*flag != seq) {
+        if ((++spins & 0xFFFF) == 0) {
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(ctx, q, "kernel");
+            if (q == cudaSuccess && *flag != seq) {
+                // stream drained but flag missing: give the PCIe write a moment, then report
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) {
+                    ctx->last_error = "mailbox sequence not published";
+                    return ZB_ERR_TIMEOUT;
+                }
+            }
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
+                ctx->last_error = "timeout waiting for kernel";
+                return ZB_ERR_TIMEOUT;
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return ZB_OK;
+}
+
+int32_t check_launch(zb_ctx *ctx, const char *what) {
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, what);
+    return ZB_OK;
+}
+#define LAUNCHED(what)                       \
+    do {                                     \
+        int32_t _r = check_launch(ctx, what); \
+        if (_r) return _r;                   \
+    } while (0)
+
+cudaEvent_t take_event(zb_ctx *c) {
+    if (!c->event_pool.empty()) {
+        cudaEvent_t e = c->event_pool.back();
+        c->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// drains finished event pairs into the table (all of them when `block`)
+void prof_drain(zb_ctx *c, bool block) {
+    size_t keep = 0;
+    for (size_t i = 0; i < c->prof_pending.size(); i++) {
+        auto &pp = c->prof_pending[i];
+        if (block) cudaEventSynchronize(pp.b);
+        if (block || cudaEventQuery(pp.b) == cudaSuccess) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, pp.a, pp.b);
+            c->prof[pp.entry].ms += ms;
+            c->event_pool.push_back(pp.a);
+            c->event_pool.push_back(pp.b);
+        } else {
+            c->prof_pending[keep++] = pp;
+        }
+    }
+    c->prof_pending.resize(keep);
+}
+
+// brackets one kernel launch with events on the launching stream while profiling is on
+struct ProfScope {
+    zb_ctx *c;
+    cudaEvent_t a = nullptr;
+    uint32_t entry = 0;
+    ProfScope(zb_ctx *ctx, const char *name, uint64_t bytes) : c(ctx) {
+        if (!c->profiling) return;
+        for (entry = 0; entry < c->prof.size(); entry++)
+            if (c->prof[entry].name == name) break;
+        if (entry == c->prof.size()) {
+            c->prof.emplace_back();
+            c->prof.back().name = name;
+        }
+        c->prof[entry].launches++;
+        c->prof[entry].bytes += bytes;
+        a = take_event(c);
+        cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEvent_t b = take_event(c);
+        cudaEventRecord(b, c->stream);
+        c->prof_pending.push_back({a, b, entry});
+        if (c->prof_pending.size() > 256) prof_drain(c, false);
+    }
+};
+
+Mle *get_mle(zb_ctx *ctx, zb_mle h) {
+    auto it = ctx->mles.find(h);
+    return it == ctx->mles.end() ? nullptr : &it->second;
+}
+Tree *get_tree(zb_ctx *ctx, zb_tree h) {
+    auto it = ctx->trees.find(h);
+    return it == ctx->trees.end() ? nullptr : &it->second;
+}
+
+int32_t new_mle(zb_ctx *ctx, uint64_t n, zb_mle *out, Mle **m) {
+    BufRef b;
+    int32_t rc = dev_alloc(ctx, n * sizeof(uint32_t), &b);
+    if (rc) return rc;
+    uint64_t h = ctx->next_handle++;
+    ctx->mles[h] = Mle{b, n};
+    *out = h;
+    if (m) *m = &ctx->mles[h];
+    return ZB_OK;
+}
+
+int32_t check_pow2(uint64_t n) {
+    if (n == 0) return ZB_ERR_EMPTY_EVALUATIONS; // multilinear.zig:38
+    if (n & (n - 1)) return ZB_ERR_LENGTH_NOT_POW2; // multilinear.zig:43
+    return ZB_OK;
+}
+
+int32_t read_err_flag(zb_ctx *ctx) {
+    unsigned int flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->d_err, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flag) {
+        CK(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+        return ZB_ERR_NOT_CANONICAL;
+    }
+    return ZB_OK;
+}
+
+// chunked upload of host u64 data into a device u32 buffer (narrowing on the device)
+int32_t upload_narrow(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32_t *dst) {
+    uint64_t chunk = n < STAGE_ELEMS ? n : STAGE_ELEMS;
+    BufRef stage;
+    int32_t rc = dev_alloc(ctx, chunk * sizeof(uint64_t), &stage);
+    if (rc) return rc;
+    for (uint64_t off = 0; off < n; off += chunk) {
+        uint64_t m = n - off < chunk ? n - off : chunk;
+        CK(cudaMemcpyAsync(stage->ptr, host + off, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        {
+            ProfScope _ps(ctx, "narrow_u64", m * 12);
+            launch_narrow_u64((const uint64_t *)stage->ptr, dst + off, m, ctx->d_err, ctx->stream);
+        }
+        LAUNCHED("narrow");
+    }
+    return read_err_flag(ctx);
+}
+
+} // namespace
+
+extern "C" {
+
+const char *zb_status_name(int32_t s) {
+    switch (s) {
+    case ZB_OK: return "ok";
+    case ZB_ERR_EMPTY_EVALUATIONS: return "EmptyEvaluations";
+    case ZB_ERR_LENGTH_NOT_POW2: return "LengthNotPowerOfTwo";
+    case ZB_ERR_WRONG_NUM_VARS: return "WrongNumberOfVariables";
+    case ZB_ERR_NO_VARIABLES: return "NoVariables";
+    case ZB_ERR_EMPTY_VALUES: return "EmptyValues";
+    case ZB_ERR_INDEX_OUT_OF_BOUNDS: return "IndexOutOfBounds";
+    case ZB_ERR_POINT_DIM_MISMATCH: return "PointDimensionMismatch";
+    case ZB_ERR_NO_QUERIES: return "NoQueries";
+    case ZB_ERR_MAPPING_LEN_MISMATCH: return "MappingLengthMismatch";
+    case ZB_ERR_INVALID_MAPPING: return "InvalidMapping";
+    case ZB_ERR_QUERY_TABLE_MISMATCH: return "QueryTableMismatch";
+    case ZB_ERR_WRONG_NUM_CHALLENGES: return "WrongNumberOfChallenges";
+    case ZB_ERR_DIFFERENT_NUM_VARS: return "DifferentNumberOfVariables";
+    case ZB_ERR_NOT_CANONICAL: return "NotCanonical";
+    case ZB_ERR_BAD_HANDLE: return "BadHandle";
+    case ZB_ERR_BAD_ARGUMENT: return "BadArgument";
+    case ZB_ERR_OOM: return "OutOfMemory";
+    case ZB_ERR_NO_DEVICE: return "NoCudaDevice";
+    case ZB_ERR_CUDA: return "CudaError";
+    case ZB_ERR_TIMEOUT: return "Timeout";
+    default: return "Unknown";
+    }
+}
+
+int32_t zb_ctx_create(int32_t device, zb_ctx **out) {
+    if (!out) return ZB_ERR_BAD_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return ZB_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return ZB_ERR_BAD_ARGUMENT;
+    zb_ctx *ctx = new zb_ctx();
+    ctx->device = device;
+    auto fail = [&](cudaError_t err, const char *what) {
+        fprintf(stderr, "zigz_b200: %s: %s\n", what, cudaGetErrorString(err));
+        delete ctx;
+        return (int32_t)ZB_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    size_t mail_bytes = BULK_OFFSET + BULK_BYTES;
+    if ((e = cudaHostAlloc((void **)&ctx->h_mail, mail_bytes, cudaHostAllocMapped)) != cudaSuccess) return fail(e, "cudaHostAlloc");
+    memset(ctx->h_mail, 0, mail_bytes);
+    if ((e = cudaHostGetDevicePointer((void **)&ctx->d_mail, ctx->h_mail, 0)) != cudaSuccess) return fail(e, "cudaHostGetDevicePointer");
+    if ((e = cudaMalloc(&ctx->d_acc, MAIL_WORDS * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
+    ctx->d_err = ctx->d_ticket + 1;
+    cudaMemsetAsync(ctx->d_acc, 0, MAIL_WORDS * sizeof(unsigned long long), ctx->stream);
+    cudaMemsetAsync(ctx->d_ticket, 0, 2 * sizeof(unsigned int), ctx->stream);
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "init");
+    *out = ctx;
+    return ZB_OK;
+}
+
+void zb_ctx_destroy(zb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->mles.clear();
+    ctx->trees.clear();
+    release_cache(ctx);
+    prof_drain(ctx, true);
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    cudaFree(ctx->d_acc);
+    cudaFree(ctx->d_ticket);
+    cudaFreeHost(ctx->h_mail);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *zb_last_error(zb_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+uint64_t zb_kernel_launches(zb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *zb_stream(zb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int32_t zb_sync(zb_ctx *ctx) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZB_OK;
+}
+
+int32_t zb_timer_start(zb_ctx *ctx) {
+    if (!ctx->t0) {
+        CK(cudaEventCreate(&ctx->t0));
+        CK(cudaEventCreate(&ctx->t1));
+    }
+    CK(cudaEventRecord(ctx->t0, ctx->stream));
+    return ZB_OK;
+}
+
+int32_t zb_timer_stop(zb_ctx *ctx, float *ms) {
+    if (!ctx->t0 || !ms) return ZB_ERR_BAD_ARGUMENT;
+    CK(cudaEventRecord(ctx->t1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->t1));
+    CK(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return ZB_OK;
+}
+
+int32_t zb_profile_enable(zb_ctx *ctx, int32_t on) {
+    prof_drain(ctx, true);
+    if (on) ctx->prof.clear();
+    ctx->profiling = on != 0;
+    return ZB_OK;
+}
+
+uint32_t zb_profile_count(zb_ctx *ctx) {
+    prof_drain(ctx, true);
+    return (uint32_t)ctx->prof.size();
+}
+
+int32_t zb_profile_entry(zb_ctx *ctx, uint32_t i, char *name, uint32_t cap, uint64_t *launches, double *ms, uint64_t *bytes) {
+    if (i >= ctx->prof.size()) return ZB_ERR_BAD_ARGUMENT;
+    const auto &e = ctx->prof[i];
+    if (name && cap) snprintf(name, cap, "%s", e.name.c_str());
+    if (launches) *launches = e.launches;
+    if (ms) *ms = e.ms;
+    if (bytes) *bytes = e.bytes;
+    return ZB_OK;
+}
+
+int32_t zb_host_alloc(zb_ctx *ctx, size_t bytes, void **out) {
+    CK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return ZB_OK;
+}
+int32_t zb_host_free(zb_ctx *ctx, void *p) {
+    CK(cudaFreeHost(p));
+    return ZB_OK;
+}
+
+int32_t zb_device_info(zb_ctx *ctx, int32_t *sm_count, uint64_t *total_mem, uint64_t *free_mem) {
+    size_t f = 0, t = 0;
+    CK(cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (total_mem) *total_mem = t;
+    if (free_mem) *free_mem = f + ctx->cached_bytes;
+    return ZB_OK;
+}
+
+/* ------------------------------------------------------------------ Multilinear */
+
+int32_t zb_mle_upload(zb_ctx *ctx, const uint64_t *evals, uint64_t n, zb_mle *out) {
+    int32_t rc = check_pow2(n);
+    if (rc) return rc;
+    if (!evals || !out) return ZB_ERR_BAD_ARGUMENT;
+    Mle *m = nullptr;
+    rc = new_mle(ctx, n, out, &m);
+    if (rc) return rc;
+    rc = upload_narrow(ctx, evals, n, m->d());
+    if (rc) {
+        ctx->mles.erase(*out);
+        *out = 0;
+    }
+    return rc;
+}
+
+int32_t zb_mle_upload_u32(zb_ctx *ctx, const uint32_t *evals, uint64_t n, zb_mle *out) {
+    int32_t rc = check_pow2(n);
+    if (rc) return rc;
+    if (!evals || !out) return ZB_ERR_BAD_ARGUMENT;
+    Mle *m = nullptr;
+    rc = new_mle(ctx, n, out, &m);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(m->d(), evals, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ProfScope _ps(ctx, "check_u32", n * 4);
+        launch_check_u32(m->d(), n, ctx->d_err, ctx->stream);
+    }
+    LAUNCHED("check");
+    rc = read_err_flag(ctx);
+    if (rc) {
+        ctx->mles.erase(*out);
+        *out = 0;
+    }
+    return rc;
+}
+
+int32_t zb_mle_constant(zb_ctx *ctx, uint32_t num_vars, uint64_t value, zb_mle *out) {
+    if (num_vars > 40 || value >= bb::P || !out) return value >= bb::P ? ZB_ERR_NOT_CANONICAL : ZB_ERR_BAD_ARGUMENT;
+    Mle *m = nullptr;
+    int32_t rc = new_mle(ctx, 1ull << num_vars, out, &m);
+    if (rc) return rc;
+    {
+        ProfScope _ps(ctx, "fill", m->n * 4);
+        launch_fill(m->d(), m->n, (uint32_t)value, ctx->stream);
+    }
+    LAUNCHED("fill");
+    return zb_sync(ctx);
+}
+
+int32_t zb_mle_synthetic(zb_ctx *ctx, uint64_t seed, uint64_t start, uint64_t stride, uint64_t n, zb_mle *out) {
+    int32_t rc = check_pow2(n);
+    if (rc) return rc;
+    Mle *m = nullptr;
+    rc = new_mle(ctx, n, out, &m);
+    if (rc) return rc;
+    {
+        ProfScope _ps(ctx, "synthetic", n * 4);
+        launch_synthetic(m->d(), n, seed, start, stride, ctx->stream);
+    }
+    LAUNCHED("synthetic");
+    return zb_sync(ctx);
+}
+
+int32_t zb_mle_clone(zb_ctx *ctx, zb_mle src, zb_mle *out) {
+    Mle *s = get_mle(ctx, src);
+    if (!s) return ZB_ERR_BAD_HANDLE;
+    uint64_t n = s->n;
+    BufRef sb = s->buf;
+    Mle *m = nullptr;
+    int32_t rc = new_mle(ctx, n, out, &m);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(m->d(), sb->ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    return zb_sync(ctx);
+}
+
+int32_t zb_mle_free(zb_ctx *ctx, zb_mle h) {
+    if (!ctx->mles.erase(h)) return ZB_ERR_BAD_HANDLE;
+    return ZB_OK;
+}
+
+int32_t zb_mle_len(zb_ctx *ctx, zb_mle h, uint64_t *n, uint32_t *num_vars) {
+    Mle *m = get_mle(ctx, h);
+    if (!m) return ZB_ERR_BAD_HANDLE;
+    if (n) *n = m->n;
+    if (num_vars) *num_vars = (uint32_t)__builtin_ctzll(m->n);
+    return ZB_OK;
+}
+
+int32_t zb_mle_download(zb_ctx *ctx, zb_mle h, uint64_t *out, uint64_t n) { return zb_mle_download_range(ctx, h, 0, out, n); }
+
+int32_t zb_mle_download_range(zb_ctx *ctx, zb_mle h, uint64_t offset, uint64_t *out, uint64_t n) {
+    Mle *m = get_mle(ctx, h);
+    if (!m) return ZB_ERR_BAD_HANDLE;
+    if (offset > m->n || n > m->n - offset || !out) return ZB_ERR_BAD_ARGUMENT;
+    uint64_t chunk = n < STAGE_ELEMS ? n : STAGE_ELEMS;
+    BufRef stage;
+    int32_t rc = dev_alloc(ctx, chunk * sizeof(uint64_t), &stage);
+    if (rc) return rc;
+    for (uint64_t off = 0; off < n; off += chunk) {
+        uint64_t k = n - off < chunk ? n - off : chunk;
+        {
+            ProfScope _ps(ctx, "widen_u32", k * 12);
+            launch_widen_u32(m->d() + offset + off, (uint64_t *)stage->ptr, k, ctx->stream);
+        }
+        LAUNCHED("widen");
+        CK(cudaMemcpyAsync(out + off, stage->ptr, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return zb_sync(ctx);
+}
+
+int32_t zb_mle_sum(zb_ctx *ctx, zb_mle h, uint64_t *out) {
+    Mle *m = get_mle(ctx, h);
+    if (!m) return ZB_ERR_BAD_HANDLE;
+    Mailbox mb = ctx->mailbox();
+    {
+        ProfScope _ps(ctx, "sum", m->n * 4);
+        launch_sum(m->d(), m->n, mb, ctx->sm_count, ctx->stream);
+    }
+    LAUNCHED("sum");
+    int32_t rc = wait_mail(ctx, mb.seq);
+    if (rc) return rc;
+    *out = ctx->h_mail[0];
+    return ZB_OK;
+}
+
+int32_t zb_mle_round_sums(zb_ctx *ctx, zb_mle h, uint64_t out[2]) {
+    Mle *m = get_mle(ctx, h);
+    if (!m) return ZB_ERR_BAD_HANDLE;
+    if (m->n < 2) return ZB_ERR_NO_VARIABLES; // multilinear.zig:207
+    PolySet ps{};
+    ps.src[0] = m->d();
+    Mailbox mb = ctx->mailbox();
+    {
+        ProfScope _ps(ctx, "round_sums_d1", m->n * 4);
+        launch_round_sums(1, ps, m->n, mb, ctx->sm_count, ctx->stream);
+    }
+    LAUNCHED("round_sums");
+    int32_t rc = wait_mail(ctx, mb.seq);
+    if (rc) return rc;
+    out[0] = ctx->h_mail[0];
+    out[1] = ctx->h_mail[1];
+    return ZB_OK;
+}
+
+static int32_t fold_common(zb_ctx *ctx, const uint32_t *src, uint32_t *dst, uint64_t n, uint64_t r, uint64_t next[2]) {
+    if (r >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    PolySet ps{};
+    ps.src[0] = src;
+    ps.dst[0] = dst;
+    Mailbox mb = ctx->mailbox();
+    {
+        ProfScope _ps(ctx, "fold_sums_d1", n * 6);
+        launch_fold_sums(1, ps, n, (uint32_t)r, mb, ctx->sm_count, ctx->stream);
+    }
+    LAUNCHED("fold_sums");
+    int32_t rc = wait_mail(ctx, mb.seq);
+    if (rc) return rc;
+    if (next) {
+        next[0] = ctx->h_mail[0];
+        next[1] = n == 2 ? 0 : ctx->h_mail[1];
+    }
+    return ZB_OK;
+}
+
+int32_t zb_mle_partial_eval(zb_ctx *ctx, zb_mle h, uint64_t r, zb_mle *out, uint64_t next[2]) {
+    Mle *m = get_mle(ctx, h);
+    if (!m) return ZB_ERR_BAD_HANDLE;
+    if (m->n < 2) return ZB_ERR_NO_VARIABLES; // multilinear.zig:156
+    if (!out) return ZB_ERR_BAD_ARGUMENT;
+    uint64_t n = m->n;
+    BufRef src = m->buf; // keep alive across the map insertion below
+    Mle *d = nullptr;
+    int32_t rc = new_mle(ctx, n / 2, out, &d);
+    if (rc) return rc;
+    rc = fold_common(ctx, (const uint32_t *)src->ptr, d->d(), n, r, next);
+    if (rc) {
+        ctx->mles.erase(*out);
+        *out = 0;
+    }
+    return rc;
+}
+
+int32_t zb_mle_fold_inplace(zb_ctx *ctx, zb_mle h, uint64_t r, uint64_t next[2]) {
+    Mle *m = get_mle(ctx, h);
+    if (!m) return ZB_ERR_BAD_HANDLE;
+    if (m->n < 2) return ZB_ERR_NO_VARIABLES;
+    int32_t rc = fold_common(ctx, m->d(), m->d(), m->n, r, next);
+    if (rc == ZB_OK) m->n /= 2;
+    return rc;
+}
+
+int32_t zb_mle_eval(zb_ctx *ctx, zb_mle h, const uint64_t *point, uint32_t npoint, uint64_t *out) {
+    Mle *m = get_mle(ctx, h);
+    if (!m) return ZB_ERR_BAD_HANDLE;
+    uint32_t v = (uint32_t)__builtin_ctzll(m->n);
+    if (npoint != v) return ZB_ERR_WRONG_NUM_VARS; // multilinear.zig:112
+    for (uint32_t i = 0; i < v; i++)
+        if (point[i] >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    const uint32_t *src = m->d();
+    uint64_t n = m->n;
+    BufRef scratch[2];
+    int which = 0;
+    uint32_t done = 0;
+    Mailbox mb = ctx->mailbox();
+    // each stage folds up to 12 variables; the last stage publishes the value
+    do {
+        int nv = (int)(v - done < 12 ? v - done : 12);
+        EvalPoint pt{};
+        for (int k = 0; k < nv; k++) {
+            pt.r[k] = (uint32_t)point[done + k];
+            pt.rp[k] = bb::shoup_pre(pt.r[k]);
+        }
+        uint64_t n_out = n >> nv;
+        int32_t rc = dev_alloc(ctx, (n_out < 128 ? 128 : n_out) * sizeof(uint32_t), &scratch[which]);
+        if (rc) return rc;
+        bool last = (done + nv == v);
+        {
+            ProfScope _ps(ctx, "eval_stage", (n + n_out) * 4);
+            launch_eval_stage(src, n, nv, pt, (uint32_t *)scratch[which]->ptr, last ? &mb : nullptr, ctx->sm_count, ctx->stream);
+        }
+        LAUNCHED("eval_stage");
+        src = (const uint32_t *)scratch[which]->ptr;
+        n = n_out;
+        done += nv;
+        which ^= 1;
+    } while (done < v);
+    int32_t rc = wait_mail(ctx, mb.seq);
+    if (rc) return rc;
+    *out = ctx->h_mail[0];
+    return ZB_OK;
+}
+
+int32_t zb_mle_add(zb_ctx *ctx, zb_mle a, zb_mle b, zb_mle *out) {
+    Mle *ma = get_mle(ctx, a), *mb_ = get_mle(ctx, b);
+    if (!ma || !mb_) return ZB_ERR_BAD_HANDLE;
+    if (ma->n != mb_->n) return ZB_ERR_DIFFERENT_NUM_VARS; // multilinear.zig:237
+    BufRef ba = ma->buf, bbuf = mb_->buf;
+    uint64_t n = ma->n;
+    Mle *o = nullptr;
+    int32_t rc = new_mle(ctx, n, out, &o);
+    if (rc) return rc;
+    {
+        ProfScope _ps(ctx, "add", n * 12);
+        launch_add((const uint32_t *)ba->ptr, (const uint32_t *)bbuf->ptr, o->d(), n, ctx->stream);
+    }
+    LAUNCHED("add");
+    return zb_sync(ctx);
+}
+
+int32_t zb_mle_scalar_mul(zb_ctx *ctx, zb_mle a, uint64_t scalar, zb_mle *out) {
+    Mle *ma = get_mle(ctx, a);
+    if (!ma) return ZB_ERR_BAD_HANDLE;
+    if (scalar >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    BufRef ba = ma->buf;
+    uint64_t n = ma->n;
+    Mle *o = nullptr;
+    int32_t rc = new_mle(ctx, n, out, &o);
+    if (rc) return rc;
+    {
+        ProfScope _ps(ctx, "scalar_mul", n * 8);
+        launch_scalar_mul((const uint32_t *)ba->ptr, (uint32_t)scalar, o->d(), n, ctx->stream);
+    }
+    LAUNCHED("scalar_mul");
+    return zb_sync(ctx);
+}
+
+/* ------------------------------------------------------------------ product sumcheck rounds */
+
+static inline uint32_t f_add(uint32_t a, uint32_t b) { return bb::add(a, b); }
+static inline uint32_t f_sub(uint32_t a, uint32_t b) { return bb::sub(a, b); }
+static inline uint32_t f_half(uint32_t a) { return bb::mul(a, (bb::P + 1) / 2); }
+
+// mailbox payload (evaluations) -> coefficient form [a0..ad]
+static void evals_to_coeffs(uint32_t d, const unsigned long long *mail, uint64_t *out) {
+    if (d == 1) {
+        uint32_t s0 = (uint32_t)mail[0], s1 = (uint32_t)mail[1];
+        out[0] = s0;
+        out[1] = f_sub(s1, s0); // multilinear.zig:229
+    } else if (d == 2) {
+        uint32_t g0 = (uint32_t)mail[0], g1 = (uint32_t)mail[1], gi = (uint32_t)mail[2];
+        out[0] = g0;
+        out[2] = gi;
+        out[1] = f_sub(f_sub(g1, g0), gi);
+    } else {
+        uint32_t g0 = (uint32_t)mail[0], g1 = (uint32_t)mail[1], gm = (uint32_t)mail[2], gi = (uint32_t)mail[3];
+        out[0] = g0;
+        out[3] = gi;
+        out[2] = f_sub(f_half(f_add(g1, gm)), g0);
+        out[1] = f_sub(f_half(f_sub(g1, gm)), gi);
+    }
+}
+
+static int32_t gather_polys(zb_ctx *ctx, const zb_mle *polys, uint32_t d, Mle **ms) {
+    if (d < 1 || d > (uint32_t)MAX_POLYS || !polys) return ZB_ERR_BAD_ARGUMENT;
+    for (uint32_t k = 0; k < d; k++) {
+        ms[k] = get_mle(ctx, polys[k]);
+        if (!ms[k]) return ZB_ERR_BAD_HANDLE;
+        if (ms[k]->n != ms[0]->n) return ZB_ERR_DIFFERENT_NUM_VARS;
+        for (uint32_t j = 0; j < k; j++)
+            if (polys[j] == polys[k]) return ZB_ERR_BAD_ARGUMENT;
+    }
+    return ZB_OK;
+}
+
+int32_t zb_prod_round_coeffs(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *out) {
+    Mle *ms[MAX_POLYS];
+    int32_t rc = gather_polys(ctx, polys, d, ms);
+    if (rc) return rc;
+    if (ms[0]->n < 2) return ZB_ERR_NO_VARIABLES;
+    PolySet ps{};
+    for (uint32_t k = 0; k < d; k++) ps.src[k] = ms[k]->d();
+    Mailbox mb = ctx->mailbox();
+    {
+        ProfScope _ps(ctx, d == 1 ? "round_sums_d1" : d == 2 ? "round_sums_d2" : "round_sums_d3", ms[0]->n * 4 * d);
+        launch_round_sums((int)d, ps, ms[0]->n, mb, ctx->sm_count, ctx->stream);
+    }
+    LAUNCHED("prod_round_sums");
+    rc = wait_mail(ctx, mb.seq);
+    if (rc) return rc;
+    evals_to_coeffs(d, ctx->h_mail, out);
+    return ZB_OK;
+}
+
+int32_t zb_prod_fold_inplace(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, uint64_t *next) {
+    Mle *ms[MAX_POLYS];
+    int32_t rc = gather_polys(ctx, polys, d, ms);
+    if (rc) return rc;
+    uint64_t n = ms[0]->n;
+    if (n < 2) return ZB_ERR_NO_VARIABLES;
+    if (r >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    PolySet ps{};
+    for (uint32_t k = 0; k < d; k++) {
+        ps.src[k] = ms[k]->d();
+        ps.dst[k] = ms[k]->d();
+    }
+    Mailbox mb = ctx->mailbox();
+    {
+        ProfScope _ps(ctx, d == 1 ? "fold_sums_d1" : d == 2 ? "fold_sums_d2" : "fold_sums_d3", n * 6 * d);
+        launch_fold_sums((int)d, ps, n, (uint32_t)r, mb, ctx->sm_count, ctx->stream);
+    }
+    LAUNCHED("prod_fold_sums");
+    rc = wait_mail(ctx, mb.seq);
+    if (rc) return rc;
+    for (uint32_t k = 0; k < d; k++) ms[k]->n = n / 2;
+    if (next) {
+        if (n == 2)
+            for (uint32_t k = 0; k < d; k++) next[k] = ctx->h_mail[k];
+        else
+            evals_to_coeffs(d, ctx->h_mail, next);
+    }
+    return ZB_OK;
+}
+
+int32_t zb_prod_partial_eval(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, zb_mle *out, uint64_t *next) {
+    Mle *ms[MAX_POLYS];
+    int32_t rc = gather_polys(ctx, polys, d, ms);
+    if (rc) return rc;
+    if (!out) return ZB_ERR_BAD_ARGUMENT;
+    uint64_t n = ms[0]->n;
+    if (n < 2) return ZB_ERR_NO_VARIABLES; // multilinear.zig:156
+    if (r >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    PolySet ps{};
+    BufRef keep[MAX_POLYS];
+    for (uint32_t k = 0; k < d; k++) {
+        ps.src[k] = ms[k]->d();
+        keep[k] = ms[k]->buf;
+    }
+    for (uint32_t k = 0; k < d; k++) { // allocation may rehash the handle table: ms[] is dead from here on
+        Mle *o = nullptr;
+        rc = new_mle(ctx, n / 2, &out[k], &o);
+        if (rc) {
+            for (uint32_t j = 0; j < k; j++) ctx->mles.erase(out[j]);
+            return rc;
+        }
+        ps.dst[k] = o->d();
+    }
+    Mailbox mb = ctx->mailbox();
+    {
+        ProfScope _ps(ctx, d == 1 ? "fold_sums_d1" : d == 2 ? "fold_sums_d2" : "fold_sums_d3", n * 6 * d);
+        launch_fold_sums((int)d, ps, n, (uint32_t)r, mb, ctx->sm_count, ctx->stream);
+    }
+    rc = check_launch(ctx, "prod_partial_eval");
+    if (rc == ZB_OK) rc = wait_mail(ctx, mb.seq);
+    if (rc) {
+        for (uint32_t k = 0; k < d; k++) ctx->mles.erase(out[k]);
+        return rc;
+    }
+    if (next) {
+        if (n == 2)
+            for (uint32_t k = 0; k < d; k++) next[k] = ctx->h_mail[k];
+        else
+            evals_to_coeffs(d, ctx->h_mail, next);
+    }
+    return ZB_OK;
+}
+
+/* ------------------------------------------------------------------ Merkle */
+
+static int32_t build_batch(zb_ctx *ctx, Tree **ts, uint32_t count, uint8_t *roots) {
+    const uint64_t padded = ts[0]->padded;
+    const uint32_t height = ts[0]->height;
+    MerkleBatch b{};
+    b.count = count;
+    for (uint32_t t = 0; t < count; t++) {
+        b.values[t] = (const uint32_t *)ts[t]->values->ptr;
+        b.n_values[t] = ts[t]->n_values;
+        b.tree[t] = (uint8_t *)ts[t]->store->ptr;
+    }
+    {
+        ProfScope _ps(ctx, "merkle_leaves", padded * 36 * count);
+        launch_merkle_leaves(b, padded, ctx->stream);
+    }
+    LAUNCHED("merkle_leaves");
+    uint32_t level = 0;
+    while ((padded >> level) > MERKLE_TOP_WIDTH) {
+        {
+            ProfScope _ps(ctx, "merkle_level", (padded >> (level + 1)) * 96 * count);
+            launch_merkle_level(b, padded, level, ctx->stream);
+        }
+        LAUNCHED("merkle_level");
+        level++;
+    }
+    if (level < height) {
+        {
+            ProfScope _ps(ctx, "merkle_top", (padded >> level) * 96 * count);
+            launch_merkle_top(b, padded, level, ctx->stream);
+        }
+        LAUNCHED("merkle_top");
+    }
+    Mailbox mb = ctx->mailbox();
+    {
+        ProfScope _ps(ctx, "merkle_roots", 64ull * count);
+        launch_merkle_roots(b, padded, ctx->d_bulk(), mb, ctx->stream);
+    }
+    LAUNCHED("merkle_roots");
+    int32_t rc = wait_mail(ctx, mb.seq);
+    if (rc) return rc;
+    for (uint32_t t = 0; t < count; t++) {
+        memcpy(ts[t]->root, ctx->h_bulk() + 32 * t, 32);
+        if (roots) memcpy(roots + 32 * t, ts[t]->root, 32);
+    }
+    return ZB_OK;
+}
+
+static int32_t new_tree(zb_ctx *ctx, BufRef values, uint64_t n_values, zb_tree *out, Tree **tp) {
+    uint64_t padded = 1;
+    while (padded < n_values) padded <<= 1;
+    BufRef store;
+    int32_t rc = dev_alloc(ctx, (2 * padded - 1) * 32, &store);
+    if (rc) return rc;
+    uint64_t h = ctx->next_handle++;
+    Tree t{};
+    t.values = values;
+    t.n_values = n_values;
+    t.padded = padded;
+    t.height = (uint32_t)__builtin_ctzll(padded);
+    t.store = store;
+    ctx->trees[h] = t;
+    *out = h;
+    *tp = &ctx->trees[h];
+    return ZB_OK;
+}
+
+int32_t zb_merkle_build(zb_ctx *ctx, const zb_mle *polys, uint32_t count, zb_tree *trees, uint8_t *roots) {
+    if (!polys || !trees || count == 0) return ZB_ERR_BAD_ARGUMENT;
+    uint64_t n0 = 0;
+    for (uint32_t i = 0; i < count; i++) {
+        Mle *m = get_mle(ctx, polys[i]);
+        if (!m) return ZB_ERR_BAD_HANDLE;
+        if (i == 0) n0 = m->n;
+        else if (m->n != n0) return ZB_ERR_DIFFERENT_NUM_VARS;
+    }
+    for (uint32_t base = 0; base < count; base += MAX_BATCH) {
+        uint32_t c = count - base < (uint32_t)MAX_BATCH ? count - base : MAX_BATCH;
+        std::vector<zb_tree> hs(c);
+        for (uint32_t t = 0; t < c; t++) {
+            Mle *m = get_mle(ctx, polys[base + t]);
+            Tree *tp = nullptr;
+            int32_t rc = new_tree(ctx, m->buf, m->n, &hs[t], &tp);
+            if (rc) {
+                for (uint32_t j = 0; j < t; j++) ctx->trees.erase(hs[j]);
+                return rc;
+            }
+        }
+        Tree *ts[MAX_BATCH];
+        for (uint32_t t = 0; t < c; t++) ts[t] = get_tree(ctx, hs[t]); // map is stable now
+        int32_t rc = build_batch(ctx, ts, c, roots ? roots + 32 * (size_t)base : nullptr);
+        if (rc) {
+            for (uint32_t t = 0; t < c; t++) ctx->trees.erase(hs[t]);
+            return rc;
+        }
+        for (uint32_t t = 0; t < c; t++) trees[base + t] = hs[t];
+    }
+    return ZB_OK;
+}
+
+int32_t zb_merkle_build_values(zb_ctx *ctx, const uint64_t *values, uint64_t n, zb_tree *tree, uint8_t root[32]) {
+    if (n == 0) return ZB_ERR_EMPTY_VALUES; // merkle_tree.zig:284
+    if (!values || !tree) return ZB_ERR_BAD_ARGUMENT;
+    BufRef vals;
+    int32_t rc = dev_alloc(ctx, n * sizeof(uint32_t), &vals);
+    if (rc) return rc;
+    rc = upload_narrow(ctx, values, n, (uint32_t *)vals->ptr);
+    if (rc) return rc;
+    Tree *tp = nullptr;
+    rc = new_tree(ctx, vals, n, tree, &tp);
+    if (rc) return rc;
+    rc = build_batch(ctx, &tp, 1, root);
+    if (rc) {
+        ctx->trees.erase(*tree);
+        *tree = 0;
+    }
+    return rc;
+}
+
+int32_t zb_merkle_info(zb_ctx *ctx, zb_tree h, uint64_t *n_values, uint32_t *height, uint8_t root[32]) {
+    Tree *t = get_tree(ctx, h);
+    if (!t) return ZB_ERR_BAD_HANDLE;
+    if (n_values) *n_values = t->n_values;
+    if (height) *height = t->height;
+    if (root) memcpy(root, t->root, 32);
+    return ZB_OK;
+}
+
+int32_t zb_merkle_open(zb_ctx *ctx, zb_tree h, uint64_t index, uint8_t *siblings, uint8_t *dirs, uint64_t *leaf_value) {
+    Tree *t = get_tree(ctx, h);
+    if (!t) return ZB_ERR_BAD_HANDLE;
+    if (index >= t->n_values) return ZB_ERR_INDEX_OUT_OF_BOUNDS; // merkle_tree.zig:325
+    if (t->height > 64) return ZB_ERR_BAD_ARGUMENT;
+    // leaf value rides along in the bulk area after the digests: copy it with the same gather launch's stream
+    Mailbox mb = ctx->mailbox();
+    CK(cudaMemcpyAsync(ctx->h_bulk() + 64 * 32, (const uint32_t *)t->values->ptr + index, sizeof(uint32_t),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    {
+        ProfScope _ps(ctx, "merkle_path", 64ull * t->height);
+        launch_merkle_path((const uint8_t *)t->store->ptr, t->padded, t->height, index, ctx->d_bulk(), mb, ctx->stream);
+    }
+    LAUNCHED("merkle_path");
+    int32_t rc = wait_mail(ctx, mb.seq);
+    if (rc) return rc;
+    if (t->height) memcpy(siblings, ctx->h_bulk(), (size_t)t->height * 32);
+    for (uint32_t l = 0; l < t->height; l++) dirs[l] = (uint8_t)((index >> l) & 1); // :341-345
+    if (leaf_value) {
+        uint32_t v;
+        memcpy(&v, ctx->h_bulk() + 64 * 32, sizeof(v));
+        *leaf_value = v;
+    }
+    return ZB_OK;
+}
+
+int32_t zb_merkle_leaf_hashes(zb_ctx *ctx, zb_tree h, uint8_t *out, uint64_t n_digests) {
+    Tree *t = get_tree(ctx, h);
+    if (!t) return ZB_ERR_BAD_HANDLE;
+    if (n_digests > 2 * t->padded - 1) return ZB_ERR_BAD_ARGUMENT;
+    CK(cudaMemcpyAsync(out, t->store->ptr, n_digests * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    return zb_sync(ctx);
+}
+
+int32_t zb_merkle_free(zb_ctx *ctx, zb_tree h) {
+    if (!ctx->trees.erase(h)) return ZB_ERR_BAD_HANDLE;
+    return ZB_OK;
+}
+
+/* ------------------------------------------------------------------ Lasso */
+
+int32_t zb_xxh3_rows(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, zb_mle *out) {
+    int32_t rc = check_pow2(n_padded);
+    if (rc) return rc;
+    if (n_rows > n_padded || arity == 0 || (!rows && n_rows) || !out) return ZB_ERR_BAD_ARGUMENT;
+    Mle *m = nullptr;
+    rc = new_mle(ctx, n_padded, out, &m);
+    if (rc) return rc;
+    // rows are streamed through a device staging buffer in chunks of whole rows
+    uint64_t rows_per_chunk = STAGE_ELEMS / arity;
+    if (rows_per_chunk > n_rows) rows_per_chunk = n_rows ? n_rows : 1;
+    BufRef stage;
+    rc = dev_alloc(ctx, rows_per_chunk * arity * sizeof(uint64_t), &stage);
+    if (rc) return rc;
+    uint64_t off = 0;
+    while (off < n_rows) {
+        uint64_t k = n_rows - off < rows_per_chunk ? n_rows - off : rows_per_chunk;
+        CK(cudaMemcpyAsync(stage->ptr, rows + off * arity, k * arity * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        {
+            ProfScope _ps(ctx, "xxh3_rows", k * (8ull * arity + 4));
+            launch_xxh3_rows((const uint64_t *)stage->ptr, k, arity, k, m->d() + off, ctx->d_err, ctx->stream);
+        }
+        LAUNCHED("xxh3_rows");
+        off += k;
+    }
+    if (n_padded > n_rows) {
+        {
+            ProfScope _ps(ctx, "fill", (n_padded - n_rows) * 4);
+            launch_fill(m->d() + n_rows, n_padded - n_rows, 0, ctx->stream); // lasso_prover.zig:140-142
+        }
+        LAUNCHED("fill");
+    }
+    rc = read_err_flag(ctx);
+    if (rc) {
+        ctx->mles.erase(*out);
+        *out = 0;
+    }
+    return rc;
+}
+
+int32_t zb_table_mle(zb_ctx *ctx, int32_t op, uint32_t bits, zb_mle *out) {
+    if (op < 0 || op > 2 || bits == 0 || bits > 15 || !out) return ZB_ERR_BAD_ARGUMENT;
+    Mle *m = nullptr;
+    int32_t rc = new_mle(ctx, 1ull << (2 * bits), out, &m);
+    if (rc) return rc;
+    {
+        ProfScope _ps(ctx, "table_mle", 4ull << (2 * bits));
+        launch_table_mle(op, bits, m->d(), ctx->stream);
+    }
+    LAUNCHED("table_mle");
+    return zb_sync(ctx);
+}
+
+} // extern "C"

@@ -1,0 +1,317 @@
+// Host twin of the zigz prover-side API (include/zigz_host.h). Everything here runs on the CPU and reaches the
+// GPU only through the public device C ABI (zb_* of include/zigz_b200.h): this file is what the reference's Zig
+// bodies become once their hot loops are replaced by extern calls (INTEGRATION.md shows the Zig side).
+#include "../../include/zigz_host.h"
+#include "sha3_host.hpp"
+
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using zigz::Sha3_256;
+
+namespace {
+constexpr uint64_t P = ZB_BABYBEAR_P;
+
+inline uint64_t f_add(uint64_t a, uint64_t b) { // field.zig:73-88
+    uint64_t s = a + b;
+    return s >= P ? s - P : s;
+}
+inline uint64_t f_sub(uint64_t a, uint64_t b) { return a >= b ? a - b : P - (b - a); } // field.zig:91-98
+inline uint64_t f_mul(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) % P); } // field.zig:112-147
+
+inline uint64_t digest_to_field(const uint8_t d[32]) { // hash.zig:228-242: first 8 bytes LE, then F.init = mod p
+    uint64_t v;
+    memcpy(&v, d, 8);
+    return v % P;
+}
+} // namespace
+
+struct zh_transcript {
+    Sha3_256 h;
+};
+
+extern "C" {
+
+zh_transcript *zh_transcript_new(void) { return new (std::nothrow) zh_transcript(); }
+zh_transcript *zh_transcript_clone(const zh_transcript *t) { return t ? new (std::nothrow) zh_transcript(*t) : nullptr; }
+void zh_transcript_free(zh_transcript *t) { delete t; }
+void zh_transcript_append_field(zh_transcript *t, uint64_t v) { t->h.update_words(&v, 1); }
+void zh_transcript_append_fields(zh_transcript *t, const uint64_t *v, size_t n) { t->h.update_words(v, n); }
+void zh_transcript_append_bytes(zh_transcript *t, const void *d, size_t n) { t->h.update(d, n); }
+uint64_t zh_transcript_challenge(zh_transcript *t) { // hash.zig:301-316
+    uint8_t digest[32];
+    t->h.peek(digest);
+    uint64_t r = digest_to_field(digest);
+    t->h.update(digest, 32); // the transcript absorbs its own digest
+    return r;
+}
+void zh_transcript_finalize(zh_transcript *t, uint8_t out[32]) { t->h.peek(out); }
+void zh_sha3_256(const void *d, size_t n, uint8_t out[32]) { Sha3_256::hash(d, n, out); }
+uint64_t zh_digest_to_field(const uint8_t digest[32]) { return digest_to_field(digest); }
+
+uint64_t zh_f_add(uint64_t a, uint64_t b) { return f_add(a % P, b % P); }
+uint64_t zh_f_sub(uint64_t a, uint64_t b) { return f_sub(a % P, b % P); }
+uint64_t zh_f_mul(uint64_t a, uint64_t b) { return f_mul(a % P, b % P); }
+
+uint64_t zh_eval_univariate(const uint64_t *c, uint32_t n, uint64_t x) { // sumcheck_protocol.zig:113-123 (Horner)
+    if (n == 0) return 0;
+    uint64_t r = c[n - 1];
+    for (uint32_t i = n - 1; i > 0; i--) r = f_add(f_mul(r, x), c[i - 1]);
+    return r;
+}
+
+/* ------------------------------------------------------------------ sumcheck */
+
+// The round loop of SumcheckProver.prove for d polynomials (d == 1: sumcheck_prover.zig:50-77).
+//   device: round coefficients  ->  host: absorb + challenge  ->  device: fold (fused with the next round's sums)
+// `consume`: fold the caller's polynomials in place; otherwise the first fold goes to fresh buffers (the
+// reference's copy at :47 costs a full pass; folding out of place in round 0 gives the same isolation for free).
+static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool consume, const uint64_t *fixed_challenges,
+                            uint64_t *round_polys, uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum) {
+    if (d < 1 || d > 3 || !polys) return ZB_ERR_BAD_ARGUMENT;
+    uint64_t n = 0;
+    uint32_t v = 0;
+    int32_t rc = zb_mle_len(ctx, polys[0], &n, &v);
+    if (rc) return rc;
+    if (v == 0) return ZB_ERR_NO_VARIABLES; // sumcheck_prover.zig:30-32
+    const uint32_t nc = d + 1;
+    zh_transcript tr; // State.init -> FiatShamirTranscript.init (sumcheck_protocol.zig:149-164)
+    uint64_t coeffs[4];
+    rc = zb_prod_round_coeffs(ctx, polys, d, coeffs);
+    if (rc) return rc;
+    if (claimed_sum) {
+        // sum over the hypercube == g(0) + g(1) == 2 a0 + a1 + ... + ad   (== sumOverHypercube for d == 1, :40)
+        uint64_t s = coeffs[0];
+        for (uint32_t k = 0; k < nc; k++) s = f_add(s, coeffs[k]);
+        *claimed_sum = s;
+    }
+    zb_mle cur[3] = {polys[0], d > 1 ? polys[1] : 0, d > 2 ? polys[2] : 0};
+    bool owned = false;
+    auto cleanup = [&]() {
+        if (owned)
+            for (uint32_t k = 0; k < d; k++) zb_mle_free(ctx, cur[k]);
+    };
+    for (uint32_t round = 0; round < v; round++) {
+        for (uint32_t k = 0; k < nc; k++) round_polys[(size_t)round * nc + k] = coeffs[k];
+        uint64_t r;
+        if (fixed_challenges) {
+            r = fixed_challenges[round]; // proveInteractive :127
+        } else {
+            zh_transcript_append_fields(&tr, coeffs, nc); // generateChallenge, sumcheck_protocol.zig:176-184
+            r = zh_transcript_challenge(&tr);
+        }
+        final_point[round] = r;
+        // (the reference also evaluates the round polynomial at r to advance its claim, :63-70; the value never
+        //  reaches the proof, so it is not computed here)
+        if (round == 0 && !consume) {
+            zb_mle next[3];
+            rc = zb_prod_partial_eval(ctx, polys, d, r, next, coeffs);
+            if (rc) return rc;
+            for (uint32_t k = 0; k < d; k++) cur[k] = next[k];
+            owned = true;
+        } else {
+            rc = zb_prod_fold_inplace(ctx, cur, d, r, coeffs);
+            if (rc) {
+                cleanup();
+                return rc;
+            }
+        }
+    }
+    // after the last fold `coeffs` holds the d final evaluations (current_poly.evaluations[0], :88)
+    for (uint32_t k = 0; k < d; k++) final_evals[k] = coeffs[k];
+    cleanup();
+    return ZB_OK;
+}
+
+int32_t zh_sumcheck_prove(zb_ctx *ctx, zb_mle poly, uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval,
+                          uint64_t *claimed_sum) {
+    return prove_rounds(ctx, &poly, 1, false, nullptr, round_polys, final_point, final_eval, claimed_sum);
+}
+
+int32_t zh_sumcheck_prove_interactive(zb_ctx *ctx, zb_mle poly, const uint64_t *challenges, uint32_t n_challenges,
+                                      uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval) {
+    uint64_t n;
+    uint32_t v;
+    int32_t rc = zb_mle_len(ctx, poly, &n, &v);
+    if (rc) return rc;
+    if (v == 0) return ZB_ERR_NO_VARIABLES;                       // :102-104
+    if (n_challenges != v) return ZB_ERR_WRONG_NUM_CHALLENGES;    // :105-107
+    for (uint32_t i = 0; i < v; i++)
+        if (challenges[i] >= P) return ZB_ERR_NOT_CANONICAL;
+    return prove_rounds(ctx, &poly, 1, false, challenges, round_polys, final_point, final_eval, nullptr);
+}
+
+size_t zh_sumcheck_proof_to_bytes(uint32_t v, const uint64_t *round_polys, const uint64_t *final_point, uint64_t final_eval,
+                                  uint8_t *out) { // sumcheck_protocol.zig:76-109, little-endian u64s
+    uint64_t *w = reinterpret_cast<uint64_t *>(out);
+    size_t k = 0;
+    auto put = [&](uint64_t x) { memcpy(out + 8 * k++, &x, 8); };
+    (void)w;
+    put(v);
+    for (uint32_t i = 0; i < 2 * v; i++) put(round_polys[i]);
+    for (uint32_t i = 0; i < v; i++) put(final_point[i]);
+    put(final_eval);
+    return 8 * k;
+}
+
+int32_t zh_prodcheck_prove(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *round_polys, uint64_t *final_point,
+                           uint64_t *final_evals, uint64_t *claimed_sum) {
+    return prove_rounds(ctx, polys, d, false, nullptr, round_polys, final_point, final_evals, claimed_sum);
+}
+
+int32_t zh_prodcheck_prove_consume(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *round_polys, uint64_t *final_point,
+                                   uint64_t *final_evals, uint64_t *claimed_sum) {
+    return prove_rounds(ctx, polys, d, true, nullptr, round_polys, final_point, final_evals, claimed_sum);
+}
+
+/* ------------------------------------------------------------------ commitment scheme */
+
+int32_t zh_commit(zb_ctx *ctx, zb_mle poly, zb_tree *tree, uint8_t root[32], uint32_t *num_vars) { // :69-83
+    uint64_t n;
+    uint32_t v;
+    int32_t rc = zb_mle_len(ctx, poly, &n, &v);
+    if (rc) return rc;
+    rc = zb_merkle_build(ctx, &poly, 1, tree, root);
+    if (rc == ZB_OK && num_vars) *num_vars = v;
+    return rc;
+}
+
+int32_t zh_batch_commit(zb_ctx *ctx, const zb_mle *polys, uint32_t count, zb_tree *trees, uint8_t *roots) { // :132-157
+    if (count == 0) return ZB_OK;
+    return zb_merkle_build(ctx, polys, count, trees, roots);
+}
+
+uint64_t zh_point_to_index(const uint64_t *point, uint32_t npoint) { // :178-183
+    if (npoint == 0) return 0;
+    return npoint >= 64 ? point[0] : point[0] % (1ull << npoint);
+}
+
+int32_t zh_commit_open(zb_ctx *ctx, zb_mle poly, zb_tree tree, const uint64_t *point, uint32_t npoint, uint64_t *value,
+                       uint64_t *leaf_index, uint64_t *leaf_value, uint8_t *siblings, uint8_t *dirs) { // :86-115
+    uint64_t n;
+    uint32_t v;
+    int32_t rc = zb_mle_len(ctx, poly, &n, &v);
+    if (rc) return rc;
+    if (npoint != v) return ZB_ERR_POINT_DIM_MISMATCH; // :92-94
+    rc = zb_mle_eval(ctx, poly, point, npoint, value);  // :97
+    if (rc) return rc;
+    uint64_t index = zh_point_to_index(point, npoint); // :102
+    if (leaf_index) *leaf_index = index;
+    return zb_merkle_open(ctx, tree, index, siblings, dirs, leaf_value); // :105
+}
+
+int32_t zh_merkle_verify(const uint8_t root[32], uint64_t value, const uint8_t *siblings, const uint8_t *dirs, uint32_t height) {
+    // merkle_tree.zig:362-373: current = hashLeaf(value); per level current = hashInternal(left, right)
+    uint8_t cur[32], buf[64];
+    Sha3_256::hash(&value, 8, cur);
+    for (uint32_t l = 0; l < height; l++) {
+        if (dirs[l]) { // we are the right child
+            memcpy(buf, siblings + 32 * l, 32);
+            memcpy(buf + 32, cur, 32);
+        } else {
+            memcpy(buf, cur, 32);
+            memcpy(buf + 32, siblings + 32 * l, 32);
+        }
+        Sha3_256::hash(buf, 64, cur);
+    }
+    return memcmp(cur, root, 32) == 0;
+}
+
+int32_t zh_commit_verify(const uint8_t root[32], uint64_t leaf_value, const uint8_t *siblings, const uint8_t *dirs,
+                         uint32_t height) { // polynomial_commit.zig:118-129 (dimension check is the caller's: height)
+    return zh_merkle_verify(root, leaf_value, siblings, dirs, height);
+}
+
+/* ------------------------------------------------------------------ Lasso */
+
+int32_t zh_lasso_commit_poly(zb_ctx *ctx, zb_mle poly, uint8_t out[32]) { // lasso_prover.zig:242-252
+    uint64_t n;
+    uint32_t v;
+    int32_t rc = zb_mle_len(ctx, poly, &n, &v);
+    if (rc) return rc;
+    // the sponge is one sequential chain over 8n bytes: it stays on one host core, fed in pipelined chunks
+    const uint64_t CH = 1ull << 20;
+    uint64_t *buf = nullptr;
+    rc = zb_host_alloc(ctx, (n < CH ? n : CH) * sizeof(uint64_t), (void **)&buf);
+    if (rc) return rc;
+    Sha3_256 h;
+    for (uint64_t off = 0; off < n && rc == ZB_OK; off += CH) {
+        uint64_t k = n - off < CH ? n - off : CH;
+        rc = zb_mle_download_range(ctx, poly, off, buf, k);
+        if (rc == ZB_OK) h.update_words(buf, k);
+    }
+    zb_host_free(ctx, buf);
+    if (rc == ZB_OK) h.peek(out);
+    return rc;
+}
+
+static int32_t lasso_finish(zb_ctx *ctx, zb_mle table_poly, zb_mle query_poly, uint64_t *round_polys, uint64_t *final_point,
+                            uint64_t *final_eval, uint32_t *num_vars, uint8_t qc[32], uint8_t tc[32]) {
+    uint64_t n;
+    uint32_t v;
+    int32_t rc = zb_mle_len(ctx, query_poly, &n, &v);
+    if (rc) return rc;
+    if (num_vars) *num_vars = v;
+    // :154 `_ = query_poly.sumOverHypercube()` is discarded by the reference; nothing to do.
+    rc = zh_sumcheck_prove(ctx, query_poly, round_polys, final_point, final_eval, nullptr); // :160
+    if (rc) return rc;
+    rc = zh_lasso_commit_poly(ctx, query_poly, qc); // :163
+    if (rc) return rc;
+    return zh_lasso_commit_poly(ctx, table_poly, tc); // :164
+}
+
+static uint64_t ceil_pow2(uint64_t n) {
+    uint64_t r = 1;
+    while (r < n) r <<= 1;
+    return r;
+}
+
+int32_t zh_lasso_prove(zb_ctx *ctx, const uint64_t *table_rows, uint64_t n_table, const uint64_t *query_rows,
+                       uint64_t n_queries, uint32_t arity, uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval,
+                       uint32_t *num_vars, uint8_t qc[32], uint8_t tc[32]) {
+    if (n_queries == 0) return ZB_ERR_NO_QUERIES; // :108-110
+    // Multilinear.init(table_evals) :124 -> EmptyEvaluations / LengthNotPowerOfTwo
+    if (n_table == 0) return ZB_ERR_EMPTY_EVALUATIONS;
+    if (n_table & (n_table - 1)) return ZB_ERR_LENGTH_NOT_POW2;
+    zb_mle table_poly = 0, query_poly = 0;
+    int32_t rc = zb_xxh3_rows(ctx, table_rows, n_table, arity, n_table, &table_poly); // :119-122
+    if (rc) return rc;
+    rc = zb_xxh3_rows(ctx, query_rows, n_queries, arity, ceil_pow2(n_queries), &query_poly); // :131-142
+    if (rc == ZB_OK) rc = lasso_finish(ctx, table_poly, query_poly, round_polys, final_point, final_eval, num_vars, qc, tc);
+    if (query_poly) zb_mle_free(ctx, query_poly);
+    zb_mle_free(ctx, table_poly);
+    return rc;
+}
+
+int32_t zh_lasso_prove_with_mapping(zb_ctx *ctx, const uint64_t *table_rows, uint64_t n_table, const uint64_t *query_rows,
+                                    uint64_t n_queries, const uint64_t *mapping, uint64_t n_mapping, uint32_t arity,
+                                    uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars,
+                                    uint8_t qc[32], uint8_t tc[32]) {
+    if (n_queries != n_mapping) return ZB_ERR_MAPPING_LEN_MISMATCH; // :186-188
+    // :191-201 — an O(#queries * arity) host comparison over data that is already on the host
+    for (uint64_t j = 0; j < n_queries; j++) {
+        if (mapping[j] >= n_table) return ZB_ERR_INVALID_MAPPING;
+        if (memcmp(query_rows + j * arity, table_rows + mapping[j] * arity, arity * sizeof(uint64_t)) != 0)
+            return ZB_ERR_QUERY_TABLE_MISMATCH; // entriesMatch :255-268
+    }
+    return zh_lasso_prove(ctx, table_rows, n_table, query_rows, n_queries, arity, round_polys, final_point, final_eval, num_vars,
+                          qc, tc);
+}
+
+int32_t zh_lasso_prove_builtin(zb_ctx *ctx, int32_t op, uint32_t bits, const uint64_t *query_rows, uint64_t n_queries,
+                               uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars,
+                               uint8_t qc[32], uint8_t tc[32]) {
+    if (n_queries == 0) return ZB_ERR_NO_QUERIES;
+    zb_mle table_poly = 0, query_poly = 0;
+    int32_t rc = zb_table_mle(ctx, op, bits, &table_poly);
+    if (rc) return rc;
+    rc = zb_xxh3_rows(ctx, query_rows, n_queries, 3, ceil_pow2(n_queries), &query_poly);
+    if (rc == ZB_OK) rc = lasso_finish(ctx, table_poly, query_poly, round_polys, final_point, final_eval, num_vars, qc, tc);
+    if (query_poly) zb_mle_free(ctx, query_poly);
+    zb_mle_free(ctx, table_poly);
+    return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,156 @@
+// Keccak-f[1600] on 32-bit register pairs for sm_100a (no 64-bit integer ALU on the SM).
+// SHA3-256 as used by the reference: std.crypto.hash.sha3.Sha3_256 in
+// /root/reference/src/core/hash.zig:135-147 (leaf) and :187-195 (node).
+//   theta : 5-input XOR columns as two LOP3 (lut 0x96); D is never materialised:
+//           A ^ C[x-1] ^ rotl(C[x+1],1) is one LOP3 per half lane
+//   rho/pi: one SHF.L.W funnel shift per half lane, compile-time amounts
+//   chi   : a ^ (~b & c) = one LOP3 (lut 0xD2) per half lane
+// => ~180 ALU-pipe instructions per round, 24 rounds.
+#pragma once
+#include <cstdint>
+
+namespace keccak {
+
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t chi(uint32_t a, uint32_t b, uint32_t c) { // a ^ (~b & c)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD2;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+static __device__ __constant__ const uint32_t RC_LO[24] = {
+    0x00000001u, 0x00008082u, 0x0000808au, 0x80008000u, 0x0000808bu, 0x80000001u, 0x80008081u, 0x00008009u,
+    0x0000008au, 0x00000088u, 0x80008009u, 0x8000000au, 0x8000808bu, 0x0000008bu, 0x00008089u, 0x00008003u,
+    0x00008002u, 0x00000080u, 0x0000800au, 0x8000000au, 0x80008081u, 0x00008080u, 0x80000001u, 0x80008008u};
+static __device__ __constant__ const uint32_t RC_HI[24] = {
+    0x00000000u, 0x00000000u, 0x80000000u, 0x80000000u, 0x00000000u, 0x00000000u, 0x80000000u, 0x80000000u,
+    0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x80000000u, 0x80000000u, 0x80000000u,
+    0x80000000u, 0x80000000u, 0x00000000u, 0x80000000u, 0x80000000u, 0x80000000u, 0x00000000u, 0x80000000u};
+
+// rho offsets indexed by lane x + 5y
+__device__ constexpr int RHO[25] = {0,  1,  62, 28, 27, 36, 44, 6,  55, 20, 3,  10, 43,
+                                    25, 39, 41, 45, 15, 21, 8,  18, 2,  61, 56, 14};
+
+template <int N>
+__device__ __forceinline__ void rotl64(uint32_t lo, uint32_t hi, uint32_t &olo, uint32_t &ohi) {
+    if constexpr (N == 0) {
+        olo = lo;
+        ohi = hi;
+    } else if constexpr (N < 32) {
+        ohi = __funnelshift_l(lo, hi, N);
+        olo = __funnelshift_l(hi, lo, N);
+    } else if constexpr (N == 32) {
+        olo = hi;
+        ohi = lo;
+    } else {
+        ohi = __funnelshift_l(hi, lo, N - 32);
+        olo = __funnelshift_l(lo, hi, N - 32);
+    }
+}
+
+template <int I>
+__device__ __forceinline__ void rho_pi_lane(const uint32_t (&al)[25], const uint32_t (&ah)[25], const uint32_t (&dl)[5],
+                                            const uint32_t (&dh)[5], const uint32_t (&el)[5], const uint32_t (&eh)[5],
+                                            uint32_t (&bl)[25], uint32_t (&bh)[25]) {
+    constexpr int x = I % 5, y = I / 5;
+    constexpr int dst = y + 5 * ((2 * x + 3 * y) % 5);
+    // theta folded in: t = A ^ C[x-1] ^ rotl(C[x+1], 1)
+    uint32_t tl = xor3(al[I], dl[x], el[x]);
+    uint32_t th = xor3(ah[I], dh[x], eh[x]);
+    rotl64<RHO[I]>(tl, th, bl[dst], bh[dst]);
+    if constexpr (I + 1 < 25) rho_pi_lane<I + 1>(al, ah, dl, dh, el, eh, bl, bh);
+}
+
+__device__ __forceinline__ void round(uint32_t (&al)[25], uint32_t (&ah)[25], uint32_t rcl, uint32_t rch) {
+    uint32_t cl[5], ch[5];
+#pragma unroll
+    for (int x = 0; x < 5; x++) {
+        cl[x] = xor3(xor3(al[x], al[x + 5], al[x + 10]), al[x + 15], al[x + 20]);
+        ch[x] = xor3(xor3(ah[x], ah[x + 5], ah[x + 10]), ah[x + 15], ah[x + 20]);
+    }
+    // dl/dh = C[x-1]; el/eh = rotl(C[x+1], 1)
+    uint32_t dl[5], dh[5], el[5], eh[5];
+#pragma unroll
+    for (int x = 0; x < 5; x++) {
+        dl[x] = cl[(x + 4) % 5];
+        dh[x] = ch[(x + 4) % 5];
+        rotl64<1>(cl[(x + 1) % 5], ch[(x + 1) % 5], el[x], eh[x]);
+    }
+    uint32_t bl[25], bh[25];
+    rho_pi_lane<0>(al, ah, dl, dh, el, eh, bl, bh);
+#pragma unroll
+    for (int y = 0; y < 25; y += 5) {
+#pragma unroll
+        for (int x = 0; x < 5; x++) {
+            al[y + x] = chi(bl[y + x], bl[y + (x + 1) % 5], bl[y + (x + 2) % 5]);
+            ah[y + x] = chi(bh[y + x], bh[y + (x + 1) % 5], bh[y + (x + 2) % 5]);
+        }
+    }
+    al[0] ^= rcl;
+    ah[0] ^= rch;
+}
+
+// UNROLL = rounds per loop iteration (24 = fully unrolled, constants folded)
+template <int UNROLL>
+__device__ __forceinline__ void f1600(uint32_t (&al)[25], uint32_t (&ah)[25]) {
+    if constexpr (UNROLL >= 24) {
+#pragma unroll
+        for (int r = 0; r < 24; r++) round(al, ah, RC_LO[r], RC_HI[r]);
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < 24; r += UNROLL) {
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++) round(al, ah, RC_LO[r + k], RC_HI[r + k]);
+        }
+    }
+}
+
+// SHA3-256 of the 8-byte little-endian encoding of a field element (leaf hash, merkle_tree.zig:298-300)
+template <int UNROLL>
+__device__ __forceinline__ void sha3_leaf(uint32_t value, uint32_t (&out)[8]) {
+    uint32_t al[25], ah[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) {
+        al[i] = 0;
+        ah[i] = 0;
+    }
+    al[0] = value;       // le64(value), high word is zero: value < 2^31
+    al[1] = 0x06u;       // SHA-3 domain separation + first pad bit right after the 8 message bytes
+    ah[16] = 0x80000000u; // last pad bit: byte 135 of the 136-byte rate
+    f1600<UNROLL>(al, ah);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        out[2 * i] = al[i];
+        out[2 * i + 1] = ah[i];
+    }
+}
+
+// SHA3-256(left || right) of two 32-byte digests (node hash, merkle_tree.zig:390-392)
+template <int UNROLL>
+__device__ __forceinline__ void sha3_node(const uint32_t (&in)[16], uint32_t (&out)[8]) {
+    uint32_t al[25], ah[25];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        al[i] = in[2 * i];
+        ah[i] = in[2 * i + 1];
+    }
+#pragma unroll
+    for (int i = 8; i < 25; i++) {
+        al[i] = 0;
+        ah[i] = 0;
+    }
+    al[8] = 0x06u;
+    ah[16] = 0x80000000u;
+    f1600<UNROLL>(al, ah);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        out[2 * i] = al[i];
+        out[2 * i + 1] = ah[i];
+    }
+}
+
+} // namespace keccak

@@ -1,0 +1,87 @@
+// Internal launch interface between the context layer (ctx.cu) and the sm_100a kernels.
+// Every launcher enqueues on `st` and returns; results that the host needs come back through the
+// Mailbox (mapped pinned memory written by the last CTA of the kernel, then polled by the host).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace zk {
+
+constexpr int MAX_POLYS = 3;    // product sumcheck degree
+constexpr int MAX_BATCH = 64;   // trees per batched Merkle launch
+constexpr int MAIL_WORDS = 16;  // u64 payload words per mailbox
+
+// Completion mailbox. `acc`/`ticket` live in device memory; `mail` is mapped pinned host memory.
+// mail[0..MAIL_WORDS) payload, mail[MAIL_WORDS] = sequence number written last (release, system scope).
+struct Mailbox {
+    unsigned long long *acc;    // device: MAIL_WORDS u64 accumulators (zero between launches)
+    unsigned int *ticket;       // device: CTA arrival counter (zero between launches)
+    unsigned long long *mail;   // device alias of the mapped host mailbox
+    unsigned long long seq;     // sequence value this launch must publish
+};
+
+struct PolySet {
+    const uint32_t *src[MAX_POLYS];
+    uint32_t *dst[MAX_POLYS];
+};
+
+// Round sums of the current polynomials over MSB-first pairs (i, i + n/2), n >= 2.
+//   D=1: payload {s0, s1}            D=2: {g(0), g(1), g(inf)}      D=3: {g(0), g(1), g(-1), g(inf)}
+// all canonical mod p.
+void launch_round_sums(int d, const PolySet &ps, uint64_t n, const Mailbox &mb, int sm_count, cudaStream_t st);
+
+// Fold every polynomial with challenge r (new[i] = e[i] + r (e[i + n/2] - e[i])) writing n/2 values to dst
+// (dst may equal src: in place), and, fused, the round sums of the folded polynomials (same payload as above).
+// If n == 2 the payload is the d final evaluations instead.
+void launch_fold_sums(int d, const PolySet &ps, uint64_t n, uint32_t r, const Mailbox &mb, int sm_count, cudaStream_t st);
+
+// Plain sum of all n evaluations: payload {sum mod p}
+void launch_sum(const uint32_t *src, uint64_t n, const Mailbox &mb, int sm_count, cudaStream_t st);
+
+// LSB-first evaluation (Multilinear.eval): one stage folds up to 12 variables: out[j] = fold of src[4096 j ..)
+// `point` are canonical challenges for the variables this stage folds (lowest first).
+struct EvalPoint {
+    uint32_t r[12];
+    uint32_t rp[12];
+};
+void launch_eval_stage(const uint32_t *src, uint64_t n, int nvars, const EvalPoint &pt, uint32_t *out, const Mailbox *mb,
+                       int sm_count, cudaStream_t st);
+
+// element-wise helpers
+void launch_narrow_u64(const uint64_t *src, uint32_t *dst, uint64_t n, unsigned int *err_flag, cudaStream_t st);
+void launch_check_u32(const uint32_t *src, uint64_t n, unsigned int *err_flag, cudaStream_t st);
+void launch_widen_u32(const uint32_t *src, uint64_t *dst, uint64_t n, cudaStream_t st);
+void launch_fill(uint32_t *dst, uint64_t n, uint32_t value, cudaStream_t st);
+void launch_synthetic(uint32_t *dst, uint64_t n, uint64_t seed, uint64_t start, uint64_t stride, cudaStream_t st);
+void launch_add(const uint32_t *a, const uint32_t *b, uint32_t *out, uint64_t n, cudaStream_t st);
+void launch_scalar_mul(const uint32_t *a, uint32_t s, uint32_t *out, uint64_t n, cudaStream_t st);
+
+// Lasso row hashing (hashEntry / hashQuery). rows: n_rows * arity u64 on the device; out: n_padded u32.
+void launch_xxh3_rows(const uint64_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, uint32_t *out,
+                      unsigned int *err_flag, cudaStream_t st);
+void launch_table_mle(int op, uint32_t bits, uint32_t *out, cudaStream_t st);
+
+// Merkle. Tree storage = all levels concatenated: level l starts at digest offset level_offset(padded, l).
+struct MerkleBatch {
+    const uint32_t *values[MAX_BATCH]; // per tree
+    uint64_t n_values[MAX_BATCH];      // real (unpadded) number of values per tree
+    uint8_t *tree[MAX_BATCH];          // per tree storage base
+    uint32_t count;
+};
+inline uint64_t merkle_level_offset(uint64_t padded, uint32_t level) { // in digests
+    return 2 * padded - (2 * padded >> level);
+}
+void launch_merkle_leaves(const MerkleBatch &b, uint64_t padded, cudaStream_t st);
+// hashes level `level` -> `level + 1` for every tree of the batch
+void launch_merkle_level(const MerkleBatch &b, uint64_t padded, uint32_t level, cudaStream_t st);
+// finishes all levels from `level` (width <= 1024) to the root inside one CTA per tree
+void launch_merkle_top(const MerkleBatch &b, uint64_t padded, uint32_t level, cudaStream_t st);
+constexpr uint64_t MERKLE_TOP_WIDTH = 1024;
+// copies the `height` (<= 64) sibling digests of leaf `index` (leaf -> root) to `out` (host-mapped bulk area), then
+// publishes mb.seq
+void launch_merkle_path(const uint8_t *tree, uint64_t padded, uint32_t height, uint64_t index, uint8_t *out, const Mailbox &mb,
+                        cudaStream_t st);
+// copies the root of every tree of the batch to `out` (host-mapped bulk area), then publishes mb.seq
+void launch_merkle_roots(const MerkleBatch &b, uint64_t padded, uint8_t *out, const Mailbox &mb, cudaStream_t st);
+
+} // namespace zk

@@ -1,0 +1,131 @@
+// sm_100a kernels for SimpleMerkleTree(BabyBear, SHA3Hasher) — /root/reference/src/commitments/merkle_tree.zig:283-400.
+//   leaves : leaf_hashes[i] = SHA3-256(le64(values[i])), padded with SHA3-256(le64(0))      (:298-306)
+//   levels : next[i] = SHA3-256(cur[2i] || cur[2i+1])                                        (:386-396)
+//   open   : sibling gather from the retained levels (the reference recomputes them, :335-353)
+// Level-synchronous, batched over the trees of one commit batch (blockIdx.y = tree). This path is bound by the
+// integer ALU pipe (one Keccak-f[1600] per digest, ~4.3k LOP3/SHF each), not by HBM: each thread owns one
+// permutation, state in 50 registers, no shared memory, no spills.
+#include "keccak.cuh"
+#include "kernels.h"
+
+namespace zk {
+
+#ifndef ZB_KECCAK_UNROLL
+#define ZB_KECCAK_UNROLL 24
+#endif
+constexpr int KT = 128; // threads per CTA for the hashing kernels
+
+__device__ __forceinline__ void store_digest(uint8_t *dst, const uint32_t (&d)[8]) {
+    uint4 *o = reinterpret_cast<uint4 *>(dst);
+    o[0] = make_uint4(d[0], d[1], d[2], d[3]);
+    o[1] = make_uint4(d[4], d[5], d[6], d[7]);
+}
+
+__global__ void __launch_bounds__(KT) k_merkle_leaves(MerkleBatch b, uint64_t padded) {
+    const uint32_t t = blockIdx.y;
+    const uint32_t *vals = b.values[t];
+    const uint64_t n = b.n_values[t];
+    uint8_t *tree = b.tree[t];
+    const uint64_t stride = (uint64_t)gridDim.x * KT;
+    for (uint64_t i = (uint64_t)blockIdx.x * KT + threadIdx.x; i < padded; i += stride) {
+        uint32_t v = i < n ? vals[i] : 0u;
+        uint32_t d[8];
+        keccak::sha3_leaf<ZB_KECCAK_UNROLL>(v, d);
+        store_digest(tree + i * 32, d);
+    }
+}
+
+__device__ __forceinline__ void hash_pair(const uint8_t *in, uint8_t *out) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(in);
+    uint4 a = p[0], b4 = p[1], c = p[2], e = p[3];
+    uint32_t m[16] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w, c.x, c.y, c.z, c.w, e.x, e.y, e.z, e.w};
+    uint32_t d[8];
+    keccak::sha3_node<ZB_KECCAK_UNROLL>(m, d);
+    store_digest(out, d);
+}
+
+__global__ void __launch_bounds__(KT) k_merkle_level(MerkleBatch b, uint64_t in_off, uint64_t out_off, uint64_t width_out) {
+    uint8_t *tree = b.tree[blockIdx.y];
+    const uint8_t *in = tree + in_off * 32;
+    uint8_t *out = tree + out_off * 32;
+    const uint64_t stride = (uint64_t)gridDim.x * KT;
+    for (uint64_t i = (uint64_t)blockIdx.x * KT + threadIdx.x; i < width_out; i += stride) hash_pair(in + i * 64, out + i * 32);
+}
+
+// all remaining levels of one tree inside one CTA: width (<= MERKLE_TOP_WIDTH) digests at `level` down to the root
+__global__ void __launch_bounds__(KT) k_merkle_top(MerkleBatch b, uint64_t padded, uint32_t level, uint64_t width) {
+    uint8_t *tree = b.tree[blockIdx.x];
+    while (width > 1) {
+        const uint8_t *in = tree + (2 * padded - (2 * padded >> level)) * 32;
+        uint8_t *out = tree + (2 * padded - (2 * padded >> (level + 1))) * 32;
+        const uint64_t width_out = width / 2;
+        for (uint64_t i = threadIdx.x; i < width_out; i += KT) hash_pair(in + i * 64, out + i * 32);
+        __syncthreads(); // global writes of this CTA are visible to the CTA after the barrier
+        width = width_out;
+        level++;
+    }
+}
+
+// single-CTA gathers into the host-mapped bulk area, then publish the mailbox sequence number
+__device__ __forceinline__ void publish_seq(const Mailbox &mb) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
+    }
+}
+
+__global__ void k_merkle_path(const uint8_t *tree, uint64_t padded, uint32_t height, uint64_t index, uint8_t *out, Mailbox mb) {
+    // thread = (level, 16-byte half)
+    const uint32_t l = threadIdx.x >> 1, half = threadIdx.x & 1;
+    if (l < height) {
+        const uint64_t sib = (index >> l) ^ 1ull;
+        const uint64_t off = (2 * padded - (2 * padded >> l)) + sib;
+        const uint4 *p = reinterpret_cast<const uint4 *>(tree + off * 32);
+        reinterpret_cast<uint4 *>(out + (uint64_t)l * 32)[half] = p[half];
+    }
+    publish_seq(mb);
+}
+
+__global__ void k_merkle_roots(MerkleBatch b, uint64_t padded, uint8_t *out, Mailbox mb) {
+    const uint32_t t = threadIdx.x >> 1, half = threadIdx.x & 1;
+    if (t < b.count) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(b.tree[t] + (2 * padded - 2) * 32);
+        reinterpret_cast<uint4 *>(out + (uint64_t)t * 32)[half] = p[half];
+    }
+    publish_seq(mb);
+}
+
+static inline unsigned hash_grid(uint64_t items) {
+    uint64_t g = (items + KT - 1) / KT;
+    const uint64_t cap = 148ull * 64; // grid-stride beyond this
+    if (g < 1) g = 1;
+    return (unsigned)(g > cap ? cap : g);
+}
+
+void launch_merkle_leaves(const MerkleBatch &b, uint64_t padded, cudaStream_t st) {
+    dim3 grid(hash_grid(padded), b.count);
+    k_merkle_leaves<<<grid, KT, 0, st>>>(b, padded);
+}
+
+void launch_merkle_level(const MerkleBatch &b, uint64_t padded, uint32_t level, cudaStream_t st) {
+    uint64_t width_out = padded >> (level + 1);
+    dim3 grid(hash_grid(width_out), b.count);
+    k_merkle_level<<<grid, KT, 0, st>>>(b, merkle_level_offset(padded, level), merkle_level_offset(padded, level + 1), width_out);
+}
+
+void launch_merkle_top(const MerkleBatch &b, uint64_t padded, uint32_t level, cudaStream_t st) {
+    k_merkle_top<<<b.count, KT, 0, st>>>(b, padded, level, padded >> level);
+}
+
+void launch_merkle_path(const uint8_t *tree, uint64_t padded, uint32_t height, uint64_t index, uint8_t *out, const Mailbox &mb,
+                        cudaStream_t st) {
+    k_merkle_path<<<1, 2 * 64, 0, st>>>(tree, padded, height, index, out, mb);
+}
+
+void launch_merkle_roots(const MerkleBatch &b, uint64_t padded, uint8_t *out, const Mailbox &mb, cudaStream_t st) {
+    k_merkle_roots<<<1, 2 * MAX_BATCH, 0, st>>>(b, padded, out, mb);
+}
+
+} // namespace zk

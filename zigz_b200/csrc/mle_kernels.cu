@@ -1,0 +1,561 @@
+// sm_100a kernels for the BabyBear multilinear hot loops of zigz:
+//   sumOverHypercube   /root/reference/src/poly/multilinear.zig:188-194
+//   roundPolynomial    /root/reference/src/poly/multilinear.zig:205-232
+//   partialEval        /root/reference/src/poly/multilinear.zig:154-180   (fused with the NEXT round's sums)
+//   eval               /root/reference/src/poly/multilinear.zig:110-144   (O(N) LSB-first fold)
+// All of them are HBM-bound streaming kernels: 128-bit coalesced loads, u64 per-thread accumulators
+// (sums of < 2^33 canonical 31-bit values cannot overflow), warp-shuffle + shared-memory block reduction,
+// one u64 atomicAdd per CTA and sum, and the last CTA to arrive publishes the canonical results to the
+// host-mapped mailbox — no separate reduction kernel, no D2H copy.
+#include "bb.cuh"
+#include "kernels.h"
+
+namespace zk {
+
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-reduce NS u64 partial sums, add them to the global accumulators; the last CTA converts the totals with
+// `fin` (called by one thread with the raw totals) and publishes payload + sequence number to the mailbox.
+template <int NS, typename Fin>
+__device__ __forceinline__ void publish_sums(unsigned long long (&s)[NS], const Mailbox &mb, Fin fin) {
+    __shared__ unsigned long long sm[NS][THREADS / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        unsigned long long v = warp_sum(s[k]);
+        if (lane == 0) sm[k][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NS; k++) {
+            unsigned long long v = 0;
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; w++) v += sm[k][w];
+            atomicAdd(&mb.acc[k], v);
+        }
+        __threadfence();
+        unsigned int t = atomicAdd(mb.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) {
+            __threadfence();
+            unsigned long long tot[NS];
+#pragma unroll
+            for (int k = 0; k < NS; k++) tot[k] = atomicExch(&mb.acc[k], 0ull); // read + re-arm
+            *mb.ticket = 0u;
+            fin(tot);
+#pragma unroll
+            for (int k = 0; k < NS; k++) ((volatile unsigned long long *)mb.mail)[k] = tot[k];
+            __threadfence_system();
+            ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
+        }
+    }
+}
+
+template <int D>
+struct NSums {
+    static constexpr int value = D == 1 ? 2 : D + 1;
+};
+
+// accumulate the round-polynomial evaluations contributed by one MSB-first pair (lo_k, hi_k), k < D
+template <int D>
+__device__ __forceinline__ void accum_pair(const uint32_t (&lo)[D], const uint32_t (&hi)[D],
+                                           unsigned long long (&s)[NSums<D>::value]) {
+    if constexpr (D == 1) {
+        s[0] += lo[0];
+        s[1] += hi[0];
+    } else if constexpr (D == 2) {
+        uint32_t d0 = bb::sub(hi[0], lo[0]), d1 = bb::sub(hi[1], lo[1]);
+        s[0] += bb::mont_mul(lo[0], lo[1]);
+        s[1] += bb::mont_mul(hi[0], hi[1]);
+        s[2] += bb::mont_mul(d0, d1);
+    } else {
+        uint32_t d0 = bb::sub(hi[0], lo[0]), d1 = bb::sub(hi[1], lo[1]), d2 = bb::sub(hi[2], lo[2]);
+        uint32_t m0 = bb::sub(lo[0], d0), m1 = bb::sub(lo[1], d1), m2 = bb::sub(lo[2], d2); // value at X = -1
+        s[0] += bb::mont_mul(bb::mont_mul(lo[0], lo[1]), lo[2]);
+        s[1] += bb::mont_mul(bb::mont_mul(hi[0], hi[1]), hi[2]);
+        s[2] += bb::mont_mul(bb::mont_mul(m0, m1), m2);
+        s[3] += bb::mont_mul(bb::mont_mul(d0, d1), d2);
+    }
+}
+
+// raw u64 totals -> canonical field elements (undoing the Montgomery factors R^-(D-1))
+template <int D>
+struct Finish {
+    __device__ void operator()(unsigned long long (&t)[NSums<D>::value]) const {
+#pragma unroll
+        for (int k = 0; k < NSums<D>::value; k++) {
+            uint32_t v = (uint32_t)(t[k] % bb::P);
+            if constexpr (D == 2) v = bb::mul(v, bb::R_MOD_P);
+            if constexpr (D == 3) v = bb::mul(v, bb::R2_MOD_P);
+            t[k] = v;
+        }
+    }
+};
+
+#define UNPACK4(v, a) \
+    {                 \
+        a[0] = v.x;   \
+        a[1] = v.y;   \
+        a[2] = v.z;   \
+        a[3] = v.w;   \
+    }
+
+// ---------------------------------------------------------------------------------------------
+// round sums only (first round): pairs (i, i + h); h4 = h / 4 uint4 per half
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(THREADS) k_round_sums_v4(PolySet ps, uint64_t h4, Mailbox mb) {
+    constexpr int NS = NSums<D>::value;
+    unsigned long long s[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) s[k] = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * THREADS;
+#pragma unroll 2
+    for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < h4; i += stride) {
+        uint32_t lo[D][4], hi[D][4];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(ps.src[k]);
+            uint4 a = p[i], b = p[i + h4];
+            UNPACK4(a, lo[k]);
+            UNPACK4(b, hi[k]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t l[D], h[D];
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                l[k] = lo[k][c];
+                h[k] = hi[k][c];
+            }
+            accum_pair<D>(l, h, s);
+        }
+    }
+    publish_sums<NS>(s, mb, Finish<D>());
+}
+
+// scalar variant for tiny / unaligned sizes: h pairs
+template <int D>
+__global__ void __launch_bounds__(THREADS) k_round_sums_s(PolySet ps, uint64_t h, Mailbox mb) {
+    constexpr int NS = NSums<D>::value;
+    unsigned long long s[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) s[k] = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < h; i += stride) {
+        uint32_t l[D], hh[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            l[k] = ps.src[k][i];
+            hh[k] = ps.src[k][i + h];
+        }
+        accum_pair<D>(l, hh, s);
+    }
+    publish_sums<NS>(s, mb, Finish<D>());
+}
+
+// ---------------------------------------------------------------------------------------------
+// fold + next-round sums. Current length n = 4q. Thread handles i in [0, q):
+//   new[i]     = lerp(e[i],     e[i + 2q])      (pair (i, i + n/2))
+//   new[i + q] = lerp(e[i + q], e[i + 3q])
+// and (new[i], new[i + q]) is exactly the next round's MSB-first pair. q4 = q / 4.
+// In place is safe: a thread only touches indices congruent to its own i modulo q.
+// ---------------------------------------------------------------------------------------------
+template <int D, int U>
+__global__ void __launch_bounds__(THREADS) k_fold_sums_v4(PolySet ps, uint64_t q4, uint32_t r, uint32_t rp, Mailbox mb) {
+    constexpr int NS = NSums<D>::value;
+    unsigned long long s[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) s[k] = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * THREADS;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i0 < q4; i0 += U * stride) {
+        // issue every load of the U independent items first: src may alias dst (in place), so the compiler
+        // cannot hoist the next item's loads above this item's stores on its own
+        uint4 v[U][D][4];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t i = i0 + u * stride;
+            if (i < q4) {
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const uint4 *p = reinterpret_cast<const uint4 *>(ps.src[k]);
+                    v[u][k][0] = p[i];
+                    v[u][k][1] = p[i + q4];
+                    v[u][k][2] = p[i + 2 * q4];
+                    v[u][k][3] = p[i + 3 * q4];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t i = i0 + u * stride;
+            if (i < q4) {
+                uint32_t nlo[D][4], nhi[D][4];
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    uint32_t e0[4], e1[4], e2[4], e3[4];
+                    UNPACK4(v[u][k][0], e0);
+                    UNPACK4(v[u][k][1], e1);
+                    UNPACK4(v[u][k][2], e2);
+                    UNPACK4(v[u][k][3], e3);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        nlo[k][c] = bb::lerp(e0[c], e2[c], r, rp);
+                        nhi[k][c] = bb::lerp(e1[c], e3[c], r, rp);
+                    }
+                    uint4 *o = reinterpret_cast<uint4 *>(ps.dst[k]);
+                    o[i] = make_uint4(nlo[k][0], nlo[k][1], nlo[k][2], nlo[k][3]);
+                    o[i + q4] = make_uint4(nhi[k][0], nhi[k][1], nhi[k][2], nhi[k][3]);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t l[D], h[D];
+#pragma unroll
+                    for (int k = 0; k < D; k++) {
+                        l[k] = nlo[k][c];
+                        h[k] = nhi[k][c];
+                    }
+                    accum_pair<D>(l, h, s);
+                }
+            }
+        }
+    }
+    publish_sums<NS>(s, mb, Finish<D>());
+}
+
+// scalar variant, q >= 1 quarter length
+template <int D>
+__global__ void __launch_bounds__(THREADS) k_fold_sums_s(PolySet ps, uint64_t q, uint32_t r, uint32_t rp, Mailbox mb) {
+    constexpr int NS = NSums<D>::value;
+    unsigned long long s[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) s[k] = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < q; i += stride) {
+        uint32_t l[D], h[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const uint32_t *p = ps.src[k];
+            uint32_t e0 = p[i], e1 = p[i + q], e2 = p[i + 2 * q], e3 = p[i + 3 * q];
+            l[k] = bb::lerp(e0, e2, r, rp);
+            h[k] = bb::lerp(e1, e3, r, rp);
+            ps.dst[k][i] = l[k];
+            ps.dst[k][i + q] = h[k];
+        }
+        accum_pair<D>(l, h, s);
+    }
+    publish_sums<NS>(s, mb, Finish<D>());
+}
+
+// last fold (n == 2): one value per polynomial remains; payload = the D final evaluations
+template <int D>
+__global__ void k_fold_last(PolySet ps, uint32_t r, uint32_t rp, Mailbox mb) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            uint32_t v = bb::lerp(ps.src[k][0], ps.src[k][1], r, rp);
+            ps.dst[k][0] = v;
+            ((volatile unsigned long long *)mb.mail)[k] = v;
+        }
+        __threadfence_system();
+        ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
+    }
+}
+
+static inline int grid_for(uint64_t work_items, int sm_count, int ctas_per_sm) {
+    uint64_t need = (work_items + THREADS - 1) / THREADS;
+    uint64_t cap = (uint64_t)sm_count * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+template <int D>
+static void round_sums_t(const PolySet &ps, uint64_t n, const Mailbox &mb, int sm, cudaStream_t st) {
+    uint64_t h = n / 2;
+    if (h % 4 == 0) {
+        k_round_sums_v4<D><<<grid_for(h / 4, sm, 8), THREADS, 0, st>>>(ps, h / 4, mb);
+    } else {
+        k_round_sums_s<D><<<1, THREADS, 0, st>>>(ps, h, mb);
+    }
+}
+
+void launch_round_sums(int d, const PolySet &ps, uint64_t n, const Mailbox &mb, int sm, cudaStream_t st) {
+    if (d == 1) round_sums_t<1>(ps, n, mb, sm, st);
+    else if (d == 2) round_sums_t<2>(ps, n, mb, sm, st);
+    else round_sums_t<3>(ps, n, mb, sm, st);
+}
+
+template <int D>
+static void fold_sums_t(const PolySet &ps, uint64_t n, uint32_t r, const Mailbox &mb, int sm, cudaStream_t st) {
+    uint32_t rp = bb::shoup_pre(r);
+    if (n == 2) {
+        k_fold_last<D><<<1, 32, 0, st>>>(ps, r, rp, mb);
+        return;
+    }
+    uint64_t q = n / 4;
+    if (q % 4 == 0) {
+        k_fold_sums_v4<D, (D == 1 ? 2 : 1)><<<grid_for(q / 4, sm, 4), THREADS, 0, st>>>(ps, q / 4, r, rp, mb);
+    } else {
+        k_fold_sums_s<D><<<1, THREADS, 0, st>>>(ps, q, r, rp, mb);
+    }
+}
+
+void launch_fold_sums(int d, const PolySet &ps, uint64_t n, uint32_t r, const Mailbox &mb, int sm, cudaStream_t st) {
+    if (d == 1) fold_sums_t<1>(ps, n, r, mb, sm, st);
+    else if (d == 2) fold_sums_t<2>(ps, n, r, mb, sm, st);
+    else fold_sums_t<3>(ps, n, r, mb, sm, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// plain sum (sumOverHypercube)
+// ---------------------------------------------------------------------------------------------
+struct FinishSum {
+    __device__ void operator()(unsigned long long (&t)[1]) const { t[0] = t[0] % bb::P; }
+};
+
+__global__ void __launch_bounds__(THREADS) k_sum(const uint32_t *src, uint64_t n, Mailbox mb) {
+    unsigned long long s[1] = {0};
+    const uint64_t stride = (uint64_t)gridDim.x * THREADS;
+    const uint64_t n4 = n / 4;
+    const uint4 *p = reinterpret_cast<const uint4 *>(src);
+#pragma unroll 4
+    for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n4; i += stride) {
+        uint4 v = p[i];
+        s[0] += (unsigned long long)(v.x + v.y) + (unsigned long long)(v.z + v.w); // each pair < 2^32
+    }
+    for (uint64_t i = n4 * 4 + (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) s[0] += src[i];
+    publish_sums<1>(s, mb, FinishSum());
+}
+
+void launch_sum(const uint32_t *src, uint64_t n, const Mailbox &mb, int sm, cudaStream_t st) {
+    k_sum<<<grid_for((n + 3) / 4, sm, 8), THREADS, 0, st>>>(src, n, mb);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multilinear.eval, LSB-first. One stage folds NV <= 12 variables: a CTA folds a tile of 2^NV consecutive
+// elements to one value: 16 elements per thread in registers (4 variables), 5 variables by warp shuffle,
+// 3 variables through shared memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) k_eval_stage(const uint32_t *src, uint64_t n_tiles, int nv, EvalPoint pt,
+                                                        uint32_t *out, Mailbox mb, int publish) {
+    __shared__ uint32_t sm[THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t tile_elems = 1ull << nv;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t *base = src + tile * tile_elems;
+        uint32_t v = 0;
+        int var = 0;
+        if (nv >= 4) {
+            const uint64_t chunk = (uint64_t)threadIdx.x * 16;
+            uint32_t e[16];
+            if (chunk < tile_elems) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(base + chunk);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint4 q = p[j];
+                    e[4 * j] = q.x;
+                    e[4 * j + 1] = q.y;
+                    e[4 * j + 2] = q.z;
+                    e[4 * j + 3] = q.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++) e[j] = 0;
+            }
+#pragma unroll
+            for (int lv = 0; lv < 4; lv++) {
+#pragma unroll
+                for (int j = 0; j < (8 >> lv); j++) e[j] = bb::lerp(e[2 * j], e[2 * j + 1], pt.r[lv], pt.rp[lv]);
+            }
+            v = e[0];
+            var = 4;
+        } else {
+            // tiny tile (< 16 elements): lane j of warp 0 holds element j, the shuffle tree below does the rest
+            v = (threadIdx.x < tile_elems) ? base[threadIdx.x] : 0;
+        }
+        // warp-level: lane L holds group L; fold adjacent lanes
+#pragma unroll
+        for (int step = 0; step < 5; step++) {
+            uint32_t other = __shfl_down_sync(0xffffffffu, v, 1 << step);
+            if (var < nv) {
+                v = bb::lerp(v, other, pt.r[var], pt.rp[var]);
+                var++;
+            }
+        }
+        if (lane == 0) sm[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t w[THREADS / 32];
+#pragma unroll
+            for (int j = 0; j < THREADS / 32; j++) w[j] = sm[j];
+            int vv = var;
+#pragma unroll
+            for (int lv = 0; lv < 3; lv++) {
+                if (vv < nv) {
+#pragma unroll
+                    for (int j = 0; j < (4 >> lv); j++) w[j] = bb::lerp(w[2 * j], w[2 * j + 1], pt.r[vv], pt.rp[vv]);
+                    vv++;
+                }
+            }
+            out[tile] = w[0];
+            if (publish) {
+                ((volatile unsigned long long *)mb.mail)[0] = w[0];
+                __threadfence_system();
+                ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void launch_eval_stage(const uint32_t *src, uint64_t n, int nvars, const EvalPoint &pt, uint32_t *out, const Mailbox *mb,
+                       int sm, cudaStream_t st) {
+    uint64_t n_tiles = n >> nvars;
+    uint64_t cap = (uint64_t)sm * 8;
+    int grid = (int)(n_tiles < cap ? n_tiles : cap);
+    Mailbox m = mb ? *mb : Mailbox{nullptr, nullptr, nullptr, 0};
+    k_eval_stage<<<grid, THREADS, 0, st>>>(src, n_tiles, nvars, pt, out, m, mb != nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// element-wise helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void k_narrow(const uint64_t *src, uint32_t *dst, uint64_t n, unsigned int *err) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t v = src[i];
+        bad |= (v >= bb::P);
+        dst[i] = (uint32_t)v;
+    }
+    if (bad) atomicOr(err, 1u);
+}
+__global__ void k_check(const uint32_t *src, uint64_t n, unsigned int *err) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) bad |= (src[i] >= bb::P);
+    if (bad) atomicOr(err, 1u);
+}
+__global__ void k_widen(const uint32_t *src, uint64_t *dst, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+__global__ void k_fill(uint32_t *dst, uint64_t n, uint32_t v) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
+}
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void k_synthetic(uint32_t *dst, uint64_t n, uint64_t seed, uint64_t start, uint64_t step) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = (uint32_t)(splitmix64(seed + start + i * step) % bb::P);
+}
+__global__ void k_add(const uint32_t *a, const uint32_t *b, uint32_t *o, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) o[i] = bb::add(a[i], b[i]);
+}
+__global__ void k_scalar_mul(const uint32_t *a, uint32_t s, uint32_t sp, uint32_t *o, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) o[i] = bb::mul_shoup(a[i], s, sp);
+}
+
+static inline int ew_grid(uint64_t n) {
+    uint64_t g = (n + 255) / 256;
+    if (g < 1) g = 1;
+    return (int)(g > 148 * 16 ? 148 * 16 : g);
+}
+void launch_narrow_u64(const uint64_t *src, uint32_t *dst, uint64_t n, unsigned int *err, cudaStream_t st) {
+    k_narrow<<<ew_grid(n), 256, 0, st>>>(src, dst, n, err);
+}
+void launch_check_u32(const uint32_t *src, uint64_t n, unsigned int *err, cudaStream_t st) {
+    k_check<<<ew_grid(n), 256, 0, st>>>(src, n, err);
+}
+void launch_widen_u32(const uint32_t *src, uint64_t *dst, uint64_t n, cudaStream_t st) {
+    k_widen<<<ew_grid(n), 256, 0, st>>>(src, dst, n);
+}
+void launch_fill(uint32_t *dst, uint64_t n, uint32_t v, cudaStream_t st) { k_fill<<<ew_grid(n), 256, 0, st>>>(dst, n, v); }
+void launch_synthetic(uint32_t *dst, uint64_t n, uint64_t seed, uint64_t start, uint64_t step, cudaStream_t st) {
+    k_synthetic<<<ew_grid(n), 256, 0, st>>>(dst, n, seed, start, step);
+}
+void launch_add(const uint32_t *a, const uint32_t *b, uint32_t *o, uint64_t n, cudaStream_t st) {
+    k_add<<<ew_grid(n), 256, 0, st>>>(a, b, o, n);
+}
+void launch_scalar_mul(const uint32_t *a, uint32_t s, uint32_t *o, uint64_t n, cudaStream_t st) {
+    k_scalar_mul<<<ew_grid(n), 256, 0, st>>>(a, s, bb::shoup_pre(s), o, n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lasso row hashing: hashEntry / hashQuery — /root/reference/src/lookups/lasso_prover.zig:208-239
+// XXH3-64 of an 8-byte input with seed 0 (the 4..8-byte path of the XXH3 spec)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+__device__ __forceinline__ uint64_t xxh3_8(uint64_t h) {
+    // input64 = in2 + (in1 << 32) with in1 = low word, in2 = high word of le64(h): i.e. the words swapped
+    const uint64_t bitflip = 0x1cad21f72c81017cull ^ 0xdb979083e96dd4deull; // secret[8..16) ^ secret[16..24), seed 0
+    uint64_t x = ((h >> 32) | (h << 32)) ^ bitflip;
+    x ^= rotl64(x, 49) ^ rotl64(x, 24);
+    x *= 0x9FB21C651E98DF25ull;
+    x ^= (x >> 35) + 8;
+    x *= 0x9FB21C651E98DF25ull;
+    return x ^ (x >> 28);
+}
+__device__ __forceinline__ uint32_t hash_row3(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t h = xxh3_8(a);
+    h = xxh3_8(h ^ b);
+    h = xxh3_8(h ^ c);
+    return (uint32_t)(h % bb::P);
+}
+
+__global__ void k_xxh3_rows(const uint64_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, uint32_t *out,
+                            unsigned int *err) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += stride) {
+        uint32_t v = 0;
+        if (i < n_rows) {
+            uint64_t h = 0;
+            for (uint32_t k = 0; k < arity; k++) {
+                uint64_t x = rows[i * arity + k];
+                bad |= (x >= bb::P);
+                h = xxh3_8(h ^ x);
+            }
+            v = (uint32_t)(h % bb::P);
+        }
+        out[i] = v;
+    }
+    if (bad) atomicOr(err, 1u);
+}
+void launch_xxh3_rows(const uint64_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, uint32_t *out,
+                      unsigned int *err, cudaStream_t st) {
+    k_xxh3_rows<<<ew_grid(n_padded), 256, 0, st>>>(rows, n_rows, arity, n_padded, out, err);
+}
+
+// buildAddTable / buildXorTable / buildAndTable (table_builder.zig:126-213) generated and hashed in registers
+__global__ void k_table_mle(int op, uint32_t bits, uint32_t *out) {
+    const uint64_t n = 1ull << (2 * bits);
+    const uint64_t mask = (1ull << bits) - 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t a = i >> bits, b = i & mask;
+        uint64_t r = op == 0 ? ((a + b) & mask) : op == 1 ? (a ^ b) : (a & b);
+        out[i] = hash_row3(a % bb::P, b % bb::P, r % bb::P);
+    }
+}
+void launch_table_mle(int op, uint32_t bits, uint32_t *out, cudaStream_t st) {
+    k_table_mle<<<ew_grid(1ull << (2 * bits)), 256, 0, st>>>(op, bits, out);
+}
+
+} // namespace zk
