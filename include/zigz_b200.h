@@ -51,7 +51,8 @@ enum zb_status {
     ZB_ERR_OOM = -100,                 /* error.OutOfMemory */
     ZB_ERR_NO_DEVICE = -200,           /* no CUDA device / driver: there is no CPU fallback */
     ZB_ERR_CUDA = -201,                /* see zb_last_error() */
-    ZB_ERR_TIMEOUT = -202
+    ZB_ERR_TIMEOUT = -202,
+    ZB_ERR_NCCL = -203                 /* libnccl missing or an NCCL call failed; see zb_last_error() */
 };
 
 /* ---- context ---- */
@@ -142,6 +143,17 @@ int32_t zb_xxh3_rows(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint32_
 /* buildAddTable (op 0) / buildXorTable (1) / buildAndTable (2) hashed directly on the device:
  * entry index = a * 2^bits + b -> hashEntry((a, b) -> op(a, b)) */
 int32_t zb_table_mle(zb_ctx *ctx, int32_t op, uint32_t bits, zb_mle *out);
+
+/* ---- multi-GPU: one context per process and GPU; NCCL over NVLink/NVSwitch carries the per-round exchange ----
+ * The hypercube is sharded CYCLICALLY (rank = low log2(world) index bits) so that every MSB-first pair (i, i + n/2)
+ * of partialEval / roundPolynomial is local to one GPU; per round only the d+1 partial coefficients cross GPUs.
+ * libnccl is dlopen()ed on first use (`nccl_path` may be NULL: then ZIGZ_NCCL_LIB, then "libnccl.so.2"). */
+int32_t zb_comm_unique_id(const char *nccl_path, uint8_t out[128]);
+int32_t zb_comm_init(zb_ctx *ctx, const char *nccl_path, const uint8_t unique_id[128], int32_t rank, int32_t world);
+int32_t zb_comm_info(zb_ctx *ctx, int32_t *rank, int32_t *world); /* world == 1 when no communicator is attached */
+/* exact element-wise sum over all ranks of n (<= 64) u64 values, in place (host memory) */
+int32_t zb_comm_allreduce_u64(zb_ctx *ctx, uint64_t *vals, uint32_t n);
+int32_t zb_comm_destroy(zb_ctx *ctx);
 
 #ifdef __cplusplus
 }

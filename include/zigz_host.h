@@ -58,6 +58,9 @@ size_t zh_sumcheck_proof_to_bytes(uint32_t num_vars, const uint64_t *round_polys
  * The inputs are left untouched. */
 int32_t zh_prodcheck_prove(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *round_polys, uint64_t *final_point,
                            uint64_t *final_evals, uint64_t *claimed_sum);
+/* Multi-GPU: when a communicator is attached to ctx (zb_comm_init, world = P) the three prove entry points above and
+ * below take this rank's CYCLIC shard (local element j = global element rank + P*j) and prove the sum over the whole
+ * 2^(v_local + log2 P) hypercube: round_polys / final_point then hold v_local + log2(P) rounds, identical on all ranks. */
 /* same, consuming the inputs (folded in place: no extra device memory; handles end with length 1) */
 int32_t zh_prodcheck_prove_consume(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *round_polys,
                                    uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum);
@@ -67,6 +70,10 @@ int32_t zh_prodcheck_prove_consume(zb_ctx *ctx, const zb_mle *polys, uint32_t d,
 int32_t zh_commit(zb_ctx *ctx, zb_mle poly, zb_tree *tree, uint8_t root[32], uint32_t *num_vars);
 /* batchCommit :132-157 */
 int32_t zh_batch_commit(zb_ctx *ctx, const zb_mle *polys, uint32_t count, zb_tree *trees, uint8_t *roots);
+/* commit of a polynomial sharded over the context's communicator by CONTIGUOUS blocks (rank g holds leaves
+ * [g N/P, (g+1) N/P)): each GPU builds its subtree, the P subtree roots are gathered and the top log2(P) levels are
+ * hashed on the host. `root` is the SimpleMerkleTree root of the whole polynomial, identical on every rank. */
+int32_t zh_commit_sharded(zb_ctx *ctx, zb_mle local_poly, zb_tree *tree, uint8_t local_root[32], uint8_t root[32]);
 /* open :86-115 — value = poly.eval(point), leaf_index = pointToIndex(point) (:178-183), Merkle path of that leaf.
  * siblings: num_vars*32 bytes, dirs: num_vars bytes. error.PointDimensionMismatch when npoint != num_vars */
 int32_t zh_commit_open(zb_ctx *ctx, zb_mle poly, zb_tree tree, const uint64_t *point, uint32_t npoint, uint64_t *value,

@@ -75,6 +75,7 @@ def lib():
         L.zo_sumcheck_proof_to_bytes.argtypes = [u32, P64, P64, u64, P8]
         L.zo_sumcheck_verify_rounds.argtypes = [u64, u32, u32, P64, u64, C.POINTER(C.c_int), P64]
         L.zo_prodcheck_prove.argtypes = [u64, C.POINTER(P64), u32, u64, P64, P64, P64, P64]
+        L.zo_prod_round_coeffs.argtypes = [u64, C.POINTER(P64), u32, u64, P64]
         L.zo_ceil_pow2.restype = u64
         L.zo_ceil_pow2.argtypes = [u64]
         L.zo_merkle_build.argtypes = [P64, u64, P8, P8, C.POINTER(u32)]
@@ -245,6 +246,15 @@ def prodcheck_prove(p, polys) -> SumcheckProof:
     for x in fes:
         fe = fe * int(x) % p
     return SumcheckProof(v, rp[:v], fp[:v], fe, cs.value, tuple(int(x) for x in fes))
+
+
+def prod_round_coeffs(p, polys) -> list:
+    arrs = [_a(x) for x in polys]
+    d = len(arrs)
+    ptrs = (P64 * d)(*[_p(a) for a in arrs])
+    out = np.zeros(d + 1, np.uint64)
+    _chk(lib().zo_prod_round_coeffs(p, ptrs, d, arrs[0].size, _p(out)))
+    return [int(x) for x in out]
 
 
 def eval_univariate(p, coeffs, x) -> int:

@@ -283,6 +283,28 @@ int zo_sumcheck_verify_rounds(uint64_t p, uint32_t v, uint32_t ncoef, const uint
 }
 
 /* ---- extension: product of d multilinears (no reference behaviour for d > 1) ---- */
+/* coefficients [a0..ad] of g(X) = sum_i prod_k (lo_k[i] + (hi_k[i] - lo_k[i]) X) over MSB-first pairs (i, i + n/2) */
+int zo_prod_round_coeffs(uint64_t p, const uint64_t *const *polys, uint32_t d, uint64_t n, uint64_t *out) {
+    if (n < 2 || d == 0 || d > 3) return ZO_ERR_NO_VARIABLES;
+    uint64_t half = n / 2;
+    uint64_t acc[4] = {0, 0, 0, 0};
+    for (uint64_t i = 0; i < half; i++) {
+        uint64_t c[4] = {1 % p, 0, 0, 0};
+        for (uint32_t k = 0; k < d; k++) {
+            uint64_t lo = polys[k][i], df = zo_f_sub(p, polys[k][i + half], lo);
+            uint64_t nc[4] = {0, 0, 0, 0};
+            for (uint32_t j = 0; j <= k; j++) {
+                nc[j] = zo_f_add(p, nc[j], zo_f_mul(p, c[j], lo));
+                nc[j + 1] = zo_f_add(p, nc[j + 1], zo_f_mul(p, c[j], df));
+            }
+            memcpy(c, nc, sizeof(c));
+        }
+        for (uint32_t j = 0; j <= d; j++) acc[j] = zo_f_add(p, acc[j], c[j]);
+    }
+    for (uint32_t j = 0; j <= d; j++) out[j] = acc[j];
+    return ZO_OK;
+}
+
 int zo_prodcheck_prove(uint64_t p, const uint64_t *const *polys, uint32_t d, uint64_t n, uint64_t *round_polys,
                        uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum) {
     uint32_t v;
@@ -310,20 +332,7 @@ int zo_prodcheck_prove(uint64_t p, const uint64_t *const *polys, uint32_t d, uin
     for (uint32_t round = 0; round < v; round++) {
         uint64_t half = len / 2;
         uint64_t acc[4] = {0, 0, 0, 0};
-        for (uint64_t i = 0; i < half; i++) {
-            /* g_i(X) = prod_k (lo_k + (hi_k - lo_k) X), coefficient form */
-            uint64_t c[4] = {1 % p, 0, 0, 0};
-            for (uint32_t k = 0; k < d; k++) {
-                uint64_t lo = cur[k][i], df = zo_f_sub(p, cur[k][i + half], lo);
-                uint64_t nc[4] = {0, 0, 0, 0};
-                for (uint32_t j = 0; j <= k; j++) {
-                    nc[j] = zo_f_add(p, nc[j], zo_f_mul(p, c[j], lo));
-                    nc[j + 1] = zo_f_add(p, nc[j + 1], zo_f_mul(p, c[j], df));
-                }
-                memcpy(c, nc, sizeof(c));
-            }
-            for (uint32_t j = 0; j <= d; j++) acc[j] = zo_f_add(p, acc[j], c[j]);
-        }
+        zo_prod_round_coeffs(p, (const uint64_t *const *)cur, d, len, acc);
         for (uint32_t j = 0; j <= d; j++) {
             round_polys[(size_t)round * (d + 1) + j] = acc[j];
             zo_transcript_append_field(&tr, acc[j]);

@@ -90,6 +90,7 @@ int zo_sumcheck_verify_rounds(uint64_t p, uint32_t v, uint32_t ncoef, const uint
 /* ---- OUR EXTENSION in reference conventions: product sumcheck of d MLEs, d in 1..3.
  * Round polynomial in COEFFICIENT form [a0..ad], MSB-first binding, transcript absorbs each coefficient
  * as le64 and then challenge(). d == 1 is bit-identical to zo_sumcheck_prove. No reference behaviour exists for d>1. */
+int zo_prod_round_coeffs(uint64_t p, const uint64_t *const *polys, uint32_t d, uint64_t n, uint64_t *out /* d+1 */);
 int zo_prodcheck_prove(uint64_t p, const uint64_t *const *polys, uint32_t d, uint64_t n, uint64_t *round_polys /* v*(d+1) */,
                        uint64_t *final_point, uint64_t *final_evals /* d */, uint64_t *claimed_sum);
 

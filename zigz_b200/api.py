@@ -64,6 +64,36 @@ class Context:
     def sync(self):
         self.check(lib().zb_sync(self._h))
 
+    # ---- multi-GPU: NCCL communicator attached to this context (one process per GPU)
+    def comm_init(self, unique_id: bytes, rank: int, world: int, nccl_path: Optional[str] = None):
+        uid = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self.check(lib().zb_comm_init(self._h, nccl_path.encode() if nccl_path else None, uid, rank, world))
+
+    @staticmethod
+    def comm_unique_id(nccl_path: Optional[str] = None) -> bytes:
+        uid = (C.c_uint8 * 128)()
+        rc = lib().zb_comm_unique_id(nccl_path.encode() if nccl_path else None, uid)
+        if rc != 0:
+            raise ZigzError(rc, "zb_comm_unique_id")
+        return bytes(uid)
+
+    @property
+    def world(self) -> int:
+        r, w = C.c_int32(0), C.c_int32(1)
+        lib().zb_comm_info(self._h, C.byref(r), C.byref(w))
+        return w.value
+
+    @property
+    def rank(self) -> int:
+        r, w = C.c_int32(0), C.c_int32(1)
+        lib().zb_comm_info(self._h, C.byref(r), C.byref(w))
+        return r.value
+
+    def allreduce_u64(self, vals) -> np.ndarray:
+        a = _a64(vals).copy()
+        self.check(lib().zb_comm_allreduce_u64(self._h, _p64(a), a.size))
+        return a
+
     def device_info(self):
         sm, tot, free = C.c_int32(0), u64(0), u64(0)
         self.check(lib().zb_device_info(self._h, C.byref(sm), C.byref(tot), C.byref(free)))
@@ -301,7 +331,7 @@ class SumcheckProver:
     @staticmethod
     def prove(poly: Multilinear) -> SumcheckProof:  # :26-91
         ctx = poly.ctx
-        v = max(poly.num_vars, 1)
+        v = max(poly.num_vars + (ctx.world - 1).bit_length(), 1)
         rp, fp = np.zeros((v, 2), np.uint64), np.zeros(v, np.uint64)
         fe, cs = u64(0), u64(0)
         ctx.check(lib().zh_sumcheck_prove(ctx.handle, poly.handle, _p64(rp), _p64(fp), C.byref(fe), C.byref(cs)))
@@ -326,7 +356,7 @@ class ProductSumcheckProver:
     def prove(polys: Sequence[Multilinear], consume: bool = False) -> SumcheckProof:
         ctx = polys[0].ctx
         d = len(polys)
-        v = max(polys[0].num_vars, 1)
+        v = max(polys[0].num_vars + (ctx.world - 1).bit_length(), 1)  # sharded: v_local + log2(world) rounds
         hs = (u64 * d)(*[p.handle for p in polys])
         rp, fp, fes = np.zeros((v, d + 1), np.uint64), np.zeros(v, np.uint64), np.zeros(d, np.uint64)
         cs = u64(0)
@@ -438,6 +468,16 @@ class CommitmentScheme:
         root = np.zeros(32, np.uint8)
         ctx.check(lib().zh_commit(ctx.handle, poly.handle, C.byref(h), _p8(root), C.byref(v)))
         return PolynomialCommitment(root.tobytes(), v.value), SimpleMerkleTree(ctx, h.value, root.tobytes())
+
+    @staticmethod
+    def commit_sharded(local_poly: Multilinear):
+        """Contiguous-block shard of a polynomial spread over the context's communicator -> (global commitment, local tree)."""
+        ctx = local_poly.ctx
+        h = u64(0)
+        lroot, root = np.zeros(32, np.uint8), np.zeros(32, np.uint8)
+        ctx.check(lib().zh_commit_sharded(ctx.handle, local_poly.handle, C.byref(h), _p8(lroot), _p8(root)))
+        v = local_poly.num_vars + (ctx.world - 1).bit_length()
+        return PolynomialCommitment(root.tobytes(), v), SimpleMerkleTree(ctx, h.value, lroot.tobytes())
 
     @staticmethod
     def batch_commit(polys: Sequence[Multilinear]):  # :132-157

@@ -9,6 +9,8 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
+#include <dlfcn.h>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -86,6 +88,11 @@ struct zb_ctx {
     std::vector<ProfEntry> prof;
     std::vector<ProfPending> prof_pending;
     std::vector<cudaEvent_t> event_pool;
+    // multi-GPU
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    unsigned long long *d_comm = nullptr; // 64 u64 exchange buffer
+    unsigned long long *h_comm = nullptr; // pinned twin
 
     Mailbox mailbox() {
         Mailbox m;
@@ -342,6 +349,7 @@ const char *zb_status_name(int32_t s) {
     case ZB_ERR_NO_DEVICE: return "NoCudaDevice";
     case ZB_ERR_CUDA: return "CudaError";
     case ZB_ERR_TIMEOUT: return "Timeout";
+    case ZB_ERR_NCCL: return "NcclError";
     default: return "Unknown";
     }
 }
@@ -389,6 +397,7 @@ void zb_ctx_destroy(zb_ctx *ctx) {
     ctx->mles.clear();
     ctx->trees.clear();
     release_cache(ctx);
+    zb_comm_destroy(ctx);
     prof_drain(ctx, true);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
@@ -1083,6 +1092,120 @@ int32_t zb_table_mle(zb_ctx *ctx, int32_t op, uint32_t bits, zb_mle *out) {
     }
     LAUNCHED("table_mle");
     return zb_sync(ctx);
+}
+
+/* ------------------------------------------------------------------ multi-GPU (NCCL, dlopen'ed) */
+
+struct NcclId { // ncclUniqueId (nccl.h:38-39), passed by value
+    char internal[128];
+};
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int NCCL_UINT64 = 5, NCCL_SUM = 0; // nccl.h: ncclUint64, ncclSum
+
+int32_t nccl_load(zb_ctx *ctx, const char *path) {
+    if (g_nccl.lib) return ZB_OK;
+    const char *cands[3] = {path, getenv("ZIGZ_NCCL_LIB"), "libnccl.so.2"};
+    void *h = nullptr;
+    for (const char *c : cands)
+        if (c && *c && (h = dlopen(c, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) {
+        if (ctx) ctx->last_error = std::string("dlopen libnccl: ") + dlerror();
+        return ZB_ERR_NCCL;
+    }
+    NcclApi a;
+    a.lib = h;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy || !a.GetErrorString) {
+        if (ctx) ctx->last_error = "libnccl lacks a required symbol";
+        return ZB_ERR_NCCL;
+    }
+    g_nccl = a;
+    return ZB_OK;
+}
+
+int32_t nccl_fail(zb_ctx *ctx, int r, const char *what) {
+    if (ctx) ctx->last_error = std::string(what) + ": " + g_nccl.GetErrorString(r);
+    return ZB_ERR_NCCL;
+}
+} // namespace
+
+int32_t zb_comm_unique_id(const char *nccl_path, uint8_t out[128]) {
+    int32_t rc = nccl_load(nullptr, nccl_path);
+    if (rc) return rc;
+    NcclId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r) return ZB_ERR_NCCL;
+    memcpy(out, id.internal, 128);
+    return ZB_OK;
+}
+
+int32_t zb_comm_init(zb_ctx *ctx, const char *nccl_path, const uint8_t unique_id[128], int32_t rank, int32_t world) {
+    if (world < 1 || rank < 0 || rank >= world || (world & (world - 1))) return ZB_ERR_BAD_ARGUMENT;
+    if (ctx->nccl_comm) return ZB_ERR_BAD_ARGUMENT;
+    int32_t rc = nccl_load(ctx, nccl_path);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    NcclId id;
+    memcpy(id.internal, unique_id, 128);
+    int r = g_nccl.CommInitRank(&ctx->nccl_comm, world, id, rank);
+    if (r) return nccl_fail(ctx, r, "ncclCommInitRank");
+    ctx->rank = rank;
+    ctx->world = world;
+    CK(cudaMalloc(&ctx->d_comm, 64 * sizeof(unsigned long long)));
+    CK(cudaHostAlloc((void **)&ctx->h_comm, 64 * sizeof(unsigned long long), cudaHostAllocDefault));
+    // first collective pays the connection setup: do it now
+    uint64_t warm[1] = {1};
+    rc = zb_comm_allreduce_u64(ctx, warm, 1);
+    if (rc) return rc;
+    return warm[0] == (uint64_t)world ? ZB_OK : ZB_ERR_NCCL;
+}
+
+int32_t zb_comm_info(zb_ctx *ctx, int32_t *rank, int32_t *world) {
+    if (rank) *rank = ctx->rank;
+    if (world) *world = ctx->world;
+    return ZB_OK;
+}
+
+int32_t zb_comm_allreduce_u64(zb_ctx *ctx, uint64_t *vals, uint32_t n) {
+    if (!vals || n == 0 || n > 64) return ZB_ERR_BAD_ARGUMENT;
+    if (ctx->world == 1) return ZB_OK;
+    if (!ctx->nccl_comm) return ZB_ERR_BAD_ARGUMENT;
+    memcpy(ctx->h_comm, vals, n * sizeof(uint64_t));
+    CK(cudaMemcpyAsync(ctx->d_comm, ctx->h_comm, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    int r = g_nccl.AllReduce(ctx->d_comm, ctx->d_comm, n, NCCL_UINT64, NCCL_SUM, ctx->nccl_comm, ctx->stream);
+    if (r) return nccl_fail(ctx, r, "ncclAllReduce");
+    CK(cudaMemcpyAsync(ctx->h_comm, ctx->d_comm, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(vals, ctx->h_comm, n * sizeof(uint64_t));
+    return ZB_OK;
+}
+
+int32_t zb_comm_destroy(zb_ctx *ctx) {
+    if (ctx->nccl_comm) {
+        cudaStreamSynchronize(ctx->stream);
+        g_nccl.CommDestroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+        cudaFree(ctx->d_comm);
+        cudaFreeHost(ctx->h_comm);
+        ctx->d_comm = nullptr;
+        ctx->h_comm = nullptr;
+        ctx->rank = 0;
+        ctx->world = 1;
+    }
+    return ZB_OK;
 }
 
 } // extern "C"

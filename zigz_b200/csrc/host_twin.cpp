@@ -64,22 +64,46 @@ uint64_t zh_eval_univariate(const uint64_t *c, uint32_t n, uint64_t x) { // sumc
 
 /* ------------------------------------------------------------------ sumcheck */
 
+// Sum the per-GPU partial round coefficients over all ranks (exact u64 sums of canonical values, then mod p).
+// The coefficient map evals -> [a0..ad] is linear, so the sum of per-shard coefficients is the coefficient vector
+// of the whole hypercube's round polynomial. No-op on a single GPU.
+static int32_t reduce_over_ranks(zb_ctx *ctx, int32_t world, uint64_t *vals, uint32_t n) {
+    if (world == 1) return ZB_OK;
+    int32_t rc = zb_comm_allreduce_u64(ctx, vals, n);
+    if (rc) return rc;
+    for (uint32_t k = 0; k < n; k++) vals[k] %= P;
+    return ZB_OK;
+}
+
 // The round loop of SumcheckProver.prove for d polynomials (d == 1: sumcheck_prover.zig:50-77).
 //   device: round coefficients  ->  host: absorb + challenge  ->  device: fold (fused with the next round's sums)
 // `consume`: fold the caller's polynomials in place; otherwise the first fold goes to fresh buffers (the
 // reference's copy at :47 costs a full pass; folding out of place in round 0 gives the same isolation for free).
+//
+// Multi-GPU (a communicator is attached to ctx, world = P): `polys` are this rank's CYCLIC shards (local element j
+// is global index rank + P*j), so the first v_local rounds pair only local elements; per round the d+1 partial
+// coefficients are all-reduced and every rank runs the same transcript. After v_local rounds each rank holds one
+// element per polynomial (global index = rank); they are gathered and the last log2(P) rounds run on P-element
+// polynomials on every GPU redundantly (identical, deterministic), exactly as a single GPU would finish them.
 static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool consume, const uint64_t *fixed_challenges,
                             uint64_t *round_polys, uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum) {
     if (d < 1 || d > 3 || !polys) return ZB_ERR_BAD_ARGUMENT;
     uint64_t n = 0;
-    uint32_t v = 0;
-    int32_t rc = zb_mle_len(ctx, polys[0], &n, &v);
+    uint32_t v_local = 0;
+    int32_t rc = zb_mle_len(ctx, polys[0], &n, &v_local);
     if (rc) return rc;
+    int32_t rank = 0, world = 1;
+    zb_comm_info(ctx, &rank, &world);
+    uint32_t v_tail = 0;
+    while ((1 << v_tail) < world) v_tail++;
+    const uint32_t v = v_local + v_tail;
     if (v == 0) return ZB_ERR_NO_VARIABLES; // sumcheck_prover.zig:30-32
+    if (world > 1 && (v_local == 0 || d * (uint32_t)world > 64)) return ZB_ERR_BAD_ARGUMENT; // >= one local pair per shard
     const uint32_t nc = d + 1;
     zh_transcript tr; // State.init -> FiatShamirTranscript.init (sumcheck_protocol.zig:149-164)
     uint64_t coeffs[4];
     rc = zb_prod_round_coeffs(ctx, polys, d, coeffs);
+    if (rc == ZB_OK) rc = reduce_over_ranks(ctx, world, coeffs, nc);
     if (rc) return rc;
     if (claimed_sum) {
         // sum over the hypercube == g(0) + g(1) == 2 a0 + a1 + ... + ad   (== sumOverHypercube for d == 1, :40)
@@ -92,6 +116,7 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
     auto cleanup = [&]() {
         if (owned)
             for (uint32_t k = 0; k < d; k++) zb_mle_free(ctx, cur[k]);
+        owned = false;
     };
     for (uint32_t round = 0; round < v; round++) {
         for (uint32_t k = 0; k < nc; k++) round_polys[(size_t)round * nc + k] = coeffs[k];
@@ -113,10 +138,31 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
             owned = true;
         } else {
             rc = zb_prod_fold_inplace(ctx, cur, d, r, coeffs);
+        }
+        if (rc == ZB_OK && world > 1 && round + 1 < v_local) rc = reduce_over_ranks(ctx, world, coeffs, nc);
+        if (rc == ZB_OK && world > 1 && round + 1 == v_local) {
+            // local shards are down to one element each (in coeffs[0..d)): gather the P*d survivors ...
+            uint64_t slots[3 * 64] = {0};
+            for (uint32_t k = 0; k < d; k++) slots[k * world + rank] = coeffs[k];
+            rc = zb_comm_allreduce_u64(ctx, slots, d * world); // all-gather as a sum with zeros: exact
+            // ... and continue on P-element polynomials (index = rank), every rank alike
+            cleanup();
+            for (uint32_t k = 0; k < d; k++) cur[k] = 0;
+            for (uint32_t k = 0; k < d && rc == ZB_OK; k++) {
+                rc = zb_mle_upload(ctx, slots + k * world, world, &cur[k]);
+                if (rc == ZB_OK) owned = true;
+            }
+            if (rc == ZB_OK) rc = zb_prod_round_coeffs(ctx, cur, d, coeffs);
             if (rc) {
-                cleanup();
+                for (uint32_t k = 0; k < d; k++)
+                    if (cur[k]) zb_mle_free(ctx, cur[k]);
                 return rc;
             }
+            consume = true; // the tail polynomials are ours
+        }
+        if (rc) {
+            cleanup();
+            return rc;
         }
     }
     // after the last fold `coeffs` holds the d final evaluations (current_poly.evaluations[0], :88)
@@ -181,6 +227,33 @@ int32_t zh_commit(zb_ctx *ctx, zb_mle poly, zb_tree *tree, uint8_t root[32], uin
 int32_t zh_batch_commit(zb_ctx *ctx, const zb_mle *polys, uint32_t count, zb_tree *trees, uint8_t *roots) { // :132-157
     if (count == 0) return ZB_OK;
     return zb_merkle_build(ctx, polys, count, trees, roots);
+}
+
+int32_t zh_commit_sharded(zb_ctx *ctx, zb_mle local_poly, zb_tree *tree, uint8_t local_root[32], uint8_t root[32]) {
+    // Subtree sharding: rank g holds the CONTIGUOUS leaves [g N/P, (g+1) N/P); its subtree root is
+    // the node at height log2(N/P); the top log2(P) levels are P-1 host hashes (mergeHashesSHA3, hash.zig:187-195).
+    int32_t rank = 0, world = 1;
+    zb_comm_info(ctx, &rank, &world);
+    if (world > 16) return ZB_ERR_BAD_ARGUMENT;
+    uint8_t mine[32];
+    int32_t rc = zb_merkle_build(ctx, &local_poly, 1, tree, mine);
+    if (rc) return rc;
+    if (local_root) memcpy(local_root, mine, 32);
+    uint64_t slots[64] = {0};
+    memcpy(slots + 4 * rank, mine, 32);
+    rc = zb_comm_allreduce_u64(ctx, slots, 4 * (uint32_t)world); // all-gather as a sum with zeros: exact
+    if (rc) return rc;
+    uint8_t level[16][32];
+    memcpy(level, slots, 32 * (size_t)world);
+    for (int32_t w = world; w > 1; w /= 2)
+        for (int32_t i = 0; i < w / 2; i++) {
+            uint8_t buf[64];
+            memcpy(buf, level[2 * i], 32);
+            memcpy(buf + 32, level[2 * i + 1], 32);
+            Sha3_256::hash(buf, 64, level[i]);
+        }
+    memcpy(root, level[0], 32);
+    return ZB_OK;
 }
 
 uint64_t zh_point_to_index(const uint64_t *point, uint32_t npoint) { // :178-183
