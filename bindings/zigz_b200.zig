@@ -1,0 +1,102 @@
+//! Zig bindings for libzigz_b200.so — the reference-side glue a zigz maintainer would add.
+//! NOT compiled in this repo's image (no Zig toolchain there); it mirrors include/zigz_b200.h and
+//! include/zigz_host.h one to one and is checked against them by tests/test_cabi_cpu.py (same names).
+//! Link with: exe.linkSystemLibrary("zigz_b200"); exe.addLibraryPath(...); exe.linkLibC();
+const std = @import("std");
+
+pub const Ctx = opaque {};
+pub const Mle = u64; // device-resident Multilinear(BabyBear)
+pub const Tree = u64; // device-resident SimpleMerkleTree(BabyBear, SHA3Hasher)
+pub const Transcript = opaque {};
+
+pub const Error = error{
+    EmptyEvaluations, LengthNotPowerOfTwo, WrongNumberOfVariables, NoVariables, EmptyValues, IndexOutOfBounds,
+    PointDimensionMismatch, NoQueries, MappingLengthMismatch, InvalidMapping, QueryTableMismatch,
+    WrongNumberOfChallenges, DifferentNumberOfVariables, NotCanonical, BadHandle, BadArgument, OutOfMemory,
+    NoCudaDevice, CudaError, Timeout, NcclError,
+};
+
+/// int32 status of the C ABI -> the reference's Zig error names
+pub fn check(rc: i32) Error!void {
+    return switch (rc) {
+        0 => {},
+        -1 => error.EmptyEvaluations, -2 => error.LengthNotPowerOfTwo, -3 => error.WrongNumberOfVariables,
+        -4 => error.NoVariables, -5 => error.EmptyValues, -6 => error.IndexOutOfBounds,
+        -7 => error.PointDimensionMismatch, -8 => error.NoQueries, -9 => error.MappingLengthMismatch,
+        -10 => error.InvalidMapping, -11 => error.QueryTableMismatch, -12 => error.WrongNumberOfChallenges,
+        -13 => error.DifferentNumberOfVariables, -20 => error.NotCanonical, -21 => error.BadHandle,
+        -22 => error.BadArgument, -100 => error.OutOfMemory, -200 => error.NoCudaDevice, -201 => error.CudaError,
+        -202 => error.Timeout, -203 => error.NcclError,
+        else => error.CudaError,
+    };
+}
+
+// ---- device layer (include/zigz_b200.h) ----
+pub extern fn zb_ctx_create(device: i32, out: *?*Ctx) i32;
+pub extern fn zb_ctx_destroy(ctx: *Ctx) void;
+pub extern fn zb_last_error(ctx: *Ctx) [*:0]const u8;
+pub extern fn zb_mle_upload(ctx: *Ctx, evals: [*]const u64, n: u64, out: *Mle) i32;
+pub extern fn zb_mle_free(ctx: *Ctx, m: Mle) i32;
+pub extern fn zb_mle_len(ctx: *Ctx, m: Mle, n: ?*u64, num_vars: ?*u32) i32;
+pub extern fn zb_mle_download(ctx: *Ctx, m: Mle, out: [*]u64, n: u64) i32;
+pub extern fn zb_mle_sum(ctx: *Ctx, m: Mle, out: *u64) i32;
+pub extern fn zb_mle_round_sums(ctx: *Ctx, m: Mle, out_s0_s1: *[2]u64) i32;
+pub extern fn zb_mle_partial_eval(ctx: *Ctx, m: Mle, r: u64, out: *Mle, next_s0_s1: ?*[2]u64) i32;
+pub extern fn zb_mle_fold_inplace(ctx: *Ctx, m: Mle, r: u64, next_s0_s1: ?*[2]u64) i32;
+pub extern fn zb_mle_eval(ctx: *Ctx, m: Mle, point: ?[*]const u64, npoint: u32, out: *u64) i32;
+pub extern fn zb_mle_add(ctx: *Ctx, a: Mle, b: Mle, out: *Mle) i32;
+pub extern fn zb_mle_scalar_mul(ctx: *Ctx, a: Mle, scalar: u64, out: *Mle) i32;
+pub extern fn zb_prod_round_coeffs(ctx: *Ctx, polys: [*]const Mle, d: u32, out_coeffs: [*]u64) i32;
+pub extern fn zb_prod_fold_inplace(ctx: *Ctx, polys: [*]const Mle, d: u32, r: u64, next_coeffs: ?[*]u64) i32;
+pub extern fn zb_prod_partial_eval(ctx: *Ctx, polys: [*]const Mle, d: u32, r: u64, out: [*]Mle, next_coeffs: ?[*]u64) i32;
+pub extern fn zb_merkle_build(ctx: *Ctx, polys: [*]const Mle, count: u32, trees: [*]Tree, roots: ?[*]u8) i32;
+pub extern fn zb_merkle_build_values(ctx: *Ctx, values: [*]const u64, n: u64, tree: *Tree, root: *[32]u8) i32;
+pub extern fn zb_merkle_info(ctx: *Ctx, t: Tree, n_values: ?*u64, height: ?*u32, root: ?*[32]u8) i32;
+pub extern fn zb_merkle_open(ctx: *Ctx, t: Tree, index: u64, siblings: [*]u8, dirs: [*]u8, leaf_value: ?*u64) i32;
+pub extern fn zb_merkle_free(ctx: *Ctx, t: Tree) i32;
+pub extern fn zb_xxh3_rows(ctx: *Ctx, rows: ?[*]const u64, n_rows: u64, arity: u32, n_padded: u64, out: *Mle) i32;
+pub extern fn zb_table_mle(ctx: *Ctx, op: i32, bits: u32, out: *Mle) i32;
+
+// ---- host twin (include/zigz_host.h): only needed if the Zig bodies are not kept ----
+pub extern fn zh_sumcheck_prove(ctx: *Ctx, poly: Mle, round_polys: [*]u64, final_point: [*]u64, final_eval: *u64, claimed_sum: ?*u64) i32;
+pub extern fn zh_commit_open(ctx: *Ctx, poly: Mle, tree: Tree, point: ?[*]const u64, npoint: u32, value: *u64, leaf_index: *u64, leaf_value: *u64, siblings: [*]u8, dirs: [*]u8) i32;
+pub extern fn zh_lasso_prove(ctx: *Ctx, table_rows: [*]const u64, n_table: u64, query_rows: [*]const u64, n_queries: u64, arity: u32, round_polys: [*]u64, final_point: [*]u64, final_eval: *u64, num_vars: *u32, query_commitment: *[32]u8, table_commitment: *[32]u8) i32;
+
+/// Drop-in body for `SumcheckProver(BabyBear).prove` (src/proofs/sumcheck_prover.zig:26-91): the transcript,
+/// the proof container and the challenge derivation stay exactly as in the reference; only the two hot loops
+/// (roundPolynomial :53, partialEval :72) become device calls. `F` is the reference's BabyBear field type.
+pub fn sumcheckProve(comptime F: type, comptime protocol: type, ctx: *Ctx, evaluations: []const F, allocator: std.mem.Allocator) !protocol.SumcheckProof(F) {
+    const num_vars: usize = std.math.log2_int(usize, evaluations.len);
+    if (num_vars == 0) return error.NoVariables;
+    var proof = try protocol.SumcheckProof(F).init(allocator, num_vars);
+    errdefer proof.deinit();
+
+    var poly: Mle = 0;
+    // F is `struct { value: u64 }` (src/core/field.zig:26-27): the slice IS the u64 array the ABI takes
+    try check(zb_mle_upload(ctx, @ptrCast(evaluations.ptr), evaluations.len, &poly));
+    defer _ = zb_mle_free(ctx, poly);
+
+    var s: [2]u64 = undefined;
+    try check(zb_mle_round_sums(ctx, poly, &s));
+    const claimed_sum = F.init(s[0]).add(F.init(s[1])); // == poly.sumOverHypercube() (:40)
+    var state = try protocol.SumcheckState(F).init(allocator, num_vars, claimed_sum);
+    defer state.deinit();
+
+    var cur: Mle = 0;
+    for (0..num_vars) |round| {
+        const coeffs = [2]F{ F.init(s[0]), F.init(s[1]).sub(F.init(s[0])) }; // [s0, s1 - s0] (multilinear.zig:227-230)
+        proof.round_polynomials[round][0] = coeffs[0];
+        proof.round_polynomials[round][1] = coeffs[1];
+        const challenge = state.generateChallenge(&coeffs); // host SHA3 transcript, unchanged
+        state.advance(challenge, protocol.evalUnivariateCoeffs(F, &coeffs, challenge));
+        if (round == 0) {
+            try check(zb_mle_partial_eval(ctx, poly, challenge.value, &cur, &s)); // keeps `poly` intact (:47)
+        } else {
+            try check(zb_mle_fold_inplace(ctx, cur, challenge.value, &s));
+        }
+    }
+    defer _ = zb_mle_free(ctx, cur);
+    for (state.challenges, 0..) |c, i| proof.final_point[i] = c;
+    proof.final_eval = F.init(s[0]); // after the last fold s[0] is current_poly.evaluations[0] (:88)
+    return proof;
+}
