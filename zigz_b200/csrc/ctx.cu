@@ -385,7 +385,9 @@ int32_t zb_ctx_create(int32_t device, zb_ctx **out) {
     ctx->d_err = ctx->d_ticket + 1;
     cudaMemsetAsync(ctx->d_acc, 0, MAIL_WORDS * sizeof(unsigned long long), ctx->stream);
     cudaMemsetAsync(ctx->d_ticket, 0, 2 * sizeof(unsigned int), ctx->stream);
+    keccak_init_constants();
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "init");
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(e, "init constants");
     *out = ctx;
     return ZB_OK;
 }
@@ -681,9 +683,11 @@ int32_t zb_mle_eval(zb_ctx *ctx, zb_mle h, const uint64_t *point, uint32_t npoin
     int which = 0;
     uint32_t done = 0;
     Mailbox mb = ctx->mailbox();
-    // each stage folds up to 12 variables; the last stage publishes the value
+    // big stages fold 10 variables per pass with the warp-autonomous kernel; the remainder (< 2^20 elements) goes
+    // through the block kernel, up to 12 variables per pass; the last pass publishes the value
     do {
-        int nv = (int)(v - done < 12 ? v - done : 12);
+        const bool big = (n >= (1ull << 20));
+        int nv = big ? 10 : (int)(v - done < 12 ? v - done : 12);
         EvalPoint pt{};
         for (int k = 0; k < nv; k++) {
             pt.r[k] = (uint32_t)point[done + k];
@@ -694,8 +698,11 @@ int32_t zb_mle_eval(zb_ctx *ctx, zb_mle h, const uint64_t *point, uint32_t npoin
         if (rc) return rc;
         bool last = (done + nv == v);
         {
-            ProfScope _ps(ctx, "eval_stage", (n + n_out) * 4);
-            launch_eval_stage(src, n, nv, pt, (uint32_t *)scratch[which]->ptr, last ? &mb : nullptr, ctx->sm_count, ctx->stream);
+            ProfScope _ps(ctx, big ? "eval_warp10" : "eval_stage", (n + n_out) * 4);
+            if (big)
+                launch_eval_warp10(src, n, pt, (uint32_t *)scratch[which]->ptr, ctx->sm_count, ctx->stream);
+            else
+                launch_eval_stage(src, n, nv, pt, (uint32_t *)scratch[which]->ptr, last ? &mb : nullptr, ctx->sm_count, ctx->stream);
         }
         LAUNCHED("eval_stage");
         src = (const uint32_t *)scratch[which]->ptr;

@@ -47,6 +47,9 @@ struct EvalPoint {
 void launch_eval_stage(const uint32_t *src, uint64_t n, int nvars, const EvalPoint &pt, uint32_t *out, const Mailbox *mb,
                        int sm_count, cudaStream_t st);
 
+// Large stage: folds the 10 low variables of `src` (n a multiple of 1024): out[j] = fold of src[1024 j ..). pt.r[0..10).
+void launch_eval_warp10(const uint32_t *src, uint64_t n, const EvalPoint &pt, uint32_t *out, int sm_count, cudaStream_t st);
+
 // element-wise helpers
 void launch_narrow_u64(const uint64_t *src, uint32_t *dst, uint64_t n, unsigned int *err_flag, cudaStream_t st);
 void launch_check_u32(const uint32_t *src, uint64_t n, unsigned int *err_flag, cudaStream_t st);
@@ -71,6 +74,7 @@ struct MerkleBatch {
 inline uint64_t merkle_level_offset(uint64_t padded, uint32_t level) { // in digests
     return 2 * padded - (2 * padded >> level);
 }
+void keccak_init_constants(); // once per context, before the first hashing launch
 void launch_merkle_leaves(const MerkleBatch &b, uint64_t padded, cudaStream_t st);
 // hashes level `level` -> `level + 1` for every tree of the batch
 void launch_merkle_level(const MerkleBatch &b, uint64_t padded, uint32_t level, cudaStream_t st);

@@ -8,6 +8,8 @@
 #include "keccak.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace zk {
 
 #ifndef ZB_KECCAK_UNROLL
@@ -21,6 +23,31 @@ __device__ __forceinline__ void store_digest(uint8_t *dst, const uint32_t (&d)[8
     o[1] = make_uint4(d[4], d[5], d[6], d[7]);
 }
 
+// Share of the 29 rotations per round (24 rho + 5 theta) that run on the FMA pipe instead of the ALU pipe.
+// MEASURED (profiles/r01_sweep1_tuning.txt, 2^24 leaves): 0 -> 8.38 ms, 8 lanes -> 9.01, 16 -> 10.09, 24 -> 11.19,
+// all 29 -> 12.01 ms: IMAD.WIDE / IMAD.HI cost more issue slots than the two SHF they replace, so the all-ALU form
+// stays the default; the variants are compiled only with -DZB_KECCAK_FMA_VARIANTS (ZB_KECCAK_V=1..4 selects).
+constexpr uint32_t FMA_MASKS[5] = {0u, 0x1FEu, 0x1FFFEu, 0x1FFFFFEu, 0x3FFFFFFEu};
+#ifndef ZB_KECCAK_DEFAULT_VARIANT
+#define ZB_KECCAK_DEFAULT_VARIANT 0
+#endif
+static int keccak_variant() {
+    static const int v = [] {
+        const char *e = getenv("ZB_KECCAK_V");
+        int x = e && *e ? atoi(e) : ZB_KECCAK_DEFAULT_VARIANT;
+        return x < 0 || x > 4 ? 0 : x;
+    }();
+    return v;
+}
+
+void keccak_init_constants() {
+    uint32_t pow2[33];
+    for (int i = 0; i < 32; i++) pow2[i] = 1u << i;
+    pow2[32] = 1u;
+    cudaMemcpyToSymbol(keccak::POW2, pow2, sizeof(pow2));
+}
+
+template <uint32_t FM>
 __global__ void __launch_bounds__(KT) k_merkle_leaves(MerkleBatch b, uint64_t padded) {
     const uint32_t t = blockIdx.y;
     const uint32_t *vals = b.values[t];
@@ -30,26 +57,28 @@ __global__ void __launch_bounds__(KT) k_merkle_leaves(MerkleBatch b, uint64_t pa
     for (uint64_t i = (uint64_t)blockIdx.x * KT + threadIdx.x; i < padded; i += stride) {
         uint32_t v = i < n ? vals[i] : 0u;
         uint32_t d[8];
-        keccak::sha3_leaf<ZB_KECCAK_UNROLL>(v, d);
+        keccak::sha3_leaf<ZB_KECCAK_UNROLL, FM>(v, d);
         store_digest(tree + i * 32, d);
     }
 }
 
+template <uint32_t FM>
 __device__ __forceinline__ void hash_pair(const uint8_t *in, uint8_t *out) {
     const uint4 *p = reinterpret_cast<const uint4 *>(in);
     uint4 a = p[0], b4 = p[1], c = p[2], e = p[3];
     uint32_t m[16] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w, c.x, c.y, c.z, c.w, e.x, e.y, e.z, e.w};
     uint32_t d[8];
-    keccak::sha3_node<ZB_KECCAK_UNROLL>(m, d);
+    keccak::sha3_node<ZB_KECCAK_UNROLL, FM>(m, d);
     store_digest(out, d);
 }
 
+template <uint32_t FM>
 __global__ void __launch_bounds__(KT) k_merkle_level(MerkleBatch b, uint64_t in_off, uint64_t out_off, uint64_t width_out) {
     uint8_t *tree = b.tree[blockIdx.y];
     const uint8_t *in = tree + in_off * 32;
     uint8_t *out = tree + out_off * 32;
     const uint64_t stride = (uint64_t)gridDim.x * KT;
-    for (uint64_t i = (uint64_t)blockIdx.x * KT + threadIdx.x; i < width_out; i += stride) hash_pair(in + i * 64, out + i * 32);
+    for (uint64_t i = (uint64_t)blockIdx.x * KT + threadIdx.x; i < width_out; i += stride) hash_pair<FM>(in + i * 64, out + i * 32);
 }
 
 // all remaining levels of one tree inside one CTA: width (<= MERKLE_TOP_WIDTH) digests at `level` down to the root
@@ -59,7 +88,7 @@ __global__ void __launch_bounds__(KT) k_merkle_top(MerkleBatch b, uint64_t padde
         const uint8_t *in = tree + (2 * padded - (2 * padded >> level)) * 32;
         uint8_t *out = tree + (2 * padded - (2 * padded >> (level + 1))) * 32;
         const uint64_t width_out = width / 2;
-        for (uint64_t i = threadIdx.x; i < width_out; i += KT) hash_pair(in + i * 64, out + i * 32);
+        for (uint64_t i = threadIdx.x; i < width_out; i += KT) hash_pair<0>(in + i * 64, out + i * 32);
         __syncthreads(); // global writes of this CTA are visible to the CTA after the barrier
         width = width_out;
         level++;
@@ -106,13 +135,30 @@ static inline unsigned hash_grid(uint64_t items) {
 
 void launch_merkle_leaves(const MerkleBatch &b, uint64_t padded, cudaStream_t st) {
     dim3 grid(hash_grid(padded), b.count);
-    k_merkle_leaves<<<grid, KT, 0, st>>>(b, padded);
+    switch (keccak_variant()) {
+#ifdef ZB_KECCAK_FMA_VARIANTS
+    case 1: k_merkle_leaves<FMA_MASKS[1]><<<grid, KT, 0, st>>>(b, padded); break;
+    case 2: k_merkle_leaves<FMA_MASKS[2]><<<grid, KT, 0, st>>>(b, padded); break;
+    case 3: k_merkle_leaves<FMA_MASKS[3]><<<grid, KT, 0, st>>>(b, padded); break;
+    case 4: k_merkle_leaves<FMA_MASKS[4]><<<grid, KT, 0, st>>>(b, padded); break;
+#endif
+    default: k_merkle_leaves<0><<<grid, KT, 0, st>>>(b, padded); break;
+    }
 }
 
 void launch_merkle_level(const MerkleBatch &b, uint64_t padded, uint32_t level, cudaStream_t st) {
     uint64_t width_out = padded >> (level + 1);
     dim3 grid(hash_grid(width_out), b.count);
-    k_merkle_level<<<grid, KT, 0, st>>>(b, merkle_level_offset(padded, level), merkle_level_offset(padded, level + 1), width_out);
+    const uint64_t io = merkle_level_offset(padded, level), oo = merkle_level_offset(padded, level + 1);
+    switch (keccak_variant()) {
+#ifdef ZB_KECCAK_FMA_VARIANTS
+    case 1: k_merkle_level<FMA_MASKS[1]><<<grid, KT, 0, st>>>(b, io, oo, width_out); break;
+    case 2: k_merkle_level<FMA_MASKS[2]><<<grid, KT, 0, st>>>(b, io, oo, width_out); break;
+    case 3: k_merkle_level<FMA_MASKS[3]><<<grid, KT, 0, st>>>(b, io, oo, width_out); break;
+    case 4: k_merkle_level<FMA_MASKS[4]><<<grid, KT, 0, st>>>(b, io, oo, width_out); break;
+#endif
+    default: k_merkle_level<0><<<grid, KT, 0, st>>>(b, io, oo, width_out); break;
+    }
 }
 
 void launch_merkle_top(const MerkleBatch &b, uint64_t padded, uint32_t level, cudaStream_t st) {

@@ -10,9 +10,17 @@
 #include "bb.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace zk {
 
 constexpr int THREADS = 256;
+
+// launch-shape knobs, overridable from the environment for tuning runs (read once)
+static int tune(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
@@ -118,7 +126,7 @@ __global__ void __launch_bounds__(THREADS) k_round_sums_v4(PolySet ps, uint64_t 
 #pragma unroll
     for (int k = 0; k < NS; k++) s[k] = 0;
     const uint64_t stride = (uint64_t)gridDim.x * THREADS;
-#pragma unroll 2
+#pragma unroll(D == 1 ? 4 : 2)
     for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < h4; i += stride) {
         uint32_t lo[D][4], hi[D][4];
 #pragma unroll
@@ -281,7 +289,8 @@ template <int D>
 static void round_sums_t(const PolySet &ps, uint64_t n, const Mailbox &mb, int sm, cudaStream_t st) {
     uint64_t h = n / 2;
     if (h % 4 == 0) {
-        k_round_sums_v4<D><<<grid_for(h / 4, sm, 8), THREADS, 0, st>>>(ps, h / 4, mb);
+        static const int CPS = tune("ZB_RSUM_CPS", 16);
+        k_round_sums_v4<D><<<grid_for(h / 4, sm, CPS), THREADS, 0, st>>>(ps, h / 4, mb);
     } else {
         k_round_sums_s<D><<<1, THREADS, 0, st>>>(ps, h, mb);
     }
@@ -302,7 +311,15 @@ static void fold_sums_t(const PolySet &ps, uint64_t n, uint32_t r, const Mailbox
     }
     uint64_t q = n / 4;
     if (q % 4 == 0) {
-        k_fold_sums_v4<D, (D == 1 ? 2 : 1)><<<grid_for(q / 4, sm, 4), THREADS, 0, st>>>(ps, q / 4, r, rp, mb);
+        static const int U = tune("ZB_FOLD_U", D == 3 ? 1 : 2);
+        static const int CPS = tune("ZB_FOLD_CPS", D == 3 ? 8 : 4);
+        const uint64_t q4 = q / 4;
+        if (U >= 4 && D == 1)
+            k_fold_sums_v4<D, (D == 1 ? 4 : 1)><<<grid_for((q4 + 3) / 4, sm, CPS), THREADS, 0, st>>>(ps, q4, r, rp, mb);
+        else if (U >= 2 && D <= 2)
+            k_fold_sums_v4<D, (D <= 2 ? 2 : 1)><<<grid_for((q4 + 1) / 2, sm, CPS), THREADS, 0, st>>>(ps, q4, r, rp, mb);
+        else
+            k_fold_sums_v4<D, 1><<<grid_for(q4, sm, CPS), THREADS, 0, st>>>(ps, q4, r, rp, mb);
     } else {
         k_fold_sums_s<D><<<1, THREADS, 0, st>>>(ps, q, r, rp, mb);
     }
@@ -414,6 +431,67 @@ __global__ void __launch_bounds__(THREADS) k_eval_stage(const uint32_t *src, uin
         }
         __syncthreads();
     }
+}
+
+// Big stages: one WARP folds a tile of 1024 consecutive elements (10 variables) with fully coalesced 512-byte
+// loads and no block barrier. The multilinear extension is symmetric in the order variables are bound (exact
+// arithmetic), so the kernel binds them in the order the data arrives: bits 0,1 (inside a uint4), bits 7,8,9 (the
+// thread's 8 loads, 128 elements apart), then bits 2..6 (lanes, by shuffle). UT tiles are in flight per warp.
+template <int UT>
+__global__ void __launch_bounds__(THREADS) k_eval_warp10(const uint32_t *__restrict__ src, uint64_t n_tiles, EvalPoint pt,
+                                                         uint32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * THREADS) >> 5;
+    for (uint64_t t0 = warp * UT; t0 < n_tiles; t0 += n_warps * UT) {
+        uint4 v[UT][8];
+#pragma unroll
+        for (int u = 0; u < UT; u++) {
+            if (t0 + u < n_tiles) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(src + (t0 + u) * 1024) + lane;
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[u][j] = __ldg(p + 32 * j);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UT; u++) {
+            if (t0 + u < n_tiles) {
+                uint32_t e[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    uint32_t a = bb::lerp(v[u][j].x, v[u][j].y, pt.r[0], pt.rp[0]);
+                    uint32_t b = bb::lerp(v[u][j].z, v[u][j].w, pt.r[0], pt.rp[0]);
+                    e[j] = bb::lerp(a, b, pt.r[1], pt.rp[1]);
+                }
+#pragma unroll
+                for (int lv = 0; lv < 3; lv++) {
+#pragma unroll
+                    for (int j = 0; j < (4 >> lv); j++) e[j] = bb::lerp(e[2 * j], e[2 * j + 1], pt.r[7 + lv], pt.rp[7 + lv]);
+                }
+                uint32_t x = e[0];
+#pragma unroll
+                for (int step = 0; step < 5; step++) {
+                    uint32_t other = __shfl_down_sync(0xffffffffu, x, 1 << step);
+                    x = bb::lerp(x, other, pt.r[2 + step], pt.rp[2 + step]);
+                }
+                if (lane == 0) out[t0 + u] = x;
+            }
+        }
+    }
+}
+
+void launch_eval_warp10(const uint32_t *src, uint64_t n, const EvalPoint &pt, uint32_t *out, int sm, cudaStream_t st) {
+    const uint64_t n_tiles = n >> 10;
+    static const int UT = tune("ZB_EVAL_UT", 2);
+    static const int CPS = tune("ZB_EVAL_CPS", 2);
+    const uint64_t warps_needed = (n_tiles + UT - 1) / UT;
+    uint64_t ctas = (warps_needed + THREADS / 32 - 1) / (THREADS / 32);
+    const uint64_t cap = (uint64_t)sm * CPS;
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    if (UT >= 4) k_eval_warp10<4><<<(int)ctas, THREADS, 0, st>>>(src, n_tiles, pt, out);
+    else if (UT >= 2) k_eval_warp10<2><<<(int)ctas, THREADS, 0, st>>>(src, n_tiles, pt, out);
+    else k_eval_warp10<1><<<(int)ctas, THREADS, 0, st>>>(src, n_tiles, pt, out);
 }
 
 void launch_eval_stage(const uint32_t *src, uint64_t n, int nvars, const EvalPoint &pt, uint32_t *out, const Mailbox *mb,
