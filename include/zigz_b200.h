@@ -69,6 +69,13 @@ int32_t zb_device_info(zb_ctx *ctx, int32_t *sm_count, uint64_t *total_mem, uint
 /* raw stream handle (cudaStream_t) the context launches on: for CUDA-event timing by a harness */
 void *zb_stream(zb_ctx *ctx);
 int32_t zb_sync(zb_ctx *ctx);
+/* tuning knobs. "tail_log2": tables of <= 2^value entries run all their remaining fold rounds inside ONE persistent
+ * kernel that receives the challenges through host-mapped memory (0 disables; default 14, env ZB_TAIL_LOG2). */
+/* "comm_reduce" (0/1, needs a communicator): zb_prod_round_coeffs / zb_prod_fold_inplace / zb_prod_partial_eval return
+ * the coefficients of the WHOLE (sharded) round polynomial: the kernel's partial sums are all-reduced over NCCL in stream
+ * order and published once, without a host hop in between. The d final evaluations of the last fold are never summed. */
+int32_t zb_set_option(zb_ctx *ctx, const char *key, int64_t value);
+int32_t zb_get_option(zb_ctx *ctx, const char *key, int64_t *value);
 /* CUDA-event stopwatch on the context's stream (device time between the two calls, in milliseconds) */
 int32_t zb_timer_start(zb_ctx *ctx);
 int32_t zb_timer_stop(zb_ctx *ctx, float *ms);
@@ -153,6 +160,9 @@ int32_t zb_comm_init(zb_ctx *ctx, const char *nccl_path, const uint8_t unique_id
 int32_t zb_comm_info(zb_ctx *ctx, int32_t *rank, int32_t *world); /* world == 1 when no communicator is attached */
 /* exact element-wise sum over all ranks of n (<= 64) u64 values, in place (host memory) */
 int32_t zb_comm_allreduce_u64(zb_ctx *ctx, uint64_t *vals, uint32_t n);
+/* all-gather of cyclic shards: out[rank + world*j] = shard_rank[j] (a NEW polynomial of world * n_local entries,
+ * identical on every rank) — used to leave the sharded regime once the tables are small */
+int32_t zb_comm_allgather_cyclic(zb_ctx *ctx, zb_mle local, zb_mle *out);
 int32_t zb_comm_destroy(zb_ctx *ctx);
 
 #ifdef __cplusplus

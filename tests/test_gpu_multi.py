@@ -18,6 +18,8 @@ def test_sharded_prover_and_commit_on_two_gpus():
     world = 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29731", os.path.join(ROOT, "tools", "multi_gpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert f"multi_gpu_check ok on {world} GPUs" in r.stdout
+    for gather in ("16", "2"):  # default: leave the sharded regime early; 2: stay sharded down to 4-entry shards
+        env = dict(os.environ, ZB_GATHER_LOG2=gather)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        assert f"multi_gpu_check ok on {world} GPUs" in r.stdout

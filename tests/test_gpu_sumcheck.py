@@ -117,3 +117,51 @@ def test_full_size_properties(zlib, ctx, po, d, lg):
         assert t.challenge(BB) == int(pr.final_point[r])
     for p in polys:
         p.deinit()
+
+
+# ---------------------------------------------------------------- persistent tail kernel (zb_set_option "tail_log2")
+@pytest.mark.parametrize("tail_log2", [0, 2, 3, 10, 14, 20])
+def test_tail_kernel_settings_give_identical_proofs(zlib, ctx, po, tail_log2):
+    old = ctx.get_option("tail_log2")
+    try:
+        ctx.set_option("tail_log2", tail_log2)
+        for d, lg in ((1, 1), (1, 2), (1, 9), (1, 16), (3, 2), (3, 11), (2, 13), (3, 17)):
+            es = [po.fill_synthetic(BB, 900 + k, 0, 1 << lg) for k in range(d)]
+            polys = [zlib.Multilinear.init(ctx, e) for e in es]
+            want = po.prodcheck_prove(BB, es)
+            for consume in (False, True):
+                pr = zlib.ProductSumcheckProver.prove(polys, consume=consume)
+                assert pr.round_polynomials.tolist() == want.round_polys.tolist(), (tail_log2, d, lg)
+                assert pr.final_evals == want.final_evals and pr.final_point.tolist() == want.final_point.tolist()
+    finally:
+        ctx.set_option("tail_log2", old)
+
+
+def test_tail_session_survives_interleaved_calls(zlib, ctx, po):
+    """Any other call on the context ends the running persistent kernel; the tables must stay consistent with the
+    rounds completed and folding must be resumable (new session)."""
+    rng = np.random.default_rng(5)
+    e = po.fill_synthetic(BB, 31, 0, 1 << 10)
+    f = po.fill_synthetic(BB, 32, 0, 1 << 8)
+    a, b = zlib.Multilinear.init(ctx, e), zlib.Multilinear.init(ctx, f)
+    cur_a, cur_b = e, f
+    for step in range(8):
+        r = int(rng.integers(0, BB))
+        nxt = a.fold_inplace(r)  # tail session on `a`
+        cur_a = po.mle_partial_eval(BB, cur_a, r)
+        rp = po.mle_round_poly(BB, cur_a)
+        assert [nxt[0], (nxt[1] - nxt[0]) % BB] == rp
+        if step % 3 == 0:
+            assert np.array_equal(a.evaluations, cur_a)  # download: quiesces the session
+        if step % 3 == 1:
+            r2 = int(rng.integers(0, BB))
+            b.fold_inplace(r2)  # a different table: session switches
+            cur_b = po.mle_partial_eval(BB, cur_b, r2)
+        if step % 3 == 2:
+            assert a.round_polynomial() == rp
+    assert np.array_equal(a.evaluations, cur_a) and np.array_equal(b.evaluations, cur_b)
+    a.deinit()  # freeing a table with a live session
+    assert np.array_equal(b.evaluations, cur_b)
+    with pytest.raises(zlib.ZigzError):
+        b.fold_inplace(BB)  # not canonical: rejected without disturbing the table
+    assert np.array_equal(b.evaluations, cur_b)

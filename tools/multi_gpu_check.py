@@ -22,7 +22,7 @@ comm = sharded.Comm(ctx, dist, rank, world)
 assert ctx.world == world and ctx.rank == rank
 got = ctx.allreduce_u64([rank + 1, 2**40 + rank])
 assert got.tolist() == [world * (world + 1) // 2, world * 2**40 + world * (world - 1) // 2]
-for d, lg_local in ((1, 10), (3, 1), (3, 5), (3, 14), (2, 12)):
+for d, lg_local in ((1, 10), (3, 1), (3, 5), (3, 14), (2, 12), (3, 18)):
     lg = lg_local + (world - 1).bit_length()
     full = [po.fill_synthetic(BB, 0x5A49475A + k, 0, 1 << lg) for k in range(d)]
     want = po.prodcheck_prove(BB, full)
@@ -49,6 +49,6 @@ assert com.commitment == po.merkle_build(full).root and com.num_vars == lg
 assert tree.get_root() == po.merkle_build(sharded.block_shard(full, rank, world)).root
 dist.barrier()
 if rank == 0:
-    print(f"multi_gpu_check ok on {world} GPUs")
+    print(f"multi_gpu_check ok on {world} GPUs (ZB_GATHER_LOG2={os.environ.get('ZB_GATHER_LOG2', 'default')})")
 ctx.close()
 dist.destroy_process_group()

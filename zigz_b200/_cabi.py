@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libzigz_b200.so")
 HEADERS = [os.path.join(ROOT, "include", "zigz_b200.h"), os.path.join(ROOT, "include", "zigz_host.h")]
 
 _CTYPES = {
-    "int32_t": C.c_int32, "uint32_t": C.c_uint32, "uint64_t": C.c_uint64, "size_t": C.c_size_t, "int": C.c_int,
+    "int32_t": C.c_int32, "int64_t": C.c_int64, "uint32_t": C.c_uint32, "uint64_t": C.c_uint64, "size_t": C.c_size_t, "int": C.c_int,
     "uint8_t": C.c_uint8, "zb_mle": C.c_uint64, "zb_tree": C.c_uint64, "void": None, "char": C.c_char, "float": C.c_float,
     "double": C.c_double,
 }

@@ -64,6 +64,14 @@ class Context:
     def sync(self):
         self.check(lib().zb_sync(self._h))
 
+    def set_option(self, key: str, value: int):
+        self.check(lib().zb_set_option(self._h, key.encode(), value))
+
+    def get_option(self, key: str) -> int:
+        v = C.c_int64(0)
+        self.check(lib().zb_get_option(self._h, key.encode(), C.byref(v)))
+        return v.value
+
     # ---- multi-GPU: NCCL communicator attached to this context (one process per GPU)
     def comm_init(self, unique_id: bytes, rank: int, world: int, nccl_path: Optional[str] = None):
         uid = (C.c_uint8 * 128).from_buffer_copy(unique_id)

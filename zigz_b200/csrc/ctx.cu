@@ -88,11 +88,23 @@ struct zb_ctx {
     std::vector<ProfEntry> prof;
     std::vector<ProfPending> prof_pending;
     std::vector<cudaEvent_t> event_pool;
+    // persistent tail session (launch_tail_rounds): host -> device challenge word, mapped pinned
+    unsigned long long *h_chal = nullptr, *d_chal = nullptr;
+    unsigned int chal_seq = 0;
+    unsigned int *d_tail_status = nullptr;
+    struct Tail {
+        bool active = false;
+        uint32_t d = 0;
+        zb_mle h[3] = {0, 0, 0};
+        uint64_t n = 0;
+    } tail;
+    int tail_log2 = 14; // tables of <= 2^tail_log2 entries finish inside the persistent kernel (0 = never)
     // multi-GPU
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
     unsigned long long *d_comm = nullptr; // 64 u64 exchange buffer
     unsigned long long *h_comm = nullptr; // pinned twin
+    bool comm_reduce = false;             // round payloads are summed over the ranks on the device before publication
 
     Mailbox mailbox() {
         Mailbox m;
@@ -198,6 +210,17 @@ int32_t wait_mail(zb_ctx *ctx, unsigned long long seq) {
     return ZB_OK;
 }
 
+int32_t comm_publish(zb_ctx *ctx, unsigned long long seq, int nwords); // defined with the NCCL layer
+
+// Mailbox for a kernel whose payload must be summed over the ranks: the kernel writes into the device exchange
+// buffer, comm_publish() then all-reduces it in stream order and publishes the reduced words to the host mailbox.
+inline bool reduce_on_device(const zb_ctx *c) { return c->comm_reduce && c->world > 1 && c->nccl_comm; }
+inline Mailbox round_mailbox(zb_ctx *c, bool reduce) {
+    Mailbox m = c->mailbox();
+    if (reduce) m.mail = c->d_comm;
+    return m;
+}
+
 int32_t check_launch(zb_ctx *ctx, const char *what) {
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
@@ -266,6 +289,15 @@ struct ProfScope {
         if (c->prof_pending.size() > 256) prof_drain(c, false);
     }
 };
+
+// Ends a running persistent tail kernel (abort tag) so that other work can use the stream. The tables stay
+// consistent: every round it completed was written back in place and the handle lengths were updated per round.
+void tail_quiesce(zb_ctx *c) {
+    if (!c->tail.active) return;
+    __atomic_store_n(c->h_chal, (unsigned long long)0xFFFFFFFFu << 32, __ATOMIC_RELEASE);
+    cudaStreamSynchronize(c->stream);
+    c->tail.active = false;
+}
 
 Mle *get_mle(zb_ctx *ctx, zb_mle h) {
     auto it = ctx->mles.find(h);
@@ -383,6 +415,12 @@ int32_t zb_ctx_create(int32_t device, zb_ctx **out) {
     if ((e = cudaMalloc(&ctx->d_acc, MAIL_WORDS * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMalloc(&ctx->d_ticket, 2 * sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
     ctx->d_err = ctx->d_ticket + 1;
+    if ((e = cudaHostAlloc((void **)&ctx->h_chal, 64, cudaHostAllocMapped)) != cudaSuccess) return fail(e, "cudaHostAlloc");
+    memset(ctx->h_chal, 0, 64);
+    if ((e = cudaHostGetDevicePointer((void **)&ctx->d_chal, ctx->h_chal, 0)) != cudaSuccess) return fail(e, "cudaHostGetDevicePointer");
+    if ((e = cudaMalloc(&ctx->d_tail_status, sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
+    cudaMemsetAsync(ctx->d_tail_status, 0, sizeof(unsigned int), ctx->stream);
+    if (const char *t = getenv("ZB_TAIL_LOG2")) ctx->tail_log2 = atoi(t);
     cudaMemsetAsync(ctx->d_acc, 0, MAIL_WORDS * sizeof(unsigned long long), ctx->stream);
     cudaMemsetAsync(ctx->d_ticket, 0, 2 * sizeof(unsigned int), ctx->stream);
     keccak_init_constants();
@@ -394,6 +432,7 @@ int32_t zb_ctx_create(int32_t device, zb_ctx **out) {
 
 void zb_ctx_destroy(zb_ctx *ctx) {
     if (!ctx) return;
+    tail_quiesce(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->mles.clear();
@@ -406,6 +445,8 @@ void zb_ctx_destroy(zb_ctx *ctx) {
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     cudaFree(ctx->d_acc);
     cudaFree(ctx->d_ticket);
+    cudaFree(ctx->d_tail_status);
+    cudaFreeHost(ctx->h_chal);
     cudaFreeHost(ctx->h_mail);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -416,11 +457,39 @@ uint64_t zb_kernel_launches(zb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void *zb_stream(zb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int32_t zb_sync(zb_ctx *ctx) {
+    tail_quiesce(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     return ZB_OK;
 }
 
+int32_t zb_set_option(zb_ctx *ctx, const char *key, int64_t value) {
+    tail_quiesce(ctx);
+    if (key && !strcmp(key, "tail_log2")) {
+        if (value < 0 || value > 20) return ZB_ERR_BAD_ARGUMENT;
+        ctx->tail_log2 = (int)value;
+        return ZB_OK;
+    }
+    if (key && !strcmp(key, "comm_reduce")) {
+        ctx->comm_reduce = value != 0;
+        return ZB_OK;
+    }
+    return ZB_ERR_BAD_ARGUMENT;
+}
+
+int32_t zb_get_option(zb_ctx *ctx, const char *key, int64_t *value) {
+    if (key && value && !strcmp(key, "tail_log2")) {
+        *value = ctx->tail_log2;
+        return ZB_OK;
+    }
+    if (key && value && !strcmp(key, "comm_reduce")) {
+        *value = ctx->comm_reduce ? 1 : 0;
+        return ZB_OK;
+    }
+    return ZB_ERR_BAD_ARGUMENT;
+}
+
 int32_t zb_timer_start(zb_ctx *ctx) {
+    tail_quiesce(ctx);
     if (!ctx->t0) {
         CK(cudaEventCreate(&ctx->t0));
         CK(cudaEventCreate(&ctx->t1));
@@ -430,6 +499,7 @@ int32_t zb_timer_start(zb_ctx *ctx) {
 }
 
 int32_t zb_timer_stop(zb_ctx *ctx, float *ms) {
+    tail_quiesce(ctx);
     if (!ctx->t0 || !ms) return ZB_ERR_BAD_ARGUMENT;
     CK(cudaEventRecord(ctx->t1, ctx->stream));
     CK(cudaEventSynchronize(ctx->t1));
@@ -438,6 +508,7 @@ int32_t zb_timer_stop(zb_ctx *ctx, float *ms) {
 }
 
 int32_t zb_profile_enable(zb_ctx *ctx, int32_t on) {
+    tail_quiesce(ctx);
     prof_drain(ctx, true);
     if (on) ctx->prof.clear();
     ctx->profiling = on != 0;
@@ -445,6 +516,7 @@ int32_t zb_profile_enable(zb_ctx *ctx, int32_t on) {
 }
 
 uint32_t zb_profile_count(zb_ctx *ctx) {
+    tail_quiesce(ctx);
     prof_drain(ctx, true);
     return (uint32_t)ctx->prof.size();
 }
@@ -460,15 +532,18 @@ int32_t zb_profile_entry(zb_ctx *ctx, uint32_t i, char *name, uint32_t cap, uint
 }
 
 int32_t zb_host_alloc(zb_ctx *ctx, size_t bytes, void **out) {
+    tail_quiesce(ctx);
     CK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
     return ZB_OK;
 }
 int32_t zb_host_free(zb_ctx *ctx, void *p) {
+    tail_quiesce(ctx);
     CK(cudaFreeHost(p));
     return ZB_OK;
 }
 
 int32_t zb_device_info(zb_ctx *ctx, int32_t *sm_count, uint64_t *total_mem, uint64_t *free_mem) {
+    tail_quiesce(ctx);
     size_t f = 0, t = 0;
     CK(cudaMemGetInfo(&f, &t));
     if (sm_count) *sm_count = ctx->sm_count;
@@ -480,6 +555,7 @@ int32_t zb_device_info(zb_ctx *ctx, int32_t *sm_count, uint64_t *total_mem, uint
 /* ------------------------------------------------------------------ Multilinear */
 
 int32_t zb_mle_upload(zb_ctx *ctx, const uint64_t *evals, uint64_t n, zb_mle *out) {
+    tail_quiesce(ctx);
     int32_t rc = check_pow2(n);
     if (rc) return rc;
     if (!evals || !out) return ZB_ERR_BAD_ARGUMENT;
@@ -495,6 +571,7 @@ int32_t zb_mle_upload(zb_ctx *ctx, const uint64_t *evals, uint64_t n, zb_mle *ou
 }
 
 int32_t zb_mle_upload_u32(zb_ctx *ctx, const uint32_t *evals, uint64_t n, zb_mle *out) {
+    tail_quiesce(ctx);
     int32_t rc = check_pow2(n);
     if (rc) return rc;
     if (!evals || !out) return ZB_ERR_BAD_ARGUMENT;
@@ -516,6 +593,7 @@ int32_t zb_mle_upload_u32(zb_ctx *ctx, const uint32_t *evals, uint64_t n, zb_mle
 }
 
 int32_t zb_mle_constant(zb_ctx *ctx, uint32_t num_vars, uint64_t value, zb_mle *out) {
+    tail_quiesce(ctx);
     if (num_vars > 40 || value >= bb::P || !out) return value >= bb::P ? ZB_ERR_NOT_CANONICAL : ZB_ERR_BAD_ARGUMENT;
     Mle *m = nullptr;
     int32_t rc = new_mle(ctx, 1ull << num_vars, out, &m);
@@ -529,6 +607,7 @@ int32_t zb_mle_constant(zb_ctx *ctx, uint32_t num_vars, uint64_t value, zb_mle *
 }
 
 int32_t zb_mle_synthetic(zb_ctx *ctx, uint64_t seed, uint64_t start, uint64_t stride, uint64_t n, zb_mle *out) {
+    tail_quiesce(ctx);
     int32_t rc = check_pow2(n);
     if (rc) return rc;
     Mle *m = nullptr;
@@ -543,6 +622,7 @@ int32_t zb_mle_synthetic(zb_ctx *ctx, uint64_t seed, uint64_t start, uint64_t st
 }
 
 int32_t zb_mle_clone(zb_ctx *ctx, zb_mle src, zb_mle *out) {
+    tail_quiesce(ctx);
     Mle *s = get_mle(ctx, src);
     if (!s) return ZB_ERR_BAD_HANDLE;
     uint64_t n = s->n;
@@ -555,6 +635,7 @@ int32_t zb_mle_clone(zb_ctx *ctx, zb_mle src, zb_mle *out) {
 }
 
 int32_t zb_mle_free(zb_ctx *ctx, zb_mle h) {
+    tail_quiesce(ctx);
     if (!ctx->mles.erase(h)) return ZB_ERR_BAD_HANDLE;
     return ZB_OK;
 }
@@ -570,6 +651,7 @@ int32_t zb_mle_len(zb_ctx *ctx, zb_mle h, uint64_t *n, uint32_t *num_vars) {
 int32_t zb_mle_download(zb_ctx *ctx, zb_mle h, uint64_t *out, uint64_t n) { return zb_mle_download_range(ctx, h, 0, out, n); }
 
 int32_t zb_mle_download_range(zb_ctx *ctx, zb_mle h, uint64_t offset, uint64_t *out, uint64_t n) {
+    tail_quiesce(ctx);
     Mle *m = get_mle(ctx, h);
     if (!m) return ZB_ERR_BAD_HANDLE;
     if (offset > m->n || n > m->n - offset || !out) return ZB_ERR_BAD_ARGUMENT;
@@ -590,6 +672,7 @@ int32_t zb_mle_download_range(zb_ctx *ctx, zb_mle h, uint64_t offset, uint64_t *
 }
 
 int32_t zb_mle_sum(zb_ctx *ctx, zb_mle h, uint64_t *out) {
+    tail_quiesce(ctx);
     Mle *m = get_mle(ctx, h);
     if (!m) return ZB_ERR_BAD_HANDLE;
     Mailbox mb = ctx->mailbox();
@@ -605,6 +688,7 @@ int32_t zb_mle_sum(zb_ctx *ctx, zb_mle h, uint64_t *out) {
 }
 
 int32_t zb_mle_round_sums(zb_ctx *ctx, zb_mle h, uint64_t out[2]) {
+    tail_quiesce(ctx);
     Mle *m = get_mle(ctx, h);
     if (!m) return ZB_ERR_BAD_HANDLE;
     if (m->n < 2) return ZB_ERR_NO_VARIABLES; // multilinear.zig:207
@@ -644,6 +728,7 @@ static int32_t fold_common(zb_ctx *ctx, const uint32_t *src, uint32_t *dst, uint
 }
 
 int32_t zb_mle_partial_eval(zb_ctx *ctx, zb_mle h, uint64_t r, zb_mle *out, uint64_t next[2]) {
+    tail_quiesce(ctx);
     Mle *m = get_mle(ctx, h);
     if (!m) return ZB_ERR_BAD_HANDLE;
     if (m->n < 2) return ZB_ERR_NO_VARIABLES; // multilinear.zig:156
@@ -661,16 +746,23 @@ int32_t zb_mle_partial_eval(zb_ctx *ctx, zb_mle h, uint64_t r, zb_mle *out, uint
     return rc;
 }
 
+static int32_t fold_inplace_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, unsigned long long payload[4],
+                                 bool *was_last);
+
 int32_t zb_mle_fold_inplace(zb_ctx *ctx, zb_mle h, uint64_t r, uint64_t next[2]) {
-    Mle *m = get_mle(ctx, h);
-    if (!m) return ZB_ERR_BAD_HANDLE;
-    if (m->n < 2) return ZB_ERR_NO_VARIABLES;
-    int32_t rc = fold_common(ctx, m->d(), m->d(), m->n, r, next);
-    if (rc == ZB_OK) m->n /= 2;
-    return rc;
+    unsigned long long payload[4];
+    bool last = false;
+    int32_t rc = fold_inplace_impl(ctx, &h, 1, r, payload, &last);
+    if (rc) return rc;
+    if (next) {
+        next[0] = payload[0];
+        next[1] = last ? 0 : payload[1];
+    }
+    return ZB_OK;
 }
 
 int32_t zb_mle_eval(zb_ctx *ctx, zb_mle h, const uint64_t *point, uint32_t npoint, uint64_t *out) {
+    tail_quiesce(ctx);
     Mle *m = get_mle(ctx, h);
     if (!m) return ZB_ERR_BAD_HANDLE;
     uint32_t v = (uint32_t)__builtin_ctzll(m->n);
@@ -717,6 +809,7 @@ int32_t zb_mle_eval(zb_ctx *ctx, zb_mle h, const uint64_t *point, uint32_t npoin
 }
 
 int32_t zb_mle_add(zb_ctx *ctx, zb_mle a, zb_mle b, zb_mle *out) {
+    tail_quiesce(ctx);
     Mle *ma = get_mle(ctx, a), *mb_ = get_mle(ctx, b);
     if (!ma || !mb_) return ZB_ERR_BAD_HANDLE;
     if (ma->n != mb_->n) return ZB_ERR_DIFFERENT_NUM_VARS; // multilinear.zig:237
@@ -734,6 +827,7 @@ int32_t zb_mle_add(zb_ctx *ctx, zb_mle a, zb_mle b, zb_mle *out) {
 }
 
 int32_t zb_mle_scalar_mul(zb_ctx *ctx, zb_mle a, uint64_t scalar, zb_mle *out) {
+    tail_quiesce(ctx);
     Mle *ma = get_mle(ctx, a);
     if (!ma) return ZB_ERR_BAD_HANDLE;
     if (scalar >= bb::P) return ZB_ERR_NOT_CANONICAL;
@@ -789,55 +883,112 @@ static int32_t gather_polys(zb_ctx *ctx, const zb_mle *polys, uint32_t d, Mle **
 }
 
 int32_t zb_prod_round_coeffs(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *out) {
+    tail_quiesce(ctx);
     Mle *ms[MAX_POLYS];
     int32_t rc = gather_polys(ctx, polys, d, ms);
     if (rc) return rc;
     if (ms[0]->n < 2) return ZB_ERR_NO_VARIABLES;
     PolySet ps{};
     for (uint32_t k = 0; k < d; k++) ps.src[k] = ms[k]->d();
-    Mailbox mb = ctx->mailbox();
+    const bool red = reduce_on_device(ctx);
+    Mailbox mb = round_mailbox(ctx, red);
     {
         ProfScope _ps(ctx, d == 1 ? "round_sums_d1" : d == 2 ? "round_sums_d2" : "round_sums_d3", ms[0]->n * 4 * d);
         launch_round_sums((int)d, ps, ms[0]->n, mb, ctx->sm_count, ctx->stream);
     }
     LAUNCHED("prod_round_sums");
+    if (red) {
+        rc = comm_publish(ctx, mb.seq, d == 1 ? 2 : (int)d + 1);
+        if (rc) return rc;
+    }
     rc = wait_mail(ctx, mb.seq);
     if (rc) return rc;
     evals_to_coeffs(d, ctx->h_mail, out);
     return ZB_OK;
 }
 
-int32_t zb_prod_fold_inplace(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, uint64_t *next) {
+// One in-place fold round of d polynomials with challenge r; payload = the kernel's raw mailbox words
+// (round evaluations of the folded tables, or the d final evaluations when the tables had 2 entries).
+// Small tables go through the persistent tail session, everything else through one launch per round.
+static int32_t fold_inplace_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, unsigned long long payload[4],
+                                 bool *was_last) {
+    if (d < 1 || d > (uint32_t)MAX_POLYS || !polys) return ZB_ERR_BAD_ARGUMENT;
+    bool same = ctx->tail.active && ctx->tail.d == d;
+    for (uint32_t k = 0; same && k < d; k++) same = (ctx->tail.h[k] == polys[k]);
+    if (!same) tail_quiesce(ctx);
     Mle *ms[MAX_POLYS];
     int32_t rc = gather_polys(ctx, polys, d, ms);
     if (rc) return rc;
-    uint64_t n = ms[0]->n;
+    const uint64_t n = ms[0]->n;
     if (n < 2) return ZB_ERR_NO_VARIABLES;
     if (r >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    *was_last = (n == 2);
     PolySet ps{};
     for (uint32_t k = 0; k < d; k++) {
         ps.src[k] = ms[k]->d();
         ps.dst[k] = ms[k]->d();
     }
-    Mailbox mb = ctx->mailbox();
-    {
-        ProfScope _ps(ctx, d == 1 ? "fold_sums_d1" : d == 2 ? "fold_sums_d2" : "fold_sums_d3", n * 6 * d);
-        launch_fold_sums((int)d, ps, n, (uint32_t)r, mb, ctx->sm_count, ctx->stream);
+    const char *name = d == 1 ? "fold_sums_d1" : d == 2 ? "fold_sums_d2" : "fold_sums_d3";
+    const bool red = reduce_on_device(ctx) && n > 2; // the final evaluations (n == 2) are per-rank values, never summed
+    Mailbox mb = round_mailbox(ctx, red);
+    if (!red && !ctx->tail.active && ctx->tail_log2 > 0 && n >= 4 && n <= (1ull << ctx->tail_log2)) {
+        // start a session: the kernel serves this and every later round of these tables
+        if (ctx->chal_seq > 0xF0000000u) ctx->chal_seq = 0;
+        {
+            ProfScope _ps(ctx, d == 1 ? "tail_rounds_d1" : d == 2 ? "tail_rounds_d2" : "tail_rounds_d3", 0);
+            launch_tail_rounds((int)d, ps, n, mb, ctx->d_chal, ctx->chal_seq + 1, ctx->d_tail_status, ctx->stream);
+        }
+        rc = check_launch(ctx, "tail_rounds");
+        if (rc) return rc;
+        ctx->tail.active = true;
+        ctx->tail.d = d;
+        ctx->tail.n = n;
+        for (uint32_t k = 0; k < d; k++) ctx->tail.h[k] = polys[k];
     }
-    LAUNCHED("prod_fold_sums");
-    rc = wait_mail(ctx, mb.seq);
-    if (rc) return rc;
+    if (ctx->tail.active) {
+        __atomic_store_n(ctx->h_chal, ((unsigned long long)(++ctx->chal_seq) << 32) | (unsigned long long)r, __ATOMIC_RELEASE);
+        rc = wait_mail(ctx, mb.seq);
+        if (rc) {
+            tail_quiesce(ctx);
+            return rc;
+        }
+        ctx->tail.n = n / 2;
+        if (n == 2) ctx->tail.active = false; // the kernel returns after the last round
+    } else {
+        {
+            ProfScope _ps(ctx, name, n * 6 * d);
+            launch_fold_sums((int)d, ps, n, (uint32_t)r, mb, ctx->sm_count, ctx->stream);
+        }
+        rc = check_launch(ctx, "fold_sums");
+        if (rc) return rc;
+        if (red) {
+            rc = comm_publish(ctx, mb.seq, d == 1 ? 2 : (int)d + 1);
+            if (rc) return rc;
+        }
+        rc = wait_mail(ctx, mb.seq);
+        if (rc) return rc;
+    }
     for (uint32_t k = 0; k < d; k++) ms[k]->n = n / 2;
+    for (int k = 0; k < 4; k++) payload[k] = ctx->h_mail[k];
+    return ZB_OK;
+}
+
+int32_t zb_prod_fold_inplace(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, uint64_t *next) {
+    unsigned long long payload[4];
+    bool last = false;
+    int32_t rc = fold_inplace_impl(ctx, polys, d, r, payload, &last);
+    if (rc) return rc;
     if (next) {
-        if (n == 2)
-            for (uint32_t k = 0; k < d; k++) next[k] = ctx->h_mail[k];
+        if (last)
+            for (uint32_t k = 0; k < d; k++) next[k] = payload[k];
         else
-            evals_to_coeffs(d, ctx->h_mail, next);
+            evals_to_coeffs(d, payload, next);
     }
     return ZB_OK;
 }
 
 int32_t zb_prod_partial_eval(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, zb_mle *out, uint64_t *next) {
+    tail_quiesce(ctx);
     Mle *ms[MAX_POLYS];
     int32_t rc = gather_polys(ctx, polys, d, ms);
     if (rc) return rc;
@@ -860,12 +1011,14 @@ int32_t zb_prod_partial_eval(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint6
         }
         ps.dst[k] = o->d();
     }
-    Mailbox mb = ctx->mailbox();
+    const bool red = reduce_on_device(ctx) && n > 2;
+    Mailbox mb = round_mailbox(ctx, red);
     {
         ProfScope _ps(ctx, d == 1 ? "fold_sums_d1" : d == 2 ? "fold_sums_d2" : "fold_sums_d3", n * 6 * d);
         launch_fold_sums((int)d, ps, n, (uint32_t)r, mb, ctx->sm_count, ctx->stream);
     }
     rc = check_launch(ctx, "prod_partial_eval");
+    if (rc == ZB_OK && red) rc = comm_publish(ctx, mb.seq, d == 1 ? 2 : (int)d + 1);
     if (rc == ZB_OK) rc = wait_mail(ctx, mb.seq);
     if (rc) {
         for (uint32_t k = 0; k < d; k++) ctx->mles.erase(out[k]);
@@ -948,6 +1101,7 @@ static int32_t new_tree(zb_ctx *ctx, BufRef values, uint64_t n_values, zb_tree *
 }
 
 int32_t zb_merkle_build(zb_ctx *ctx, const zb_mle *polys, uint32_t count, zb_tree *trees, uint8_t *roots) {
+    tail_quiesce(ctx);
     if (!polys || !trees || count == 0) return ZB_ERR_BAD_ARGUMENT;
     uint64_t n0 = 0;
     for (uint32_t i = 0; i < count; i++) {
@@ -981,6 +1135,7 @@ int32_t zb_merkle_build(zb_ctx *ctx, const zb_mle *polys, uint32_t count, zb_tre
 }
 
 int32_t zb_merkle_build_values(zb_ctx *ctx, const uint64_t *values, uint64_t n, zb_tree *tree, uint8_t root[32]) {
+    tail_quiesce(ctx);
     if (n == 0) return ZB_ERR_EMPTY_VALUES; // merkle_tree.zig:284
     if (!values || !tree) return ZB_ERR_BAD_ARGUMENT;
     BufRef vals;
@@ -1009,6 +1164,7 @@ int32_t zb_merkle_info(zb_ctx *ctx, zb_tree h, uint64_t *n_values, uint32_t *hei
 }
 
 int32_t zb_merkle_open(zb_ctx *ctx, zb_tree h, uint64_t index, uint8_t *siblings, uint8_t *dirs, uint64_t *leaf_value) {
+    tail_quiesce(ctx);
     Tree *t = get_tree(ctx, h);
     if (!t) return ZB_ERR_BAD_HANDLE;
     if (index >= t->n_values) return ZB_ERR_INDEX_OUT_OF_BOUNDS; // merkle_tree.zig:325
@@ -1035,6 +1191,7 @@ int32_t zb_merkle_open(zb_ctx *ctx, zb_tree h, uint64_t index, uint8_t *siblings
 }
 
 int32_t zb_merkle_leaf_hashes(zb_ctx *ctx, zb_tree h, uint8_t *out, uint64_t n_digests) {
+    tail_quiesce(ctx);
     Tree *t = get_tree(ctx, h);
     if (!t) return ZB_ERR_BAD_HANDLE;
     if (n_digests > 2 * t->padded - 1) return ZB_ERR_BAD_ARGUMENT;
@@ -1043,6 +1200,7 @@ int32_t zb_merkle_leaf_hashes(zb_ctx *ctx, zb_tree h, uint8_t *out, uint64_t n_d
 }
 
 int32_t zb_merkle_free(zb_ctx *ctx, zb_tree h) {
+    tail_quiesce(ctx);
     if (!ctx->trees.erase(h)) return ZB_ERR_BAD_HANDLE;
     return ZB_OK;
 }
@@ -1050,6 +1208,7 @@ int32_t zb_merkle_free(zb_ctx *ctx, zb_tree h) {
 /* ------------------------------------------------------------------ Lasso */
 
 int32_t zb_xxh3_rows(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, zb_mle *out) {
+    tail_quiesce(ctx);
     int32_t rc = check_pow2(n_padded);
     if (rc) return rc;
     if (n_rows > n_padded || arity == 0 || (!rows && n_rows) || !out) return ZB_ERR_BAD_ARGUMENT;
@@ -1089,6 +1248,7 @@ int32_t zb_xxh3_rows(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint32_
 }
 
 int32_t zb_table_mle(zb_ctx *ctx, int32_t op, uint32_t bits, zb_mle *out) {
+    tail_quiesce(ctx);
     if (op < 0 || op > 2 || bits == 0 || bits > 15 || !out) return ZB_ERR_BAD_ARGUMENT;
     Mle *m = nullptr;
     int32_t rc = new_mle(ctx, 1ull << (2 * bits), out, &m);
@@ -1112,11 +1272,12 @@ struct NcclApi {
     int (*GetUniqueId)(void *) = nullptr;
     int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
     int (*CommDestroy)(void *) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
-constexpr int NCCL_UINT64 = 5, NCCL_SUM = 0; // nccl.h: ncclUint64, ncclSum
+constexpr int NCCL_UINT64 = 5, NCCL_UINT32 = 3, NCCL_SUM = 0; // nccl.h: ncclUint64, ncclUint32, ncclSum
 
 int32_t nccl_load(zb_ctx *ctx, const char *path) {
     if (g_nccl.lib) return ZB_OK;
@@ -1133,9 +1294,10 @@ int32_t nccl_load(zb_ctx *ctx, const char *path) {
     a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
     a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
     a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+    a.AllGather = (decltype(a.AllGather))dlsym(h, "ncclAllGather");
     a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
-    if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy || !a.GetErrorString) {
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.AllGather || !a.CommDestroy || !a.GetErrorString) {
         if (ctx) ctx->last_error = "libnccl lacks a required symbol";
         return ZB_ERR_NCCL;
     }
@@ -1149,6 +1311,44 @@ int32_t nccl_fail(zb_ctx *ctx, int r, const char *what) {
 }
 } // namespace
 
+extern "C++" {
+namespace {
+// sum the first nwords of the device exchange buffer over all ranks (stream order, behind the kernel that wrote
+// them) and publish them mod p with sequence number `seq`
+int32_t comm_publish(zb_ctx *ctx, unsigned long long seq, int nwords) {
+    int r = g_nccl.AllReduce(ctx->d_comm, ctx->d_comm, (size_t)nwords, NCCL_UINT64, NCCL_SUM, ctx->nccl_comm, ctx->stream);
+    if (r) return nccl_fail(ctx, r, "ncclAllReduce");
+    launch_publish_reduced(ctx->d_comm, nwords, ctx->d_mail, seq, ctx->stream);
+    return check_launch(ctx, "publish_reduced");
+}
+} // namespace
+} // extern "C++"
+
+int32_t zb_comm_allgather_cyclic(zb_ctx *ctx, zb_mle local, zb_mle *out) {
+    tail_quiesce(ctx);
+    Mle *m = get_mle(ctx, local);
+    if (!m || !out) return m ? ZB_ERR_BAD_ARGUMENT : ZB_ERR_BAD_HANDLE;
+    if (ctx->world == 1) return zb_mle_clone(ctx, local, out);
+    if (!ctx->nccl_comm) return ZB_ERR_BAD_ARGUMENT;
+    const uint64_t n = m->n;
+    BufRef src = m->buf, tmp;
+    int32_t rc = dev_alloc(ctx, n * ctx->world * sizeof(uint32_t), &tmp);
+    if (rc) return rc;
+    Mle *o = nullptr;
+    rc = new_mle(ctx, n * ctx->world, out, &o);
+    if (rc) return rc;
+    int r = g_nccl.AllGather(src->ptr, tmp->ptr, (size_t)n, NCCL_UINT32, ctx->nccl_comm, ctx->stream);
+    if (r) {
+        ctx->mles.erase(*out);
+        return nccl_fail(ctx, r, "ncclAllGather");
+    }
+    launch_interleave((const uint32_t *)tmp->ptr, o->d(), n, (uint32_t)ctx->world, ctx->stream);
+    rc = check_launch(ctx, "interleave");
+    if (rc == ZB_OK) rc = zb_sync(ctx);
+    if (rc) ctx->mles.erase(*out);
+    return rc;
+}
+
 int32_t zb_comm_unique_id(const char *nccl_path, uint8_t out[128]) {
     int32_t rc = nccl_load(nullptr, nccl_path);
     if (rc) return rc;
@@ -1160,6 +1360,7 @@ int32_t zb_comm_unique_id(const char *nccl_path, uint8_t out[128]) {
 }
 
 int32_t zb_comm_init(zb_ctx *ctx, const char *nccl_path, const uint8_t unique_id[128], int32_t rank, int32_t world) {
+    tail_quiesce(ctx);
     if (world < 1 || rank < 0 || rank >= world || (world & (world - 1))) return ZB_ERR_BAD_ARGUMENT;
     if (ctx->nccl_comm) return ZB_ERR_BAD_ARGUMENT;
     int32_t rc = nccl_load(ctx, nccl_path);
@@ -1187,6 +1388,7 @@ int32_t zb_comm_info(zb_ctx *ctx, int32_t *rank, int32_t *world) {
 }
 
 int32_t zb_comm_allreduce_u64(zb_ctx *ctx, uint64_t *vals, uint32_t n) {
+    tail_quiesce(ctx);
     if (!vals || n == 0 || n > 64) return ZB_ERR_BAD_ARGUMENT;
     if (ctx->world == 1) return ZB_OK;
     if (!ctx->nccl_comm) return ZB_ERR_BAD_ARGUMENT;
@@ -1201,6 +1403,7 @@ int32_t zb_comm_allreduce_u64(zb_ctx *ctx, uint64_t *vals, uint32_t n) {
 }
 
 int32_t zb_comm_destroy(zb_ctx *ctx) {
+    tail_quiesce(ctx);
     if (ctx->nccl_comm) {
         cudaStreamSynchronize(ctx->stream);
         g_nccl.CommDestroy(ctx->nccl_comm);

@@ -64,27 +64,27 @@ uint64_t zh_eval_univariate(const uint64_t *c, uint32_t n, uint64_t x) { // sumc
 
 /* ------------------------------------------------------------------ sumcheck */
 
-// Sum the per-GPU partial round coefficients over all ranks (exact u64 sums of canonical values, then mod p).
-// The coefficient map evals -> [a0..ad] is linear, so the sum of per-shard coefficients is the coefficient vector
-// of the whole hypercube's round polynomial. No-op on a single GPU.
-static int32_t reduce_over_ranks(zb_ctx *ctx, int32_t world, uint64_t *vals, uint32_t n) {
-    if (world == 1) return ZB_OK;
-    int32_t rc = zb_comm_allreduce_u64(ctx, vals, n);
-    if (rc) return rc;
-    for (uint32_t k = 0; k < n; k++) vals[k] %= P;
-    return ZB_OK;
-}
-
 // The round loop of SumcheckProver.prove for d polynomials (d == 1: sumcheck_prover.zig:50-77).
 //   device: round coefficients  ->  host: absorb + challenge  ->  device: fold (fused with the next round's sums)
 // `consume`: fold the caller's polynomials in place; otherwise the first fold goes to fresh buffers (the
 // reference's copy at :47 costs a full pass; folding out of place in round 0 gives the same isolation for free).
 //
 // Multi-GPU (a communicator is attached to ctx, world = P): `polys` are this rank's CYCLIC shards (local element j
-// is global index rank + P*j), so the first v_local rounds pair only local elements; per round the d+1 partial
-// coefficients are all-reduced and every rank runs the same transcript. After v_local rounds each rank holds one
-// element per polynomial (global index = rank); they are gathered and the last log2(P) rounds run on P-element
-// polynomials on every GPU redundantly (identical, deterministic), exactly as a single GPU would finish them.
+// is global index rank + P*j), so MSB-first pairs never cross GPUs while the shards have >= 2 entries.
+//   phase 1 (big tables): one launch per round; the kernel's partial sums are all-reduced over NCCL in stream order
+//            ("comm_reduce") and every rank's host runs the same transcript on the same coefficients;
+//   phase 2 (shards <= 2^ZB_GATHER_LOG2 entries, default 2^16): the shards are all-gathered once into the global order
+//            and every GPU finishes the remaining rounds on the whole (small) table, redundantly and without any
+//            further exchange — latency-bound rounds should not pay a collective each.
+static int gather_log2() {
+    static const int v = [] {
+        const char *e = getenv("ZB_GATHER_LOG2");
+        int x = e && *e ? atoi(e) : 16;
+        return x < 1 ? 1 : (x > 24 ? 24 : x); // >= 2 entries: the round coefficients in hand must still be sums
+    }();
+    return v;
+}
+
 static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool consume, const uint64_t *fixed_challenges,
                             uint64_t *round_polys, uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum) {
     if (d < 1 || d > 3 || !polys) return ZB_ERR_BAD_ARGUMENT;
@@ -98,12 +98,32 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
     while ((1 << v_tail) < world) v_tail++;
     const uint32_t v = v_local + v_tail;
     if (v == 0) return ZB_ERR_NO_VARIABLES; // sumcheck_prover.zig:30-32
-    if (world > 1 && (v_local == 0 || d * (uint32_t)world > 64)) return ZB_ERR_BAD_ARGUMENT; // >= one local pair per shard
     const uint32_t nc = d + 1;
+    bool sharded = world > 1;
+    // while sharded: device-side reduction on, persistent tail off (the per-round collective needs the stream)
+    int64_t tail_log2 = 0, comm_reduce = 0;
+    zb_get_option(ctx, "tail_log2", &tail_log2);
+    zb_get_option(ctx, "comm_reduce", &comm_reduce);
+    struct Restore {
+        zb_ctx *c;
+        int64_t tail, red;
+        bool armed;
+        void now() {
+            if (armed) {
+                zb_set_option(c, "tail_log2", tail);
+                zb_set_option(c, "comm_reduce", red);
+            }
+            armed = false;
+        }
+        ~Restore() { now(); }
+    } restore{ctx, tail_log2, comm_reduce, sharded};
+    if (sharded) {
+        zb_set_option(ctx, "tail_log2", 0);
+        zb_set_option(ctx, "comm_reduce", 1);
+    }
     zh_transcript tr; // State.init -> FiatShamirTranscript.init (sumcheck_protocol.zig:149-164)
     uint64_t coeffs[4];
     rc = zb_prod_round_coeffs(ctx, polys, d, coeffs);
-    if (rc == ZB_OK) rc = reduce_over_ranks(ctx, world, coeffs, nc);
     if (rc) return rc;
     if (claimed_sum) {
         // sum over the hypercube == g(0) + g(1) == 2 a0 + a1 + ... + ad   (== sumOverHypercube for d == 1, :40)
@@ -113,12 +133,33 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
     }
     zb_mle cur[3] = {polys[0], d > 1 ? polys[1] : 0, d > 2 ? polys[2] : 0};
     bool owned = false;
+    uint64_t n_cur = n; // current (local) table length
     auto cleanup = [&]() {
         if (owned)
-            for (uint32_t k = 0; k < d; k++) zb_mle_free(ctx, cur[k]);
+            for (uint32_t k = 0; k < d; k++)
+                if (cur[k]) zb_mle_free(ctx, cur[k]);
         owned = false;
     };
     for (uint32_t round = 0; round < v; round++) {
+        if (sharded && n_cur <= (1ull << gather_log2())) {
+            // leave the sharded regime: all-gather the shards into the global order; `coeffs` already hold the
+            // (global) coefficients of this round, so nothing is recomputed
+            zb_mle full[3] = {0, 0, 0};
+            for (uint32_t k = 0; k < d && rc == ZB_OK; k++) rc = zb_comm_allgather_cyclic(ctx, cur[k], &full[k]);
+            if (rc) {
+                for (uint32_t k = 0; k < d; k++)
+                    if (full[k]) zb_mle_free(ctx, full[k]);
+                cleanup();
+                return rc;
+            }
+            cleanup();
+            for (uint32_t k = 0; k < d; k++) cur[k] = full[k];
+            owned = true;
+            consume = true; // the gathered tables are ours
+            sharded = false;
+            n_cur *= (uint64_t)world;
+            restore.now();
+        }
         for (uint32_t k = 0; k < nc; k++) round_polys[(size_t)round * nc + k] = coeffs[k];
         uint64_t r;
         if (fixed_challenges) {
@@ -139,31 +180,11 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
         } else {
             rc = zb_prod_fold_inplace(ctx, cur, d, r, coeffs);
         }
-        if (rc == ZB_OK && world > 1 && round + 1 < v_local) rc = reduce_over_ranks(ctx, world, coeffs, nc);
-        if (rc == ZB_OK && world > 1 && round + 1 == v_local) {
-            // local shards are down to one element each (in coeffs[0..d)): gather the P*d survivors ...
-            uint64_t slots[3 * 64] = {0};
-            for (uint32_t k = 0; k < d; k++) slots[k * world + rank] = coeffs[k];
-            rc = zb_comm_allreduce_u64(ctx, slots, d * world); // all-gather as a sum with zeros: exact
-            // ... and continue on P-element polynomials (index = rank), every rank alike
-            cleanup();
-            for (uint32_t k = 0; k < d; k++) cur[k] = 0;
-            for (uint32_t k = 0; k < d && rc == ZB_OK; k++) {
-                rc = zb_mle_upload(ctx, slots + k * world, world, &cur[k]);
-                if (rc == ZB_OK) owned = true;
-            }
-            if (rc == ZB_OK) rc = zb_prod_round_coeffs(ctx, cur, d, coeffs);
-            if (rc) {
-                for (uint32_t k = 0; k < d; k++)
-                    if (cur[k]) zb_mle_free(ctx, cur[k]);
-                return rc;
-            }
-            consume = true; // the tail polynomials are ours
-        }
         if (rc) {
             cleanup();
             return rc;
         }
+        n_cur /= 2;
     }
     // after the last fold `coeffs` holds the d final evaluations (current_poly.evaluations[0], :88)
     for (uint32_t k = 0; k < d; k++) final_evals[k] = coeffs[k];

@@ -35,6 +35,18 @@ void launch_round_sums(int d, const PolySet &ps, uint64_t n, const Mailbox &mb, 
 // If n == 2 the payload is the d final evaluations instead.
 void launch_fold_sums(int d, const PolySet &ps, uint64_t n, uint32_t r, const Mailbox &mb, int sm_count, cudaStream_t st);
 
+// Persistent single-CTA kernel that performs ALL remaining fold rounds of d polynomials of length n (in place,
+// ps.dst == ps.src). Round k (k = 0, 1, ...) waits until the host-mapped word *chal holds (chal_seq0 + k) << 32 | r_k,
+// folds with r_k and publishes the same payload as launch_fold_sums with sequence number mb.seq + k.
+// A tag of 0xFFFFFFFF aborts (arrays stay consistent with the rounds completed); *status = 1 on a 2 s starvation exit.
+void launch_tail_rounds(int d, const PolySet &ps, uint64_t n, const Mailbox &mb, const unsigned long long *chal,
+                        unsigned int chal_seq0, unsigned int *status, cudaStream_t st);
+
+// multi-GPU: src[0..n) (NCCL-summed canonical payload words) -> mailbox payload mod p + sequence number
+void launch_publish_reduced(const unsigned long long *src, int n, unsigned long long *mail, unsigned long long seq, cudaStream_t st);
+// multi-GPU: all-gathered cyclic shards [rank][j] -> global order out[rank + world * j]
+void launch_interleave(const uint32_t *gathered, uint32_t *out, uint64_t n_local, uint32_t world, cudaStream_t st);
+
 // Plain sum of all n evaluations: payload {sum mod p}
 void launch_sum(const uint32_t *src, uint64_t n, const Mailbox &mb, int sm_count, cudaStream_t st);
 

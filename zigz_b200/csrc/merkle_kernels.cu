@@ -27,7 +27,9 @@ __device__ __forceinline__ void store_digest(uint8_t *dst, const uint32_t (&d)[8
 // MEASURED (profiles/r01_sweep1_tuning.txt, 2^24 leaves): 0 -> 8.38 ms, 8 lanes -> 9.01, 16 -> 10.09, 24 -> 11.19,
 // all 29 -> 12.01 ms: IMAD.WIDE / IMAD.HI cost more issue slots than the two SHF they replace, so the all-ALU form
 // stays the default; the variants are compiled only with -DZB_KECCAK_FMA_VARIANTS (ZB_KECCAK_V=1..4 selects).
+#ifdef ZB_KECCAK_FMA_VARIANTS
 constexpr uint32_t FMA_MASKS[5] = {0u, 0x1FEu, 0x1FFFEu, 0x1FFFFFEu, 0x3FFFFFFEu};
+#endif
 #ifndef ZB_KECCAK_DEFAULT_VARIANT
 #define ZB_KECCAK_DEFAULT_VARIANT 0
 #endif

@@ -278,6 +278,173 @@ __global__ void k_fold_last(PolySet ps, uint32_t r, uint32_t rp, Mailbox mb) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent tail: once the tables are small (n <= 2^14 by default) a launch per round is pure latency
+// (launch + drain ~ 10 us against < 2 us of work). One CTA stays resident for ALL remaining rounds: thread 0 polls a
+// host-mapped word for the next challenge (tag = expected sequence number, so a stale value can never match), the CTA
+// folds in place (global memory, L2-resident) and publishes the next round's sums through the same mailbox. The host
+// side keeps the transcript and only swaps "launch + wait" for "store challenge + wait".
+// The kernel leaves on its own after the last round, on an abort tag, or after ~2 s without a challenge.
+// ---------------------------------------------------------------------------------------------
+constexpr int TAIL_THREADS = 1024;
+constexpr unsigned int TAIL_ABORT_TAG = 0xFFFFFFFFu;
+
+template <int D>
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail_rounds(PolySet ps, uint64_t n, Mailbox mb, const unsigned long long *chal,
+                                                              unsigned int chal_seq0, unsigned int *status) {
+    constexpr int NS = NSums<D>::value;
+    __shared__ unsigned long long sm[NS][TAIL_THREADS / 32];
+    __shared__ uint32_t s_r, s_rp;
+    __shared__ int s_abort;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    volatile unsigned long long *mail = (volatile unsigned long long *)mb.mail;
+    for (unsigned int round = 0; n >= 2; round++, n >>= 1) {
+        if (tid == 0) {
+            const unsigned int want = chal_seq0 + round;
+            const long long t0 = clock64();
+            int ab = 0;
+            unsigned long long w;
+            for (;;) {
+                w = *(const volatile unsigned long long *)chal;
+                const unsigned int tag = (unsigned int)(w >> 32);
+                if (tag == want) break;
+                if (tag == TAIL_ABORT_TAG) {
+                    ab = 1;
+                    break;
+                }
+                if (clock64() - t0 > 4000000000ll) {
+                    ab = 2;
+                    break;
+                }
+            }
+            s_abort = ab;
+            s_r = (uint32_t)w;
+            s_rp = bb::shoup_pre((uint32_t)w);
+        }
+        __syncthreads();
+        if (s_abort) {
+            if (tid == 0 && s_abort == 2) *status = 1u;
+            return;
+        }
+        const uint32_t r = s_r, rp = s_rp;
+        if (n == 2) { // last fold: one value per polynomial remains; payload = the D final evaluations
+            if (tid == 0) {
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    uint32_t v = bb::lerp(ps.src[k][0], ps.src[k][1], r, rp);
+                    ps.dst[k][0] = v;
+                    mail[k] = v;
+                }
+                __threadfence_system();
+                mail[MAIL_WORDS] = mb.seq + round;
+            }
+            return;
+        }
+        unsigned long long s[NS];
+#pragma unroll
+        for (int k = 0; k < NS; k++) s[k] = 0;
+        const uint64_t q = n / 4;
+        if ((q & 3) == 0) {
+            const uint64_t q4 = q / 4;
+            for (uint64_t i = tid; i < q4; i += TAIL_THREADS) {
+                uint32_t nlo[D][4], nhi[D][4];
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const uint4 *p = reinterpret_cast<const uint4 *>(ps.src[k]);
+                    uint4 v0 = p[i], v1 = p[i + q4], v2 = p[i + 2 * q4], v3 = p[i + 3 * q4];
+                    uint32_t e0[4], e1[4], e2[4], e3[4];
+                    UNPACK4(v0, e0);
+                    UNPACK4(v1, e1);
+                    UNPACK4(v2, e2);
+                    UNPACK4(v3, e3);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        nlo[k][c] = bb::lerp(e0[c], e2[c], r, rp);
+                        nhi[k][c] = bb::lerp(e1[c], e3[c], r, rp);
+                    }
+                    uint4 *o = reinterpret_cast<uint4 *>(ps.dst[k]);
+                    o[i] = make_uint4(nlo[k][0], nlo[k][1], nlo[k][2], nlo[k][3]);
+                    o[i + q4] = make_uint4(nhi[k][0], nhi[k][1], nhi[k][2], nhi[k][3]);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t l[D], h[D];
+#pragma unroll
+                    for (int k = 0; k < D; k++) {
+                        l[k] = nlo[k][c];
+                        h[k] = nhi[k][c];
+                    }
+                    accum_pair<D>(l, h, s);
+                }
+            }
+        } else {
+            for (uint64_t i = tid; i < q; i += TAIL_THREADS) {
+                uint32_t l[D], h[D];
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const uint32_t *p = ps.src[k];
+                    uint32_t e0 = p[i], e1 = p[i + q], e2 = p[i + 2 * q], e3 = p[i + 3 * q];
+                    l[k] = bb::lerp(e0, e2, r, rp);
+                    h[k] = bb::lerp(e1, e3, r, rp);
+                    ps.dst[k][i] = l[k];
+                    ps.dst[k][i + q] = h[k];
+                }
+                accum_pair<D>(l, h, s);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NS; k++) {
+            unsigned long long v = warp_sum(s[k]);
+            if (lane == 0) sm[k][warp] = v;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long tot[NS];
+#pragma unroll
+            for (int k = 0; k < NS; k++) tot[k] = warp_sum(sm[k][lane]);
+            if (lane == 0) {
+                Finish<D>()(tot);
+#pragma unroll
+                for (int k = 0; k < NS; k++) mail[k] = tot[k];
+                __threadfence_system();
+                mail[MAIL_WORDS] = mb.seq + round;
+            }
+        }
+        __syncthreads(); // this round's stores are visible to the whole CTA before the next round reads them
+    }
+}
+
+void launch_tail_rounds(int d, const PolySet &ps, uint64_t n, const Mailbox &mb, const unsigned long long *chal,
+                        unsigned int chal_seq0, unsigned int *status, cudaStream_t st) {
+    if (d == 1) k_tail_rounds<1><<<1, TAIL_THREADS, 0, st>>>(ps, n, mb, chal, chal_seq0, status);
+    else if (d == 2) k_tail_rounds<2><<<1, TAIL_THREADS, 0, st>>>(ps, n, mb, chal, chal_seq0, status);
+    else k_tail_rounds<3><<<1, TAIL_THREADS, 0, st>>>(ps, n, mb, chal, chal_seq0, status);
+}
+
+// multi-GPU helpers: publish NCCL-summed payload words (canonical values summed over <= 16 ranks: < 2^35) mod p
+__global__ void k_publish_reduced(const unsigned long long *src, int n, unsigned long long *mail, unsigned long long seq) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        for (int k = 0; k < n; k++) ((volatile unsigned long long *)mail)[k] = src[k] % bb::P;
+        __threadfence_system();
+        ((volatile unsigned long long *)mail)[MAIL_WORDS] = seq;
+    }
+}
+void launch_publish_reduced(const unsigned long long *src, int n, unsigned long long *mail, unsigned long long seq, cudaStream_t st) {
+    k_publish_reduced<<<1, 32, 0, st>>>(src, n, mail, seq);
+}
+
+// all-gathered cyclic shards [rank][j] -> global order out[rank + world * j]
+__global__ void k_interleave(const uint32_t *gathered, uint32_t *out, uint64_t n_local, uint32_t world) {
+    const uint64_t total = n_local * world;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+        out[i] = gathered[(i % world) * n_local + i / world];
+}
+void launch_interleave(const uint32_t *gathered, uint32_t *out, uint64_t n_local, uint32_t world, cudaStream_t st) {
+    uint64_t g = (n_local * world + 255) / 256;
+    k_interleave<<<(int)(g > 148 * 16 ? 148 * 16 : (g ? g : 1)), 256, 0, st>>>(gathered, out, n_local, world);
+}
+
 static inline int grid_for(uint64_t work_items, int sm_count, int ctas_per_sm) {
     uint64_t need = (work_items + THREADS - 1) / THREADS;
     uint64_t cap = (uint64_t)sm_count * ctas_per_sm;
