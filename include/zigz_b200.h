@@ -151,6 +151,14 @@ int32_t zb_xxh3_rows(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint32_
  * entry index = a * 2^bits + b -> hashEntry((a, b) -> op(a, b)) */
 int32_t zb_table_mle(zb_ctx *ctx, int32_t op, uint32_t bits, zb_mle *out);
 
+/* ---- WitnessGenerator.generate: src/constraints/witness.zig:29-270, on a column (SoA) view of the execution trace ----
+ * cols: n_cols columns of num_steps raw u64 values each (column-major), in the polynomial order of prover.zig:376-390
+ * (pc, x0..x31, opcode, rd, rs1, rs2, funct3, funct7, imm, mem.address, mem.value, mem.is_read => n_cols = 43, n_hold = 33).
+ * Every value is reduced mod p (F.init); tables are padded to 2^ceil(log2 num_steps): the first n_hold columns repeat
+ * their last value (:80-87, :116-123), the others pad with zero (:174-182, :249-253). out: n_cols new polynomials. */
+int32_t zb_witness_pack(zb_ctx *ctx, const uint64_t *cols, uint64_t num_steps, uint32_t n_cols, uint32_t n_hold, zb_mle *out,
+                        uint32_t *num_vars);
+
 /* ---- multi-GPU: one context per process and GPU; NCCL over NVLink/NVSwitch carries the per-round exchange ----
  * The hypercube is sharded CYCLICALLY (rank = low log2(world) index bits) so that every MSB-first pair (i, i + n/2)
  * of partialEval / roundPolynomial is local to one GPU; per round only the d+1 partial coefficients cross GPUs.

@@ -86,6 +86,15 @@ int32_t zh_merkle_verify(const uint8_t root[32], uint64_t value, const uint8_t *
 int32_t zh_commit_verify(const uint8_t root[32], uint64_t leaf_value, const uint8_t *siblings, const uint8_t *dirs,
                          uint32_t height);
 
+/* ---- Prover.generateCommitments: src/prover/prover.zig:366-467 ----
+ * commit all `count` (43) witness polynomials, absorb "POLY_COMMITMENTS" + roots, then per polynomial derive its v opening
+ * challenges, evaluate, open leaf pointToIndex(point); finally absorb "OPENING_CLAIMS" + values. The transcript is the
+ * caller's (it already holds program hash, sumcheck and Lasso traffic). roots: count*32, points: count*v, values /
+ * leaf_indices / leaf_values: count, siblings: count*v*32, dirs: count*v. */
+int32_t zh_generate_commitments(zb_ctx *ctx, zh_transcript *tr, const zb_mle *polys, uint32_t count, uint8_t *roots,
+                                uint64_t *points, uint64_t *values, uint64_t *leaf_indices, uint64_t *leaf_values,
+                                uint8_t *siblings, uint8_t *dirs);
+
 /* ---- LassoProver(BabyBear): src/lookups/lasso_prover.zig ---- */
 /* prove :103-173. Rows are flattened (inputs || outputs), `arity` u64 each (the reference's TableEntry / LookupQuery
  * hold separately allocated slices, table_builder.zig:14-35, lasso_prover.zig:65-86).

@@ -91,6 +91,9 @@ def lib():
         L.zo_lasso_prove.argtypes = [u64, P64, u64, P64, u64, u32, P64, P64, P64, C.POINTER(u32), P8, P8]
         L.zo_lasso_prove_with_mapping.argtypes = [u64, P64, u64, P64, u64, P64, u64, u32, P64, P64, P64,
                                                   C.POINTER(u32), P8, P8]
+        L.zo_generate_commitments.argtypes = [u64, C.c_void_p, C.POINTER(P64), u32, u64, P8, P64, P64, P64, P64, P8, P8]
+        L.zo_witness_pack.restype = u64
+        L.zo_witness_pack.argtypes = [u64, P64, u64, u32, u32, P64]
         L.zo_splitmix64.restype = u64
         L.zo_splitmix64.argtypes = [u64]
         L.zo_fill_synthetic.argtypes = [u64, u64, u64, u64, P64]
@@ -323,6 +326,49 @@ def hash_leaf(value: int) -> bytes:
     out = np.zeros(32, np.uint8)
     lib().zo_hash_field_element(value, _p8(out))
     return out.tobytes()
+
+
+@dataclass
+class Commitments:
+    roots: np.ndarray         # (count, 32)
+    points: np.ndarray        # (count, v)
+    values: np.ndarray        # (count,)
+    leaf_indices: np.ndarray  # (count,)
+    leaf_values: np.ndarray   # (count,)
+    siblings: np.ndarray      # (count, v, 32)
+    dirs: np.ndarray          # (count, v)
+
+
+def generate_commitments(p, transcript: "Transcript", polys) -> Commitments:
+    """Prover.generateCommitments (prover.zig:366-467); the transcript is advanced exactly as the reference does."""
+    arrs = [_a(x) for x in polys]
+    k, n = len(arrs), arrs[0].size
+    v = mle_check(n)
+    ptrs = (P64 * k)(*[_p(a) for a in arrs])
+    vv = max(v, 1)
+    out = Commitments(np.zeros((k, 32), np.uint8), np.zeros((k, vv), np.uint64), np.zeros(k, np.uint64), np.zeros(k, np.uint64),
+                      np.zeros(k, np.uint64), np.zeros((k, vv, 32), np.uint8), np.zeros((k, vv), np.uint8))
+    # the C side strides by v (not max(v,1)): use flat buffers of the exact size
+    pts, sib, dirs = np.zeros(k * vv, np.uint64), np.zeros(k * vv * 32, np.uint8), np.zeros(k * vv, np.uint8)
+    _chk(lib().zo_generate_commitments(p, C.byref(transcript._t), ptrs, k, n, _p8(out.roots), _p(pts), _p(out.values),
+                                       _p(out.leaf_indices), _p(out.leaf_values), _p8(sib), _p8(dirs)))
+    out.points = pts[:k * v].reshape(k, v)
+    out.siblings = sib[:k * v * 32].reshape(k, v, 32)
+    out.dirs = dirs[:k * v].reshape(k, v)
+    return out
+
+
+def witness_pack(p, cols, n_hold=33) -> np.ndarray:
+    """cols: (n_cols, num_steps) raw u64 -> (n_cols, padded) canonical evaluations (witness.zig:29-270)."""
+    c = _a(cols)
+    n_cols, steps = c.shape
+    padded = 1
+    while padded < steps:
+        padded <<= 1
+    out = np.zeros((n_cols, padded), np.uint64)
+    got = lib().zo_witness_pack(p, _p(c.reshape(-1)) if c.size else _p(np.zeros(1, np.uint64)), steps, n_cols, n_hold, _p(out.reshape(-1)))
+    assert got == padded
+    return out
 
 
 # ---------------------------------------------------------------- lasso

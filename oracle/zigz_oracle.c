@@ -464,6 +464,68 @@ int zo_commit_open(uint64_t p, const uint64_t *evals, uint64_t n, const uint8_t 
 }
 
 /* ------------------------------------------------------------------ */
+/* Prover.generateCommitments — /root/reference/src/prover/prover.zig:366-467 */
+/* ------------------------------------------------------------------ */
+int zo_generate_commitments(uint64_t p, zo_transcript *tr, const uint64_t *const *polys, uint32_t count, uint64_t n,
+                            uint8_t *roots, uint64_t *points, uint64_t *values, uint64_t *leaf_indices, uint64_t *leaf_values,
+                            uint8_t *siblings, uint8_t *dirs) {
+    uint32_t v;
+    int rc = zo_mle_check(n, &v);
+    if (rc) return rc;
+    uint8_t **lh = calloc(count, sizeof(uint8_t *));
+    if (!lh) return ZO_ERR_OOM;
+    /* PHASE 1 (:405-410): commit every polynomial */
+    for (uint32_t i = 0; i < count && rc == ZO_OK; i++) {
+        lh[i] = malloc(n * 32);
+        if (!lh[i]) rc = ZO_ERR_OOM;
+        else rc = zo_merkle_build(polys[i], n, lh[i], roots + 32 * (size_t)i, NULL);
+    }
+    if (rc == ZO_OK) {
+        /* PHASE 2 (:413-416): bind all commitments */
+        zo_transcript_append_bytes(tr, "POLY_COMMITMENTS", 16);
+        for (uint32_t i = 0; i < count; i++) zo_transcript_append_bytes(tr, roots + 32 * (size_t)i, 32);
+        /* PHASE 3 (:420-443): challenges, evaluation, opening */
+        for (uint32_t i = 0; i < count && rc == ZO_OK; i++) {
+            uint64_t *pt = points + (size_t)i * v;
+            for (uint32_t j = 0; j < v; j++) pt[j] = zo_transcript_challenge(tr, p);
+            rc = zo_mle_eval(p, polys[i], n, pt, v, &values[i]); /* :427 */
+            if (rc) break;
+            uint64_t v2;
+            rc = zo_commit_open(p, polys[i], n, lh[i], pt, v, &v2, &leaf_indices[i], &leaf_values[i],
+                                siblings + (size_t)i * v * 32, dirs + (size_t)i * v); /* :431 (evaluates again) */
+        }
+        /* PHASE 4 (:463-466): bind the opening claims */
+        if (rc == ZO_OK) {
+            zo_transcript_append_bytes(tr, "OPENING_CLAIMS", 14);
+            for (uint32_t i = 0; i < count; i++) zo_transcript_append_field(tr, values[i]);
+        }
+    }
+    for (uint32_t i = 0; i < count; i++) free(lh[i]);
+    free(lh);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ */
+/* WitnessGenerator.generate — /root/reference/src/constraints/witness.zig:29-270, on a column (SoA) view of the trace:
+ * cols[c][i] = raw u64 of column c at step i, in the order of prover.zig:376-390 (pc, x0..x31, opcode, rd, rs1, rs2,
+ * funct3, funct7, imm, mem.address, mem.value, mem.is_read). The first n_hold columns (pc + registers) pad by repeating
+ * the last value (:80-87, :116-123), the others pad with zero (:174-182, :249-253). F.init = value mod p. */
+/* ------------------------------------------------------------------ */
+uint64_t zo_witness_pack(uint64_t p, const uint64_t *cols, uint64_t num_steps, uint32_t n_cols, uint32_t n_hold, uint64_t *out) {
+    uint32_t num_vars = 0;
+    while (((uint64_t)1 << num_vars) < num_steps) num_vars++; /* log2_int_ceil, 0 for 0 or 1 steps (:36-39) */
+    uint64_t padded = (uint64_t)1 << num_vars;
+    for (uint32_t c = 0; c < n_cols; c++) {
+        const uint64_t *col = cols + (size_t)c * num_steps;
+        uint64_t *o = out + (size_t)c * padded;
+        for (uint64_t i = 0; i < num_steps; i++) o[i] = zo_f_init(p, col[i]);
+        uint64_t fill = (c < n_hold && num_steps > 0) ? zo_f_init(p, col[num_steps - 1]) : 0;
+        for (uint64_t i = num_steps; i < padded; i++) o[i] = fill;
+    }
+    return padded;
+}
+
+/* ------------------------------------------------------------------ */
 /* Lasso — lasso_prover.zig, table_builder.zig                          */
 /* ------------------------------------------------------------------ */
 uint64_t zo_lasso_hash_row(uint64_t p, const uint64_t *row, uint32_t arity) { /* hashEntry/hashQuery :208-239 */

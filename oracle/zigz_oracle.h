@@ -110,6 +110,15 @@ uint64_t zo_point_to_index(const uint64_t *point, uint32_t npoint); /* :178-183 
 int zo_commit_open(uint64_t p, const uint64_t *evals, uint64_t n, const uint8_t *leaf_hashes, const uint64_t *point,
                    uint32_t npoint, uint64_t *value, uint64_t *leaf_index, uint64_t *leaf_value, uint8_t *siblings, uint8_t *dirs);
 
+/* ---- Prover.generateCommitments: src/prover/prover.zig:366-467 (transcript interleave included) ----
+ * roots: count*32, points: count*v, values/leaf_indices/leaf_values: count, siblings: count*v*32, dirs: count*v */
+int zo_generate_commitments(uint64_t p, zo_transcript *tr, const uint64_t *const *polys, uint32_t count, uint64_t n,
+                            uint8_t *roots, uint64_t *points, uint64_t *values, uint64_t *leaf_indices, uint64_t *leaf_values,
+                            uint8_t *siblings, uint8_t *dirs);
+/* ---- WitnessGenerator.generate on SoA trace columns: src/constraints/witness.zig:29-270. Returns the padded length;
+ * out: n_cols * padded */
+uint64_t zo_witness_pack(uint64_t p, const uint64_t *cols, uint64_t num_steps, uint32_t n_cols, uint32_t n_hold, uint64_t *out);
+
 /* ---- Lasso: src/lookups/lasso_prover.zig, table_builder.zig ---- */
 /* rows are flattened (inputs || outputs), `arity` u64 per row */
 uint64_t zo_lasso_hash_row(uint64_t p, const uint64_t *row, uint32_t arity);          /* hashEntry/hashQuery :208-239 */

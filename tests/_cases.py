@@ -43,3 +43,8 @@ def assert_sumcheck_equal(proof, gold, ncoef=2):
         assert proof.final_eval == gold["final_eval"]
     if "final_evals" in gold:
         assert list(proof.final_evals) == gold["final_evals"]
+
+
+def witness_cols(steps, n_cols=43):
+    """Synthetic SoA trace columns used by the witness_pack golden cases (make_golden.py)."""
+    return np.array([[splitmix64(1000 * c + i) >> (c % 3) for i in range(steps)] for c in range(n_cols)], dtype=np.uint64).reshape(n_cols, steps)

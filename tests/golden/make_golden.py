@@ -182,6 +182,39 @@ def lasso_prove(p, table, queries):  # :103-173
             "table_commitment": flat_commit(t_evals), "num_lookups": len(queries)}
 
 
+def generate_commitments(p, tr, polys):  # src/prover/prover.zig:366-467
+    v = len(polys[0]).bit_length() - 1
+    levels = [merkle(e) for e in polys]
+    roots = [lv[-1][0] for lv in levels]
+    tr.append_bytes(b"POLY_COMMITMENTS")
+    for r in roots:
+        tr.append_bytes(r)
+    out = []
+    for e, lv in zip(polys, levels):
+        pt = [tr.challenge(p) for _ in range(v)]
+        value = mle_eval(p, e, pt)
+        idx = pt[0] % (1 << v) if v else 0  # pointToIndex, polynomial_commit.zig:178-183
+        sib, dirs = merkle_open(lv, idx)
+        out.append({"point": pt, "value": value, "leaf_index": idx, "leaf_value": e[idx], "siblings": sib, "dirs": dirs})
+    tr.append_bytes(b"OPENING_CLAIMS")
+    for o in out:
+        tr.append_field(o["value"])
+    return {"roots": [r.hex() for r in roots], "openings": out, "next_challenge": tr.challenge(p)}
+
+
+def witness_pack(p, cols, n_hold):  # src/constraints/witness.zig:29-270
+    steps = len(cols[0])
+    padded = 1
+    while padded < steps:
+        padded <<= 1
+    out = []
+    for c, col in enumerate(cols):
+        vals = [x % p for x in col]
+        fill = vals[-1] if (c < n_hold and steps) else 0
+        out.append(vals + [fill] * (padded - steps))
+    return out
+
+
 def main():
     g = {"_generator": "tests/golden/make_golden.py (independent pure-Python restatement; hashlib + xxhash)"}
     t = Transcript()
@@ -249,6 +282,23 @@ def main():
             qs.append([a, b, f(a, b)])
         ls[f"{op}4_200"] = {"bits": 4, "n_queries": 200, **lasso_prove(BABYBEAR, tab, qs)}
     g["lasso"] = ls
+
+    gc = {}
+    for lg, count in ((0, 3), (3, 43), (6, 5)):
+        polys = [synthetic(BABYBEAR, 700 + i, 1 << lg) for i in range(count)]
+        tr = Transcript()
+        tr.append_bytes(b"PROGRAM")  # the caller's earlier traffic
+        tr.append_field(4096)
+        gc[f"2^{lg}_x{count}"] = {"lg": lg, "count": count, "seed": 700, **generate_commitments(BABYBEAR, tr, polys)}
+    g["generate_commitments"] = gc
+
+    wp = {}
+    for steps in (1, 4, 5, 13):
+        cols = [[splitmix64(1000 * c + i) >> (c % 3) for i in range(steps)] for c in range(43)]
+        wp[str(steps)] = {"steps": steps, "packed_sha3": hashlib.sha3_256(
+            b"".join(int(x).to_bytes(8, "little") for col in witness_pack(BABYBEAR, cols, 33) for x in col)).hexdigest(),
+            "first_col": witness_pack(BABYBEAR, cols, 33)[0], "last_col": witness_pack(BABYBEAR, cols, 33)[42]}
+    g["witness_pack"] = wp
 
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "zigz_golden.json")
     with open(out, "w") as f:

@@ -91,3 +91,27 @@ def test_lasso(po, golden):
         assert pr.sumcheck.num_vars == c["num_vars"] == 8
         assert_sumcheck_equal(pr.sumcheck, c["sumcheck"])
         assert (pr.query_commitment.hex(), pr.table_commitment.hex()) == (c["query_commitment"], c["table_commitment"])
+
+
+def test_generate_commitments(po, golden):
+    for name, case in golden["generate_commitments"].items():
+        polys = [synthetic(case["seed"] + i, 1 << case["lg"]) for i in range(case["count"])]
+        tr = po.Transcript()
+        tr.append_bytes(b"PROGRAM")
+        tr.append_field(4096)
+        c = po.generate_commitments(BB, tr, polys)
+        assert [r.tobytes().hex() for r in c.roots] == case["roots"], name
+        for i, o in enumerate(case["openings"]):
+            assert c.points[i].tolist() == o["point"] and int(c.values[i]) == o["value"]
+            assert (int(c.leaf_indices[i]), int(c.leaf_values[i])) == (o["leaf_index"], o["leaf_value"])
+            assert [s.tobytes().hex() for s in c.siblings[i]] == o["siblings"] and c.dirs[i].tolist() == o["dirs"]
+        assert tr.challenge(BB) == case["next_challenge"]  # the transcript was advanced identically
+
+
+def test_witness_pack(po, golden):
+    import hashlib
+    from _cases import witness_cols
+    for name, case in golden["witness_pack"].items():
+        out = po.witness_pack(BB, witness_cols(case["steps"]), 33)
+        assert hashlib.sha3_256(out.astype("<u8").tobytes()).hexdigest() == case["packed_sha3"], name
+        assert out[0].tolist() == case["first_col"] and out[42].tolist() == case["last_col"]

@@ -529,6 +529,49 @@ class CommitmentScheme:
         return int(lib().zh_point_to_index(_p64(pt) if pt.size else None, pt.size))
 
 
+@dataclass
+class CommitmentOpenings:
+    """The `witness_commitments` of a proof (src/prover/proof.zig:147-190), struct-of-arrays."""
+    roots: np.ndarray         # (count, 32)
+    points: np.ndarray        # (count, v)
+    values: np.ndarray        # (count,)
+    leaf_indices: np.ndarray  # (count,)
+    leaf_values: np.ndarray   # (count,)
+    siblings: np.ndarray      # (count, v, 32)
+    dirs: np.ndarray          # (count, v)
+
+
+def generate_commitments(transcript: FiatShamirTranscript, polys: Sequence[Multilinear]) -> CommitmentOpenings:
+    """Prover.generateCommitments (src/prover/prover.zig:366-467): one batched commit, transcript interleave, openings."""
+    ctx = polys[0].ctx
+    k, v = len(polys), polys[0].num_vars
+    hs = (u64 * k)(*[p.handle for p in polys])
+    vv = max(v, 1)
+    roots = np.zeros((k, 32), np.uint8)
+    pts, vals = np.zeros(k * vv, np.uint64), np.zeros(k, np.uint64)
+    li, lv = np.zeros(k, np.uint64), np.zeros(k, np.uint64)
+    sib, dirs = np.zeros(k * vv * 32, np.uint8), np.zeros(k * vv, np.uint8)
+    ctx.check(lib().zh_generate_commitments(ctx.handle, transcript._t, hs, k, _p8(roots), _p64(pts), _p64(vals), _p64(li), _p64(lv),
+                                            _p8(sib), _p8(dirs)))
+    return CommitmentOpenings(roots, pts[:k * v].reshape(k, v), vals, li, lv, sib[:k * v * 32].reshape(k, v, 32),
+                              dirs[:k * v].reshape(k, v))
+
+
+WITNESS_COLUMNS = (["pc"] + [f"x{i}" for i in range(32)] +
+                   ["opcode", "rd", "rs1", "rs2", "funct3", "funct7", "imm", "mem_address", "mem_value", "mem_is_read"])
+
+
+def witness_pack(ctx: Context, cols, n_hold: int = 33) -> List[Multilinear]:
+    """WitnessGenerator.generate (src/constraints/witness.zig:29-270) from SoA trace columns: cols is (n_cols, num_steps)
+    raw u64 in the order WITNESS_COLUMNS (= prover.zig:376-390). Returns the n_cols padded polynomials."""
+    c = _a64(cols)
+    n_cols, steps = c.shape
+    out = (u64 * n_cols)()
+    nv = u32(0)
+    ctx.check(lib().zb_witness_pack(ctx.handle, _p64(c.reshape(-1)) if c.size else None, steps, n_cols, n_hold, out, C.byref(nv)))
+    return [Multilinear(ctx, out[i]) for i in range(n_cols)]
+
+
 # --------------------------------------------------------------------------- Lasso
 TABLE_ADD, TABLE_XOR, TABLE_AND = 0, 1, 2
 

@@ -1261,6 +1261,59 @@ int32_t zb_table_mle(zb_ctx *ctx, int32_t op, uint32_t bits, zb_mle *out) {
     return zb_sync(ctx);
 }
 
+/* ------------------------------------------------------------------ witness packing */
+
+int32_t zb_witness_pack(zb_ctx *ctx, const uint64_t *cols, uint64_t num_steps, uint32_t n_cols, uint32_t n_hold, zb_mle *out,
+                        uint32_t *num_vars) {
+    tail_quiesce(ctx);
+    if (n_cols == 0 || n_cols > 64 || n_hold > n_cols || !out || (!cols && num_steps)) return ZB_ERR_BAD_ARGUMENT;
+    uint32_t v = 0;
+    while ((1ull << v) < num_steps) v++; // witness.zig:36-39 (0 steps -> one zero entry)
+    const uint64_t padded = 1ull << v;
+    if (num_vars) *num_vars = v;
+    uint32_t *ptrs[64];
+    for (uint32_t c = 0; c < n_cols; c++) {
+        Mle *m = nullptr;
+        int32_t rc = new_mle(ctx, padded, &out[c], &m);
+        if (rc) {
+            for (uint32_t j = 0; j < c; j++) ctx->mles.erase(out[j]);
+            return rc;
+        }
+        ptrs[c] = m->d();
+    }
+    auto fail = [&](int32_t rc) {
+        for (uint32_t c = 0; c < n_cols; c++) ctx->mles.erase(out[c]);
+        return rc;
+    };
+    // padding values: F.init(last real value) of the "hold" columns (witness.zig:80-87, :116-123)
+    uint32_t h_last[64] = {0};
+    for (uint32_t c = 0; c < n_hold && num_steps; c++) h_last[c] = (uint32_t)(cols[(size_t)c * num_steps + num_steps - 1] % bb::P);
+    BufRef d_last, stage;
+    int32_t rc = dev_alloc(ctx, sizeof(h_last), &d_last);
+    if (rc) return fail(rc);
+    CK(cudaMemcpyAsync(d_last->ptr, h_last, sizeof(h_last), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // h_last is a stack buffer
+    uint64_t chunk = STAGE_ELEMS / n_cols;
+    if (chunk > padded) chunk = padded;
+    rc = dev_alloc(ctx, chunk * n_cols * sizeof(uint64_t), &stage);
+    if (rc) return fail(rc);
+    for (uint64_t step0 = 0; step0 < padded; step0 += chunk) {
+        const uint64_t real = step0 < num_steps ? (num_steps - step0 < chunk ? num_steps - step0 : chunk) : 0;
+        for (uint32_t c = 0; c < n_cols && real; c++)
+            CK(cudaMemcpyAsync((uint64_t *)stage->ptr + (size_t)c * chunk, cols + (size_t)c * num_steps + step0, real * sizeof(uint64_t),
+                               cudaMemcpyHostToDevice, ctx->stream));
+        {
+            ProfScope _ps(ctx, "witness_pack", (uint64_t)n_cols * (real * 8 + chunk * 4));
+            launch_witness_pack((const uint64_t *)stage->ptr, chunk, step0, num_steps, padded, n_cols, n_hold,
+                                (const uint32_t *)d_last->ptr, ptrs, ctx->stream);
+        }
+        rc = check_launch(ctx, "witness_pack");
+        if (rc) return fail(rc);
+    }
+    rc = zb_sync(ctx);
+    return rc ? fail(rc) : ZB_OK;
+}
+
 /* ------------------------------------------------------------------ multi-GPU (NCCL, dlopen'ed) */
 
 struct NcclId { // ncclUniqueId (nccl.h:38-39), passed by value

@@ -318,6 +318,35 @@ int32_t zh_commit_verify(const uint8_t root[32], uint64_t leaf_value, const uint
     return zh_merkle_verify(root, leaf_value, siblings, dirs, height);
 }
 
+int32_t zh_generate_commitments(zb_ctx *ctx, zh_transcript *tr, const zb_mle *polys, uint32_t count, uint8_t *roots,
+                                uint64_t *points, uint64_t *values, uint64_t *leaf_indices, uint64_t *leaf_values,
+                                uint8_t *siblings, uint8_t *dirs) {
+    // Prover.generateCommitments, src/prover/prover.zig:366-467. Same transcript traffic, same outputs; the 43 commits
+    // are ONE batched device build (trees retained), each opening is an O(N) evaluation + a gather.
+    if (!tr || !polys || count == 0) return ZB_ERR_BAD_ARGUMENT;
+    uint64_t n;
+    uint32_t v;
+    int32_t rc = zb_mle_len(ctx, polys[0], &n, &v);
+    if (rc) return rc;
+    std::vector<zb_tree> trees(count, 0);
+    rc = zb_merkle_build(ctx, polys, count, trees.data(), roots); // PHASE 1 (:405-410)
+    if (rc) return rc;
+    zh_transcript_append_bytes(tr, "POLY_COMMITMENTS", 16); // PHASE 2 (:413-416)
+    for (uint32_t i = 0; i < count; i++) zh_transcript_append_bytes(tr, roots + 32 * (size_t)i, 32);
+    for (uint32_t i = 0; i < count && rc == ZB_OK; i++) { // PHASE 3 (:420-443)
+        uint64_t *pt = points + (size_t)i * v;
+        for (uint32_t j = 0; j < v; j++) pt[j] = zh_transcript_challenge(tr);
+        // :427 and Scheme.open :431 evaluate the same polynomial at the same point twice; once is enough
+        rc = zh_commit_open(ctx, polys[i], trees[i], pt, v, &values[i], &leaf_indices[i], &leaf_values[i],
+                            siblings + (size_t)i * v * 32, dirs + (size_t)i * v);
+    }
+    for (uint32_t i = 0; i < count; i++) zb_merkle_free(ctx, trees[i]); // :446-448
+    if (rc) return rc;
+    zh_transcript_append_bytes(tr, "OPENING_CLAIMS", 14); // PHASE 4 (:463-466)
+    zh_transcript_append_fields(tr, values, count);
+    return ZB_OK;
+}
+
 /* ------------------------------------------------------------------ Lasso */
 
 int32_t zh_lasso_commit_poly(zb_ctx *ctx, zb_mle poly, uint8_t out[32]) { // lasso_prover.zig:242-252

@@ -717,6 +717,34 @@ __global__ void k_scalar_mul(const uint32_t *a, uint32_t s, uint32_t sp, uint32_
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) o[i] = bb::mul_shoup(a[i], s, sp);
 }
 
+// WitnessGenerator.generate on SoA trace columns — /root/reference/src/constraints/witness.zig:29-270.
+// One launch packs a chunk [step0, step0 + chunk) of all columns: value mod p (F.init), and, for the part of the
+// chunk past num_steps, the padding rule of the column (first n_hold columns repeat the last real value, the others
+// are zero). cols: chunk-local staging, column-major [n_cols][chunk]; last_vals: per column F.init(last real value).
+struct WitnessOut {
+    uint32_t *col[64];
+};
+__global__ void k_witness_pack(const uint64_t *cols, uint64_t chunk, uint64_t step0, uint64_t num_steps, uint64_t padded,
+                               uint32_t n_hold, const uint32_t *last_vals, WitnessOut out) {
+    const uint32_t c = blockIdx.y;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t *o = out.col[c];
+    const uint32_t fill = c < n_hold ? last_vals[c] : 0u;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < chunk; j += stride) {
+        const uint64_t i = step0 + j;
+        if (i >= padded) break;
+        o[i] = i < num_steps ? (uint32_t)(cols[c * chunk + j] % bb::P) : fill;
+    }
+}
+void launch_witness_pack(const uint64_t *cols, uint64_t chunk, uint64_t step0, uint64_t num_steps, uint64_t padded,
+                         uint32_t n_cols, uint32_t n_hold, const uint32_t *last_vals, uint32_t *const *out_cols, cudaStream_t st) {
+    WitnessOut w{};
+    for (uint32_t c = 0; c < n_cols; c++) w.col[c] = out_cols[c];
+    uint64_t g = (chunk + 255) / 256;
+    dim3 grid((unsigned)(g > 148 * 4 ? 148 * 4 : (g ? g : 1)), n_cols);
+    k_witness_pack<<<grid, 256, 0, st>>>(cols, chunk, step0, num_steps, padded, n_hold, last_vals, w);
+}
+
 static inline int ew_grid(uint64_t n) {
     uint64_t g = (n + 255) / 256;
     if (g < 1) g = 1;
