@@ -103,6 +103,10 @@ int32_t zb_mle_len(zb_ctx *ctx, zb_mle m, uint64_t *n, uint32_t *num_vars);
 int32_t zb_mle_download(zb_ctx *ctx, zb_mle m, uint64_t *out, uint64_t n);
 /* evaluations [offset, offset + n) */
 int32_t zb_mle_download_range(zb_ctx *ctx, zb_mle m, uint64_t offset, uint64_t *out, uint64_t n);
+/* evaluations [offset, offset + n) in the device representation (canonical u32): a plain D2H copy */
+int32_t zb_mle_download_u32(zb_ctx *ctx, zb_mle m, uint64_t offset, uint32_t *out, uint64_t n);
+/* a context-owned pinned scratch buffer of at least `bytes` bytes (grown on demand, released with the context) */
+int32_t zb_host_scratch(zb_ctx *ctx, size_t bytes, void **out);
 /* sumOverHypercube :188-194 */
 int32_t zb_mle_sum(zb_ctx *ctx, zb_mle m, uint64_t *out);
 /* roundPolynomial :205-232 — returns the two half sums (s0, s1) mod p; the host forms [s0, s1 - s0] */

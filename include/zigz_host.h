@@ -114,6 +114,10 @@ int32_t zh_lasso_prove_with_mapping(zb_ctx *ctx, const uint64_t *table_rows, uin
 int32_t zh_lasso_prove_builtin(zb_ctx *ctx, int32_t op, uint32_t bits, const uint64_t *query_rows, uint64_t n_queries,
                                uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars,
                                uint8_t query_commitment[32], uint8_t table_commitment[32]);
+/* commitToPolynomial :242-252 over host evaluations: SHA3-256 of le64(e[0]) || ... || le64(e[n-1]) (8-byte elements,
+ * or canonical 4-byte elements that are absorbed zero-extended) */
+void zh_flat_commit(const uint64_t *evals, uint64_t n, uint8_t out[32]);
+void zh_flat_commit_u32(const uint32_t *evals, uint64_t n, uint8_t out[32]);
 /* commitToPolynomial :242-252 of a device-resident polynomial */
 int32_t zh_lasso_commit_poly(zb_ctx *ctx, zb_mle poly, uint8_t out[32]);
 

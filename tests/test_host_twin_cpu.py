@@ -90,3 +90,44 @@ def test_table_builders_match_oracle(zlib, po):
         assert np.array_equal(zlib.build_add_table(bits), po.build_table(BB, po.TABLE_ADD, bits))
         assert np.array_equal(zlib.build_xor_table(bits), po.build_table(BB, po.TABLE_XOR, bits))
         assert np.array_equal(zlib.build_and_table(bits), po.build_table(BB, po.TABLE_AND, bits))
+
+
+def test_sha3_long_streams_hit_the_simd_absorb_loop(zlib):
+    """Long word-aligned runs go through the AVX-512 absorb loop when the CPU has it; every split must agree with hashlib."""
+    rng = random.Random(11)
+    blob = bytes(rng.getrandbits(8) for _ in range(136 * 300 + 77))
+    for n in (136 * 4 - 8, 136 * 4, 136 * 4 + 8, 136 * 5 + 64, 136 * 64, 136 * 257 + 40, len(blob)):
+        assert zlib.sha3_256(blob[:n]) == hashlib.sha3_256(blob[:n]).digest(), n
+    # transcript: partial block, then a long run of field elements, then bytes, then more elements
+    for pre in (0, 1, 8, 64, 135, 136, 200):
+        t = zlib.FiatShamirTranscript()
+        h = hashlib.sha3_256()
+        t.append_bytes(blob[:pre])
+        h.update(blob[:pre])
+        vals = [rng.randrange(BB) for _ in range(17 * 40 + 5)]
+        t.append_field_elements(vals)
+        h.update(b"".join(v.to_bytes(8, "little") for v in vals))
+        t.append_bytes(blob[:3])
+        h.update(blob[:3])
+        t.append_field_elements(vals)
+        h.update(b"".join(v.to_bytes(8, "little") for v in vals))
+        assert t.finalize() == h.digest(), pre
+
+
+def test_flat_commit_u64_and_u32_forms(zlib, po, golden):
+    import ctypes as C
+    L = zlib.lib()
+    rng = np.random.default_rng(3)
+    for n in (1, 4, 16, 17, 67, 68, 69, 17 * 9, 17 * 64 + 3, 50000):
+        e = rng.integers(0, BB, size=n, dtype=np.uint64)
+        want = hashlib.sha3_256(e.astype("<u8").tobytes()).digest()
+        out = np.zeros(32, np.uint8)
+        L.zh_flat_commit(e.ctypes.data_as(C.POINTER(C.c_uint64)), n, out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert out.tobytes() == want == po.lasso_commit_poly(e), n
+        e32 = e.astype(np.uint32)
+        L.zh_flat_commit_u32(e32.ctypes.data_as(C.POINTER(C.c_uint32)), n, out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert out.tobytes() == want, n
+    out = np.zeros(32, np.uint8)
+    e = np.array([1, 2, 3, 4], np.uint64)
+    L.zh_flat_commit(e.ctypes.data_as(C.POINTER(C.c_uint64)), 4, out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    assert out.tobytes().hex() == golden["lasso"]["flat_commit_1234"]

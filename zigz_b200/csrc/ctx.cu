@@ -4,6 +4,7 @@
 // without a CUDA device zb_ctx_create fails with ZB_ERR_NO_DEVICE.
 #include "../../include/zigz_b200.h"
 #include "bb.cuh"
+#include "hostpack.hpp"
 #include "kernels.h"
 
 #include <atomic>
@@ -15,6 +16,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -99,6 +101,12 @@ struct zb_ctx {
         uint64_t n = 0;
     } tail;
     int tail_log2 = 14; // tables of <= 2^tail_log2 entries finish inside the persistent kernel (0 = never)
+    void *scratch = nullptr; // zb_host_scratch
+    size_t scratch_bytes = 0;
+    // host-narrowing upload path
+    std::unique_ptr<zigz::HostPool> pool;
+    uint32_t *pack_buf[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pack_done[3] = {nullptr, nullptr, nullptr};
     // multi-GPU
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
@@ -336,8 +344,57 @@ int32_t read_err_flag(zb_ctx *ctx) {
     return ZB_OK;
 }
 
-// chunked upload of host u64 data into a device u32 buffer (narrowing on the device)
+// Upload of host u64 field elements into a device u32 table.
+//  host-narrow mode (default when >= 4 host threads are available): worker threads pack u64 -> u32 into pinned
+//    staging buffers (canonical check included) while the previous chunk's H2D copy is in flight: 4 bytes per
+//    element cross PCIe instead of 8;
+//  direct mode: the u64 data is copied as is and narrowed by a kernel (k_narrow).
+constexpr uint64_t PACK_CHUNK = 8ull << 20; // elements per staging buffer (32 MiB narrowed)
+constexpr int PACK_BUFS = 3;
+
+int upload_threads(zb_ctx *ctx) {
+    if (const char *e = getenv("ZB_UPLOAD_THREADS")) return atoi(e) < 1 ? 1 : atoi(e);
+    int hw = (int)std::thread::hardware_concurrency();
+    int t = hw / (ctx->world > 0 ? ctx->world : 1);
+    return t > 16 ? 16 : (t < 1 ? 1 : t);
+}
+
+int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32_t *dst) {
+    if (!ctx->pool) ctx->pool.reset(new zigz::HostPool(upload_threads(ctx)));
+    if (!ctx->pack_buf[0]) {
+        for (int b = 0; b < PACK_BUFS; b++) {
+            CK(cudaHostAlloc((void **)&ctx->pack_buf[b], PACK_CHUNK * sizeof(uint32_t), cudaHostAllocDefault));
+            CK(cudaEventCreateWithFlags(&ctx->pack_done[b], cudaEventDisableTiming));
+        }
+    }
+    const int T = ctx->pool->size();
+    std::vector<char> bad(T, 0);
+    int buf = 0;
+    for (uint64_t off = 0; off < n; off += PACK_CHUNK, buf = (buf + 1) % PACK_BUFS) {
+        const uint64_t m = n - off < PACK_CHUNK ? n - off : PACK_CHUNK;
+        CK(cudaEventSynchronize(ctx->pack_done[buf])); // the copy that last used this staging buffer has finished
+        uint32_t *stage = ctx->pack_buf[buf];
+        const uint64_t *src = host + off;
+        ctx->pool->run([&](int tid) {
+            const uint64_t per = ((m + T - 1) / T + 15) & ~15ull;
+            const uint64_t lo = per * tid < m ? per * tid : m, hi = lo + per < m ? lo + per : m;
+            if (hi > lo && zigz::narrow_u64_to_u32(src + lo, stage + lo, hi - lo, bb::P)) bad[tid] = 1;
+        });
+        CK(cudaMemcpyAsync(dst + off, stage, m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->pack_done[buf], ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (char b : bad)
+        if (b) return ZB_ERR_NOT_CANONICAL;
+    return ZB_OK;
+}
+
 int32_t upload_narrow(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32_t *dst) {
+    static const int mode = [] {
+        const char *e = getenv("ZB_UPLOAD_MODE"); // "host" | "device"
+        return e && !strcmp(e, "device") ? 0 : (e && !strcmp(e, "host") ? 1 : -1);
+    }();
+    if (mode == 1 || (mode == -1 && upload_threads(ctx) >= 4 && n >= (1u << 16))) return upload_narrow_host(ctx, host, n, dst);
     uint64_t chunk = n < STAGE_ELEMS ? n : STAGE_ELEMS;
     BufRef stage;
     int32_t rc = dev_alloc(ctx, chunk * sizeof(uint64_t), &stage);
@@ -446,6 +503,11 @@ void zb_ctx_destroy(zb_ctx *ctx) {
     cudaFree(ctx->d_acc);
     cudaFree(ctx->d_ticket);
     cudaFree(ctx->d_tail_status);
+    if (ctx->scratch) cudaFreeHost(ctx->scratch);
+    for (int b = 0; b < 3; b++) {
+        if (ctx->pack_buf[b]) cudaFreeHost(ctx->pack_buf[b]);
+        if (ctx->pack_done[b]) cudaEventDestroy(ctx->pack_done[b]);
+    }
     cudaFreeHost(ctx->h_chal);
     cudaFreeHost(ctx->h_mail);
     cudaStreamDestroy(ctx->stream);
@@ -669,6 +731,30 @@ int32_t zb_mle_download_range(zb_ctx *ctx, zb_mle h, uint64_t offset, uint64_t *
         CK(cudaMemcpyAsync(out + off, stage->ptr, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     return zb_sync(ctx);
+}
+
+int32_t zb_mle_download_u32(zb_ctx *ctx, zb_mle h, uint64_t offset, uint32_t *out, uint64_t n) {
+    tail_quiesce(ctx);
+    Mle *m = get_mle(ctx, h);
+    if (!m) return ZB_ERR_BAD_HANDLE;
+    if (offset > m->n || n > m->n - offset || !out) return ZB_ERR_BAD_ARGUMENT;
+    CK(cudaMemcpyAsync(out, m->d() + offset, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return zb_sync(ctx);
+}
+
+int32_t zb_host_scratch(zb_ctx *ctx, size_t bytes, void **out) {
+    if (!out) return ZB_ERR_BAD_ARGUMENT;
+    if (bytes > ctx->scratch_bytes) {
+        tail_quiesce(ctx);
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->scratch) cudaFreeHost(ctx->scratch);
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        CK(cudaHostAlloc(&ctx->scratch, bytes, cudaHostAllocDefault));
+        ctx->scratch_bytes = bytes;
+    }
+    *out = ctx->scratch;
+    return ZB_OK;
 }
 
 int32_t zb_mle_sum(zb_ctx *ctx, zb_mle h, uint64_t *out) {
@@ -1215,36 +1301,29 @@ int32_t zb_xxh3_rows(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint32_
     Mle *m = nullptr;
     rc = new_mle(ctx, n_padded, out, &m);
     if (rc) return rc;
-    // rows are streamed through a device staging buffer in chunks of whole rows
-    uint64_t rows_per_chunk = STAGE_ELEMS / arity;
-    if (rows_per_chunk > n_rows) rows_per_chunk = n_rows ? n_rows : 1;
-    BufRef stage;
-    rc = dev_alloc(ctx, rows_per_chunk * arity * sizeof(uint64_t), &stage);
-    if (rc) return rc;
-    uint64_t off = 0;
-    while (off < n_rows) {
-        uint64_t k = n_rows - off < rows_per_chunk ? n_rows - off : rows_per_chunk;
-        CK(cudaMemcpyAsync(stage->ptr, rows + off * arity, k * arity * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    // the rows are field elements (canonical, < 2^31): narrow them on the way up like any other table, then hash
+    if (n_rows) {
+        BufRef drows;
+        rc = dev_alloc(ctx, n_rows * arity * sizeof(uint32_t), &drows);
+        if (rc == ZB_OK) rc = upload_narrow(ctx, rows, n_rows * arity, (uint32_t *)drows->ptr);
+        if (rc) {
+            ctx->mles.erase(*out);
+            *out = 0;
+            return rc;
+        }
         {
-            ProfScope _ps(ctx, "xxh3_rows", k * (8ull * arity + 4));
-            launch_xxh3_rows((const uint64_t *)stage->ptr, k, arity, k, m->d() + off, ctx->d_err, ctx->stream);
+            ProfScope _ps(ctx, "xxh3_rows", n_rows * (4ull * arity) + n_padded * 4);
+            launch_xxh3_rows((const uint32_t *)drows->ptr, n_rows, arity, n_padded, m->d(), ctx->stream);
         }
         LAUNCHED("xxh3_rows");
-        off += k;
-    }
-    if (n_padded > n_rows) {
+    } else {
         {
-            ProfScope _ps(ctx, "fill", (n_padded - n_rows) * 4);
-            launch_fill(m->d() + n_rows, n_padded - n_rows, 0, ctx->stream); // lasso_prover.zig:140-142
+            ProfScope _ps(ctx, "fill", n_padded * 4);
+            launch_fill(m->d(), n_padded, 0, ctx->stream);
         }
         LAUNCHED("fill");
     }
-    rc = read_err_flag(ctx);
-    if (rc) {
-        ctx->mles.erase(*out);
-        *out = 0;
-    }
-    return rc;
+    return zb_sync(ctx);
 }
 
 int32_t zb_table_mle(zb_ctx *ctx, int32_t op, uint32_t bits, zb_mle *out) {

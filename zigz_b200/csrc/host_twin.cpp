@@ -349,25 +349,39 @@ int32_t zh_generate_commitments(zb_ctx *ctx, zh_transcript *tr, const zb_mle *po
 
 /* ------------------------------------------------------------------ Lasso */
 
+void zh_flat_commit(const uint64_t *evals, uint64_t n, uint8_t out[32]) { // lasso_prover.zig:242-252
+    Sha3_256 h;
+    h.update_words(evals, n);
+    h.peek(out);
+}
+
+void zh_flat_commit_u32(const uint32_t *evals, uint64_t n, uint8_t out[32]) {
+    Sha3_256 h;
+    h.update_words_u32(evals, n);
+    h.peek(out);
+}
+
 int32_t zh_lasso_commit_poly(zb_ctx *ctx, zb_mle poly, uint8_t out[32]) { // lasso_prover.zig:242-252
     uint64_t n;
     uint32_t v;
     int32_t rc = zb_mle_len(ctx, poly, &n, &v);
     if (rc) return rc;
-    // the sponge is one sequential chain over 8n bytes: it stays on one host core, fed in pipelined chunks
-    const uint64_t CH = 1ull << 20;
-    uint64_t *buf = nullptr;
-    rc = zb_host_alloc(ctx, (n < CH ? n : CH) * sizeof(uint64_t), (void **)&buf);
+    // The sponge is one sequential chain over 8n bytes (n/17 dependent permutations): it stays on one host core.
+    // The evaluations come down in their 4-byte device form into the context's pinned scratch and are absorbed as
+    // le64 words (zero-extended on the fly).
+    const uint64_t CH = 4ull << 20;
+    uint32_t *buf = nullptr;
+    rc = zb_host_scratch(ctx, (n < CH ? n : CH) * sizeof(uint32_t), (void **)&buf);
     if (rc) return rc;
     Sha3_256 h;
-    for (uint64_t off = 0; off < n && rc == ZB_OK; off += CH) {
+    for (uint64_t off = 0; off < n; off += CH) {
         uint64_t k = n - off < CH ? n - off : CH;
-        rc = zb_mle_download_range(ctx, poly, off, buf, k);
-        if (rc == ZB_OK) h.update_words(buf, k);
+        rc = zb_mle_download_u32(ctx, poly, off, buf, k);
+        if (rc) return rc;
+        h.update_words_u32(buf, k);
     }
-    zb_host_free(ctx, buf);
-    if (rc == ZB_OK) h.peek(out);
-    return rc;
+    h.peek(out);
+    return ZB_OK;
 }
 
 static int32_t lasso_finish(zb_ctx *ctx, zb_mle table_poly, zb_mle query_poly, uint64_t *round_polys, uint64_t *final_point,

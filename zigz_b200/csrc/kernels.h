@@ -75,9 +75,8 @@ void launch_scalar_mul(const uint32_t *a, uint32_t s, uint32_t *out, uint64_t n,
 void launch_witness_pack(const uint64_t *cols, uint64_t chunk, uint64_t step0, uint64_t num_steps, uint64_t padded,
                          uint32_t n_cols, uint32_t n_hold, const uint32_t *last_vals, uint32_t *const *out_cols, cudaStream_t st);
 
-// Lasso row hashing (hashEntry / hashQuery). rows: n_rows * arity u64 on the device; out: n_padded u32.
-void launch_xxh3_rows(const uint64_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, uint32_t *out,
-                      unsigned int *err_flag, cudaStream_t st);
+// Lasso row hashing (hashEntry / hashQuery). rows: n_rows * arity canonical u32 on the device; out: n_padded u32.
+void launch_xxh3_rows(const uint32_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, uint32_t *out, cudaStream_t st);
 void launch_table_mle(int op, uint32_t bits, uint32_t *out, cudaStream_t st);
 
 // Merkle. Tree storage = all levels concatenated: level l starts at digest offset level_offset(padded, l).

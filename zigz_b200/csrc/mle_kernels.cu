@@ -792,28 +792,20 @@ __device__ __forceinline__ uint32_t hash_row3(uint64_t a, uint64_t b, uint64_t c
     return (uint32_t)(h % bb::P);
 }
 
-__global__ void k_xxh3_rows(const uint64_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, uint32_t *out,
-                            unsigned int *err) {
+__global__ void k_xxh3_rows(const uint32_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, uint32_t *out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    bool bad = false;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += stride) {
         uint32_t v = 0;
         if (i < n_rows) {
             uint64_t h = 0;
-            for (uint32_t k = 0; k < arity; k++) {
-                uint64_t x = rows[i * arity + k];
-                bad |= (x >= bb::P);
-                h = xxh3_8(h ^ x);
-            }
+            for (uint32_t k = 0; k < arity; k++) h = xxh3_8(h ^ (uint64_t)rows[i * arity + k]);
             v = (uint32_t)(h % bb::P);
         }
         out[i] = v;
     }
-    if (bad) atomicOr(err, 1u);
 }
-void launch_xxh3_rows(const uint64_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, uint32_t *out,
-                      unsigned int *err, cudaStream_t st) {
-    k_xxh3_rows<<<ew_grid(n_padded), 256, 0, st>>>(rows, n_rows, arity, n_padded, out, err);
+void launch_xxh3_rows(const uint32_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, uint32_t *out, cudaStream_t st) {
+    k_xxh3_rows<<<ew_grid(n_padded), 256, 0, st>>>(rows, n_rows, arity, n_padded, out);
 }
 
 // buildAddTable / buildXorTable / buildAndTable (table_builder.zig:126-213) generated and hashed in registers

@@ -1,6 +1,8 @@
 // Keccak-f[1600] for the host-resident sponges (see sha3_host.hpp).
 #include "sha3_host.hpp"
 
+#include <cstdlib>
+
 namespace zigz {
 
 namespace {
@@ -36,6 +38,27 @@ inline __attribute__((always_inline)) void round_fn(const uint64_t *__restrict i
     out[0] ^= rc;
 }
 } // namespace
+
+void keccak_absorb_avx512(uint64_t state[25], const uint64_t *words, size_t nblocks, size_t lanes_per_block);
+void keccak_absorb_u32_avx512(uint64_t state[25], const uint32_t *words, size_t nblocks);
+
+bool Sha3_256::have_avx512() {
+    static const bool ok = [] {
+        const char *e = getenv("ZB_HOST_SHA3"); // "scalar" forces the portable path
+        if (e && !strcmp(e, "scalar")) return false;
+        __builtin_cpu_init();
+        return (bool)__builtin_cpu_supports("avx512f");
+    }();
+    return ok;
+}
+
+void Sha3_256::absorb_blocks_avx512(uint64_t s[25], const uint64_t *words, size_t nblocks) {
+    keccak_absorb_avx512(s, words, nblocks, RATE / 8);
+}
+
+void Sha3_256::absorb_blocks_u32_avx512(uint64_t s[25], const uint32_t *words, size_t nblocks) {
+    keccak_absorb_u32_avx512(s, words, nblocks);
+}
 
 void Sha3_256::permute(uint64_t s[25]) {
     uint64_t t[25];

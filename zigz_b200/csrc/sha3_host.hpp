@@ -27,7 +27,13 @@ class Sha3_256 {
             xor_byte(*p++);
             len--;
         }
-        // whole lanes
+        // whole lanes (long aligned runs take the word path, which may use the AVX-512 absorb loop)
+        if (len >= 8 * 17 * 4 && (pos_ & 7) == 0 && (reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+            const size_t words = len / 8;
+            update_words(reinterpret_cast<const uint64_t *>(p), words);
+            p += words * 8;
+            len -= words * 8;
+        }
         while (len >= 8) {
             uint64_t w;
             memcpy(&w, p, 8);
@@ -51,7 +57,56 @@ class Sha3_256 {
             update(w, n * 8);
             return;
         }
+        if (pos_ != 0 && n >= 17 * 5) { // finish the partial block first so the bulk starts block-aligned
+            size_t lane0 = pos_ >> 3;
+            while (lane0 != 0) {
+                a_[lane0++] ^= *w++;
+                n--;
+                if (lane0 == RATE / 8) {
+                    permute(a_);
+                    lane0 = 0;
+                }
+            }
+            pos_ = 0;
+        }
+        if (pos_ == 0 && n >= 17 * 4 && have_avx512()) { // long runs: whole blocks through the AVX-512 absorb loop
+            const size_t blocks = n / 17;
+            absorb_blocks_avx512(a_, w, blocks);
+            w += blocks * 17;
+            n -= blocks * 17;
+        }
         size_t lane = pos_ >> 3;
+        for (size_t i = 0; i < n; i++) {
+            a_[lane++] ^= w[i];
+            if (lane == RATE / 8) {
+                permute(a_);
+                lane = 0;
+            }
+        }
+        pos_ = lane << 3;
+    }
+    // absorb n field elements stored as canonical u32 (the device representation), each as its 8-byte LE encoding
+    void update_words_u32(const uint32_t *w, size_t n) {
+        while (n && (pos_ & 7)) { // not lane aligned: byte path
+            uint64_t v = *w++;
+            update(&v, 8);
+            n--;
+        }
+        size_t lane = pos_ >> 3;
+        while (n && lane != 0) { // finish the partial block
+            a_[lane++] ^= *w++;
+            n--;
+            if (lane == RATE / 8) {
+                permute(a_);
+                lane = 0;
+            }
+        }
+        if (lane == 0 && n >= 17 * 4 && have_avx512()) {
+            const size_t blocks = n / 17;
+            absorb_blocks_u32_avx512(a_, w, blocks);
+            w += blocks * 17;
+            n -= blocks * 17;
+        }
         for (size_t i = 0; i < n; i++) {
             a_[lane++] ^= w[i];
             if (lane == RATE / 8) {
@@ -76,6 +131,9 @@ class Sha3_256 {
         h.peek(out);
     }
     static void permute(uint64_t s[25]);
+    static bool have_avx512();
+    static void absorb_blocks_avx512(uint64_t s[25], const uint64_t *words, size_t nblocks);
+    static void absorb_blocks_u32_avx512(uint64_t s[25], const uint32_t *words, size_t nblocks);
 
   private:
     void xor_byte(uint8_t b) {
