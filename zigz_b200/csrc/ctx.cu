@@ -394,7 +394,17 @@ int32_t upload_narrow(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32_t *d
         const char *e = getenv("ZB_UPLOAD_MODE"); // "host" | "device"
         return e && !strcmp(e, "device") ? 0 : (e && !strcmp(e, "host") ? 1 : -1);
     }();
-    if (mode == 1 || (mode == -1 && upload_threads(ctx) >= 4 && n >= (1u << 16))) return upload_narrow_host(ctx, host, n, dst);
+    if (mode == 1) return upload_narrow_host(ctx, host, n, dst);
+    if (mode == -1 && n >= (1u << 16)) {
+        // measured on the pool's hosts (tools/upload_bench.py, profiles/r01_upload_modes.txt): packing on the host beats
+        // the direct 8-byte copy from PINNED memory only with >= ~12 threads per GPU (70.7 vs 54.5 GB/s at 16), but beats
+        // the driver's staged copy from PAGEABLE memory already with 3-4 threads (33 vs 11 GB/s)
+        cudaPointerAttributes attr{};
+        const bool pinned = cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const int t = upload_threads(ctx);
+        if ((pinned && t >= 12) || (!pinned && t >= 3)) return upload_narrow_host(ctx, host, n, dst);
+    }
     uint64_t chunk = n < STAGE_ELEMS ? n : STAGE_ELEMS;
     BufRef stage;
     int32_t rc = dev_alloc(ctx, chunk * sizeof(uint64_t), &stage);
