@@ -18,7 +18,6 @@ sample of the same workload.  Nothing here reads /root/reference.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -42,45 +41,53 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region through NVML (a 2 ms polling thread; the
+    nvidia-smi recipe of B200_PROFILING.md reads the same counters but cannot sample a 50-200 ms region reliably)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.th, self.err = index, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES if the launcher set it
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.stop_flag = False
+        self.th = threading.Thread(target=self._poll, daemon=True)
+        self.th.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.th is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        self.stop_flag = True
         self.th.join(timeout=2)
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                    if r[col].lower().startswith("active"):
-                        reasons.add(name)
-        # clocks under load = upper half of the samples (idle samples before/after the region drag the median down)
-        sm.sort()
-        load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in self.rows))
+        sm = [c for c, _ in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                "sm_max_mhz": float(self.max_sm), "reasons": reasons, "samples": len(sm), "source": "nvml, 2 ms polling inside the timed region"}
 
 
 def dist_setup(n_gpus):
@@ -372,7 +379,7 @@ def cpu_baseline(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=30, help="log2 of the per-GPU table length")

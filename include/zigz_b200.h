@@ -71,7 +71,7 @@ void *zb_stream(zb_ctx *ctx);
 int32_t zb_sync(zb_ctx *ctx);
 /* tuning knobs. "tail_log2": tables of <= 2^value entries run all their remaining fold rounds inside ONE persistent
  * kernel that receives the challenges through host-mapped memory (0 disables; default 14, env ZB_TAIL_LOG2). */
-/* "comm_reduce" (0/1, needs a communicator): zb_prod_round_coeffs / zb_prod_fold_inplace / zb_prod_partial_eval return
+/* "comm_reduce" (0/1/2, needs a communicator; 2 needs zb_comm_p2p_attach): zb_prod_round_coeffs / zb_prod_fold_inplace / zb_prod_partial_eval return
  * the coefficients of the WHOLE (sharded) round polynomial: the kernel's partial sums are all-reduced over NCCL in stream
  * order and published once, without a host hop in between. The d final evaluations of the last fold are never summed. */
 int32_t zb_set_option(zb_ctx *ctx, const char *key, int64_t value);
@@ -172,6 +172,13 @@ int32_t zb_comm_init(zb_ctx *ctx, const char *nccl_path, const uint8_t unique_id
 int32_t zb_comm_info(zb_ctx *ctx, int32_t *rank, int32_t *world); /* world == 1 when no communicator is attached */
 /* exact element-wise sum over all ranks of n (<= 64) u64 values, in place (host memory) */
 int32_t zb_comm_allreduce_u64(zb_ctx *ctx, uint64_t *vals, uint32_t n);
+/* NVLink peer exchange (optional, on top of the communicator): every rank exports a small exchange buffer over CUDA IPC
+ * (zb_comm_p2p_handle, 64 bytes), the handles of all ranks in rank order are attached (zb_comm_p2p_attach, world*64
+ * bytes), and "comm_reduce" = 2 then makes the LAST CTA of each round kernel store its partial sums into every peer's
+ * buffer, wait for the peers' flags and publish the total — the reduction rides inside the kernel that produced the
+ * sums: no NCCL call and no extra launch per round. */
+int32_t zb_comm_p2p_handle(zb_ctx *ctx, uint8_t out[64]);
+int32_t zb_comm_p2p_attach(zb_ctx *ctx, const uint8_t *handles);
 /* all-gather of cyclic shards: out[rank + world*j] = shard_rank[j] (a NEW polynomial of world * n_local entries,
  * identical on every rank) — used to leave the sharded regime once the tables are small */
 int32_t zb_comm_allgather_cyclic(zb_ctx *ctx, zb_mle local, zb_mle *out);

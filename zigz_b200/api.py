@@ -85,6 +85,16 @@ class Context:
             raise ZigzError(rc, "zb_comm_unique_id")
         return bytes(uid)
 
+    def p2p_handle(self) -> bytes:
+        h = (C.c_uint8 * 64)()
+        self.check(lib().zb_comm_p2p_handle(self._h, h))
+        return bytes(h)
+
+    def p2p_attach(self, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self.check(lib().zb_comm_p2p_attach(self._h, buf))
+
     @property
     def world(self) -> int:
         r, w = C.c_int32(0), C.c_int32(1)

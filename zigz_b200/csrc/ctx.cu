@@ -112,7 +112,12 @@ struct zb_ctx {
     int rank = 0, world = 1;
     unsigned long long *d_comm = nullptr; // 64 u64 exchange buffer
     unsigned long long *h_comm = nullptr; // pinned twin
-    bool comm_reduce = false;             // round payloads are summed over the ranks on the device before publication
+    int comm_reduce = 0; // 0: per-rank payloads; 1: NCCL all-reduce in stream order; 2: NVLink peer exchange inside the kernel
+    // NVLink peer exchange (CUDA IPC): own buffer, the peers' mappings, and the device-resident view the kernels read
+    unsigned long long *d_xchg = nullptr;
+    void *xchg_peer[16] = {nullptr};
+    XchgView *d_xchg_view = nullptr;
+    unsigned long long xchg_seq = 0;
 
     Mailbox mailbox() {
         Mailbox m;
@@ -120,6 +125,8 @@ struct zb_ctx {
         m.ticket = d_ticket;
         m.mail = d_mail;
         m.seq = ++seq;
+        m.xchg = nullptr;
+        m.xseq = 0;
         return m;
     }
     uint8_t *h_bulk() { return (uint8_t *)h_mail + BULK_OFFSET; }
@@ -215,6 +222,11 @@ int32_t wait_mail(zb_ctx *ctx, unsigned long long seq) {
         }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
+    if (ctx->comm_reduce == 2 && ctx->d_xchg_view && ctx->h_mail[MAIL_WORDS - 1] == 1ull) {
+        ctx->h_mail[MAIL_WORDS - 1] = 0;
+        ctx->last_error = "peer exchange: a rank never arrived";
+        return ZB_ERR_TIMEOUT;
+    }
     return ZB_OK;
 }
 
@@ -223,9 +235,17 @@ int32_t comm_publish(zb_ctx *ctx, unsigned long long seq, int nwords); // define
 // Mailbox for a kernel whose payload must be summed over the ranks: the kernel writes into the device exchange
 // buffer, comm_publish() then all-reduces it in stream order and publishes the reduced words to the host mailbox.
 inline bool reduce_on_device(const zb_ctx *c) { return c->comm_reduce && c->world > 1 && c->nccl_comm; }
+inline bool reduce_p2p(const zb_ctx *c) { return c->comm_reduce == 2 && c->d_xchg_view; }
 inline Mailbox round_mailbox(zb_ctx *c, bool reduce) {
     Mailbox m = c->mailbox();
-    if (reduce) m.mail = c->d_comm;
+    if (reduce) {
+        if (reduce_p2p(c)) {
+            m.xchg = c->d_xchg_view; // the kernel itself sums over the ranks and publishes
+            m.xseq = ++c->xchg_seq;
+        } else {
+            m.mail = c->d_comm; // the kernel writes the exchange buffer, comm_publish() does the rest
+        }
+    }
     return m;
 }
 
@@ -542,7 +562,8 @@ int32_t zb_set_option(zb_ctx *ctx, const char *key, int64_t value) {
         return ZB_OK;
     }
     if (key && !strcmp(key, "comm_reduce")) {
-        ctx->comm_reduce = value != 0;
+        if (value < 0 || value > 2 || (value == 2 && !ctx->d_xchg_view)) return ZB_ERR_BAD_ARGUMENT;
+        ctx->comm_reduce = (int)value;
         return ZB_OK;
     }
     return ZB_ERR_BAD_ARGUMENT;
@@ -554,7 +575,11 @@ int32_t zb_get_option(zb_ctx *ctx, const char *key, int64_t *value) {
         return ZB_OK;
     }
     if (key && value && !strcmp(key, "comm_reduce")) {
-        *value = ctx->comm_reduce ? 1 : 0;
+        *value = ctx->comm_reduce;
+        return ZB_OK;
+    }
+    if (key && value && !strcmp(key, "p2p_attached")) {
+        *value = ctx->d_xchg_view ? 1 : 0;
         return ZB_OK;
     }
     return ZB_ERR_BAD_ARGUMENT;
@@ -1458,6 +1483,7 @@ namespace {
 // sum the first nwords of the device exchange buffer over all ranks (stream order, behind the kernel that wrote
 // them) and publish them mod p with sequence number `seq`
 int32_t comm_publish(zb_ctx *ctx, unsigned long long seq, int nwords) {
+    if (reduce_p2p(ctx)) return ZB_OK; // already summed over NVLink inside the kernel
     int r = g_nccl.AllReduce(ctx->d_comm, ctx->d_comm, (size_t)nwords, NCCL_UINT64, NCCL_SUM, ctx->nccl_comm, ctx->stream);
     if (r) return nccl_fail(ctx, r, "ncclAllReduce");
     launch_publish_reduced(ctx->d_comm, nwords, ctx->d_mail, seq, ctx->stream);
@@ -1489,6 +1515,42 @@ int32_t zb_comm_allgather_cyclic(zb_ctx *ctx, zb_mle local, zb_mle *out) {
     if (rc == ZB_OK) rc = zb_sync(ctx);
     if (rc) ctx->mles.erase(*out);
     return rc;
+}
+
+int32_t zb_comm_p2p_handle(zb_ctx *ctx, uint8_t out[64]) {
+    tail_quiesce(ctx);
+    if (!out) return ZB_ERR_BAD_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+    if (!ctx->d_xchg) {
+        const size_t bytes = 2 * XCHG_SET_WORDS * sizeof(unsigned long long);
+        CK(cudaMalloc(&ctx->d_xchg, bytes));
+        CK(cudaMemset(ctx->d_xchg, 0, bytes));
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->d_xchg));
+    memcpy(out, &h, 64);
+    return ZB_OK;
+}
+
+int32_t zb_comm_p2p_attach(zb_ctx *ctx, const uint8_t *handles) {
+    tail_quiesce(ctx);
+    if (!handles || !ctx->d_xchg || ctx->world < 2 || ctx->world > XCHG_MAX_RANKS || ctx->d_xchg_view) return ZB_ERR_BAD_ARGUMENT;
+    XchgView view{};
+    view.rank = ctx->rank;
+    view.world = ctx->world;
+    for (int q = 0; q < ctx->world; q++) {
+        if (q == ctx->rank) {
+            view.peer[q] = ctx->d_xchg;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)q, 64);
+        CK(cudaIpcOpenMemHandle(&ctx->xchg_peer[q], h, cudaIpcMemLazyEnablePeerAccess));
+        view.peer[q] = (unsigned long long *)ctx->xchg_peer[q];
+    }
+    CK(cudaMalloc(&ctx->d_xchg_view, sizeof(XchgView)));
+    CK(cudaMemcpy(ctx->d_xchg_view, &view, sizeof(XchgView), cudaMemcpyHostToDevice));
+    return ZB_OK;
 }
 
 int32_t zb_comm_unique_id(const char *nccl_path, uint8_t out[128]) {
@@ -1546,6 +1608,19 @@ int32_t zb_comm_allreduce_u64(zb_ctx *ctx, uint64_t *vals, uint32_t n) {
 
 int32_t zb_comm_destroy(zb_ctx *ctx) {
     tail_quiesce(ctx);
+    if (ctx->d_xchg) {
+        cudaStreamSynchronize(ctx->stream);
+        ctx->comm_reduce = 0;
+        for (int q = 0; q < XCHG_MAX_RANKS; q++)
+            if (ctx->xchg_peer[q]) {
+                cudaIpcCloseMemHandle(ctx->xchg_peer[q]);
+                ctx->xchg_peer[q] = nullptr;
+            }
+        if (ctx->d_xchg_view) cudaFree(ctx->d_xchg_view);
+        ctx->d_xchg_view = nullptr;
+        cudaFree(ctx->d_xchg);
+        ctx->d_xchg = nullptr;
+    }
     if (ctx->nccl_comm) {
         cudaStreamSynchronize(ctx->stream);
         g_nccl.CommDestroy(ctx->nccl_comm);

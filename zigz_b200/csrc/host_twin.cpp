@@ -118,8 +118,10 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
         ~Restore() { now(); }
     } restore{ctx, tail_log2, comm_reduce, sharded};
     if (sharded) {
+        int64_t p2p = 0;
+        zb_get_option(ctx, "p2p_attached", &p2p);
         zb_set_option(ctx, "tail_log2", 0);
-        zb_set_option(ctx, "comm_reduce", 1);
+        zb_set_option(ctx, "comm_reduce", p2p ? 2 : 1); // NVLink peer exchange inside the kernels when attached, else NCCL
     }
     zh_transcript tr; // State.init -> FiatShamirTranscript.init (sumcheck_protocol.zig:149-164)
     uint64_t coeffs[4];

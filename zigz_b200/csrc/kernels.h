@@ -13,11 +13,23 @@ constexpr int MAIL_WORDS = 16;  // u64 payload words per mailbox
 
 // Completion mailbox. `acc`/`ticket` live in device memory; `mail` is mapped pinned host memory.
 // mail[0..MAIL_WORDS) payload, mail[MAIL_WORDS] = sequence number written last (release, system scope).
+// Peer exchange over NVLink (multi-GPU): every rank owns one exchange buffer that all peers have mapped (CUDA IPC).
+// Two alternating sets (seq parity); per set XCHG_MAX_RANKS payload rows of XCHG_ROW words + one flag word per source rank.
+constexpr int XCHG_MAX_RANKS = 16;
+constexpr int XCHG_ROW = 8;
+constexpr int XCHG_SET_WORDS = XCHG_MAX_RANKS * XCHG_ROW + XCHG_MAX_RANKS;
+struct XchgView {
+    unsigned long long *peer[XCHG_MAX_RANKS]; // peer[q] = rank q's exchange buffer as seen from this GPU (peer[rank] = own)
+    int rank, world;
+};
+
 struct Mailbox {
     unsigned long long *acc;    // device: MAIL_WORDS u64 accumulators (zero between launches)
     unsigned int *ticket;       // device: CTA arrival counter (zero between launches)
     unsigned long long *mail;   // device alias of the mapped host mailbox
     unsigned long long seq;     // sequence value this launch must publish
+    const XchgView *xchg;       // non-null: sum the payload over all ranks through peer memory before publishing
+    unsigned long long xseq;    // exchange round number: counts exchanged rounds only, identical on every rank
 };
 
 struct PolySet {

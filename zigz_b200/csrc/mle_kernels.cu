@@ -28,11 +28,57 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     return v;
 }
 
+// Cross-GPU sum of NS canonical words, executed by warp 0 of the last CTA of the kernel on EVERY rank at the same
+// point of the same round: lane q stores this rank's words into rank q's exchange buffer (NVLink P2P store) and
+// raises this rank's flag there; then lane q waits for rank q's flag in the LOCAL buffer and reads its words; a warp
+// shuffle adds the rows. No NCCL call, no extra launch: the reduction rides in the tail of the kernel that produced
+// the partial sums. Returns false on a ~2 s starvation (a peer never arrived).
+template <int NS>
+__device__ __forceinline__ bool xchg_allreduce(unsigned long long (&tot)[NS], const XchgView *xv, unsigned long long seq) {
+    const int lane = threadIdx.x & 31;
+    const int world = xv->world, rank = xv->rank;
+    const unsigned long long set = (seq & 1ull) * XCHG_SET_WORDS;
+    if (lane < world) {
+        volatile unsigned long long *dst = xv->peer[lane] + set;
+#pragma unroll
+        for (int k = 0; k < NS; k++) dst[rank * XCHG_ROW + k] = tot[k];
+        __threadfence_system();
+        dst[XCHG_MAX_RANKS * XCHG_ROW + rank] = seq;
+    }
+    bool ok = true;
+    unsigned long long v[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) v[k] = 0;
+    if (lane < world) {
+        volatile unsigned long long *mine = xv->peer[rank] + set;
+        const long long t0 = clock64();
+        while (mine[XCHG_MAX_RANKS * XCHG_ROW + lane] != seq) {
+            if (clock64() - t0 > 4000000000ll) {
+                ok = false;
+                break;
+            }
+        }
+        __threadfence_system();
+#pragma unroll
+        for (int k = 0; k < NS; k++) v[k] = mine[lane * XCHG_ROW + k];
+    }
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        unsigned long long x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        tot[k] = x % bb::P; // sums of <= 16 canonical words: exact
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+
 // Block-reduce NS u64 partial sums, add them to the global accumulators; the last CTA converts the totals with
-// `fin` (called by one thread with the raw totals) and publishes payload + sequence number to the mailbox.
+// `fin` (canonical field elements), optionally sums them over all GPUs (mb.xchg) and publishes payload + sequence
+// number to the mailbox.
 template <int NS, typename Fin>
 __device__ __forceinline__ void publish_sums(unsigned long long (&s)[NS], const Mailbox &mb, Fin fin) {
     __shared__ unsigned long long sm[NS][THREADS / 32];
+    __shared__ unsigned long long s_tot[NS];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -59,10 +105,32 @@ __device__ __forceinline__ void publish_sums(unsigned long long (&s)[NS], const 
             for (int k = 0; k < NS; k++) tot[k] = atomicExch(&mb.acc[k], 0ull); // read + re-arm
             *mb.ticket = 0u;
             fin(tot);
+            if (mb.xchg == nullptr) {
 #pragma unroll
-            for (int k = 0; k < NS; k++) ((volatile unsigned long long *)mb.mail)[k] = tot[k];
-            __threadfence_system();
-            ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
+                for (int k = 0; k < NS; k++) ((volatile unsigned long long *)mb.mail)[k] = tot[k];
+                __threadfence_system();
+                ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
+            } else {
+#pragma unroll
+                for (int k = 0; k < NS; k++) s_tot[k] = tot[k];
+            }
+        }
+    }
+    if (mb.xchg != nullptr) { // uniform across the grid: every CTA takes the barrier, only the last one exchanges
+        __syncthreads();
+        if (is_last && warp == 0) {
+            unsigned long long tot[NS];
+#pragma unroll
+            for (int k = 0; k < NS; k++) tot[k] = s_tot[k];
+            const bool ok = xchg_allreduce<NS>(tot, mb.xchg, mb.xseq);
+            if (lane == 0) {
+                volatile unsigned long long *mail = (volatile unsigned long long *)mb.mail;
+#pragma unroll
+                for (int k = 0; k < NS; k++) mail[k] = tot[k];
+                mail[MAIL_WORDS - 1] = ok ? 0ull : 1ull; // status word: 1 = a peer never arrived
+                __threadfence_system();
+                mail[MAIL_WORDS] = mb.seq;
+            }
         }
     }
 }
@@ -666,7 +734,7 @@ void launch_eval_stage(const uint32_t *src, uint64_t n, int nvars, const EvalPoi
     uint64_t n_tiles = n >> nvars;
     uint64_t cap = (uint64_t)sm * 8;
     int grid = (int)(n_tiles < cap ? n_tiles : cap);
-    Mailbox m = mb ? *mb : Mailbox{nullptr, nullptr, nullptr, 0};
+    Mailbox m = mb ? *mb : Mailbox{nullptr, nullptr, nullptr, 0, nullptr, 0};
     k_eval_stage<<<grid, THREADS, 0, st>>>(src, n_tiles, nvars, pt, out, m, mb != nullptr);
 }
 

@@ -30,6 +30,14 @@ class Comm:
         box = [Context.comm_unique_id(path) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         ctx.comm_init(box[0], rank, world, path)
+        # NVLink peer exchange: every rank exports its exchange buffer (CUDA IPC), all ranks map all buffers
+        self.p2p = False
+        if os.environ.get("ZB_P2P", "1") != "0":
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.p2p_handle())
+            ctx.p2p_attach(handles)
+            dist.barrier()
+            self.p2p = True
 
     def prodcheck_prove(self, polys, consume: bool = False):
         return ProductSumcheckProver.prove(polys, consume=consume)
