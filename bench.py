@@ -384,7 +384,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=30, help="log2 of the per-GPU table length")
     ap.add_argument("--cpu-log2n", type=int, default=26)
-    ap.add_argument("--ref-log2n", type=int, default=24)
+    ap.add_argument("--ref-log2n", type=int, default=22)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
