@@ -40,12 +40,23 @@ __device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b) {
     return u >= P ? u - P : u;
 }
 
+// Lazy forms (fewer instructions in the HBM-bound kernels, which otherwise brush the issue limit under the power cap):
+//   sub_lazy  : a - b + P in [1, 2P) for canonical a, b (2P < 2^32)
+//   mont_mul_lazy : a*b*2^-32 mod P in [0, 2P), valid for a < 2^32 (lazy allowed) and b < P (canonical):
+//                   t = a*b < 2^32 P, m P < 2^32 P, so t + m P < 2^64 and the quotient is < 2P
+__host__ __device__ __forceinline__ uint32_t sub_lazy(uint32_t a, uint32_t b) { return a - b + P; }
+__device__ __forceinline__ uint32_t mont_mul_lazy(uint32_t a, uint32_t b) {
+    uint64_t t = (uint64_t)a * b;
+    uint32_t m = (uint32_t)t * P_NEG_INV;
+    return (uint32_t)((t + (uint64_t)m * P) >> 32);
+}
+
 // plain a*b mod P via two Montgomery steps is wasteful; for a one-off product use this
 __host__ __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) % P); }
 
 // linear interpolation lo + r*(hi - lo): the fold of multilinear.zig:166-173 with one modmul
 __device__ __forceinline__ uint32_t lerp(uint32_t lo, uint32_t hi, uint32_t r, uint32_t rp) {
-    return add(lo, mul_shoup(sub(hi, lo), r, rp));
+    return add(lo, mul_shoup(sub_lazy(hi, lo), r, rp)); // Shoup accepts any x < 2^32: no reduction of hi - lo needed
 }
 
 } // namespace bb

@@ -1,5 +1,6 @@
 #include "hostpack.hpp"
 
+#include <cstdlib>
 #include <immintrin.h>
 
 namespace zigz {
@@ -10,7 +11,11 @@ bool narrow_u64_to_u32(const uint64_t *src, uint32_t *dst, size_t n, uint64_t p)
 #if defined(__AVX2__)
     // 8 elements per step: two 256-bit loads, keep the low dwords, one 256-bit NON-TEMPORAL store (the staging buffer
     // is written once and read by the DMA engine: bypassing the cache saves the read-for-ownership traffic)
-    if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+    static const bool use_nt = [] {
+        const char *e = getenv("ZB_PACK_NT");
+        return !(e && *e == '0');
+    }();
+    if (use_nt && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
         const __m256i pick = _mm256_setr_epi32(0, 2, 4, 6, 0, 2, 4, 6);
         const __m256i pm1 = _mm256_set1_epi64x((long long)(p - 1));
         __m256i over = _mm256_setzero_si256();

@@ -148,17 +148,19 @@ __device__ __forceinline__ void accum_pair(const uint32_t (&lo)[D], const uint32
         s[0] += lo[0];
         s[1] += hi[0];
     } else if constexpr (D == 2) {
-        uint32_t d0 = bb::sub(hi[0], lo[0]), d1 = bb::sub(hi[1], lo[1]);
-        s[0] += bb::mont_mul(lo[0], lo[1]);
-        s[1] += bb::mont_mul(hi[0], hi[1]);
-        s[2] += bb::mont_mul(d0, d1);
+        // lazy Montgomery products (< 2P) go straight into the u64 accumulators: < 2^31 terms of < 2^32 cannot overflow
+        uint32_t d0 = bb::sub_lazy(hi[0], lo[0]), d1 = bb::sub(hi[1], lo[1]);
+        s[0] += bb::mont_mul_lazy(lo[0], lo[1]);
+        s[1] += bb::mont_mul_lazy(hi[0], hi[1]);
+        s[2] += bb::mont_mul_lazy(d0, d1);
     } else {
         uint32_t d0 = bb::sub(hi[0], lo[0]), d1 = bb::sub(hi[1], lo[1]), d2 = bb::sub(hi[2], lo[2]);
-        uint32_t m0 = bb::sub(lo[0], d0), m1 = bb::sub(lo[1], d1), m2 = bb::sub(lo[2], d2); // value at X = -1
-        s[0] += bb::mont_mul(bb::mont_mul(lo[0], lo[1]), lo[2]);
-        s[1] += bb::mont_mul(bb::mont_mul(hi[0], hi[1]), hi[2]);
-        s[2] += bb::mont_mul(bb::mont_mul(m0, m1), m2);
-        s[3] += bb::mont_mul(bb::mont_mul(d0, d1), d2);
+        // value at X = -1: lo - d; the first factor may stay lazy, the other two must be canonical (mont_mul_lazy)
+        uint32_t m0 = bb::sub_lazy(lo[0], d0), m1 = bb::sub(lo[1], d1), m2 = bb::sub(lo[2], d2);
+        s[0] += bb::mont_mul_lazy(bb::mont_mul_lazy(lo[0], lo[1]), lo[2]);
+        s[1] += bb::mont_mul_lazy(bb::mont_mul_lazy(hi[0], hi[1]), hi[2]);
+        s[2] += bb::mont_mul_lazy(bb::mont_mul_lazy(m0, m1), m2);
+        s[3] += bb::mont_mul_lazy(bb::mont_mul_lazy(d0, d1), d2);
     }
 }
 
