@@ -107,6 +107,29 @@ def test_batch_commit_43_witness_polynomials(zlib, ctx, po):
     assert not zlib.CommitmentScheme.batch_verify(coms[:-1], proofs)
 
 
+def test_config_c3_size_tree(zlib, ctx, po):
+    """BASELINE config C3: 2^26-entry witness polynomial. Openings verify on the host; the root equals the hash of the
+    roots of the two half-size trees (the identity subtree sharding relies on)."""
+    lg = 26
+    poly = zlib.Multilinear.synthetic(ctx, 0xBEEF, 1 << lg)
+    com, tree = zlib.CommitmentScheme.commit(poly)
+    rng = np.random.default_rng(2)
+    from _cases import splitmix64
+    for idx in [0, (1 << lg) - 1] + [int(x) for x in rng.integers(0, 1 << lg, size=6)]:
+        pr = tree.open(idx)
+        assert pr.value == splitmix64(0xBEEF + idx) % BB and len(pr.path.siblings) == lg
+        assert zlib.SimpleMerkleTree.verify(com.commitment, pr)
+    tree.deinit()
+    lo = zlib.Multilinear.synthetic(ctx, 0xBEEF, 1 << (lg - 1))
+    hi = zlib.Multilinear.synthetic(ctx, 0xBEEF, 1 << (lg - 1), start=1 << (lg - 1))
+    (clo, chi), trees = zlib.CommitmentScheme.batch_commit([lo, hi])
+    assert zlib.sha3_256(clo.commitment + chi.commitment) == com.commitment
+    for t in trees:
+        t.deinit()
+    for m in (poly, lo, hi):
+        m.deinit()
+
+
 def test_full_size_tree_properties(zlib, ctx, po):
     """2^22 leaves: every opened path must verify against the root with the HOST verifier, leaf digests must equal
     SHA3(le64(value)), and the root must equal the root of the two half-trees hashed together (subtree sharding)."""

@@ -379,7 +379,7 @@ int upload_threads(zb_ctx *ctx) {
     return t > 16 ? 16 : (t < 1 ? 1 : t);
 }
 
-int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32_t *dst) {
+int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32_t *dst, bool pinned) {
     if (!ctx->pool) ctx->pool.reset(new zigz::HostPool(upload_threads(ctx)));
     if (!ctx->pack_buf[0]) {
         for (int b = 0; b < PACK_BUFS; b++) {
@@ -387,11 +387,34 @@ int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32
             CK(cudaEventCreateWithFlags(&ctx->pack_done[b], cudaEventDisableTiming));
         }
     }
+    // Hybrid: the pack threads are the bottleneck (~70-80 GB/s of source on 16 cores) while PCIe still has headroom at
+    // 4 bytes per element, so every `raw_every`-th chunk of a PINNED source skips the CPU: it is copied as 8-byte words
+    // by the DMA engine while the threads pack the following chunks, and narrowed by a kernel (k_narrow).
+    static const int raw_every_cfg = [] {
+        const char *e = getenv("ZB_UPLOAD_RAW_EVERY");
+        return e && *e ? atoi(e) : 6;
+    }();
+    const int raw_every = pinned ? raw_every_cfg : 0;
+    BufRef raw_stage;
+    if (raw_every > 0 && n > PACK_CHUNK * (uint64_t)raw_every) {
+        int32_t rc = dev_alloc(ctx, PACK_CHUNK * sizeof(uint64_t), &raw_stage);
+        if (rc) return rc;
+    }
     const int T = ctx->pool->size();
     std::vector<char> bad(T, 0);
     int buf = 0;
-    for (uint64_t off = 0; off < n; off += PACK_CHUNK, buf = (buf + 1) % PACK_BUFS) {
+    uint64_t chunk_idx = 0;
+    for (uint64_t off = 0; off < n; off += PACK_CHUNK, chunk_idx++) {
         const uint64_t m = n - off < PACK_CHUNK ? n - off : PACK_CHUNK;
+        if (raw_stage && (chunk_idx % raw_every) == (uint64_t)(raw_every - 1)) {
+            CK(cudaMemcpyAsync(raw_stage->ptr, host + off, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+            {
+                ProfScope _ps(ctx, "narrow_u64", m * 12);
+                launch_narrow_u64((const uint64_t *)raw_stage->ptr, dst + off, m, ctx->d_err, ctx->stream);
+            }
+            LAUNCHED("narrow");
+            continue;
+        }
         CK(cudaEventSynchronize(ctx->pack_done[buf])); // the copy that last used this staging buffer has finished
         uint32_t *stage = ctx->pack_buf[buf];
         const uint64_t *src = host + off;
@@ -402,8 +425,11 @@ int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32
         });
         CK(cudaMemcpyAsync(dst + off, stage, m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaEventRecord(ctx->pack_done[buf], ctx->stream));
+        buf = (buf + 1) % PACK_BUFS;
     }
+    int32_t rc = raw_stage ? read_err_flag(ctx) : ZB_OK; // also drains the stream
     CK(cudaStreamSynchronize(ctx->stream));
+    if (rc) return rc;
     for (char b : bad)
         if (b) return ZB_ERR_NOT_CANONICAL;
     return ZB_OK;
@@ -414,7 +440,12 @@ int32_t upload_narrow(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32_t *d
         const char *e = getenv("ZB_UPLOAD_MODE"); // "host" | "device"
         return e && !strcmp(e, "device") ? 0 : (e && !strcmp(e, "host") ? 1 : -1);
     }();
-    if (mode == 1) return upload_narrow_host(ctx, host, n, dst);
+    if (mode == 1) {
+        cudaPointerAttributes attr{};
+        const bool pinned = cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        return upload_narrow_host(ctx, host, n, dst, pinned);
+    }
     if (mode == -1 && n >= (1u << 16)) {
         // measured on the pool's hosts (tools/upload_bench.py, profiles/r01_upload_modes.txt): packing on the host beats
         // the direct 8-byte copy from PINNED memory only with >= ~12 threads per GPU (70.7 vs 54.5 GB/s at 16), but beats
@@ -423,7 +454,7 @@ int32_t upload_narrow(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32_t *d
         const bool pinned = cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
         cudaGetLastError();
         const int t = upload_threads(ctx);
-        if ((pinned && t >= 12) || (!pinned && t >= 3)) return upload_narrow_host(ctx, host, n, dst);
+        if ((pinned && t >= 12) || (!pinned && t >= 3)) return upload_narrow_host(ctx, host, n, dst, pinned);
     }
     uint64_t chunk = n < STAGE_ELEMS ? n : STAGE_ELEMS;
     BufRef stage;
