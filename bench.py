@@ -203,8 +203,19 @@ def run_ours(args):
     dom_name, (dom_cnt, dom_ms, dom_bytes) = dom
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else 0.0
     kernel_ms = sum(v[1] for v in prof.values())
+    # DRAM traffic of the dominant kernel: ncu's dram bytes / algorithmic bytes of the committed capture of this very
+    # configuration (profiles/r01_traffic.json), applied to this run's per-launch algorithmic bytes
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if dom_name == "fold_sums_d3" and dom_cnt:
+            traffic = tj["k_fold_sums_v4<3,1>"]["ratio"] * dom_bytes / dom_cnt
+            traffic_src = "ncu dram__bytes_read+write / algorithmic = %.4f (profiles/r01_traffic.json) x this run's algorithmic bytes per launch" % tj["k_fold_sums_v4<3,1>"]["ratio"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": dom_bytes / dom_cnt if dom_cnt else None, "peak_source": peak_src,
                 "launches": dom_cnt, "avg_launch_ms": dom_ms / dom_cnt if dom_cnt else None,
                 "algorithmic_bytes_per_step": dom_bytes // max(args.steps, 1),
                 "kernel_share_of_step": dom_ms / ms if ms else None, "all_kernels_share_of_step": kernel_ms / ms if ms else None,

@@ -188,3 +188,18 @@ def test_headline_size_properties(zlib, ctx, po):
     assert pr2.round_polynomials.tolist() == pr.round_polynomials.tolist() and pr2.final_evals == pr.final_evals
     for p in polys:
         p.deinit()
+
+
+def test_tail_kernel_starvation_falls_back_to_launches(zlib, po):
+    """If the persistent kernel gives up waiting for its first challenge (a profiler serialising launches, a stalled
+    host thread) the round is redone with a plain launch, the context stops using the tail kernel, results unchanged."""
+    with zlib.Context(0) as c2:
+        assert c2.get_option("tail_log2") == 14
+        e = po.fill_synthetic(BB, 4242, 0, 1 << 12)
+        poly = zlib.Multilinear.init(c2, e)
+        want = po.sumcheck_prove(BB, e)
+        c2.set_option("tail_test_starve", 1)
+        pr = zlib.SumcheckProver.prove(poly)
+        assert pr.to_bytes() == want.to_bytes()
+        assert c2.get_option("tail_log2") == 0  # disabled after the starvation exit
+        assert zlib.SumcheckProver.prove(poly).to_bytes() == want.to_bytes()

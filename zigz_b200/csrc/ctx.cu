@@ -100,6 +100,7 @@ struct zb_ctx {
         zb_mle h[3] = {0, 0, 0};
         uint64_t n = 0;
     } tail;
+    bool tail_test_starve = false;
     int tail_log2 = 14; // tables of <= 2^tail_log2 entries finish inside the persistent kernel (0 = never)
     void *scratch = nullptr; // zb_host_scratch
     size_t scratch_bytes = 0;
@@ -590,6 +591,10 @@ int32_t zb_set_option(zb_ctx *ctx, const char *key, int64_t value) {
     if (key && !strcmp(key, "tail_log2")) {
         if (value < 0 || value > 20) return ZB_ERR_BAD_ARGUMENT;
         ctx->tail_log2 = (int)value;
+        return ZB_OK;
+    }
+    if (key && !strcmp(key, "tail_test_starve")) {
+        ctx->tail_test_starve = value != 0;
         return ZB_OK;
     }
     if (key && !strcmp(key, "comm_reduce")) {
@@ -1097,16 +1102,52 @@ static int32_t fold_inplace_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, u
         ctx->tail.n = n;
         for (uint32_t k = 0; k < d; k++) ctx->tail.h[k] = polys[k];
     }
+    bool served = false;
     if (ctx->tail.active) {
-        __atomic_store_n(ctx->h_chal, ((unsigned long long)(++ctx->chal_seq) << 32) | (unsigned long long)r, __ATOMIC_RELEASE);
-        rc = wait_mail(ctx, mb.seq);
-        if (rc) {
-            tail_quiesce(ctx);
-            return rc;
+        if (ctx->tail_test_starve) { // test hook ("tail_test_starve" option): delay the first challenge past the kernel's patience
+            std::this_thread::sleep_for(std::chrono::milliseconds(400));
+            ctx->tail_test_starve = false;
         }
-        ctx->tail.n = n / 2;
-        if (n == 2) ctx->tail.active = false; // the kernel returns after the last round
-    } else {
+        __atomic_store_n(ctx->h_chal, ((unsigned long long)(++ctx->chal_seq) << 32) | (unsigned long long)r, __ATOMIC_RELEASE);
+        // wait for the round's mailbox sequence; if the kernel has left instead (starvation exit: the launch was
+        // serialised by a profiler, or the host thread lost the CPU for too long) the tables are untouched for this
+        // round: fall back to one launch per round and stop using the persistent kernel on this context
+        volatile unsigned long long *flag = ctx->h_mail + MAIL_WORDS;
+        auto t0 = std::chrono::steady_clock::now();
+        uint64_t spins = 0;
+        bool gone = false;
+        while (*flag != mb.seq) {
+            if ((++spins & 0x3FFF) == 0) {
+                cudaError_t q = cudaStreamQuery(ctx->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(ctx, q, "tail kernel");
+                if (q == cudaSuccess) {
+                    // drained: give the mapped write 2 ms to land, then decide
+                    auto t1 = std::chrono::steady_clock::now();
+                    while (*flag != mb.seq && std::chrono::steady_clock::now() - t1 < std::chrono::milliseconds(2)) {
+                    }
+                    if (*flag != mb.seq) gone = true;
+                    break;
+                }
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
+                    tail_quiesce(ctx);
+                    ctx->last_error = "timeout waiting for the tail kernel";
+                    return ZB_ERR_TIMEOUT;
+                }
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if (!gone) {
+            served = true;
+            ctx->tail.n = n / 2;
+            if (n == 2) ctx->tail.active = false; // the kernel returns after the last round
+        } else {
+            ctx->tail.active = false;
+            ctx->tail_log2 = 0;
+            cudaMemsetAsync(ctx->d_tail_status, 0, sizeof(unsigned int), ctx->stream);
+            mb = ctx->mailbox(); // fresh sequence number for the relaunch below
+        }
+    }
+    if (!served) {
         {
             ProfScope _ps(ctx, name, n * 6 * d);
             launch_fold_sums((int)d, ps, n, (uint32_t)r, mb, ctx->sm_count, ctx->stream);
