@@ -53,6 +53,17 @@ def test_reference_unit_test_facts(zlib, ctx):  # src/commitments/merkle_tree.zi
     assert e.value.name == "IndexOutOfBounds"  # :325 (index >= values.len, NOT the padded size)
 
 
+def test_pointer_variant_alias(zlib, ctx, po):  # merkle_tree.zig:78-264: same padding, same root; open is NotImplemented
+    for n in (1, 4, 5, 100):
+        vals = synthetic(n + 9, n)
+        t = zlib.MerkleTree.build(ctx, vals)
+        assert t.root_hash() == po.merkle_build(vals).root
+        pr = zlib.SimpleMerkleTree.build(ctx, vals).open(n - 1)
+        assert zlib.MerkleTree.verify(t.root_hash(), pr)
+        with pytest.raises(zlib.ZigzError):
+            t.open(0)
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 100, 1023, 1024, 1025, 2048, 5000, 1 << 14])
 def test_build_and_open_vs_oracle(zlib, ctx, po, n):
     vals = synthetic(n, n)

@@ -461,6 +461,24 @@ class SimpleMerkleTree:
             self._h = 0
 
 
+class MerkleTree(SimpleMerkleTree):
+    """src/commitments/merkle_tree.zig:78-264 — the pointer-based variant. It pads to a power of two with hash(0) and
+    splits at the middle recursively (:87-110, :187-215), which yields exactly SimpleMerkleTree's root; its `open` is
+    unusable in the reference (`getValueAtIndex` -> error.NotImplemented, :237-243), so only build / root_hash / verify
+    are offered, aliased onto the same device tree."""
+
+    @classmethod
+    def build(cls, ctx: Context, values) -> "MerkleTree":
+        t = SimpleMerkleTree.build(ctx, values)
+        return cls(t.ctx, t.handle, t.get_root())
+
+    def root_hash(self) -> bytes:  # :113-115
+        return self.get_root()
+
+    def open(self, index: int):  # :118-150 -> getValueAtIndex :237-243
+        raise ZigzError(-22, "MerkleTree.open is error.NotImplemented in the reference; use SimpleMerkleTree")
+
+
 @dataclass
 class PolynomialCommitment:
     """src/commitments/polynomial_commit.zig:24-39"""

@@ -550,8 +550,8 @@ static void fold_sums_t(const PolySet &ps, uint64_t n, uint32_t r, const Mailbox
     }
     uint64_t q = n / 4;
     if (q % 4 == 0) {
-        static const int U = tune("ZB_FOLD_U", D == 3 ? 1 : 2);
-        static const int CPS = tune("ZB_FOLD_CPS", D == 3 ? 8 : 4);
+        static const int U = tune("ZB_FOLD_U", D == 1 ? 4 : D == 2 ? 2 : 1);
+        static const int CPS = tune("ZB_FOLD_CPS", 8);
         const uint64_t q4 = q / 4;
         if (U >= 4 && D == 1)
             k_fold_sums_v4<D, (D == 1 ? 4 : 1)><<<grid_for((q4 + 3) / 4, sm, CPS), THREADS, 0, st>>>(ps, q4, r, rp, mb);
