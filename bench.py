@@ -354,6 +354,25 @@ def run_extras(args, z, ctx, peak):
                                          "open_ms": open_ms}
     trees.pop().deinit()
     pm.deinit()
+    # C4 (the device part of `zigz prove`): 43 witness polynomials of 2^20 steps: pack from SoA trace columns, then
+    # Prover.generateCommitments (batched 43-tree commit, transcript interleave, 43 evaluations + openings)
+    lgw = min(20, args.log2n)
+    rngw = np.random.default_rng(2)
+    cols = rngw.integers(0, 1 << 63, size=(43, (1 << lgw) - 7), dtype=np.uint64)
+    for m in z.witness_pack(ctx, cols):  # warm-up (allocator cache, staging buffers)
+        m.deinit()
+    t0 = time.perf_counter()
+    wpolys = z.witness_pack(ctx, cols)
+    pack_ms = (time.perf_counter() - t0) * 1e3
+    z.generate_commitments(z.FiatShamirTranscript(), wpolys)  # warm-up
+    t0 = time.perf_counter()
+    z.generate_commitments(z.FiatShamirTranscript(), wpolys)
+    gc_ms = (time.perf_counter() - t0) * 1e3
+    out[f"C4_witness_43x2^{lgw}"] = {"witness_pack_ms": pack_ms, "generate_commitments_ms": gc_ms,
+                                      "keccak_per_s": 43 * (2 * (1 << lgw) - 1) / (gc_ms * 1e-3),
+                                      "note": "pack = H2D of 43 u64 columns + k_witness_pack; commitments = one batched build + 43 x (eval + open)"}
+    for m in wpolys:
+        m.deinit()
     # C2: Lasso over the 8-bit ADD/AND/XOR subtables, 2^22 lookups each (host rows -> proof)
     lgq = min(22, args.log2n)
     rng = np.random.default_rng(1)

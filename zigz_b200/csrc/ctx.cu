@@ -108,6 +108,7 @@ struct zb_ctx {
     std::unique_ptr<zigz::HostPool> pool;
     uint32_t *pack_buf[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pack_done[3] = {nullptr, nullptr, nullptr};
+    int pack_next = 0;
     // multi-GPU
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
@@ -380,13 +381,54 @@ int upload_threads(zb_ctx *ctx) {
     return t > 16 ? 16 : (t < 1 ? 1 : t);
 }
 
-int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32_t *dst, bool pinned) {
+int32_t ensure_pack(zb_ctx *ctx) {
     if (!ctx->pool) ctx->pool.reset(new zigz::HostPool(upload_threads(ctx)));
     if (!ctx->pack_buf[0]) {
         for (int b = 0; b < PACK_BUFS; b++) {
             CK(cudaHostAlloc((void **)&ctx->pack_buf[b], PACK_CHUNK * sizeof(uint32_t), cudaHostAllocDefault));
             CK(cudaEventCreateWithFlags(&ctx->pack_done[b], cudaEventDisableTiming));
         }
+    }
+    return ZB_OK;
+}
+
+// Plain H2D copy of `bytes` bytes that does not depend on the source being page-locked: pageable sources are copied by
+// the pool threads into the rotating pinned staging buffers while the previous piece is in flight (the driver's own
+// pageable path manages ~11 GB/s on these hosts), pinned sources go straight to the DMA engine.
+int32_t staged_h2d(zb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, h_src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned || bytes < (1u << 20)) {
+        CK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return ZB_OK;
+    }
+    int32_t rc = ensure_pack(ctx);
+    if (rc) return rc;
+    const size_t piece = PACK_CHUNK * sizeof(uint32_t);
+    const int T = ctx->pool->size();
+    for (size_t off = 0; off < bytes; off += piece) {
+        const size_t m = bytes - off < piece ? bytes - off : piece;
+        const int buf = ctx->pack_next;
+        ctx->pack_next = (ctx->pack_next + 1) % PACK_BUFS;
+        CK(cudaEventSynchronize(ctx->pack_done[buf]));
+        char *stage = (char *)ctx->pack_buf[buf];
+        const char *src = (const char *)h_src + off;
+        ctx->pool->run([&](int tid) {
+            const size_t per = ((m + T - 1) / T + 63) & ~(size_t)63;
+            const size_t lo = per * tid < m ? per * tid : m, hi = lo + per < m ? lo + per : m;
+            if (hi > lo) memcpy(stage + lo, src + lo, hi - lo);
+        });
+        CK(cudaMemcpyAsync((char *)d_dst + off, stage, m, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->pack_done[buf], ctx->stream));
+    }
+    return ZB_OK;
+}
+
+int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32_t *dst, bool pinned) {
+    {
+        int32_t rc0 = ensure_pack(ctx);
+        if (rc0) return rc0;
     }
     // Hybrid: the pack threads are the bottleneck (~70-80 GB/s of source on 16 cores) while PCIe still has headroom at
     // 4 bytes per element, so every `raw_every`-th chunk of a PINNED source skips the CPU: it is copied as 8-byte words
@@ -403,7 +445,7 @@ int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32
     }
     const int T = ctx->pool->size();
     std::vector<char> bad(T, 0);
-    int buf = 0;
+    int buf = ctx->pack_next;
     uint64_t chunk_idx = 0;
     for (uint64_t off = 0; off < n; off += PACK_CHUNK, chunk_idx++) {
         const uint64_t m = n - off < PACK_CHUNK ? n - off : PACK_CHUNK;
@@ -428,6 +470,7 @@ int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32
         CK(cudaEventRecord(ctx->pack_done[buf], ctx->stream));
         buf = (buf + 1) % PACK_BUFS;
     }
+    ctx->pack_next = buf;
     int32_t rc = raw_stage ? read_err_flag(ctx) : ZB_OK; // also drains the stream
     CK(cudaStreamSynchronize(ctx->stream));
     if (rc) return rc;
@@ -711,7 +754,12 @@ int32_t zb_mle_upload_u32(zb_ctx *ctx, const uint32_t *evals, uint64_t n, zb_mle
     Mle *m = nullptr;
     rc = new_mle(ctx, n, out, &m);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(m->d(), evals, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    rc = staged_h2d(ctx, m->d(), evals, n * sizeof(uint32_t));
+    if (rc) {
+        ctx->mles.erase(*out);
+        *out = 0;
+        return rc;
+    }
     {
         ProfScope _ps(ctx, "check_u32", n * 4);
         launch_check_u32(m->d(), n, ctx->d_err, ctx->stream);
@@ -1485,9 +1533,10 @@ int32_t zb_witness_pack(zb_ctx *ctx, const uint64_t *cols, uint64_t num_steps, u
     if (rc) return fail(rc);
     for (uint64_t step0 = 0; step0 < padded; step0 += chunk) {
         const uint64_t real = step0 < num_steps ? (num_steps - step0 < chunk ? num_steps - step0 : chunk) : 0;
-        for (uint32_t c = 0; c < n_cols && real; c++)
-            CK(cudaMemcpyAsync((uint64_t *)stage->ptr + (size_t)c * chunk, cols + (size_t)c * num_steps + step0, real * sizeof(uint64_t),
-                               cudaMemcpyHostToDevice, ctx->stream));
+        for (uint32_t c = 0; c < n_cols && real; c++) {
+            rc = staged_h2d(ctx, (uint64_t *)stage->ptr + (size_t)c * chunk, cols + (size_t)c * num_steps + step0, real * sizeof(uint64_t));
+            if (rc) return fail(rc);
+        }
         {
             ProfScope _ps(ctx, "witness_pack", (uint64_t)n_cols * (real * 8 + chunk * 4));
             launch_witness_pack((const uint64_t *)stage->ptr, chunk, step0, num_steps, padded, n_cols, n_hold,
