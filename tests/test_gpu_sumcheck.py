@@ -120,11 +120,14 @@ def test_full_size_properties(zlib, ctx, po, d, lg):
 
 
 # ---------------------------------------------------------------- persistent tail kernel (zb_set_option "tail_log2")
+@pytest.mark.parametrize("prelaunch", [1, 0])
 @pytest.mark.parametrize("tail_log2", [0, 2, 3, 10, 14, 20])
-def test_tail_kernel_settings_give_identical_proofs(zlib, ctx, po, tail_log2):
-    old = ctx.get_option("tail_log2")
+def test_tail_kernel_settings_give_identical_proofs(zlib, ctx, po, tail_log2, prelaunch):
+    """Persistent tail kernel on/off at several thresholds x pre-launched fold kernels on/off: same proofs."""
+    old, oldp = ctx.get_option("tail_log2"), ctx.get_option("prelaunch")
     try:
         ctx.set_option("tail_log2", tail_log2)
+        ctx.set_option("prelaunch", prelaunch)
         for d, lg in ((1, 1), (1, 2), (1, 9), (1, 16), (3, 2), (3, 11), (2, 13), (3, 17)):
             es = [po.fill_synthetic(BB, 900 + k, 0, 1 << lg) for k in range(d)]
             polys = [zlib.Multilinear.init(ctx, e) for e in es]
@@ -135,6 +138,8 @@ def test_tail_kernel_settings_give_identical_proofs(zlib, ctx, po, tail_log2):
                 assert pr.final_evals == want.final_evals and pr.final_point.tolist() == want.final_point.tolist()
     finally:
         ctx.set_option("tail_log2", old)
+        ctx.set_option("prelaunch", oldp)
+    assert ctx.get_option("starved") == 0  # no polling kernel ever left without its challenge
 
 
 def test_tail_session_survives_interleaved_calls(zlib, ctx, po):
@@ -195,11 +200,19 @@ def test_tail_kernel_starvation_falls_back_to_launches(zlib, po):
     host thread) the round is redone with a plain launch, the context stops using the tail kernel, results unchanged."""
     with zlib.Context(0) as c2:
         assert c2.get_option("tail_log2") == 14
-        e = po.fill_synthetic(BB, 4242, 0, 1 << 12)
-        poly = zlib.Multilinear.init(c2, e)
-        want = po.sumcheck_prove(BB, e)
+        c2.set_option("prelaunch", 1)
+        for lg in (12, 18):  # 2^12: the tail kernel starves; 2^18: a pre-launched fold kernel starves
+            e = po.fill_synthetic(BB, 4242, 0, 1 << lg)
+            poly = zlib.Multilinear.init(c2, e)
+            want = po.sumcheck_prove(BB, e)
+            before = c2.get_option("starved")
+            c2.set_option("tail_test_starve", 1)
+            assert zlib.SumcheckProver.prove(poly).to_bytes() == want.to_bytes()
+            assert c2.get_option("starved") == before + 1
+            assert c2.get_option("tail_log2") == 14  # a single hiccup does not switch the mechanism off
+            assert zlib.SumcheckProver.prove(poly).to_bytes() == want.to_bytes()
+        c2.set_option("starved", 2)
         c2.set_option("tail_test_starve", 1)
-        pr = zlib.SumcheckProver.prove(poly)
-        assert pr.to_bytes() == want.to_bytes()
-        assert c2.get_option("tail_log2") == 0  # disabled after the starvation exit
+        assert zlib.SumcheckProver.prove(poly).to_bytes() == want.to_bytes()
+        assert c2.get_option("tail_log2") == 0 and c2.get_option("prelaunch") == 0  # third time: switched off
         assert zlib.SumcheckProver.prove(poly).to_bytes() == want.to_bytes()

@@ -101,6 +101,22 @@ struct zb_ctx {
         uint64_t n = 0;
     } tail;
     bool tail_test_starve = false;
+    // pre-launched fold kernel (ChalSrc): queued behind the current round's kernel, waiting for its challenge
+    struct Pre {
+        bool active = false;
+        uint32_t d = 0;
+        zb_mle h[3] = {0, 0, 0};
+        uint64_t n = 0;
+        unsigned int tag = 0;
+        Mailbox mb{};
+        bool red = false;
+    } pre;
+    // default off: measured neutral on one GPU (8.3533 vs 8.3537 ms per 2^30 prove, profiles/r01_prelaunch.txt) — the
+    // PCIe poll of the challenge costs what the launch it replaces cost. Kept (tested) as an option: ZB_PRELAUNCH=1.
+    bool prelaunch = false;
+    int starved = 0; // polling kernels that left without their challenge
+    unsigned long long *d_bcast = nullptr; // device word the polling CTA republishes the challenge in
+    unsigned int *d_claim = nullptr;
     int tail_log2 = 14; // tables of <= 2^tail_log2 entries finish inside the persistent kernel (0 = never)
     void *scratch = nullptr; // zb_host_scratch
     size_t scratch_bytes = 0;
@@ -323,10 +339,14 @@ struct ProfScope {
 // Ends a running persistent tail kernel (abort tag) so that other work can use the stream. The tables stay
 // consistent: every round it completed was written back in place and the handle lengths were updated per round.
 void tail_quiesce(zb_ctx *c) {
-    if (!c->tail.active) return;
+    if (!c->tail.active && !c->pre.active) return;
     __atomic_store_n(c->h_chal, (unsigned long long)0xFFFFFFFFu << 32, __ATOMIC_RELEASE);
     cudaStreamSynchronize(c->stream);
+    __atomic_store_n(c->h_chal, 0ull, __ATOMIC_RELEASE); // tag 0 is never issued: the next polling kernel must not see the abort
     c->tail.active = false;
+    c->pre.active = false; // a pre-launched kernel leaves without touching the tables or the exchange counters ...
+    if (c->pre.red && c->pre.mb.xchg) c->xchg_seq--; // ... so its exchange round number is handed back
+    c->pre.red = false;
 }
 
 Mle *get_mle(zb_ctx *ctx, zb_mle h) {
@@ -583,6 +603,10 @@ int32_t zb_ctx_create(int32_t device, zb_ctx **out) {
     if ((e = cudaMalloc(&ctx->d_tail_status, sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
     cudaMemsetAsync(ctx->d_tail_status, 0, sizeof(unsigned int), ctx->stream);
     if (const char *t = getenv("ZB_TAIL_LOG2")) ctx->tail_log2 = atoi(t);
+    if (const char *t = getenv("ZB_PRELAUNCH")) ctx->prelaunch = atoi(t) != 0;
+    if ((e = cudaMalloc(&ctx->d_bcast, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
+    ctx->d_claim = (unsigned int *)(ctx->d_bcast + 1);
+    cudaMemsetAsync(ctx->d_bcast, 0, 2 * sizeof(unsigned long long), ctx->stream);
     cudaMemsetAsync(ctx->d_acc, 0, MAIL_WORDS * sizeof(unsigned long long), ctx->stream);
     cudaMemsetAsync(ctx->d_ticket, 0, 2 * sizeof(unsigned int), ctx->stream);
     keccak_init_constants();
@@ -608,6 +632,7 @@ void zb_ctx_destroy(zb_ctx *ctx) {
     cudaFree(ctx->d_acc);
     cudaFree(ctx->d_ticket);
     cudaFree(ctx->d_tail_status);
+    cudaFree(ctx->d_bcast);
     if (ctx->scratch) cudaFreeHost(ctx->scratch);
     for (int b = 0; b < 3; b++) {
         if (ctx->pack_buf[b]) cudaFreeHost(ctx->pack_buf[b]);
@@ -636,8 +661,16 @@ int32_t zb_set_option(zb_ctx *ctx, const char *key, int64_t value) {
         ctx->tail_log2 = (int)value;
         return ZB_OK;
     }
+    if (key && !strcmp(key, "prelaunch")) {
+        ctx->prelaunch = value != 0;
+        return ZB_OK;
+    }
     if (key && !strcmp(key, "tail_test_starve")) {
         ctx->tail_test_starve = value != 0;
+        return ZB_OK;
+    }
+    if (key && !strcmp(key, "starved")) {
+        ctx->starved = (int)value;
         return ZB_OK;
     }
     if (key && !strcmp(key, "comm_reduce")) {
@@ -655,6 +688,14 @@ int32_t zb_get_option(zb_ctx *ctx, const char *key, int64_t *value) {
     }
     if (key && value && !strcmp(key, "comm_reduce")) {
         *value = ctx->comm_reduce;
+        return ZB_OK;
+    }
+    if (key && value && !strcmp(key, "prelaunch")) {
+        *value = ctx->prelaunch ? 1 : 0;
+        return ZB_OK;
+    }
+    if (key && value && !strcmp(key, "starved")) {
+        *value = ctx->starved;
         return ZB_OK;
     }
     if (key && value && !strcmp(key, "p2p_attached")) {
@@ -1112,21 +1153,120 @@ int32_t zb_prod_round_coeffs(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint6
     return ZB_OK;
 }
 
+// Waits for mailbox sequence `seq` of a kernel that polls the host for its challenge (tail session or pre-launched
+// fold). *gone = true when the kernel has left instead (starvation exit: launches serialised by a profiler, or the host
+// thread lost the CPU): the tables are untouched for this round and the caller redoes it with a plain launch.
+static int32_t wait_polling_kernel(zb_ctx *ctx, unsigned long long seq, bool *gone) {
+    volatile unsigned long long *flag = ctx->h_mail + MAIL_WORDS;
+    auto t0 = std::chrono::steady_clock::now();
+    uint64_t spins = 0;
+    *gone = false;
+    while (*flag != seq) {
+        if ((++spins & 0x3FFF) == 0) {
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(ctx, q, "polling kernel");
+            if (q == cudaSuccess) { // drained: give the mapped write 2 ms to land, then decide
+                auto t1 = std::chrono::steady_clock::now();
+                while (*flag != seq && std::chrono::steady_clock::now() - t1 < std::chrono::milliseconds(2)) {
+                }
+                if (*flag != seq) *gone = true;
+                break;
+            }
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
+                tail_quiesce(ctx);
+                ctx->last_error = "timeout waiting for a polling kernel";
+                return ZB_ERR_TIMEOUT;
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (!*gone && ctx->comm_reduce == 2 && ctx->d_xchg_view && ctx->h_mail[MAIL_WORDS - 1] == 1ull) {
+        ctx->h_mail[MAIL_WORDS - 1] = 0;
+        ctx->last_error = "peer exchange: a rank never arrived";
+        return ZB_ERR_TIMEOUT;
+    }
+    return ZB_OK;
+}
+
+static void feed_challenge(zb_ctx *ctx, unsigned int tag, uint64_t r) {
+    if (ctx->tail_test_starve) { // test hook: delay the challenge past the polling kernel's patience
+        std::this_thread::sleep_for(std::chrono::milliseconds(400));
+        ctx->tail_test_starve = false;
+    }
+    __atomic_store_n(ctx->h_chal, ((unsigned long long)tag << 32) | (unsigned long long)r, __ATOMIC_RELEASE);
+}
+
+// After the kernel of the current round (tables of length n_now -> n_now / 2) has been enqueued: put the NEXT round's
+// kernel behind it right away, so that its launch latency overlaps the current kernel and the host's transcript work.
+// Small next tables start the persistent tail session early, big ones get a polling fold kernel (ChalSrc).
+static int32_t prelaunch_next(zb_ctx *ctx, const zb_mle *polys, uint32_t d, Mle **ms, uint64_t n_next) {
+    if (!ctx->prelaunch || ctx->tail.active || ctx->pre.active || n_next < 4) return ZB_OK;
+    const bool red = reduce_on_device(ctx) && n_next > 2;
+    if (red && !reduce_p2p(ctx)) return ZB_OK; // the NCCL exchange enqueues its own work between rounds
+    PolySet ps{};
+    for (uint32_t k = 0; k < d; k++) {
+        ps.src[k] = ms[k]->d();
+        ps.dst[k] = ms[k]->d();
+    }
+    if (!red && ctx->tail_log2 > 0 && n_next <= (1ull << ctx->tail_log2)) {
+        if (ctx->chal_seq > 0xF0000000u) ctx->chal_seq = 0;
+        Mailbox mb = ctx->mailbox();
+        ctx->seq--; // the session's first round takes the number the next mailbox() call hands out
+        mb.seq = ctx->seq + 1;
+        {
+            ProfScope _ps(ctx, d == 1 ? "tail_rounds_d1" : d == 2 ? "tail_rounds_d2" : "tail_rounds_d3", 0);
+            launch_tail_rounds((int)d, ps, n_next, mb, ctx->d_chal, ctx->chal_seq + 1, ctx->d_tail_status, ctx->stream);
+        }
+        int32_t rc = check_launch(ctx, "tail_rounds");
+        if (rc) return rc;
+        ctx->tail.active = true;
+        ctx->tail.d = d;
+        ctx->tail.n = n_next;
+        for (uint32_t k = 0; k < d; k++) ctx->tail.h[k] = polys[k];
+        return ZB_OK;
+    }
+    if (!fold_sums_is_vector(n_next)) return ZB_OK;
+    if (ctx->chal_seq > 0xF0000000u) ctx->chal_seq = 0;
+    ctx->pre.mb = round_mailbox(ctx, red);
+    ctx->pre.tag = ++ctx->chal_seq;
+    ctx->pre.red = red;
+    ChalSrc cs{ctx->d_chal, ctx->d_bcast, ctx->d_claim, ctx->pre.tag};
+    {
+        ProfScope _ps(ctx, d == 1 ? "fold_sums_d1" : d == 2 ? "fold_sums_d2" : "fold_sums_d3", n_next * 6 * d);
+        launch_fold_sums((int)d, ps, n_next, 0, ctx->pre.mb, ctx->sm_count, ctx->stream, &cs);
+    }
+    int32_t rc = check_launch(ctx, "fold_sums(pre)");
+    if (rc) return rc;
+    ctx->pre.active = true;
+    ctx->pre.d = d;
+    ctx->pre.n = n_next;
+    for (uint32_t k = 0; k < d; k++) ctx->pre.h[k] = polys[k];
+    return ZB_OK;
+}
+
 // One in-place fold round of d polynomials with challenge r; payload = the kernel's raw mailbox words
 // (round evaluations of the folded tables, or the d final evaluations when the tables had 2 entries).
-// Small tables go through the persistent tail session, everything else through one launch per round.
+// Small tables go through the persistent tail session, everything else through one kernel per round — launched here,
+// or already waiting on the device if the previous round pre-launched it.
 static int32_t fold_inplace_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, unsigned long long payload[4],
                                  bool *was_last) {
     if (d < 1 || d > (uint32_t)MAX_POLYS || !polys) return ZB_ERR_BAD_ARGUMENT;
-    bool same = ctx->tail.active && ctx->tail.d == d;
-    for (uint32_t k = 0; same && k < d; k++) same = (ctx->tail.h[k] == polys[k]);
-    if (!same) tail_quiesce(ctx);
+    bool in_tail = ctx->tail.active && ctx->tail.d == d, in_pre = ctx->pre.active && ctx->pre.d == d;
+    for (uint32_t k = 0; k < d; k++) {
+        in_tail = in_tail && ctx->tail.h[k] == polys[k];
+        in_pre = in_pre && ctx->pre.h[k] == polys[k];
+    }
+    if (!in_tail && !in_pre) tail_quiesce(ctx);
     Mle *ms[MAX_POLYS];
     int32_t rc = gather_polys(ctx, polys, d, ms);
     if (rc) return rc;
     const uint64_t n = ms[0]->n;
     if (n < 2) return ZB_ERR_NO_VARIABLES;
     if (r >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    if ((in_tail && ctx->tail.n != n) || (in_pre && ctx->pre.n != n)) { // cannot happen through the ABI; be safe
+        tail_quiesce(ctx);
+        in_tail = in_pre = false;
+    }
     *was_last = (n == 2);
     PolySet ps{};
     for (uint32_t k = 0; k < d; k++) {
@@ -1135,77 +1275,88 @@ static int32_t fold_inplace_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, u
     }
     const char *name = d == 1 ? "fold_sums_d1" : d == 2 ? "fold_sums_d2" : "fold_sums_d3";
     const bool red = reduce_on_device(ctx) && n > 2; // the final evaluations (n == 2) are per-rank values, never summed
-    Mailbox mb = round_mailbox(ctx, red);
-    if (!red && !ctx->tail.active && ctx->tail_log2 > 0 && n >= 4 && n <= (1ull << ctx->tail_log2)) {
-        // start a session: the kernel serves this and every later round of these tables
-        if (ctx->chal_seq > 0xF0000000u) ctx->chal_seq = 0;
-        {
-            ProfScope _ps(ctx, d == 1 ? "tail_rounds_d1" : d == 2 ? "tail_rounds_d2" : "tail_rounds_d3", 0);
-            launch_tail_rounds((int)d, ps, n, mb, ctx->d_chal, ctx->chal_seq + 1, ctx->d_tail_status, ctx->stream);
+    Mailbox mb{};
+    bool polling = false; // this round's kernel takes its challenge from the host-mapped word
+    if (in_pre) {
+        mb = ctx->pre.mb;
+        ctx->pre.active = false;
+        feed_challenge(ctx, ctx->pre.tag, r);
+        polling = true;
+    } else {
+        if (!in_tail && !red && ctx->tail_log2 > 0 && n >= 4 && n <= (1ull << ctx->tail_log2)) {
+            // start a tail session now: the kernel serves this and every later round of these tables
+            if (ctx->chal_seq > 0xF0000000u) ctx->chal_seq = 0;
+            Mailbox tmb = ctx->mailbox();
+            ctx->seq--;
+            tmb.seq = ctx->seq + 1;
+            {
+                ProfScope _ps(ctx, d == 1 ? "tail_rounds_d1" : d == 2 ? "tail_rounds_d2" : "tail_rounds_d3", 0);
+                launch_tail_rounds((int)d, ps, n, tmb, ctx->d_chal, ctx->chal_seq + 1, ctx->d_tail_status, ctx->stream);
+            }
+            rc = check_launch(ctx, "tail_rounds");
+            if (rc) return rc;
+            ctx->tail.active = true;
+            ctx->tail.d = d;
+            ctx->tail.n = n;
+            for (uint32_t k = 0; k < d; k++) ctx->tail.h[k] = polys[k];
+            in_tail = true;
         }
-        rc = check_launch(ctx, "tail_rounds");
-        if (rc) return rc;
-        ctx->tail.active = true;
-        ctx->tail.d = d;
-        ctx->tail.n = n;
-        for (uint32_t k = 0; k < d; k++) ctx->tail.h[k] = polys[k];
-    }
-    bool served = false;
-    if (ctx->tail.active) {
-        if (ctx->tail_test_starve) { // test hook ("tail_test_starve" option): delay the first challenge past the kernel's patience
-            std::this_thread::sleep_for(std::chrono::milliseconds(400));
-            ctx->tail_test_starve = false;
-        }
-        __atomic_store_n(ctx->h_chal, ((unsigned long long)(++ctx->chal_seq) << 32) | (unsigned long long)r, __ATOMIC_RELEASE);
-        // wait for the round's mailbox sequence; if the kernel has left instead (starvation exit: the launch was
-        // serialised by a profiler, or the host thread lost the CPU for too long) the tables are untouched for this
-        // round: fall back to one launch per round and stop using the persistent kernel on this context
-        volatile unsigned long long *flag = ctx->h_mail + MAIL_WORDS;
-        auto t0 = std::chrono::steady_clock::now();
-        uint64_t spins = 0;
-        bool gone = false;
-        while (*flag != mb.seq) {
-            if ((++spins & 0x3FFF) == 0) {
-                cudaError_t q = cudaStreamQuery(ctx->stream);
-                if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(ctx, q, "tail kernel");
-                if (q == cudaSuccess) {
-                    // drained: give the mapped write 2 ms to land, then decide
-                    auto t1 = std::chrono::steady_clock::now();
-                    while (*flag != mb.seq && std::chrono::steady_clock::now() - t1 < std::chrono::milliseconds(2)) {
-                    }
-                    if (*flag != mb.seq) gone = true;
-                    break;
-                }
-                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
-                    tail_quiesce(ctx);
-                    ctx->last_error = "timeout waiting for the tail kernel";
-                    return ZB_ERR_TIMEOUT;
-                }
+        if (in_tail) {
+            mb = ctx->mailbox();
+            feed_challenge(ctx, ++ctx->chal_seq, r);
+            polling = true;
+        } else {
+            mb = round_mailbox(ctx, red);
+            {
+                ProfScope _ps(ctx, name, n * 6 * d);
+                launch_fold_sums((int)d, ps, n, (uint32_t)r, mb, ctx->sm_count, ctx->stream);
+            }
+            rc = check_launch(ctx, "fold_sums");
+            if (rc) return rc;
+            if (red) {
+                rc = comm_publish(ctx, mb.seq, d == 1 ? 2 : (int)d + 1);
+                if (rc) return rc;
             }
         }
-        std::atomic_thread_fence(std::memory_order_acquire);
-        if (!gone) {
-            served = true;
+    }
+    // the next round's kernel goes behind this one before we wait for this one's sums
+    if (!in_tail) {
+        rc = prelaunch_next(ctx, polys, d, ms, n / 2);
+        if (rc) return rc;
+    }
+    if (polling) {
+        bool gone = false;
+        rc = wait_polling_kernel(ctx, mb.seq, &gone);
+        if (rc) return rc;
+        if (gone) {
+            // redo the round with a plain launch (same exchange round number) and stop using polling kernels here
+            tail_quiesce(ctx); // also ends a kernel that was pre-launched behind the one that left
+            if (++ctx->starved >= 3) { // once may be a hiccup of the host thread; repeatedly means launches are serialised
+                ctx->tail_log2 = 0;
+                ctx->prelaunch = false;
+            }
+            cudaMemsetAsync(ctx->d_tail_status, 0, sizeof(unsigned int), ctx->stream);
+            Mailbox mb2 = ctx->mailbox();
+            mb2.xchg = mb.xchg;
+            mb2.xseq = mb.xseq;
+            if (red && !mb2.xchg) mb2.mail = ctx->d_comm;
+            {
+                ProfScope _ps(ctx, name, n * 6 * d);
+                launch_fold_sums((int)d, ps, n, (uint32_t)r, mb2, ctx->sm_count, ctx->stream);
+            }
+            rc = check_launch(ctx, "fold_sums");
+            if (rc) return rc;
+            if (red) {
+                rc = comm_publish(ctx, mb2.seq, d == 1 ? 2 : (int)d + 1);
+                if (rc) return rc;
+            }
+            rc = wait_mail(ctx, mb2.seq);
+            if (rc) return rc;
+        } else if (in_tail) {
             ctx->tail.n = n / 2;
             if (n == 2) ctx->tail.active = false; // the kernel returns after the last round
-        } else {
-            ctx->tail.active = false;
-            ctx->tail_log2 = 0;
-            cudaMemsetAsync(ctx->d_tail_status, 0, sizeof(unsigned int), ctx->stream);
-            mb = ctx->mailbox(); // fresh sequence number for the relaunch below
         }
-    }
-    if (!served) {
-        {
-            ProfScope _ps(ctx, name, n * 6 * d);
-            launch_fold_sums((int)d, ps, n, (uint32_t)r, mb, ctx->sm_count, ctx->stream);
-        }
-        rc = check_launch(ctx, "fold_sums");
-        if (rc) return rc;
-        if (red) {
-            rc = comm_publish(ctx, mb.seq, d == 1 ? 2 : (int)d + 1);
-            if (rc) return rc;
-        }
+    } else {
         rc = wait_mail(ctx, mb.seq);
         if (rc) return rc;
     }
@@ -1260,8 +1411,14 @@ int32_t zb_prod_partial_eval(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint6
     }
     rc = check_launch(ctx, "prod_partial_eval");
     if (rc == ZB_OK && red) rc = comm_publish(ctx, mb.seq, d == 1 ? 2 : (int)d + 1);
+    if (rc == ZB_OK) { // the next round works on the new tables: put its kernel behind this one already
+        Mle *mo[MAX_POLYS];
+        for (uint32_t k = 0; k < d; k++) mo[k] = get_mle(ctx, out[k]);
+        rc = prelaunch_next(ctx, out, d, mo, n / 2);
+    }
     if (rc == ZB_OK) rc = wait_mail(ctx, mb.seq);
     if (rc) {
+        tail_quiesce(ctx); // a pre-launched kernel may reference the tables that are dropped here
         for (uint32_t k = 0; k < d; k++) ctx->mles.erase(out[k]);
         return rc;
     }

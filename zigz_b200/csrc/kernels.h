@@ -42,10 +42,25 @@ struct PolySet {
 // all canonical mod p.
 void launch_round_sums(int d, const PolySet &ps, uint64_t n, const Mailbox &mb, int sm_count, cudaStream_t st);
 
+// Where a fold kernel gets its challenge from. chal == nullptr: the launch parameter r (immediate).
+// Otherwise the kernel was PRE-LAUNCHED behind the previous round's kernel, before the host knew the challenge: the first
+// CTA to arrive (atomic claim) polls the host-mapped word *chal until it holds (tag << 32 | r), republishes it in the
+// device word *bcast for the other CTAs, and the fold starts — the launch latency of the round is off the critical path.
+// Tag 0xFFFFFFFF aborts (every CTA leaves without touching the tables); ~0.2 s without a challenge does the same.
+struct ChalSrc {
+    const unsigned long long *chal;
+    unsigned long long *bcast;
+    unsigned int *claim;
+    unsigned int tag;
+};
+
 // Fold every polynomial with challenge r (new[i] = e[i] + r (e[i + n/2] - e[i])) writing n/2 values to dst
 // (dst may equal src: in place), and, fused, the round sums of the folded polynomials (same payload as above).
 // If n == 2 the payload is the d final evaluations instead.
-void launch_fold_sums(int d, const PolySet &ps, uint64_t n, uint32_t r, const Mailbox &mb, int sm_count, cudaStream_t st);
+void launch_fold_sums(int d, const PolySet &ps, uint64_t n, uint32_t r, const Mailbox &mb, int sm_count, cudaStream_t st,
+                      const ChalSrc *cs = nullptr);
+// true when launch_fold_sums(n) runs the vectorised kernel (the only one that supports a polled challenge)
+inline bool fold_sums_is_vector(uint64_t n) { return n >= 16 && ((n / 4) % 4) == 0; }
 
 // Persistent single-CTA kernel that performs ALL remaining fold rounds of d polynomials of length n (in place,
 // ps.dst == ps.src). Round k (k = 0, 1, ...) waits until the host-mapped word *chal holds (chal_seq0 + k) << 32 | r_k,

@@ -15,6 +15,7 @@
 namespace zk {
 
 constexpr int THREADS = 256;
+constexpr unsigned int TAIL_ABORT_TAG = 0xFFFFFFFFu; // challenge-word tag that makes polling kernels leave
 
 // launch-shape knobs, overridable from the environment for tuning runs (read once)
 static int tune(const char *name, int dflt) {
@@ -247,8 +248,47 @@ __global__ void __launch_bounds__(THREADS) k_round_sums_s(PolySet ps, uint64_t h
 // and (new[i], new[i + q]) is exactly the next round's MSB-first pair. q4 = q / 4.
 // In place is safe: a thread only touches indices congruent to its own i modulo q.
 // ---------------------------------------------------------------------------------------------
+// pre-launched kernels: obtain the challenge (see ChalSrc). Returns false when the kernel must leave untouched.
+__device__ __forceinline__ bool acquire_challenge(const ChalSrc &cs, uint32_t &r, uint32_t &rp) {
+    __shared__ uint32_t s_r, s_rp;
+    __shared__ int s_ab;
+    if (threadIdx.x == 0) {
+        unsigned long long w = 0;
+        int ab = 0;
+        if (atomicExch(cs.claim, cs.tag) != cs.tag) { // first CTA of this launch: talk to the host
+            const long long t0 = clock64();
+            for (;;) {
+                w = *(const volatile unsigned long long *)cs.chal;
+                const unsigned int tag = (unsigned int)(w >> 32);
+                if (tag == cs.tag) break;
+                if (tag == TAIL_ABORT_TAG || clock64() - t0 > 400000000ll) {
+                    ab = 1;
+                    break;
+                }
+            }
+            if (ab) w = ((unsigned long long)cs.tag << 32) | 0x80000000ull; // bit 31 (never set in a challenge) = leave
+            *(volatile unsigned long long *)cs.bcast = w;
+            __threadfence();
+        } else {
+            for (;;) {
+                w = *(const volatile unsigned long long *)cs.bcast;
+                if ((unsigned int)(w >> 32) == cs.tag) break;
+            }
+            ab = (w & 0x80000000ull) != 0;
+        }
+        s_ab = ab;
+        s_r = (uint32_t)w & 0x7FFFFFFFu;
+        s_rp = bb::shoup_pre(s_r);
+    }
+    __syncthreads();
+    r = s_r;
+    rp = s_rp;
+    return !s_ab;
+}
+
 template <int D, int U>
-__global__ void __launch_bounds__(THREADS) k_fold_sums_v4(PolySet ps, uint64_t q4, uint32_t r, uint32_t rp, Mailbox mb) {
+__global__ void __launch_bounds__(THREADS) k_fold_sums_v4(PolySet ps, uint64_t q4, uint32_t r, uint32_t rp, Mailbox mb, ChalSrc cs) {
+    if (cs.chal != nullptr && !acquire_challenge(cs, r, rp)) return;
     constexpr int NS = NSums<D>::value;
     unsigned long long s[NS];
 #pragma unroll
@@ -357,7 +397,6 @@ __global__ void k_fold_last(PolySet ps, uint32_t r, uint32_t rp, Mailbox mb) {
 // The kernel leaves on its own after the last round, on an abort tag, or after ~2 s without a challenge.
 // ---------------------------------------------------------------------------------------------
 constexpr int TAIL_THREADS = 1024;
-constexpr unsigned int TAIL_ABORT_TAG = 0xFFFFFFFFu;
 
 template <int D>
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail_rounds(PolySet ps, uint64_t n, Mailbox mb, const unsigned long long *chal,
@@ -542,8 +581,9 @@ void launch_round_sums(int d, const PolySet &ps, uint64_t n, const Mailbox &mb, 
 }
 
 template <int D>
-static void fold_sums_t(const PolySet &ps, uint64_t n, uint32_t r, const Mailbox &mb, int sm, cudaStream_t st) {
+static void fold_sums_t(const PolySet &ps, uint64_t n, uint32_t r, const Mailbox &mb, int sm, cudaStream_t st, const ChalSrc *csp) {
     uint32_t rp = bb::shoup_pre(r);
+    const ChalSrc cs = csp ? *csp : ChalSrc{nullptr, nullptr, nullptr, 0};
     if (n == 2) {
         k_fold_last<D><<<1, 32, 0, st>>>(ps, r, rp, mb);
         return;
@@ -554,20 +594,21 @@ static void fold_sums_t(const PolySet &ps, uint64_t n, uint32_t r, const Mailbox
         static const int CPS = tune("ZB_FOLD_CPS", 8);
         const uint64_t q4 = q / 4;
         if (U >= 4 && D == 1)
-            k_fold_sums_v4<D, (D == 1 ? 4 : 1)><<<grid_for((q4 + 3) / 4, sm, CPS), THREADS, 0, st>>>(ps, q4, r, rp, mb);
+            k_fold_sums_v4<D, (D == 1 ? 4 : 1)><<<grid_for((q4 + 3) / 4, sm, CPS), THREADS, 0, st>>>(ps, q4, r, rp, mb, cs);
         else if (U >= 2 && D <= 2)
-            k_fold_sums_v4<D, (D <= 2 ? 2 : 1)><<<grid_for((q4 + 1) / 2, sm, CPS), THREADS, 0, st>>>(ps, q4, r, rp, mb);
+            k_fold_sums_v4<D, (D <= 2 ? 2 : 1)><<<grid_for((q4 + 1) / 2, sm, CPS), THREADS, 0, st>>>(ps, q4, r, rp, mb, cs);
         else
-            k_fold_sums_v4<D, 1><<<grid_for(q4, sm, CPS), THREADS, 0, st>>>(ps, q4, r, rp, mb);
+            k_fold_sums_v4<D, 1><<<grid_for(q4, sm, CPS), THREADS, 0, st>>>(ps, q4, r, rp, mb, cs);
     } else {
         k_fold_sums_s<D><<<1, THREADS, 0, st>>>(ps, q, r, rp, mb);
     }
 }
 
-void launch_fold_sums(int d, const PolySet &ps, uint64_t n, uint32_t r, const Mailbox &mb, int sm, cudaStream_t st) {
-    if (d == 1) fold_sums_t<1>(ps, n, r, mb, sm, st);
-    else if (d == 2) fold_sums_t<2>(ps, n, r, mb, sm, st);
-    else fold_sums_t<3>(ps, n, r, mb, sm, st);
+void launch_fold_sums(int d, const PolySet &ps, uint64_t n, uint32_t r, const Mailbox &mb, int sm, cudaStream_t st,
+                      const ChalSrc *cs) {
+    if (d == 1) fold_sums_t<1>(ps, n, r, mb, sm, st, cs);
+    else if (d == 2) fold_sums_t<2>(ps, n, r, mb, sm, st, cs);
+    else fold_sums_t<3>(ps, n, r, mb, sm, st, cs);
 }
 
 // ---------------------------------------------------------------------------------------------
