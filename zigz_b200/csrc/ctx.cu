@@ -199,7 +199,10 @@ int32_t dev_alloc(zb_ctx *ctx, size_t bytes, BufRef *out) {
         release_cache(ctx);
         e = cudaMalloc(&p, want);
     }
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
+    if (e != cudaSuccess) {
+        cudaGetLastError(); // the failed allocation must not surface again at the next launch check
+        return cuda_fail(ctx, e, "cudaMalloc");
+    }
     *out = std::make_shared<DevBuf>(ctx, p, want);
     return ZB_OK;
 }
