@@ -350,8 +350,12 @@ def run_extras(args, z, ctx, peak):
         trees[-1].open((i * 2654435761) % (1 << lgm))
         opens.append((time.perf_counter() - t0) * 1e3)
     open_ms = float(np.median(opens[1:]))  # 16 openings, first call excluded (warm-up)
+    ip = ctx.int_pipe_peak()  # measured LOP3/SHF ceiling of this GPU (zb_int_pipe_peak)
+    alu_ops = 4308.0  # ALU-pipe instructions per Keccak-f[1600] + SHA3 framing in k_merkle_*: 24 x (122 LOP3 + 58 SHF) - folded constants
     out[f"C3_merkle_commit_2^{lgm}"] = {"ms": ms, "keccak_per_s": hashes / (ms * 1e-3), "hbm_frac_68B_per_leaf": 68.0 * (1 << lgm) / (ms * 1e-3) / 1e9 / peak,
-                                         "open_ms": open_ms}
+                                         "open_ms": open_ms, "int_pipe_measured": ip,
+                                         "int_pipe_frac": hashes * alu_ops / (ms * 1e-3) / ip["keccak_mix_per_s"],
+                                         "bound": "integer ALU pipe (LOP3/SHF); frac = hashes x 4308 ALU ops / time / measured Keccak-mix lane-ops/s"}
     trees.pop().deinit()
     pm.deinit()
     # C4 (the device part of `zigz prove`): 43 witness polynomials of 2^20 steps: pack from SoA trace columns, then

@@ -66,6 +66,9 @@ uint64_t zb_kernel_launches(zb_ctx *ctx);
 int32_t zb_host_alloc(zb_ctx *ctx, size_t bytes, void **out);
 int32_t zb_host_free(zb_ctx *ctx, void *p);
 int32_t zb_device_info(zb_ctx *ctx, int32_t *sm_count, uint64_t *total_mem, uint64_t *free_mem);
+/* measured integer-pipe ceiling of this GPU for the hashing kernels: 32-bit lane-operations per second of independent
+ * LOP3 chains, SHF chains, and the Keccak mix (122 LOP3 : 58 SHF), each timed with CUDA events over ~ms-long launches */
+int32_t zb_int_pipe_peak(zb_ctx *ctx, double *lop3_per_s, double *shf_per_s, double *keccak_mix_per_s);
 /* raw stream handle (cudaStream_t) the context launches on: for CUDA-event timing by a harness */
 void *zb_stream(zb_ctx *ctx);
 int32_t zb_sync(zb_ctx *ctx);

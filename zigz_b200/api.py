@@ -112,6 +112,12 @@ class Context:
         self.check(lib().zb_comm_allreduce_u64(self._h, _p64(a), a.size))
         return a
 
+    def int_pipe_peak(self):
+        """Measured 32-bit lane-ops/s of LOP3 chains, SHF chains and the Keccak mix on this GPU."""
+        a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+        self.check(lib().zb_int_pipe_peak(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"lop3_per_s": a.value, "shf_per_s": b.value, "keccak_mix_per_s": c.value}
+
     def device_info(self):
         sm, tot, free = C.c_int32(0), u64(0), u64(0)
         self.check(lib().zb_device_info(self._h, C.byref(sm), C.byref(tot), C.byref(free)))

@@ -751,6 +751,36 @@ int32_t zb_profile_entry(zb_ctx *ctx, uint32_t i, char *name, uint32_t cap, uint
     return ZB_OK;
 }
 
+int32_t zb_int_pipe_peak(zb_ctx *ctx, double *lop3, double *shf, double *mix) {
+    tail_quiesce(ctx);
+    BufRef buf;
+    int32_t rc = dev_alloc(ctx, 256, &buf);
+    if (rc) return rc;
+    const int ctas = ctx->sm_count * 8, iters = 4096;
+    double *outs[3] = {lop3, shf, mix};
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    for (int mode = 0; mode < 3; mode++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) { // first repetition warms up
+            CK(cudaEventRecord(a, ctx->stream));
+            launch_int_peak(mode, (uint32_t *)buf->ptr, iters, ctas, ctx->stream);
+            ctx->launches++;
+            CK(cudaEventRecord(b, ctx->stream));
+            CK(cudaEventSynchronize(b));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, a, b));
+            if (rep && ms < best) best = ms;
+        }
+        const double ops = (double)ctas * 256.0 * iters * 64.0;
+        if (outs[mode]) *outs[mode] = ops / (best * 1e-3);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return ZB_OK;
+}
+
 int32_t zb_host_alloc(zb_ctx *ctx, size_t bytes, void **out) {
     tail_quiesce(ctx);
     CK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));

@@ -116,6 +116,8 @@ struct MerkleBatch {
 inline uint64_t merkle_level_offset(uint64_t padded, uint32_t level) { // in digests
     return 2 * padded - (2 * padded >> level);
 }
+// integer-pipe microbenchmark (int_peak.cu): mode 0 LOP3, 1 SHF, 2 Keccak-like mix; 64 ops per thread and iteration
+void launch_int_peak(int mode, uint32_t *out, int iters, int ctas, cudaStream_t st);
 void keccak_init_constants(); // once per context, before the first hashing launch
 void launch_merkle_leaves(const MerkleBatch &b, uint64_t padded, cudaStream_t st);
 // hashes level `level` -> `level + 1` for every tree of the batch
