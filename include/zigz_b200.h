@@ -136,6 +136,19 @@ int32_t zb_prod_fold_inplace(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint6
 /* the same fold out of place (partialEval semantics for all d polynomials): `out` receives d NEW handles */
 int32_t zb_prod_partial_eval(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, zb_mle *out, uint64_t *next_coeffs);
 
+/* ---- two sumcheck rounds per pass over the data ----
+ * With the top two index bits as variables (X, Y), G(X, Y) = sum_i prod_k B_k,i(X, Y) (B bilinear through the four quarter
+ * elements i, i+n/4, i+n/2, i+3n/4) holds the next TWO round polynomials: g(X) = G(X,0) + G(X,1) and, once the challenge r
+ * of that round is known, g'(Y) = G(r, Y). `grid` receives G on P x P with P = {0,1} (d=1), {0,1,inf} (d=2),
+ * {0,1,-1,inf} (d=3), row-major grid[ix*|P| + iy], canonical values (summed over the ranks under "comm_reduce").
+ * zb_prod_grid: G of the tables as they are (read only).
+ * zb_prod_fold_grid: first bind `nfold` (1 or 2) top variables with r[0] (, r[1]) — exactly partialEval applied nfold
+ * times — then G of the folded tables. out == NULL folds in place; otherwise d NEW tables are returned and the inputs stay
+ * untouched. Needs folded length >= 8 (error.BadArgument otherwise; use the single-round entries for small tables). */
+int32_t zb_prod_grid(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *grid);
+int32_t zb_prod_fold_grid(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint32_t nfold, const uint64_t *r, zb_mle *out,
+                          uint64_t *grid);
+
 /* ---- SimpleMerkleTree(F, SHA3Hasher): src/commitments/merkle_tree.zig:273-402 ---- */
 /* build :283-318 for `count` polynomials of equal length in one batch (CommitmentScheme.batchCommit,
  * polynomial_commit.zig:132-157; Prover.generateCommitments, prover.zig:405-410). roots: count*32 bytes. */

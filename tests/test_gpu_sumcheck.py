@@ -216,3 +216,84 @@ def test_tail_kernel_starvation_falls_back_to_launches(zlib, po):
         assert zlib.SumcheckProver.prove(poly).to_bytes() == want.to_bytes()
         assert c2.get_option("tail_log2") == 0 and c2.get_option("prelaunch") == 0  # third time: switched off
         assert zlib.SumcheckProver.prove(poly).to_bytes() == want.to_bytes()
+
+
+# ---------------------------------------------------------------- two rounds per pass (zb_prod_grid / zb_prod_fold_grid)
+@pytest.mark.parametrize("grid_min", [3, 5, 8, 0])
+def test_two_rounds_per_pass_gives_identical_proofs(zlib, ctx, po, grid_min):
+    """Force the bivariate-grid path down to tiny tables (and switch it off): proofs must not change by a bit."""
+    old = zlib.lib().zh_set_grid_min_log2(grid_min)
+    try:
+        for d, lg in ((1, 5), (1, 6), (1, 9), (1, 14), (2, 5), (2, 8), (2, 11), (3, 5), (3, 6), (3, 7), (3, 10), (3, 13), (3, 16)):
+            es = [po.fill_synthetic(BB, 1234 + k, 0, 1 << lg) for k in range(d)]
+            polys = [zlib.Multilinear.init(ctx, e) for e in es]
+            want = po.prodcheck_prove(BB, es)
+            for consume in (False, True):
+                pr = zlib.ProductSumcheckProver.prove(polys, consume=consume)
+                assert pr.claimed_sum == want.claimed_sum, (grid_min, d, lg)
+                assert pr.round_polynomials.tolist() == want.round_polys.tolist(), (grid_min, d, lg, consume)
+                assert pr.final_point.tolist() == want.final_point.tolist() and pr.final_evals == want.final_evals
+                if not consume:
+                    assert np.array_equal(polys[0].evaluations, es[0])  # non-consuming prove keeps the inputs
+        e = po.fill_synthetic(BB, 77, 0, 1 << 10)
+        ch = po.fill_synthetic(BB, 78, 0, 10)
+        pi = zlib.SumcheckProver.prove_interactive(zlib.Multilinear.init(ctx, e), ch)
+        wi = po.sumcheck_prove_interactive(BB, e, ch)
+        assert pi.round_polynomials.tolist() == wi.round_polys.tolist() and pi.final_eval == wi.final_eval
+    finally:
+        zlib.lib().zh_set_grid_min_log2(old)
+
+
+def test_grid_entry_points_directly(zlib, ctx, po):
+    """zb_prod_grid / zb_prod_fold_grid against the oracle's single-round functions: g(X) = G(X,0)+G(X,1), g'(Y) = G(r,Y)."""
+    import ctypes as C
+    L = zlib.lib()
+    for d in (1, 2, 3):
+        np_ = 2 if d == 1 else d + 1
+        es = [po.fill_synthetic(BB, 300 + k, 0, 1 << 9) for k in range(d)]
+        polys = [zlib.Multilinear.init(ctx, e) for e in es]
+        hs = (C.c_uint64 * d)(*[p.handle for p in polys])
+        grid = (C.c_uint64 * 16)()
+        ctx.check(L.zb_prod_grid(ctx.handle, hs, d, grid))
+        g = np.array(list(grid)[:np_ * np_], dtype=object).reshape(np_, np_)
+        want0 = po.prod_round_coeffs(BB, es)
+
+        def to_coeffs(ev):
+            ev = [int(x) for x in ev]
+            inv2 = (BB + 1) // 2
+            if d == 1:
+                return [ev[0], (ev[1] - ev[0]) % BB]
+            if d == 2:
+                return [ev[0], (ev[1] - ev[0] - ev[2]) % BB, ev[2]]
+            return [ev[0], ((ev[1] - ev[2]) * inv2 - ev[3]) % BB, ((ev[1] + ev[2]) * inv2 - ev[0]) % BB, ev[3]]
+
+        def horner(c, x):
+            acc = 0
+            for a in reversed(c):
+                acc = (acc * x + a) % BB
+            return acc
+
+        assert to_coeffs([(g[ix][0] + g[ix][1]) % BB for ix in range(np_)]) == want0
+        r1, r2 = 123456789, 987654321
+        folded = [po.mle_partial_eval(BB, e, r1) for e in es]
+        want1 = po.prod_round_coeffs(BB, folded)
+        assert to_coeffs([horner(to_coeffs([g[ix][iy] for ix in range(np_)]), r1) for iy in range(np_)]) == want1
+        # fold both variables, in place, and compare tables + next grid's first round
+        rr = (C.c_uint64 * 2)(r1, r2)
+        ctx.check(L.zb_prod_fold_grid(ctx.handle, hs, d, 2, rr, None, grid))
+        folded2 = [po.mle_partial_eval(BB, f, r2) for f in folded]
+        for p, f in zip(polys, folded2):
+            assert np.array_equal(p.evaluations, f)
+        g = np.array(list(grid)[:np_ * np_], dtype=object).reshape(np_, np_)
+        assert to_coeffs([(g[ix][0] + g[ix][1]) % BB for ix in range(np_)]) == po.prod_round_coeffs(BB, folded2)
+        # one variable, out of place
+        out = (C.c_uint64 * d)()
+        r3 = (C.c_uint64 * 2)(55555, 0)
+        ctx.check(L.zb_prod_fold_grid(ctx.handle, hs, d, 1, r3, out, grid))
+        folded3 = [po.mle_partial_eval(BB, f, 55555) for f in folded2]
+        for k in range(d):
+            assert np.array_equal(zlib.Multilinear(ctx, out[k]).evaluations, folded3[k])
+            assert np.array_equal(polys[k].evaluations, folded2[k])  # inputs untouched
+        with pytest.raises(zlib.ZigzError):  # too small for the vector kernel: the caller must use the single-round entries
+            small = zlib.Multilinear.init(ctx, [1, 2, 3, 4])
+            ctx.check(L.zb_prod_grid(ctx.handle, (C.c_uint64 * 1)(small.handle), 1, grid))

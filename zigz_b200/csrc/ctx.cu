@@ -1464,6 +1464,73 @@ int32_t zb_prod_partial_eval(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint6
     return ZB_OK;
 }
 
+static int32_t fold_grid_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint32_t nfold, const uint64_t *r, zb_mle *out,
+                              uint64_t *grid) {
+    tail_quiesce(ctx);
+    Mle *ms[MAX_POLYS];
+    int32_t rc = gather_polys(ctx, polys, d, ms);
+    if (rc) return rc;
+    if (nfold > 2 || !grid || (nfold && !r)) return ZB_ERR_BAD_ARGUMENT;
+    const uint64_t n = ms[0]->n, m = n >> nfold;
+    if ((m << nfold) != n || !fold_grid_ok(m)) return ZB_ERR_BAD_ARGUMENT;
+    for (uint32_t t = 0; t < nfold; t++)
+        if (r[t] >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    PolySet ps{};
+    BufRef keep[MAX_POLYS];
+    for (uint32_t k = 0; k < d; k++) {
+        ps.src[k] = ms[k]->d();
+        ps.dst[k] = ms[k]->d();
+        keep[k] = ms[k]->buf;
+    }
+    if (out && nfold) {
+        for (uint32_t k = 0; k < d; k++) {
+            Mle *o = nullptr;
+            rc = new_mle(ctx, m, &out[k], &o);
+            if (rc) {
+                for (uint32_t j = 0; j < k; j++) ctx->mles.erase(out[j]);
+                return rc;
+            }
+            ps.dst[k] = o->d();
+        }
+    }
+    const int np = d == 1 ? 2 : (int)d + 1, ns = np * np;
+    const bool red = reduce_on_device(ctx);
+    Mailbox mb = round_mailbox(ctx, red);
+    static const char *names[3][3] = {{"grid_d1", "fold1_grid_d1", "fold2_grid_d1"},
+                                      {"grid_d2", "fold1_grid_d2", "fold2_grid_d2"},
+                                      {"grid_d3", "fold1_grid_d3", "fold2_grid_d3"}};
+    {
+        ProfScope _ps(ctx, names[d - 1][nfold], (uint64_t)d * 4 * (n + (nfold ? m : 0)));
+        launch_fold_grid((int)d, (int)nfold, ps, m, nfold ? (uint32_t)r[0] : 0, nfold > 1 ? (uint32_t)r[1] : 0, mb, ctx->sm_count,
+                         ctx->stream);
+    }
+    rc = check_launch(ctx, "fold_grid");
+    if (rc == ZB_OK && red) rc = comm_publish(ctx, mb.seq, ns);
+    if (rc == ZB_OK) rc = wait_mail(ctx, mb.seq);
+    if (rc) {
+        if (out && nfold)
+            for (uint32_t k = 0; k < d; k++) ctx->mles.erase(out[k]);
+        return rc;
+    }
+    if (nfold && !out) {
+        Mle *mm[MAX_POLYS];
+        gather_polys(ctx, polys, d, mm); // the handle table may have been rehashed by new_mle: look the tables up again
+        for (uint32_t k = 0; k < d; k++) mm[k]->n = m;
+    }
+    for (int k = 0; k < ns; k++) grid[k] = ctx->h_mail[k];
+    return ZB_OK;
+}
+
+int32_t zb_prod_grid(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *grid) {
+    return fold_grid_impl(ctx, polys, d, 0, nullptr, nullptr, grid);
+}
+
+int32_t zb_prod_fold_grid(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint32_t nfold, const uint64_t *r, zb_mle *out,
+                          uint64_t *grid) {
+    if (nfold < 1) return ZB_ERR_BAD_ARGUMENT;
+    return fold_grid_impl(ctx, polys, d, nfold, r, out, grid);
+}
+
 /* ------------------------------------------------------------------ Merkle */
 
 static int32_t build_batch(zb_ctx *ctx, Tree **ts, uint32_t count, uint8_t *roots) {

@@ -76,6 +76,56 @@ uint64_t zh_eval_univariate(const uint64_t *c, uint32_t n, uint64_t x) { // sumc
 //   phase 2 (shards <= 2^ZB_GATHER_LOG2 entries, default 2^16): the shards are all-gathered once into the global order
 //            and every GPU finishes the remaining rounds on the whole (small) table, redundantly and without any
 //            further exchange — latency-bound rounds should not pay a collective each.
+// evaluations on the point set of degree d ({0,1} / {0,1,inf} / {0,1,-1,inf}) -> coefficients [a0..ad]
+static void evals_to_coeffs(uint32_t d, const uint64_t *e, uint64_t *c) {
+    const uint64_t half = (P + 1) / 2;
+    if (d == 1) {
+        c[0] = e[0];
+        c[1] = f_sub(e[1], e[0]); // multilinear.zig:229
+    } else if (d == 2) {
+        c[0] = e[0];
+        c[2] = e[2];
+        c[1] = f_sub(f_sub(e[1], e[0]), e[2]);
+    } else {
+        c[0] = e[0];
+        c[3] = e[3];
+        c[2] = f_sub(f_mul(f_add(e[1], e[2]), half), e[0]);
+        c[1] = f_sub(f_mul(f_sub(e[1], e[2]), half), e[3]);
+    }
+}
+
+// Round polynomials out of the bivariate grid G(X, Y) of zb_prod_grid / zb_prod_fold_grid:
+//   this round:  g(X)  = G(X, 0) + G(X, 1)
+//   next round:  g'(Y) = G(r, Y), r = this round's challenge (interpolate every column in X, evaluate at r)
+static void grid_round_a(uint32_t d, const uint64_t *grid, uint64_t *coeffs) {
+    const uint32_t np = d == 1 ? 2 : d + 1;
+    uint64_t e[4] = {0, 0, 0, 0};
+    for (uint32_t ix = 0; ix < np; ix++) e[ix] = f_add(grid[ix * np + 0], grid[ix * np + 1]);
+    evals_to_coeffs(d, e, coeffs);
+}
+static void grid_round_b(uint32_t d, const uint64_t *grid, uint64_t r, uint64_t *coeffs) {
+    const uint32_t np = d == 1 ? 2 : d + 1;
+    uint64_t ey[4] = {0, 0, 0, 0};
+    for (uint32_t iy = 0; iy < np; iy++) {
+        uint64_t col[4] = {0, 0, 0, 0}, cx[4] = {0, 0, 0, 0};
+        for (uint32_t ix = 0; ix < np; ix++) col[ix] = grid[ix * np + iy];
+        evals_to_coeffs(d, col, cx);
+        // (the Y = inf column holds the leading Y-coefficient of G: a degree-d polynomial in X like the other columns)
+        ey[iy] = zh_eval_univariate(cx, d + 1, r);
+    }
+    evals_to_coeffs(d, ey, coeffs);
+}
+
+static int g_grid_min_log2 = -1;
+static int grid_min_log2() { // tables below 2^this use one kernel per round (and the persistent tail); 0 disables the grid path
+    if (g_grid_min_log2 < 0) {
+        const char *e = getenv("ZB_GRID_MIN_LOG2");
+        int x = e && *e ? atoi(e) : 18;
+        g_grid_min_log2 = x < 0 ? 0 : x;
+    }
+    return g_grid_min_log2;
+}
+
 static int gather_log2() {
     static const int v = [] {
         const char *e = getenv("ZB_GATHER_LOG2");
@@ -125,8 +175,29 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
     }
     zh_transcript tr; // State.init -> FiatShamirTranscript.init (sumcheck_protocol.zig:149-164)
     uint64_t coeffs[4];
-    rc = zb_prod_round_coeffs(ctx, polys, d, coeffs);
-    if (rc) return rc;
+    uint64_t grid[16];
+    // large tables: two rounds per pass over the data (phase 1 below); the first pass then already yields the grid
+    const int gmin = grid_min_log2();
+    uint64_t grid_min_n = gmin ? (1ull << gmin) : ~0ull;
+    if (sharded && gmin) { // stay above the point where the sharded regime is left
+        const uint64_t g2 = 2ull << gather_log2();
+        if (grid_min_n < g2) grid_min_n = g2;
+    }
+    const bool grid_phase = gmin && n >= grid_min_n && n >= 64 && v_local >= 3;
+    // first pass of the grid phase: "grid" = G of the raw tables (no fold; arithmetic-heavy for d = 3), or "sums" = the plain
+    // round-0 sums, after which the first fold already produces the grid of rounds 1 and 2
+    static const bool first_is_grid = [] {
+        const char *e = getenv("ZB_GRID_FIRST");
+        return e && !strcmp(e, "grid");
+    }();
+    if (grid_phase && first_is_grid) {
+        rc = zb_prod_grid(ctx, polys, d, grid);
+        if (rc) return rc;
+        grid_round_a(d, grid, coeffs);
+    } else {
+        rc = zb_prod_round_coeffs(ctx, polys, d, coeffs);
+        if (rc) return rc;
+    }
     if (claimed_sum) {
         // sum over the hypercube == g(0) + g(1) == 2 a0 + a1 + ... + ad   (== sumOverHypercube for d == 1, :40)
         uint64_t s = coeffs[0];
@@ -142,7 +213,91 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
                 if (cur[k]) zb_mle_free(ctx, cur[k]);
         owned = false;
     };
-    for (uint32_t round = 0; round < v; round++) {
+    uint32_t round = 0;
+    // ---- phase 1: two rounds per pass over the data while the tables are large (zb_prod_grid / zb_prod_fold_grid) ----
+    {
+        const uint64_t min_n = grid_min_n;
+        if (grid_phase && !first_is_grid) {
+            // round 0 from the plain sums; its fold yields the grid of rounds 1 and 2
+            for (uint32_t k = 0; k < nc; k++) round_polys[k] = coeffs[k];
+            uint64_t r0;
+            if (fixed_challenges) {
+                r0 = fixed_challenges[0];
+            } else {
+                zh_transcript_append_fields(&tr, coeffs, nc);
+                r0 = zh_transcript_challenge(&tr);
+            }
+            final_point[0] = r0;
+            round = 1;
+            const bool fresh = !consume;
+            zb_mle next[3] = {0, 0, 0};
+            const uint64_t rr0[2] = {r0, 0};
+            rc = zb_prod_fold_grid(ctx, cur, d, 1, rr0, fresh ? next : nullptr, grid);
+            if (rc) return rc;
+            if (fresh) {
+                for (uint32_t k = 0; k < d; k++) cur[k] = next[k];
+                owned = true;
+            }
+            n_cur /= 2;
+            grid_round_a(d, grid, coeffs);
+        }
+        if (grid_phase) {
+            for (;;) {
+                uint64_t rr[2];
+                for (int t = 0; t < 2; t++) {
+                    if (t == 1) grid_round_b(d, grid, rr[0], coeffs);
+                    for (uint32_t k = 0; k < nc; k++) round_polys[(size_t)(round + t) * nc + k] = coeffs[k];
+                    if (fixed_challenges) {
+                        rr[t] = fixed_challenges[round + t];
+                    } else {
+                        zh_transcript_append_fields(&tr, coeffs, nc);
+                        rr[t] = zh_transcript_challenge(&tr);
+                    }
+                    final_point[round + t] = rr[t];
+                }
+                round += 2;
+                const uint64_t n_after = n_cur / 4;
+                const bool more = n_after >= min_n && n_after >= 32;
+                const bool fresh = !owned && !consume; // the caller's tables must stay intact: fold into new ones
+                if (more) {
+                    zb_mle next[3] = {0, 0, 0};
+                    rc = zb_prod_fold_grid(ctx, cur, d, 2, rr, fresh ? next : nullptr, grid);
+                    if (rc) {
+                        cleanup();
+                        return rc;
+                    }
+                    if (fresh) {
+                        for (uint32_t k = 0; k < d; k++) cur[k] = next[k];
+                        owned = true;
+                    }
+                    n_cur = n_after;
+                    grid_round_a(d, grid, coeffs);
+                    continue;
+                }
+                // last pair of this phase: bind the two variables with the single-round kernels; the second one
+                // returns the coefficients of the round after them (or the final evaluations)
+                if (fresh) {
+                    zb_mle next[3] = {0, 0, 0};
+                    rc = zb_prod_partial_eval(ctx, cur, d, rr[0], next, coeffs);
+                    if (rc) return rc;
+                    for (uint32_t k = 0; k < d; k++) cur[k] = next[k];
+                    owned = true;
+                } else {
+                    rc = zb_prod_fold_inplace(ctx, cur, d, rr[0], coeffs);
+                }
+                if (rc == ZB_OK) rc = zb_prod_fold_inplace(ctx, cur, d, rr[1], coeffs);
+                if (rc) {
+                    cleanup();
+                    return rc;
+                }
+                n_cur = n_after;
+                consume = true; // `cur` is ours from here on (or the caller allowed consumption)
+                break;
+            }
+        }
+    }
+    // ---- phase 2: one round per kernel (persistent tail for small tables) ----
+    for (; round < v; round++) {
         if (sharded && n_cur <= (1ull << gather_log2())) {
             // leave the sharded regime: all-gather the shards into the global order; `coeffs` already hold the
             // (global) coefficients of this round, so nothing is recomputed
@@ -192,6 +347,12 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
     for (uint32_t k = 0; k < d; k++) final_evals[k] = coeffs[k];
     cleanup();
     return ZB_OK;
+}
+
+int32_t zh_set_grid_min_log2(int32_t v) {
+    const int32_t old = grid_min_log2();
+    g_grid_min_log2 = v < 0 ? 0 : v;
+    return old;
 }
 
 int32_t zh_sumcheck_prove(zb_ctx *ctx, zb_mle poly, uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval,

@@ -9,14 +9,14 @@ namespace zk {
 
 constexpr int MAX_POLYS = 3;    // product sumcheck degree
 constexpr int MAX_BATCH = 64;   // trees per batched Merkle launch
-constexpr int MAIL_WORDS = 16;  // u64 payload words per mailbox
+constexpr int MAIL_WORDS = 24;  // u64 payload words per mailbox (16-word round grids + a status word)
 
 // Completion mailbox. `acc`/`ticket` live in device memory; `mail` is mapped pinned host memory.
 // mail[0..MAIL_WORDS) payload, mail[MAIL_WORDS] = sequence number written last (release, system scope).
 // Peer exchange over NVLink (multi-GPU): every rank owns one exchange buffer that all peers have mapped (CUDA IPC).
 // Two alternating sets (seq parity); per set XCHG_MAX_RANKS payload rows of XCHG_ROW words + one flag word per source rank.
 constexpr int XCHG_MAX_RANKS = 16;
-constexpr int XCHG_ROW = 8;
+constexpr int XCHG_ROW = 16;
 constexpr int XCHG_SET_WORDS = XCHG_MAX_RANKS * XCHG_ROW + XCHG_MAX_RANKS;
 struct XchgView {
     unsigned long long *peer[XCHG_MAX_RANKS]; // peer[q] = rank q's exchange buffer as seen from this GPU (peer[rank] = own)
@@ -73,6 +73,17 @@ void launch_tail_rounds(int d, const PolySet &ps, uint64_t n, const Mailbox &mb,
 void launch_publish_reduced(const unsigned long long *src, int n, unsigned long long *mail, unsigned long long seq, cudaStream_t st);
 // multi-GPU: all-gathered cyclic shards [rank][j] -> global order out[rank + world * j]
 void launch_interleave(const uint32_t *gathered, uint32_t *out, uint64_t n_local, uint32_t world, cudaStream_t st);
+
+// Two rounds per pass. With the top two index bits of the (possibly folded) tables as variables (X, Y), the bivariate
+//   G(X, Y) = sum_i prod_k B_k,i(X, Y),   B bilinear through the four quarter elements,
+// holds BOTH next round polynomials: g(X) = G(X, 0) + G(X, 1) and, once r is known, g'(Y) = G(r, Y). One pass over the
+// data therefore serves two sumcheck rounds: `nfold` (0..2) variables are bound first with r1 (and r2), the folded
+// tables (length m = n / 2^nfold) are written to dst (in place allowed), and G of the folded tables is published on the
+// grid P x P, P = {0,1} (D=1), {0,1,inf} (D=2), {0,1,-1,inf} (D=3): payload[ix * |P| + iy], canonical.
+// Needs m >= 8 and m % 8 == 0. HBM traffic per prove drops from 16 d N to ~10.7 d N bytes, host round trips halve.
+void launch_fold_grid(int d, int nfold, const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm_count,
+                      cudaStream_t st);
+inline bool fold_grid_ok(uint64_t m) { return m >= 8 && (m % 8) == 0; }
 
 // Plain sum of all n evaluations: payload {sum mod p}
 void launch_sum(const uint32_t *src, uint64_t n, const Mailbox &mb, int sm_count, cudaStream_t st);

@@ -23,6 +23,13 @@ static int tune(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
+static inline int grid_for(uint64_t work_items, int sm_count, int ctas_per_sm) {
+    uint64_t need = (work_items + THREADS - 1) / THREADS;
+    uint64_t cap = (uint64_t)sm_count * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -389,6 +396,304 @@ __global__ void k_fold_last(PolySet ps, uint32_t r, uint32_t rp, Mailbox mb) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// fold (0..2 variables) + bivariate round grid of the NEXT two variables (see launch_fold_grid in kernels.h)
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct NPts {
+    static constexpr int value = D == 1 ? 2 : D + 1;
+};
+
+// values of the line through (0 -> u, 1 -> v) on the point set of degree D: {0,1}, {0,1,inf}, {0,1,-1,inf}
+template <int D>
+__device__ __forceinline__ void expand_line(uint32_t u, uint32_t v, uint32_t (&o)[NPts<D>::value]) {
+    o[0] = u;
+    o[1] = v;
+    if constexpr (D == 2) o[2] = bb::sub(v, u);
+    if constexpr (D == 3) {
+        const uint32_t dd = bb::sub(v, u);
+        o[2] = bb::sub(u, dd);
+        o[3] = dd;
+    }
+}
+
+template <int D, int NS>
+struct FinishGrid {
+    __device__ void operator()(unsigned long long (&t)[NS]) const {
+#pragma unroll
+        for (int k = 0; k < NS; k++) {
+            uint32_t v = (uint32_t)(t[k] % bb::P);
+            if constexpr (D == 2) v = bb::mul(v, bb::R_MOD_P);
+            if constexpr (D == 3) v = bb::mul(v, bb::R2_MOD_P);
+            t[k] = v;
+        }
+    }
+};
+
+// VEC = consecutive elements per thread and load (2: 8-byte loads, one polynomial at a time; 1: 4-byte loads with the
+// loads of ALL polynomials issued before any arithmetic — more bytes in flight per register)
+template <int D, int FV, int VEC>
+__global__ void __launch_bounds__(THREADS) k_fold_grid(PolySet ps, uint64_t mq, uint32_t r1, uint32_t rp1, uint32_t r2, uint32_t rp2,
+                                                       Mailbox mb) {
+    constexpr int NP = NPts<D>::value, NS = NP * NP, NT = 1 << FV;
+    unsigned long long s[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) s[k] = 0;
+    // vector units: the folded tables have m elements = 4 mq vectors of VEC elements; an input table is NT m long
+    const uint64_t stride = (uint64_t)gridDim.x * THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < mq; i += stride) {
+        uint32_t f[D][4][VEC]; // [poly][quarter (b1 b2)][vector lane]
+        if constexpr (VEC == 2) {
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                const uint2 *p = reinterpret_cast<const uint2 *>(ps.src[k]);
+                uint2 a[4][NT];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int t = 0; t < NT; t++) a[j][t] = p[i + j * mq + t * (4 * mq)];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if constexpr (FV == 0) {
+                        f[k][j][0] = a[j][0].x;
+                        f[k][j][1] = a[j][0].y;
+                    } else if constexpr (FV == 1) {
+                        f[k][j][0] = bb::lerp(a[j][0].x, a[j][1].x, r1, rp1);
+                        f[k][j][1] = bb::lerp(a[j][0].y, a[j][1].y, r1, rp1);
+                    } else {
+                        const uint32_t lx = bb::lerp(a[j][0].x, a[j][2].x, r1, rp1), hx = bb::lerp(a[j][1].x, a[j][3].x, r1, rp1);
+                        const uint32_t ly = bb::lerp(a[j][0].y, a[j][2].y, r1, rp1), hy = bb::lerp(a[j][1].y, a[j][3].y, r1, rp1);
+                        f[k][j][0] = bb::lerp(lx, hx, r2, rp2);
+                        f[k][j][1] = bb::lerp(ly, hy, r2, rp2);
+                    }
+                }
+                if constexpr (FV > 0) {
+                    uint2 *o = reinterpret_cast<uint2 *>(ps.dst[k]);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) o[i + j * mq] = make_uint2(f[k][j][0], f[k][j][1]);
+                }
+            }
+        } else {
+            uint32_t a[D][4][NT];
+#pragma unroll
+            for (int k = 0; k < D; k++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int t = 0; t < NT; t++) a[k][j][t] = ps.src[k][i + j * mq + t * (4 * mq)];
+#pragma unroll
+            for (int k = 0; k < D; k++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if constexpr (FV == 0) f[k][j][0] = a[k][j][0];
+                    else if constexpr (FV == 1) f[k][j][0] = bb::lerp(a[k][j][0], a[k][j][1], r1, rp1);
+                    else
+                        f[k][j][0] = bb::lerp(bb::lerp(a[k][j][0], a[k][j][2], r1, rp1), bb::lerp(a[k][j][1], a[k][j][3], r1, rp1), r2, rp2);
+                    if constexpr (FV > 0) ps.dst[k][i + j * mq] = f[k][j][0];
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < VEC; c++) {
+            uint32_t val[D][NP][NP];
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                uint32_t x0[NP], x1[NP]; // the X line at Y = 0 (quarters 0 -> 2) and at Y = 1 (quarters 1 -> 3)
+                expand_line<D>(f[k][0][c], f[k][2][c], x0);
+                expand_line<D>(f[k][1][c], f[k][3][c], x1);
+#pragma unroll
+                for (int ix = 0; ix < NP; ix++) expand_line<D>(x0[ix], x1[ix], val[k][ix]);
+            }
+#pragma unroll
+            for (int ix = 0; ix < NP; ix++)
+#pragma unroll
+                for (int iy = 0; iy < NP; iy++) {
+                    if constexpr (D == 1) s[ix * NP + iy] += val[0][ix][iy];
+                    else if constexpr (D == 2) s[ix * NP + iy] += bb::mont_mul_lazy(val[0][ix][iy], val[1][ix][iy]);
+                    else s[ix * NP + iy] += bb::mont_mul_lazy(bb::mont_mul_lazy(val[0][ix][iy], val[1][ix][iy]), val[2][ix][iy]);
+                }
+        }
+    }
+    publish_sums<NS>(s, mb, FinishGrid<D, NS>());
+}
+
+// The same pass with the loads decoupled from the register file: every thread streams ITS OWN operands through a
+// private ring of shared-memory slots with cp.async (LDGSTS, 8 bytes per slot), STAGES iterations deep. No barrier is
+// needed (a thread only ever reads the slots it filled), the bytes in flight per SM are set by the ring (~100-150 KB)
+// instead of by registers x occupancy, which is what the register-heavy grid arithmetic could not provide.
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int D, int FV, int STAGES_>
+struct GridAsync {
+    static constexpr int NT = 1 << FV;
+    static constexpr int NSLOT = D * 4 * NT;
+    static constexpr int STAGE_BYTES = NSLOT * THREADS * 8;
+    static constexpr int STAGES = STAGES_;
+    static constexpr int SMEM = STAGES * STAGE_BYTES;
+    static_assert(STAGES >= 2 && SMEM <= 200 * 1024, "ring depth");
+};
+
+template <int D, int FV, int STAGES_>
+__global__ void __launch_bounds__(THREADS) k_fold_grid_async(PolySet ps, uint64_t mq, uint32_t r1, uint32_t rp1, uint32_t r2,
+                                                             uint32_t rp2, Mailbox mb) {
+    using G = GridAsync<D, FV, STAGES_>;
+    constexpr int NP = NPts<D>::value, NS = NP * NP, NT = G::NT, NSLOT = G::NSLOT, STAGES = G::STAGES;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2 *ring = reinterpret_cast<uint2 *>(smem_raw); // [STAGES][NSLOT][THREADS]
+    unsigned long long s[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) s[k] = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * THREADS;
+    const uint64_t i0 = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+    const uint64_t cnt = i0 < mq ? (mq - i0 + stride - 1) / stride : 0;
+    auto issue = [&](int stage, uint64_t i) {
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const uint2 *p = reinterpret_cast<const uint2 *>(ps.src[k]);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int t = 0; t < NT; t++)
+                    cp_async8(&ring[((size_t)stage * NSLOT + (k * 4 + j) * NT + t) * THREADS + threadIdx.x], p + i + j * mq + t * (4 * mq));
+        }
+    };
+#pragma unroll
+    for (int st = 0; st < STAGES - 1; st++) {
+        if ((uint64_t)st < cnt) issue(st, i0 + st * stride);
+        cp_async_commit();
+    }
+    for (uint64_t it = 0; it < cnt; it++) {
+        const uint64_t nxt = it + STAGES - 1;
+        if (nxt < cnt) issue((int)(nxt % STAGES), i0 + nxt * stride);
+        cp_async_commit();
+        cp_async_wait<STAGES - 1>(); // everything but the newest STAGES-1 groups has landed: iteration `it` is in its slots
+        const int stage = (int)(it % STAGES);
+        const uint64_t i = i0 + it * stride;
+        uint32_t f[D][4][2];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            uint2 a[4][NT];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int t = 0; t < NT; t++) a[j][t] = ring[((size_t)stage * NSLOT + (k * 4 + j) * NT + t) * THREADS + threadIdx.x];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if constexpr (FV == 0) {
+                    f[k][j][0] = a[j][0].x;
+                    f[k][j][1] = a[j][0].y;
+                } else if constexpr (FV == 1) {
+                    f[k][j][0] = bb::lerp(a[j][0].x, a[j][1].x, r1, rp1);
+                    f[k][j][1] = bb::lerp(a[j][0].y, a[j][1].y, r1, rp1);
+                } else {
+                    const uint32_t lx = bb::lerp(a[j][0].x, a[j][2].x, r1, rp1), hx = bb::lerp(a[j][1].x, a[j][3].x, r1, rp1);
+                    const uint32_t ly = bb::lerp(a[j][0].y, a[j][2].y, r1, rp1), hy = bb::lerp(a[j][1].y, a[j][3].y, r1, rp1);
+                    f[k][j][0] = bb::lerp(lx, hx, r2, rp2);
+                    f[k][j][1] = bb::lerp(ly, hy, r2, rp2);
+                }
+            }
+            if constexpr (FV > 0) {
+                uint2 *o = reinterpret_cast<uint2 *>(ps.dst[k]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) o[i + j * mq] = make_uint2(f[k][j][0], f[k][j][1]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            uint32_t val[D][NP][NP];
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                uint32_t x0[NP], x1[NP];
+                expand_line<D>(f[k][0][c], f[k][2][c], x0);
+                expand_line<D>(f[k][1][c], f[k][3][c], x1);
+#pragma unroll
+                for (int ix = 0; ix < NP; ix++) expand_line<D>(x0[ix], x1[ix], val[k][ix]);
+            }
+#pragma unroll
+            for (int ix = 0; ix < NP; ix++)
+#pragma unroll
+                for (int iy = 0; iy < NP; iy++) {
+                    if constexpr (D == 1) s[ix * NP + iy] += val[0][ix][iy];
+                    else if constexpr (D == 2) s[ix * NP + iy] += bb::mont_mul_lazy(val[0][ix][iy], val[1][ix][iy]);
+                    else s[ix * NP + iy] += bb::mont_mul_lazy(bb::mont_mul_lazy(val[0][ix][iy], val[1][ix][iy]), val[2][ix][iy]);
+                }
+        }
+    }
+    cp_async_wait<0>();
+    publish_sums<NS>(s, mb, FinishGrid<D, NS>());
+}
+
+template <int D, int FV, int STAGES_>
+static void fold_grid_async_launch_s(const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
+    using G = GridAsync<D, FV, STAGES_>;
+    static const bool once = [] {
+        cudaFuncSetAttribute(k_fold_grid_async<D, FV, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        return true;
+    }();
+    (void)once;
+    const uint64_t mq = m / 8;
+    const int per_sm = (227 * 1024) / (G::SMEM + 2048) < 1 ? 1 : (227 * 1024) / (G::SMEM + 2048);
+    const int grid = grid_for(mq, sm, per_sm > 4 ? 4 : per_sm);
+    k_fold_grid_async<D, FV, STAGES_><<<grid, THREADS, G::SMEM, st>>>(ps, mq, r1, bb::shoup_pre(r1), r2, bb::shoup_pre(r2), mb);
+}
+
+// ring depth per (D, FV): the slots of one iteration are D*4*2^FV*8 bytes per thread; the default keeps ~100-200 KB per SM
+template <int D, int FV>
+static void fold_grid_async_launch(const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
+    constexpr int SB = D * 4 * (1 << FV) * THREADS * 8;
+    constexpr int MAXS = (196608 / SB) > 4 ? 4 : (196608 / SB);
+    // measured (profiles/r01_grid_sweep.txt): d = 3, one folded variable: 3 stages 5978 GB/s, 4 stages 5816, 2 stages (2 CTAs/SM) 4738
+    static const int want = tune(FV == 2 ? "ZB_GRID_STAGES_F2" : FV == 1 ? "ZB_GRID_STAGES_F1" : "ZB_GRID_STAGES_F0",
+                                 (FV == 1 && MAXS >= 3) ? 3 : MAXS);
+    if constexpr (MAXS >= 4) {
+        if (want >= 4) return fold_grid_async_launch_s<D, FV, 4>(ps, m, r1, r2, mb, sm, st);
+    }
+    if constexpr (MAXS >= 3) {
+        if (want >= 3) return fold_grid_async_launch_s<D, FV, 3>(ps, m, r1, r2, mb, sm, st);
+    }
+    return fold_grid_async_launch_s<D, FV, 2>(ps, m, r1, r2, mb, sm, st);
+}
+
+template <int D, int VEC>
+static void fold_grid_v(int nfold, const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
+    static const int CPS = tune("ZB_GRID_CPS", 4);
+    const uint64_t mq = m / (4 * VEC);
+    const int grid = grid_for(mq, sm, CPS);
+    const uint32_t rp1 = bb::shoup_pre(r1), rp2 = bb::shoup_pre(r2);
+    if (nfold == 0) k_fold_grid<D, 0, VEC><<<grid, THREADS, 0, st>>>(ps, mq, r1, rp1, r2, rp2, mb);
+    else if (nfold == 1) k_fold_grid<D, 1, VEC><<<grid, THREADS, 0, st>>>(ps, mq, r1, rp1, r2, rp2, mb);
+    else k_fold_grid<D, 2, VEC><<<grid, THREADS, 0, st>>>(ps, mq, r1, rp1, r2, rp2, mb);
+}
+
+template <int D>
+static void fold_grid_t(int nfold, const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
+    static const int ASYNC = tune("ZB_GRID_ASYNC", 1);
+    static const int ASYNC_MIN = tune("ZB_GRID_ASYNC_MIN_LOG2", 16);
+    if (ASYNC && m >= (1ull << ASYNC_MIN)) { // the ring pays off once the pass is bandwidth-bound
+        if (nfold == 0) fold_grid_async_launch<D, 0>(ps, m, r1, r2, mb, sm, st);
+        else if (nfold == 1) fold_grid_async_launch<D, 1>(ps, m, r1, r2, mb, sm, st);
+        else fold_grid_async_launch<D, 2>(ps, m, r1, r2, mb, sm, st);
+        return;
+    }
+    static const int VEC = tune("ZB_GRID_VEC", 2);
+    if (VEC == 1) fold_grid_v<D, 1>(nfold, ps, m, r1, r2, mb, sm, st);
+    else fold_grid_v<D, 2>(nfold, ps, m, r1, r2, mb, sm, st);
+}
+
+void launch_fold_grid(int d, int nfold, const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm,
+                      cudaStream_t st) {
+    if (d == 1) fold_grid_t<1>(nfold, ps, m, r1, r2, mb, sm, st);
+    else if (d == 2) fold_grid_t<2>(nfold, ps, m, r1, r2, mb, sm, st);
+    else fold_grid_t<3>(nfold, ps, m, r1, r2, mb, sm, st);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Persistent tail: once the tables are small (n <= 2^14 by default) a launch per round is pure latency
 // (launch + drain ~ 10 us against < 2 us of work). One CTA stays resident for ALL remaining rounds: thread 0 polls a
 // host-mapped word for the next challenge (tag = expected sequence number, so a stale value can never match), the CTA
@@ -556,12 +861,6 @@ void launch_interleave(const uint32_t *gathered, uint32_t *out, uint64_t n_local
     k_interleave<<<(int)(g > 148 * 16 ? 148 * 16 : (g ? g : 1)), 256, 0, st>>>(gathered, out, n_local, world);
 }
 
-static inline int grid_for(uint64_t work_items, int sm_count, int ctas_per_sm) {
-    uint64_t need = (work_items + THREADS - 1) / THREADS;
-    uint64_t cap = (uint64_t)sm_count * ctas_per_sm;
-    if (need < 1) need = 1;
-    return (int)(need < cap ? need : cap);
-}
 
 template <int D>
 static void round_sums_t(const PolySet &ps, uint64_t n, const Mailbox &mb, int sm, cudaStream_t st) {
