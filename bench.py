@@ -208,18 +208,26 @@ def run_ours(args):
     traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if dom_name == "fold_sums_d3" and dom_cnt:
-            traffic = tj["k_fold_sums_v4<3,1>"]["ratio"] * dom_bytes / dom_cnt
-            traffic_src = "ncu dram__bytes_read+write / algorithmic = %.4f (profiles/r01_traffic.json) x this run's algorithmic bytes per launch" % tj["k_fold_sums_v4<3,1>"]["ratio"]
+        if dom_name in tj.get("families", {}) and dom_cnt:
+            ratio = tj["families"][dom_name]["ratio"]
+            traffic = ratio * dom_bytes / dom_cnt
+            traffic_src = ("ncu dram__bytes_read+write / algorithmic = %.4f (profiles/r01_traffic.json) x this run's algorithmic "
+                           "bytes per launch" % ratio)
     except Exception:  # noqa: BLE001
         pass
+    bytes_moved = sum(v[2] for v in prof.values()) / max(args.steps, 1)  # algorithmic bytes of every kernel of one prove
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": dom_bytes / dom_cnt if dom_cnt else None, "peak_source": peak_src,
                 "launches": dom_cnt, "avg_launch_ms": dom_ms / dom_cnt if dom_cnt else None,
                 "algorithmic_bytes_per_step": dom_bytes // max(args.steps, 1),
                 "kernel_share_of_step": dom_ms / ms if ms else None, "all_kernels_share_of_step": kernel_ms / ms if ms else None,
-                "whole_prove_frac": (48.0 * n) / (ms_per_step * 1e-3) / 1e9 / peak}
+                # whole prove: bytes the kernels of one prove actually have to move (two rounds per pass: ~32 B per element
+                # and step for d = 3) over the step time; and the same time against the one-round-per-pass model of
+                # SURVEY.md §8d (48 B per element), which the two-round schedule undercuts — that ratio may exceed 1
+                "whole_prove_bytes_per_step": bytes_moved,
+                "whole_prove_frac": bytes_moved / (ms_per_step * 1e-3) / 1e9 / peak,
+                "vs_one_round_per_pass_model_48B_per_elem": (48.0 * n) / (ms_per_step * 1e-3) / 1e9 / peak}
     by_kernel = {k: {"launches": v[0], "ms": round(v[1], 4), "GBps": round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] else None}
                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
 
