@@ -49,6 +49,9 @@ pub extern fn zb_mle_scalar_mul(ctx: *Ctx, a: Mle, scalar: u64, out: *Mle) i32;
 pub extern fn zb_prod_round_coeffs(ctx: *Ctx, polys: [*]const Mle, d: u32, out_coeffs: [*]u64) i32;
 pub extern fn zb_prod_fold_inplace(ctx: *Ctx, polys: [*]const Mle, d: u32, r: u64, next_coeffs: ?[*]u64) i32;
 pub extern fn zb_prod_partial_eval(ctx: *Ctx, polys: [*]const Mle, d: u32, r: u64, out: [*]Mle, next_coeffs: ?[*]u64) i32;
+pub extern fn zb_prod_grid(ctx: *Ctx, polys: [*]const Mle, d: u32, grid: [*]u64) i32;
+pub extern fn zb_prod_fold_grid(ctx: *Ctx, polys: [*]const Mle, d: u32, nfold: u32, r: [*]const u64, out: ?[*]Mle, grid: [*]u64) i32;
+pub extern fn zb_witness_pack(ctx: *Ctx, cols: [*]const u64, num_steps: u64, n_cols: u32, n_hold: u32, out: [*]Mle, num_vars: ?*u32) i32;
 pub extern fn zb_merkle_build(ctx: *Ctx, polys: [*]const Mle, count: u32, trees: [*]Tree, roots: ?[*]u8) i32;
 pub extern fn zb_merkle_build_values(ctx: *Ctx, values: [*]const u64, n: u64, tree: *Tree, root: *[32]u8) i32;
 pub extern fn zb_merkle_info(ctx: *Ctx, t: Tree, n_values: ?*u64, height: ?*u32, root: ?*[32]u8) i32;
