@@ -240,6 +240,22 @@ def run_ours(args):
 
     extras = None
     cpu = None
+    if world > 1 and not args.skip_extras:
+        # config C5's second half: Merkle commit of one 2^LOG2N-entry-per-GPU witness polynomial sharded by contiguous
+        # subtree (zh_commit_sharded): every GPU builds its subtree, the roots are gathered, the top levels are host hashes
+        lgm = min(26, args.log2n)
+        blk = z.Multilinear.synthetic(ctx, SEED + 9, 1 << lgm, start=rank << lgm, stride=1)
+        z.CommitmentScheme.commit_sharded(blk)[1].deinit()
+        barrier(dist)
+        ctx.sync()
+        t0 = time.perf_counter()
+        com, tree = z.CommitmentScheme.commit_sharded(blk)
+        dt = max_over_ranks(dist, time.perf_counter() - t0, local)
+        tree.deinit()
+        blk.deinit()
+        leaves = (1 << lgm) * world
+        extras = {f"C5_merkle_commit_sharded_2^{lgm}_per_gpu": {"ms": dt * 1e3, "total_leaves": leaves,
+                                                                  "keccak_per_s": (2 * leaves - 1) / dt, "root": com.commitment.hex()}}
     if rank == 0 and world == 1 and not args.skip_extras:
         extras = run_extras(args, z, ctx, peak)
     if rank == 0 and world == 1 and not args.skip_cpu:
