@@ -45,6 +45,10 @@ enum zb_status {
     ZB_ERR_QUERY_TABLE_MISMATCH = -11, /* lasso_prover.zig:199 */
     ZB_ERR_WRONG_NUM_CHALLENGES = -12, /* sumcheck_prover.zig:105 */
     ZB_ERR_DIFFERENT_NUM_VARS = -13,   /* multilinear.zig:237 */
+    ZB_ERR_EMPTY_TRACE = -14,          /* prover.zig:145 */
+    ZB_ERR_NO_SPACE_LEFT = -15,        /* serialization.zig:72-73: the reference's fixed (under-estimated) buffer */
+    ZB_ERR_PROGRAM_HASH_MISMATCH = -16, /* verifier.zig:105 */
+    ZB_ERR_INVALID_PROOF = -17,        /* serialization.zig:52-61 deserialize errors */
     ZB_ERR_NOT_CANONICAL = -20,        /* an input element was >= p (reference asserts val < MODULUS, field.zig:43) */
     ZB_ERR_BAD_HANDLE = -21,
     ZB_ERR_BAD_ARGUMENT = -22,

@@ -99,6 +99,24 @@ int32_t zh_generate_commitments(zb_ctx *ctx, zh_transcript *tr, const zb_mle *po
                                 uint64_t *points, uint64_t *values, uint64_t *leaf_indices, uint64_t *leaf_values,
                                 uint8_t *siblings, uint8_t *dirs);
 
+/* ---- Prover.prove after the VM + BinarySerializer.serialize: src/prover/prover.zig:91-226, serialization.zig:70-97 ----
+ * Everything `zigz prove` does once the execution trace exists: bind program hash / entry pc / initial registers, pack the
+ * 43 witness polynomials on the device (zb_witness_pack), placeholder constraint sumcheck and per-lookup Lasso entries
+ * with their transcript traffic (prover.zig:229-362), generateCommitments on the device, public I/O, "ZIGZ" v1 bytes.
+ * trace_cols: 43 SoA columns x num_steps raw u64 (order of prover.zig:376-390); final_regs: 32 values.
+ * compat_buffer != 0 reproduces the reference's under-estimated fixed buffer (error.NoSpaceLeft once num_vars >= 19 or
+ * with a few thousand lookup steps, serialization.zig:134-173); 0 serializes any size.
+ * out_len always receives the exact size; error.OutOfMemory if out_cap is too small (call once with out = NULL to size). */
+int32_t zh_prove_from_trace(zb_ctx *ctx, const uint8_t *program, size_t program_len, uint64_t entry_pc,
+                            const uint64_t *initial_regs, uint32_t n_initial_regs, const uint64_t *trace_cols, uint64_t num_steps,
+                            uint64_t final_pc, const uint64_t *final_regs, const uint64_t *outputs, uint32_t n_outputs,
+                            int32_t compat_buffer, uint8_t *out, size_t out_cap, size_t *out_len);
+/* Verifier.verify (src/verifier/verifier.zig:49-294) on serialized proof bytes. *verdict: 0 Accept, 1 RejectInvalidSumcheck,
+ * 2 RejectInvalidLookup, 3 RejectInvalidCommitment. error.ProgramHashMismatch / error.InvalidProof as status. Host only. */
+int32_t zh_verify_proof(const uint8_t *proof, size_t len, const uint8_t *program, size_t program_len, int32_t *verdict);
+/* std.crypto.hash.sha2.Sha256 one-shot (program hash, prover.zig:98-99) */
+void zh_sha256(const void *data, size_t n, uint8_t out[32]);
+
 /* ---- LassoProver(BabyBear): src/lookups/lasso_prover.zig ---- */
 /* prove :103-173. Rows are flattened (inputs || outputs), `arity` u64 each (the reference's TableEntry / LookupQuery
  * hold separately allocated slices, table_builder.zig:14-35, lasso_prover.zig:65-86).

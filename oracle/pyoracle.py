@@ -23,7 +23,7 @@ ERRORS = {
     -1: "EmptyEvaluations", -2: "LengthNotPowerOfTwo", -3: "WrongNumberOfVariables", -4: "NoVariables",
     -5: "EmptyValues", -6: "IndexOutOfBounds", -7: "PointDimensionMismatch", -8: "NoQueries",
     -9: "MappingLengthMismatch", -10: "InvalidMapping", -11: "QueryTableMismatch", -12: "WrongNumberOfChallenges",
-    -100: "OutOfMemory",
+    -14: "EmptyTrace", -15: "NoSpaceLeft", -16: "ProgramHashMismatch", -17: "InvalidProof", -100: "OutOfMemory",
 }
 
 
@@ -94,6 +94,15 @@ def lib():
         L.zo_generate_commitments.argtypes = [u64, C.c_void_p, C.POINTER(P64), u32, u64, P8, P64, P64, P64, P64, P8, P8]
         L.zo_witness_pack.restype = u64
         L.zo_witness_pack.argtypes = [u64, P64, u64, u32, u32, P64]
+        L.zo_count_lookups.restype = u64
+        L.zo_count_lookups.argtypes = [P64, u64]
+        L.zo_proof_exact_size.restype = C.c_size_t
+        L.zo_proof_exact_size.argtypes = [u64, u32, u32, u64]
+        L.zo_proof_estimated_size.restype = C.c_size_t
+        L.zo_proof_estimated_size.argtypes = [u64, u32, u64]
+        L.zo_prove_from_trace.argtypes = [u64, C.c_char_p, C.c_size_t, u64, P64, u32, P64, u64, u64, P64, P64, u32, C.c_int, P8,
+                                          C.c_size_t, C.POINTER(C.c_size_t)]
+        L.zo_verify_proof.argtypes = [u64, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
         L.zo_splitmix64.restype = u64
         L.zo_splitmix64.argtypes = [u64]
         L.zo_fill_synthetic.argtypes = [u64, u64, u64, u64, P64]
@@ -369,6 +378,31 @@ def witness_pack(p, cols, n_hold=33) -> np.ndarray:
     got = lib().zo_witness_pack(p, _p(c.reshape(-1)) if c.size else _p(np.zeros(1, np.uint64)), steps, n_cols, n_hold, _p(out.reshape(-1)))
     assert got == padded
     return out
+
+
+VERDICTS = {0: "Accept", 1: "RejectInvalidSumcheck", 2: "RejectInvalidLookup", 3: "RejectInvalidCommitment"}
+
+
+def prove_from_trace(p, program: bytes, entry_pc, initial_regs, cols, final_pc, final_regs, outputs, compat_buffer=False) -> bytes:
+    """Prover.prove after the VM + BinarySerializer.serialize (prover.zig:91-226, serialization.zig:70-97)."""
+    c = _a(cols)
+    steps = c.shape[1] if c.ndim == 2 else 0
+    ir, fr, out = _a(initial_regs if initial_regs is not None else []), _a(final_regs), _a(outputs if outputs is not None else [])
+    n_lookups = int(lib().zo_count_lookups(_p(np.ascontiguousarray(c[33])), steps)) if steps else 0
+    cap = int(lib().zo_proof_exact_size(max(steps, 1), ir.size, out.size, n_lookups))
+    buf = np.zeros(cap, np.uint8)
+    n = C.c_size_t(0)
+    z1 = np.zeros(1, np.uint64)
+    _chk(lib().zo_prove_from_trace(p, program, len(program), entry_pc, _p(ir) if ir.size else _p(z1), ir.size,
+                                   _p(c.reshape(-1)) if c.size else _p(z1), steps, final_pc, _p(fr), _p(out) if out.size else _p(z1),
+                                   out.size, 1 if compat_buffer else 0, _p8(buf), cap, C.byref(n)))
+    return buf[:n.value].tobytes()
+
+
+def verify_proof(p, proof: bytes, program: bytes) -> str:
+    res = C.c_int(-1)
+    _chk(lib().zo_verify_proof(p, proof, len(proof), program, len(program), C.byref(res)))
+    return VERDICTS[res.value]
 
 
 # ---------------------------------------------------------------- lasso

@@ -526,6 +526,193 @@ uint64_t zo_witness_pack(uint64_t p, const uint64_t *cols, uint64_t num_steps, u
 }
 
 /* ------------------------------------------------------------------ */
+/* Prover.prove after the VM + BinarySerializer.serialize + Verifier.verify                                          */
+/* /root/reference/src/prover/prover.zig:73-226, 229-362, 514-559; src/prover/proof.zig:194-261;                      */
+/* src/prover/serialization.zig:70-97, 134-245, 296-344, 374-429; src/verifier/verifier.zig:49-294                    */
+/* ------------------------------------------------------------------ */
+static void put32(uint8_t **w, uint32_t v) { for (int i = 0; i < 4; i++) *(*w)++ = (uint8_t)(v >> (8 * i)); }
+static void put64(uint8_t **w, uint64_t v) { for (int i = 0; i < 8; i++) *(*w)++ = (uint8_t)(v >> (8 * i)); }
+static uint32_t get32(const uint8_t **r) { uint32_t v = 0; for (int i = 0; i < 4; i++) v |= (uint32_t)(*(*r)++) << (8 * i); return v; }
+static uint64_t get64(const uint8_t **r) { uint64_t v = 0; for (int i = 0; i < 8; i++) v |= (uint64_t)(*(*r)++) << (8 * i); return v; }
+
+static int opcode_has_table(uint64_t opcode) { /* instruction_table.zig:243-275 via state.zig:151 */
+    return opcode == 0x33 || opcode == 0x13 || opcode == 0x03 || opcode == 0x23 || opcode == 0x63;
+}
+
+uint64_t zo_count_lookups(const uint64_t *opcode_col, uint64_t num_steps) { /* builder.zig:253-267 */
+    uint64_t c = 0;
+    for (uint64_t i = 0; i < num_steps; i++) c += opcode_has_table(opcode_col[i]);
+    return c;
+}
+
+static uint32_t log2_ceil(uint64_t n) {
+    uint32_t v = 0;
+    while (((uint64_t)1 << v) < n) v++;
+    return v;
+}
+
+size_t zo_proof_exact_size(uint64_t num_steps, uint32_t n_init, uint32_t n_out, uint64_t n_lookups) {
+    uint32_t v = log2_ceil(num_steps);
+    return 32 + (32 + 8 + 8 + 4 + 8 * (size_t)n_init + 4 + 8 * 32 + 8 + 4 + 8 * (size_t)n_out) + ((size_t)v * 4 * 8 + (size_t)v * 8 + 8) + 4 +
+           (size_t)n_lookups * 24 + 43 * (32 + (size_t)v * 8 + 8 + 8 + 8 + 8 + 4 + (size_t)v * 33);
+}
+
+size_t zo_proof_estimated_size(uint64_t num_steps, uint32_t n_init, uint64_t n_lookups) { /* serialization.zig:134-173 */
+    uint32_t v = log2_ceil(num_steps);
+    return 32 + (32 + 8 + 8 + 4 + 4) + 8 * (size_t)n_init + 8 * 32 + ((size_t)v * 4 * 8 + (size_t)v * 8 + 8) + 4 + (size_t)n_lookups * (4 + 8 + 8) +
+           43 * (32 + (size_t)v * 8 + 8 + 32 * 20);
+}
+
+int zo_prove_from_trace(uint64_t p, const uint8_t *program, size_t program_len, uint64_t entry_pc, const uint64_t *initial_regs,
+                        uint32_t n_init, const uint64_t *cols, uint64_t num_steps, uint64_t final_pc, const uint64_t *final_regs,
+                        const uint64_t *outputs, uint32_t n_out, int compat_buffer, uint8_t *out, size_t out_cap, size_t *out_len) {
+    if (num_steps == 0) return ZO_ERR_EMPTY_TRACE; /* prover.zig:144-146 */
+    const uint32_t v = log2_ceil(num_steps);
+    const uint64_t padded = (uint64_t)1 << v;
+    const uint64_t n_lookups = zo_count_lookups(cols + 33 * num_steps, num_steps);
+    const size_t exact = zo_proof_exact_size(num_steps, n_init, n_out, n_lookups);
+    if (compat_buffer && exact > zo_proof_estimated_size(num_steps, n_init, n_lookups)) return ZO_ERR_NO_SPACE_LEFT; /* :72-73 */
+    if (out_len) *out_len = exact;
+    if (!out || out_cap < exact) return ZO_ERR_OOM;
+    zo_transcript tr;
+    zo_transcript_init(&tr); /* :91 */
+    uint8_t program_hash[32];
+    zo_sha256_oneshot(program, program_len, program_hash); /* :98-100 */
+    zo_transcript_append_bytes(&tr, program_hash, 32);
+    zo_transcript_append_field(&tr, zo_f_init(p, entry_pc)); /* :103 */
+    for (uint32_t i = 0; i < n_init; i++) zo_transcript_append_field(&tr, zo_f_init(p, initial_regs[i])); /* :106-110 */
+    /* witness (witness.zig:29-270) */
+    uint64_t *w = malloc(43 * padded * sizeof(uint64_t));
+    if (!w) return ZO_ERR_OOM;
+    zo_witness_pack(p, cols, num_steps, 43, 33, w);
+    uint8_t *o = out;
+    /* header serialization.zig:175-182 */
+    memcpy(o, "ZIGZ", 4); o += 4;
+    put32(&o, 1); put64(&o, p); put64(&o, num_steps); put32(&o, v); put32(&o, 0);
+    /* public IO :209-245 (packagePublicIO prover.zig:514-559) */
+    memcpy(o, program_hash, 32); o += 32;
+    put64(&o, entry_pc); put64(&o, final_pc);
+    put32(&o, n_init);
+    for (uint32_t i = 0; i < n_init; i++) put64(&o, initial_regs[i]);
+    put32(&o, 32);
+    for (int i = 0; i < 32; i++) put64(&o, final_regs[i]);
+    put64(&o, num_steps);
+    put32(&o, n_out);
+    for (uint32_t i = 0; i < n_out; i++) put64(&o, outputs[i]);
+    /* constraint sumcheck placeholder prover.zig:229-289 */
+    zo_transcript_append_bytes(&tr, "SUMCHECK_BEGIN", 14);
+    zo_transcript_append_field(&tr, zo_f_init(p, num_steps));
+    zo_transcript_append_field(&tr, zo_f_init(p, v));
+    uint64_t chal[64];
+    for (uint32_t r = 0; r < v; r++) {
+        for (int k = 0; k < 4; k++) zo_transcript_append_field(&tr, 0);
+        chal[r] = zo_transcript_challenge(&tr, p);
+    }
+    for (uint32_t r = 0; r < v; r++) for (int k = 0; k < 4; k++) put64(&o, 0); /* serialization.zig:296-311 */
+    for (uint32_t r = 0; r < v; r++) put64(&o, chal[r]);
+    put64(&o, 0);
+    /* Lasso placeholders prover.zig:292-362: one 0-round proof per lookup constraint */
+    zo_transcript_append_bytes(&tr, "LASSO_BEGIN", 11);
+    put32(&o, (uint32_t)n_lookups);
+    for (uint64_t k = 0; k < n_lookups; k++) {
+        zo_transcript_append_bytes(&tr, "LASSO_TABLE", 11);
+        zo_transcript_append_field(&tr, zo_f_init(p, (uint32_t)k));
+        put32(&o, (uint32_t)k); put64(&o, 1); put32(&o, 0); put64(&o, 0); /* :333-344: id, num_lookups, num_vars, final_eval */
+    }
+    /* commitments prover.zig:366-467 */
+    const uint64_t *polys[43];
+    for (int i = 0; i < 43; i++) polys[i] = w + (size_t)i * padded;
+    uint8_t *roots = malloc(43 * 32), *sib = malloc(43 * (size_t)(v ? v : 1) * 32), *dirs = malloc(43 * (size_t)(v ? v : 1));
+    uint64_t *pts = malloc(43 * (size_t)(v ? v : 1) * 8), vals[43], li[43], lv[43];
+    int rc = (roots && sib && dirs && pts) ? zo_generate_commitments(p, &tr, polys, 43, padded, roots, pts, vals, li, lv, sib, dirs) : ZO_ERR_OOM;
+    if (rc == ZO_OK) {
+        for (int i = 0; i < 43; i++) { /* serialization.zig:374-429 */
+            memcpy(o, roots + 32 * i, 32); o += 32;
+            for (uint32_t j = 0; j < v; j++) put64(&o, pts[(size_t)i * v + j]);
+            put64(&o, vals[i]);
+            put64(&o, vals[i]); /* OpeningProof.value (the same evaluation, polynomial_commit.zig:97) */
+            put64(&o, li[i]); put64(&o, lv[i]); put32(&o, v);
+            memcpy(o, sib + (size_t)i * v * 32, (size_t)v * 32); o += (size_t)v * 32;
+            for (uint32_t j = 0; j < v; j++) *o++ = dirs[(size_t)i * v + j] ? 1 : 0;
+        }
+    }
+    free(w); free(roots); free(sib); free(dirs); free(pts);
+    if (rc == ZO_OK && (size_t)(o - out) != exact) rc = ZO_ERR_OOM; /* internal consistency */
+    return rc;
+}
+
+/* Verifier.verify on serialized bytes: 0 Accept, 1 RejectInvalidSumcheck, 2 RejectInvalidLookup, 3 RejectInvalidCommitment;
+ * negative: ZO_ERR_PROGRAM_HASH_MISMATCH / ZO_ERR_BAD_PROOF (deserialize errors) */
+int zo_verify_proof(uint64_t p, const uint8_t *proof, size_t len, const uint8_t *program, size_t program_len, int *result) {
+    const uint8_t *r = proof, *end = proof + len;
+#define NEED(nbytes) do { if ((size_t)(end - r) < (size_t)(nbytes)) return ZO_ERR_BAD_PROOF; } while (0)
+    NEED(32);
+    if (memcmp(r, "ZIGZ", 4)) return ZO_ERR_BAD_PROOF;
+    r += 4;
+    if (get32(&r) != 1) return ZO_ERR_BAD_PROOF;
+    if (get64(&r) != p) return ZO_ERR_BAD_PROOF;
+    uint64_t num_steps = get64(&r);
+    uint32_t v = get32(&r);
+    (void)get32(&r);
+    if (v != log2_ceil(num_steps) || v > 63) return ZO_ERR_BAD_PROOF; /* Proof.init derives num_vars from num_steps (serialization.zig:113) */
+    NEED(32 + 16 + 4);
+    uint8_t hash[32], ph[32];
+    memcpy(ph, r, 32); r += 32;
+    zo_sha256_oneshot(program, program_len, hash);
+    (void)get64(&r); (void)get64(&r);
+    uint32_t n = get32(&r); NEED(8 * (size_t)n + 4); r += 8 * (size_t)n;
+    n = get32(&r); NEED(8 * (size_t)n + 12); r += 8 * (size_t)n;
+    (void)get64(&r);
+    n = get32(&r); NEED(8 * (size_t)n); r += 8 * (size_t)n;
+    if (memcmp(hash, ph, 32)) return ZO_ERR_PROGRAM_HASH_MISMATCH; /* verifier.zig:101-107 */
+    /* constraint sumcheck: only round 0 is checked (verifier.zig:209-214) */
+    NEED((size_t)v * 40 + 8);
+    uint64_t g0 = 0, g1 = 0;
+    for (uint32_t rd = 0; rd < v; rd++)
+        for (int k = 0; k < 4; k++) {
+            uint64_t c = zo_f_init(p, get64(&r));
+            if (rd == 0) { if (k == 0) g0 = c; g1 = zo_f_add(p, g1, c); }
+        }
+    r += (size_t)v * 8;
+    uint64_t final_eval = zo_f_init(p, get64(&r));
+    *result = 0;
+    if (v > 0 && zo_f_add(p, g0, g1) != final_eval) { *result = 1; return ZO_OK; }
+    NEED(4);
+    uint32_t n_lasso = get32(&r);
+    for (uint32_t k = 0; k < n_lasso; k++) {
+        NEED(16);
+        (void)get32(&r); (void)get64(&r);
+        uint32_t lv_ = get32(&r);
+        NEED((size_t)lv_ * 32 + 8);
+        uint64_t a0 = 0, a1 = 0;
+        for (uint32_t rd = 0; rd < lv_; rd++)
+            for (int c3 = 0; c3 < 3; c3++) { /* LassoProof multiset_proof has 3 coefficients per round (proof.zig:102-140) */
+                uint64_t c = zo_f_init(p, get64(&r));
+                if (rd == 0) { if (c3 == 0) a0 = c; a1 = zo_f_add(p, a1, c); }
+            }
+        r += (size_t)lv_ * 8;
+        uint64_t fe = zo_f_init(p, get64(&r));
+        if (lv_ > 0 && zo_f_add(p, a0, a1) != fe && *result == 0) *result = 2;
+    }
+    for (int i = 0; i < 43; i++) {
+        NEED(32 + (size_t)v * 8 + 8 + 28);
+        const uint8_t *root = r; r += 32;
+        r += (size_t)v * 8;
+        uint64_t value = zo_f_init(p, get64(&r)), pvalue = zo_f_init(p, get64(&r));
+        (void)get64(&r);
+        uint64_t leaf = zo_f_init(p, get64(&r));
+        uint32_t plen = get32(&r);
+        NEED((size_t)plen * 33);
+        const uint8_t *sibs = r; r += (size_t)plen * 32;
+        const uint8_t *dirs = r; r += plen;
+        /* verifyOpening verifier.zig:270-294: value == proof.value, point.len == num_vars, Merkle path */
+        if (*result == 0 && (value != pvalue || !zo_merkle_verify(root, leaf, sibs, dirs, plen))) *result = 3;
+    }
+#undef NEED
+    return ZO_OK;
+}
+
+/* ------------------------------------------------------------------ */
 /* Lasso — lasso_prover.zig, table_builder.zig                          */
 /* ------------------------------------------------------------------ */
 uint64_t zo_lasso_hash_row(uint64_t p, const uint64_t *row, uint32_t arity) { /* hashEntry/hashQuery :208-239 */

@@ -42,6 +42,10 @@ enum {
     ZO_ERR_INVALID_MAPPING = -10,       /* lasso_prover.zig:192 */
     ZO_ERR_QUERY_TABLE_MISMATCH = -11,  /* lasso_prover.zig:199 */
     ZO_ERR_WRONG_NUM_CHALLENGES = -12,  /* sumcheck_prover.zig:105 */
+    ZO_ERR_EMPTY_TRACE = -14,           /* prover.zig:145 */
+    ZO_ERR_NO_SPACE_LEFT = -15,         /* serialization.zig:72-73 fixed buffer */
+    ZO_ERR_PROGRAM_HASH_MISMATCH = -16, /* verifier.zig:105 */
+    ZO_ERR_BAD_PROOF = -17,             /* deserialize failures */
     ZO_ERR_OOM = -100
 };
 
@@ -118,6 +122,18 @@ int zo_generate_commitments(uint64_t p, zo_transcript *tr, const uint64_t *const
 /* ---- WitnessGenerator.generate on SoA trace columns: src/constraints/witness.zig:29-270. Returns the padded length;
  * out: n_cols * padded */
 uint64_t zo_witness_pack(uint64_t p, const uint64_t *cols, uint64_t num_steps, uint32_t n_cols, uint32_t n_hold, uint64_t *out);
+
+/* ---- Prover.prove after the VM (prover.zig:91-110, 156-226) + BinarySerializer.serialize (serialization.zig:70-97) ----
+ * cols: the 43 witness columns of the trace (SoA, order of prover.zig:376-390), final_regs: 32 values.
+ * compat_buffer != 0 reproduces the reference's under-estimated fixed buffer: error.NoSpaceLeft where `zigz prove` fails. */
+uint64_t zo_count_lookups(const uint64_t *opcode_col, uint64_t num_steps);
+size_t zo_proof_exact_size(uint64_t num_steps, uint32_t n_init, uint32_t n_out, uint64_t n_lookups);
+size_t zo_proof_estimated_size(uint64_t num_steps, uint32_t n_init, uint64_t n_lookups);
+int zo_prove_from_trace(uint64_t p, const uint8_t *program, size_t program_len, uint64_t entry_pc, const uint64_t *initial_regs,
+                        uint32_t n_init, const uint64_t *cols, uint64_t num_steps, uint64_t final_pc, const uint64_t *final_regs,
+                        const uint64_t *outputs, uint32_t n_out, int compat_buffer, uint8_t *out, size_t out_cap, size_t *out_len);
+/* Verifier.verify (verifier.zig:49-294) on the serialized proof: *result 0 Accept, 1/2/3 = RejectInvalidSumcheck/Lookup/Commitment */
+int zo_verify_proof(uint64_t p, const uint8_t *proof, size_t len, const uint8_t *program, size_t program_len, int *result);
 
 /* ---- Lasso: src/lookups/lasso_prover.zig, table_builder.zig ---- */
 /* rows are flattened (inputs || outputs), `arity` u64 per row */

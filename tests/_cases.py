@@ -48,3 +48,32 @@ def assert_sumcheck_equal(proof, gold, ncoef=2):
 def witness_cols(steps, n_cols=43):
     """Synthetic SoA trace columns used by the witness_pack golden cases (make_golden.py)."""
     return np.array([[splitmix64(1000 * c + i) >> (c % 3) for i in range(steps)] for c in range(n_cols)], dtype=np.uint64).reshape(n_cols, steps)
+
+
+def trace_case(steps, seed):
+    """The synthetic trace of tests/golden/make_golden.py:trace_case as a (43, steps) uint64 array + the other prove inputs."""
+    ops = [0x33, 0x13, 0x03, 0x23, 0x63, 0x37, 0x17, 0x6F, 0x67, 0x73, 0x3B, 0x1B]
+    cols = np.zeros((43, steps), np.uint64)
+    for c in range(43):
+        for i in range(steps):
+            if c == 0:
+                cols[c, i] = 0x1000 + 4 * i
+            elif c == 33:
+                cols[c, i] = ops[splitmix64(seed * 7919 + i) % len(ops)]
+            elif c in (34, 35, 36):
+                cols[c, i] = splitmix64(seed + 100 * c + i) % 32
+            elif c == 42:
+                cols[c, i] = splitmix64(seed + 4200 + i) & 1
+            else:
+                cols[c, i] = splitmix64(seed + 1000 * c + i)
+    return cols
+
+
+def prove_inputs(steps, seed, n_init, n_out):
+    cols = trace_case(steps, seed)
+    program = bytes(splitmix64(seed + i) & 0xFF for i in range(4 * steps))
+    init = [splitmix64(seed + 50 + i) for i in range(n_init)]
+    final_regs = [int(cols[1 + r][-1]) for r in range(32)]
+    outputs = [splitmix64(seed + 90 + i) for i in range(n_out)]
+    return dict(program=program, entry_pc=0x1000, initial_regs=init, cols=cols, final_pc=0x1000 + 4 * steps, final_regs=final_regs,
+                outputs=outputs)

@@ -215,6 +215,64 @@ def witness_pack(p, cols, n_hold):  # src/constraints/witness.zig:29-270
     return out
 
 
+def prove_from_trace(p, program, entry_pc, initial_regs, cols, final_pc, final_regs, outputs):
+    """Prover.prove after the VM (src/prover/prover.zig:91-226) + BinarySerializer.serialize (src/prover/serialization.zig)."""
+    import struct
+    steps = len(cols[0])
+    v = (steps - 1).bit_length()
+    tr = Transcript()
+    ph = hashlib.sha256(program).digest()
+    tr.append_bytes(ph)
+    tr.append_field(entry_pc % p)
+    for r in initial_regs:
+        tr.append_field(r % p)
+    w = witness_pack(p, cols, 33)
+    out = b"ZIGZ" + struct.pack("<IQQII", 1, p, steps, v, 0)
+    out += ph + struct.pack("<QQI", entry_pc, final_pc, len(initial_regs)) + b"".join(struct.pack("<Q", r) for r in initial_regs)
+    out += struct.pack("<I", 32) + b"".join(struct.pack("<Q", r) for r in final_regs)
+    out += struct.pack("<QI", steps, len(outputs)) + b"".join(struct.pack("<Q", r) for r in outputs)
+    tr.append_bytes(b"SUMCHECK_BEGIN")
+    tr.append_field(steps % p)
+    tr.append_field(v)
+    chal = []
+    for _ in range(v):
+        for _k in range(4):
+            tr.append_field(0)
+        chal.append(tr.challenge(p))
+    out += b"\x00" * (32 * v) + b"".join(struct.pack("<Q", c) for c in chal) + struct.pack("<Q", 0)
+    lookups = sum(1 for op in cols[33] if op in (0x33, 0x13, 0x03, 0x23, 0x63))
+    tr.append_bytes(b"LASSO_BEGIN")
+    out += struct.pack("<I", lookups)
+    for k in range(lookups):
+        tr.append_bytes(b"LASSO_TABLE")
+        tr.append_field(k)
+        out += struct.pack("<IQIQ", k, 1, 0, 0)
+    gc = generate_commitments(p, tr, w)
+    for root, o in zip(gc["roots"], gc["openings"]):
+        out += bytes.fromhex(root) + b"".join(struct.pack("<Q", c) for c in o["point"]) + struct.pack("<Q", o["value"])
+        out += struct.pack("<QQQI", o["value"], o["leaf_index"], o["leaf_value"], v)
+        out += b"".join(bytes.fromhex(x) for x in o["siblings"]) + bytes(o["dirs"])
+    return out
+
+
+def trace_case(steps, seed):
+    """A synthetic but well-formed trace: opcodes drawn from the RV64I opcode set, registers / memory columns random."""
+    ops = [0x33, 0x13, 0x03, 0x23, 0x63, 0x37, 0x17, 0x6F, 0x67, 0x73, 0x3B, 0x1B]
+    cols = []
+    for c in range(43):
+        if c == 0:
+            cols.append([0x1000 + 4 * i for i in range(steps)])
+        elif c == 33:
+            cols.append([ops[splitmix64(seed * 7919 + i) % len(ops)] for i in range(steps)])
+        elif c in (34, 35, 36):
+            cols.append([splitmix64(seed + 100 * c + i) % 32 for i in range(steps)])
+        elif c == 42:
+            cols.append([splitmix64(seed + 4200 + i) & 1 for i in range(steps)])
+        else:
+            cols.append([splitmix64(seed + 1000 * c + i) for i in range(steps)])
+    return cols
+
+
 def main():
     g = {"_generator": "tests/golden/make_golden.py (independent pure-Python restatement; hashlib + xxhash)"}
     t = Transcript()
@@ -299,6 +357,18 @@ def main():
             b"".join(int(x).to_bytes(8, "little") for col in witness_pack(BABYBEAR, cols, 33) for x in col)).hexdigest(),
             "first_col": witness_pack(BABYBEAR, cols, 33)[0], "last_col": witness_pack(BABYBEAR, cols, 33)[42]}
     g["witness_pack"] = wp
+
+    pf = {}
+    for steps, seed, n_init, n_out in ((1, 3, 0, 0), (4, 5, 2, 1), (13, 7, 32, 3), (64, 9, 0, 0)):
+        cols = trace_case(steps, seed)
+        program = bytes(splitmix64(seed + i) & 0xFF for i in range(4 * steps))
+        init = [splitmix64(seed + 50 + i) for i in range(n_init)]
+        final_regs = [cols[1 + r][-1] for r in range(32)]
+        outputs = [splitmix64(seed + 90 + i) for i in range(n_out)]
+        proof = prove_from_trace(BABYBEAR, program, 0x1000, init, cols, 0x1000 + 4 * steps, final_regs, outputs)
+        pf[f"steps{steps}"] = {"steps": steps, "seed": seed, "n_init": n_init, "n_out": n_out, "proof_len": len(proof),
+                               "proof_sha3": hashlib.sha3_256(proof).hexdigest(), "proof_head": proof[:96].hex()}
+    g["prove_from_trace"] = pf
 
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "zigz_golden.json")
     with open(out, "w") as f:

@@ -72,3 +72,36 @@ def test_trace_to_openings_pipeline(zlib, ctx, po):
     c = zlib.generate_commitments(tr, polys)
     w = po.generate_commitments(BB, otr, es)
     assert np.array_equal(c.roots, w.roots) and np.array_equal(c.values, w.values) and np.array_equal(c.siblings, w.siblings)
+
+
+def test_prove_from_trace_bytes_identical(zlib, ctx, po, golden):
+    """`zigz prove` after the VM: proof bytes equal the golden digests and the oracle's bytes; the verifier accepts."""
+    from _cases import prove_inputs
+    for name, case in golden["prove_from_trace"].items():
+        inp = prove_inputs(case["steps"], case["seed"], case["n_init"], case["n_out"])
+        proof = zlib.prove_from_trace(ctx, **inp)
+        assert len(proof) == case["proof_len"] and proof[:96].hex() == case["proof_head"]
+        assert hashlib.sha3_256(proof).hexdigest() == case["proof_sha3"], name
+        assert proof == po.prove_from_trace(BB, **inp)
+        assert zlib.verify_proof(proof, inp["program"]) == "Accept" == po.verify_proof(BB, proof, inp["program"])
+        assert zlib.prove_from_trace(ctx, compat_buffer=True, **inp) == proof
+    # determinism of opening points across two provers, different entry pc => different points (integration_tests.zig:212-245)
+    inp = prove_inputs(16, 21, 3, 0)
+    a, b = zlib.prove_from_trace(ctx, **inp), zlib.prove_from_trace(ctx, **inp)
+    assert a == b
+    inp2 = dict(inp, entry_pc=0x2000)
+    assert zlib.prove_from_trace(ctx, **inp2) != a
+    with pytest.raises(zlib.ZigzError) as e:
+        zlib.prove_from_trace(ctx, b"", 0, [], np.zeros((43, 0), np.uint64), 0, [0] * 32, [])
+    assert e.value.name == "EmptyTrace"
+
+
+def test_prove_from_trace_larger_trace_vs_oracle(zlib, ctx, po):
+    from _cases import prove_inputs
+    inp = prove_inputs(1000, 33, 32, 5)  # pads to 1024 steps, ~400 lookup constraints
+    proof = zlib.prove_from_trace(ctx, **inp)
+    assert proof == po.prove_from_trace(BB, **inp)
+    assert zlib.verify_proof(proof, inp["program"]) == "Accept"
+    bad = bytearray(proof)
+    bad[len(bad) // 2] ^= 0x10
+    assert zlib.verify_proof(bytes(bad), inp["program"]) == po.verify_proof(BB, bytes(bad), inp["program"])

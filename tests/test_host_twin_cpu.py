@@ -131,3 +131,40 @@ def test_flat_commit_u64_and_u32_forms(zlib, po, golden):
     e = np.array([1, 2, 3, 4], np.uint64)
     L.zh_flat_commit(e.ctypes.data_as(C.POINTER(C.c_uint64)), 4, out.ctypes.data_as(C.POINTER(C.c_uint8)))
     assert out.tobytes().hex() == golden["lasso"]["flat_commit_1234"]
+
+
+def test_verifier_twin_on_oracle_proofs(zlib, po, golden):
+    """zh_verify_proof (host only) on proofs produced by the oracle: Accept, ProgramHashMismatch, tamper rejections
+    (tests/integration_tests.zig:55-375 behaviours), and agreement with the oracle's verifier on random corruptions."""
+    import pytest
+    from _cases import prove_inputs
+    rng = random.Random(4)
+    for name, case in golden["prove_from_trace"].items():
+        inp = prove_inputs(case["steps"], case["seed"], case["n_init"], case["n_out"])
+        proof = po.prove_from_trace(BB, **inp)
+        assert hashlib.sha3_256(proof).hexdigest() == case["proof_sha3"]
+        assert zlib.verify_proof(proof, inp["program"]) == "Accept"
+        with pytest.raises(zlib.ZigzError) as e:
+            zlib.verify_proof(proof, inp["program"] + b"x")
+        assert e.value.name == "ProgramHashMismatch"
+        with pytest.raises(zlib.ZigzError) as e:
+            zlib.verify_proof(b"ZIGX" + proof[4:], inp["program"])
+        assert e.value.name == "InvalidProof"
+        with pytest.raises(zlib.ZigzError):
+            zlib.verify_proof(proof[:-5], inp["program"])
+        for _ in range(60):  # single-byte corruptions: same verdict / error as the oracle's verifier
+            bad = bytearray(proof)
+            pos = rng.randrange(len(bad))
+            bad[pos] ^= 1 << rng.randrange(8)
+            try:
+                want = po.verify_proof(BB, bytes(bad), inp["program"])
+            except po.OracleError as oe:
+                with pytest.raises(zlib.ZigzError) as e:
+                    zlib.verify_proof(bytes(bad), inp["program"])
+                assert e.value.name == oe.name, pos
+            else:
+                assert zlib.verify_proof(bytes(bad), inp["program"]) == want, pos
+    assert zlib.lib().zh_sha256 is not None
+    out = np.zeros(32, np.uint8)
+    zlib.lib().zh_sha256(b"abc", 3, out.ctypes.data_as(zlib.api.P8))
+    assert out.tobytes() == hashlib.sha256(b"abc").digest()

@@ -115,3 +115,34 @@ def test_witness_pack(po, golden):
         out = po.witness_pack(BB, witness_cols(case["steps"]), 33)
         assert hashlib.sha3_256(out.astype("<u8").tobytes()).hexdigest() == case["packed_sha3"], name
         assert out[0].tolist() == case["first_col"] and out[42].tolist() == case["last_col"]
+
+
+def test_prove_from_trace_and_verify(po, golden):
+    import hashlib
+    from _cases import prove_inputs
+    for name, case in golden["prove_from_trace"].items():
+        inp = prove_inputs(case["steps"], case["seed"], case["n_init"], case["n_out"])
+        proof = po.prove_from_trace(BB, **inp)
+        assert len(proof) == case["proof_len"], name
+        assert proof[:96].hex() == case["proof_head"]
+        assert hashlib.sha3_256(proof).hexdigest() == case["proof_sha3"], name
+        assert po.verify_proof(BB, proof, inp["program"]) == "Accept"
+        # integration-test behaviours (tests/integration_tests.zig:55-375)
+        import pytest
+        with pytest.raises(po.OracleError) as e:
+            po.verify_proof(BB, proof, inp["program"] + b"\x00")
+        assert e.value.name == "ProgramHashMismatch"
+        if case["steps"] > 1:
+            bad = bytearray(proof)
+            bad[-40] ^= 1  # a sibling digest of the last opening
+            assert po.verify_proof(BB, bytes(bad), inp["program"]) == "RejectInvalidCommitment"
+    # the reference's fixed serialization buffer is under-estimated: large num_vars cannot be serialized
+    import pytest
+    inp = prove_inputs(64, 9, 0, 0)
+    assert po.prove_from_trace(BB, compat_buffer=True, **inp) == po.prove_from_trace(BB, **inp)
+    L = po.lib()
+    assert L.zo_proof_exact_size(1 << 18, 0, 0, 0) <= L.zo_proof_estimated_size(1 << 18, 0, 0)
+    assert L.zo_proof_exact_size(1 << 19, 0, 0, 0) > L.zo_proof_estimated_size(1 << 19, 0, 0)  # num_vars >= 19: NoSpaceLeft
+    with pytest.raises(po.OracleError) as e:
+        po.prove_from_trace(BB, b"", 0, [], np.zeros((43, 0), np.uint64), 0, [0] * 32, [])
+    assert e.value.name == "EmptyTrace"

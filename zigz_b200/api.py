@@ -35,6 +35,12 @@ def _p8(a: np.ndarray):
     return a.ctypes.data_as(P8)
 
 
+def _b8(b: bytes):
+    """bytes -> (keep-alive array, uint8_t*)"""
+    a = np.frombuffer(b if len(b) else b"\x00", np.uint8)
+    return a, a.ctypes.data_as(P8)
+
+
 class Context:
     """One GPU + one stream; calls are synchronous and serialized like the single-threaded reference."""
 
@@ -604,6 +610,39 @@ def witness_pack(ctx: Context, cols, n_hold: int = 33) -> List[Multilinear]:
     nv = u32(0)
     ctx.check(lib().zb_witness_pack(ctx.handle, _p64(c.reshape(-1)) if c.size else None, steps, n_cols, n_hold, out, C.byref(nv)))
     return [Multilinear(ctx, out[i]) for i in range(n_cols)]
+
+
+VERDICTS = {0: "Accept", 1: "RejectInvalidSumcheck", 2: "RejectInvalidLookup", 3: "RejectInvalidCommitment"}
+
+
+def prove_from_trace(ctx: Context, program: bytes, entry_pc: int, initial_regs, cols, final_pc: int, final_regs, outputs,
+                     compat_buffer: bool = False) -> bytes:
+    """Everything `zigz prove` does after the VM has produced the trace (src/prover/prover.zig:91-226) + the "ZIGZ" v1
+    serialization (src/prover/serialization.zig): returns the proof bytes."""
+    c = _a64(cols)
+    steps = c.shape[1] if c.ndim == 2 else 0
+    ir, fr, out = _a64(initial_regs if initial_regs is not None else []), _a64(final_regs), _a64(outputs if outputs is not None else [])
+    n = C.c_size_t(0)
+    _keep, pp = _b8(program)
+    args = (pp, len(program), entry_pc, _p64(ir) if ir.size else None, ir.size, _p64(c.reshape(-1)) if c.size else None, steps,
+            final_pc, _p64(fr), _p64(out) if out.size else None, out.size, 1 if compat_buffer else 0)
+    rc = lib().zh_prove_from_trace(ctx.handle, *args, None, 0, C.byref(n))
+    if rc != -100:  # sizing call: OutOfMemory carries the exact size; anything else is the real error
+        ctx.check(rc)
+    buf = np.zeros(n.value, np.uint8)
+    ctx.check(lib().zh_prove_from_trace(ctx.handle, *args, _p8(buf), buf.size, C.byref(n)))
+    return buf[:n.value].tobytes()
+
+
+def verify_proof(proof: bytes, program: bytes) -> str:
+    """Verifier.verify (src/verifier/verifier.zig:49-294) on serialized proof bytes."""
+    v = C.c_int32(-1)
+    _k1, p1 = _b8(proof)
+    _k2, p2 = _b8(program)
+    rc = lib().zh_verify_proof(p1, len(proof), p2, len(program), C.byref(v))
+    if rc != 0:
+        raise ZigzError(rc)
+    return VERDICTS[v.value]
 
 
 # --------------------------------------------------------------------------- Lasso

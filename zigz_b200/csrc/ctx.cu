@@ -559,6 +559,10 @@ const char *zb_status_name(int32_t s) {
     case ZB_ERR_QUERY_TABLE_MISMATCH: return "QueryTableMismatch";
     case ZB_ERR_WRONG_NUM_CHALLENGES: return "WrongNumberOfChallenges";
     case ZB_ERR_DIFFERENT_NUM_VARS: return "DifferentNumberOfVariables";
+    case ZB_ERR_EMPTY_TRACE: return "EmptyTrace";
+    case ZB_ERR_NO_SPACE_LEFT: return "NoSpaceLeft";
+    case ZB_ERR_PROGRAM_HASH_MISMATCH: return "ProgramHashMismatch";
+    case ZB_ERR_INVALID_PROOF: return "InvalidProof";
     case ZB_ERR_NOT_CANONICAL: return "NotCanonical";
     case ZB_ERR_BAD_HANDLE: return "BadHandle";
     case ZB_ERR_BAD_ARGUMENT: return "BadArgument";

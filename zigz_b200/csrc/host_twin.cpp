@@ -510,6 +510,247 @@ int32_t zh_generate_commitments(zb_ctx *ctx, zh_transcript *tr, const zb_mle *po
     return ZB_OK;
 }
 
+/* ------------------------------------------------------------------ prove (after the VM), serialize, verify */
+
+namespace {
+// SHA-256 (FIPS 180-4) for the program hash (std.crypto.hash.sha2.Sha256 in the reference, prover.zig:98-99)
+struct Sha256 {
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+    void block(const uint8_t *p) {
+        static const uint32_t K[64] = {
+            0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+            0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+            0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+            0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+            0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+            0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+        uint32_t w[64];
+        for (int i = 0; i < 16; i++) w[i] = (uint32_t)p[4 * i] << 24 | (uint32_t)p[4 * i + 1] << 16 | (uint32_t)p[4 * i + 2] << 8 | p[4 * i + 3];
+        for (int i = 16; i < 64; i++) {
+            const uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+            const uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+        }
+        uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+        for (int i = 0; i < 64; i++) {
+            const uint32_t t1 = hh + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
+            const uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+    static void hash(const void *data, size_t len, uint8_t out[32]) {
+        Sha256 s;
+        const uint8_t *p = static_cast<const uint8_t *>(data);
+        size_t n = len;
+        for (; n >= 64; n -= 64, p += 64) s.block(p);
+        uint8_t blk[128] = {0};
+        memcpy(blk, p, n);
+        blk[n] = 0x80;
+        const size_t tot = n + 9 <= 64 ? 64 : 128;
+        const uint64_t bits = (uint64_t)len * 8;
+        for (int i = 0; i < 8; i++) blk[tot - 1 - i] = (uint8_t)(bits >> (8 * i));
+        s.block(blk);
+        if (tot == 128) s.block(blk + 64);
+        for (int i = 0; i < 8; i++) {
+            out[4 * i] = (uint8_t)(s.h[i] >> 24); out[4 * i + 1] = (uint8_t)(s.h[i] >> 16);
+            out[4 * i + 2] = (uint8_t)(s.h[i] >> 8); out[4 * i + 3] = (uint8_t)s.h[i];
+        }
+    }
+};
+
+struct ByteWriter { // little-endian writer over a caller buffer (std.io.fixedBufferStream in the reference); never writes past `end`
+    uint8_t *p, *end;
+    bool overflow = false;
+    void bytes(const void *d, size_t n) {
+        if ((size_t)(end - p) < n) {
+            overflow = true;
+            return;
+        }
+        memcpy(p, d, n);
+        p += n;
+    }
+    void u8(uint8_t v) { bytes(&v, 1); }
+    void u32(uint32_t v) { bytes(&v, 4); }
+    void u64(uint64_t v) { bytes(&v, 8); }
+};
+struct ByteReader {
+    const uint8_t *p, *end;
+    bool need(size_t n) const { return (size_t)(end - p) >= n; }
+    uint32_t u32() { uint32_t v; memcpy(&v, p, 4); p += 4; return v; }
+    uint64_t u64() { uint64_t v; memcpy(&v, p, 8); p += 8; return v; }
+};
+
+uint32_t log2_ceil_u64(uint64_t n) { // std.math.log2_int_ceil
+    uint32_t v = 0;
+    while ((1ull << v) < n) v++;
+    return v;
+}
+bool opcode_has_table(uint64_t op) { // getTableMetadata, src/isa/instruction_table.zig:243-275 (OP, OP_IMM, LOAD, STORE, BRANCH)
+    return op == 0x33 || op == 0x13 || op == 0x03 || op == 0x23 || op == 0x63;
+}
+} // namespace
+
+void zh_sha256(const void *data, size_t n, uint8_t out[32]) { Sha256::hash(data, n, out); }
+
+int32_t zh_prove_from_trace(zb_ctx *ctx, const uint8_t *program, size_t program_len, uint64_t entry_pc,
+                            const uint64_t *initial_regs, uint32_t n_init, const uint64_t *cols, uint64_t num_steps, uint64_t final_pc,
+                            const uint64_t *final_regs, const uint64_t *outputs, uint32_t n_out, int32_t compat_buffer, uint8_t *out,
+                            size_t out_cap, size_t *out_len) {
+    if (num_steps == 0) return ZB_ERR_EMPTY_TRACE; // prover.zig:144-146
+    if (!cols || !final_regs || (n_init && !initial_regs) || (n_out && !outputs) || (program_len && !program)) return ZB_ERR_BAD_ARGUMENT;
+    const uint32_t v = log2_ceil_u64(num_steps); // Proof.init, proof.zig:225
+    uint64_t n_lookups = 0; // ConstraintSystem.extractLookupConstraints, builder.zig:253-267
+    for (uint64_t i = 0; i < num_steps; i++) n_lookups += opcode_has_table(cols[33 * num_steps + i]);
+    const size_t exact = 32 + (32 + 8 + 8 + 4 + 8 * (size_t)n_init + 4 + 8 * 32 + 8 + 4 + 8 * (size_t)n_out) + ((size_t)v * 40 + 8) + 4 +
+                         (size_t)n_lookups * 24 + 43 * (68 + (size_t)v * 41);
+    if (compat_buffer) { // estimateSize, serialization.zig:134-173
+        const size_t est = 32 + (32 + 8 + 8 + 4 + 4) + 8 * (size_t)n_init + 8 * 32 + ((size_t)v * 40 + 8) + 4 + (size_t)n_lookups * 20 +
+                           43 * (32 + (size_t)v * 8 + 8 + 640);
+        if (exact > est) return ZB_ERR_NO_SPACE_LEFT;
+    }
+    if (out_len) *out_len = exact;
+    if (!out || out_cap < exact) return ZB_ERR_OOM;
+    zh_transcript tr; // prover.zig:91
+    uint8_t program_hash[32];
+    Sha256::hash(program, program_len, program_hash); // :98-100
+    zh_transcript_append_bytes(&tr, program_hash, 32);
+    zh_transcript_append_field(&tr, entry_pc % P); // :103
+    for (uint32_t i = 0; i < n_init; i++) zh_transcript_append_field(&tr, initial_regs[i] % P); // :106-110
+    // witness polynomials straight into HBM (witness.zig:29-270)
+    zb_mle polys[43] = {0};
+    uint32_t nv = 0;
+    int32_t rc = zb_witness_pack(ctx, cols, num_steps, 43, 33, polys, &nv);
+    if (rc) return rc;
+    ByteWriter w{out, out + exact};
+    w.bytes("ZIGZ", 4); // header, serialization.zig:175-182
+    w.u32(1); w.u64(P); w.u64(num_steps); w.u32(v); w.u32(0);
+    w.bytes(program_hash, 32); // public I/O, :209-245 (packagePublicIO prover.zig:514-559)
+    w.u64(entry_pc); w.u64(final_pc);
+    w.u32(n_init);
+    for (uint32_t i = 0; i < n_init; i++) w.u64(initial_regs[i]);
+    w.u32(32);
+    for (int i = 0; i < 32; i++) w.u64(final_regs[i]);
+    w.u64(num_steps);
+    w.u32(n_out);
+    for (uint32_t i = 0; i < n_out; i++) w.u64(outputs[i]);
+    // constraint sumcheck placeholder: zero round polynomials, transcript challenges (prover.zig:229-289)
+    zh_transcript_append_bytes(&tr, "SUMCHECK_BEGIN", 14);
+    zh_transcript_append_field(&tr, num_steps % P);
+    zh_transcript_append_field(&tr, v);
+    uint64_t chal[64];
+    const uint64_t zeros[4] = {0, 0, 0, 0};
+    for (uint32_t r = 0; r < v; r++) {
+        zh_transcript_append_fields(&tr, zeros, 4);
+        chal[r] = zh_transcript_challenge(&tr);
+    }
+    for (uint32_t r = 0; r < 4 * v; r++) w.u64(0); // serialization.zig:296-311
+    for (uint32_t r = 0; r < v; r++) w.u64(chal[r]);
+    w.u64(0);
+    // Lasso placeholders: one 0-round proof per lookup constraint (prover.zig:292-362, serialization.zig:333-344)
+    zh_transcript_append_bytes(&tr, "LASSO_BEGIN", 11);
+    w.u32((uint32_t)n_lookups);
+    for (uint64_t k = 0; k < n_lookups; k++) {
+        zh_transcript_append_bytes(&tr, "LASSO_TABLE", 11);
+        zh_transcript_append_field(&tr, (uint32_t)k % P);
+        w.u32((uint32_t)k); w.u64(1); w.u32(0); w.u64(0);
+    }
+    // commitments + openings on the device (prover.zig:366-467)
+    const size_t vv = v ? v : 1;
+    std::vector<uint8_t> roots(43 * 32), sib(43 * vv * 32), dirs(43 * vv);
+    std::vector<uint64_t> pts(43 * vv), vals(43), li(43), lv(43);
+    rc = zh_generate_commitments(ctx, &tr, polys, 43, roots.data(), pts.data(), vals.data(), li.data(), lv.data(), sib.data(), dirs.data());
+    for (int i = 0; i < 43; i++) zb_mle_free(ctx, polys[i]);
+    if (rc) return rc;
+    for (int i = 0; i < 43; i++) { // serialization.zig:374-429
+        w.bytes(roots.data() + 32 * i, 32);
+        for (uint32_t j = 0; j < v; j++) w.u64(pts[(size_t)i * v + j]);
+        w.u64(vals[i]);
+        w.u64(vals[i]); // OpeningProof.value: Scheme.open evaluates the same polynomial at the same point (polynomial_commit.zig:97)
+        w.u64(li[i]); w.u64(lv[i]); w.u32(v);
+        w.bytes(sib.data() + (size_t)i * v * 32, (size_t)v * 32);
+        for (uint32_t j = 0; j < v; j++) w.u8(dirs[(size_t)i * v + j] ? 1 : 0);
+    }
+    return (!w.overflow && (size_t)(w.p - out) == exact) ? ZB_OK : ZB_ERR_BAD_ARGUMENT;
+}
+
+int32_t zh_verify_proof(const uint8_t *proof, size_t len, const uint8_t *program, size_t program_len, int32_t *verdict) {
+    if (!proof || !verdict) return ZB_ERR_BAD_ARGUMENT;
+    ByteReader r{proof, proof + len};
+    if (!r.need(32) || memcmp(r.p, "ZIGZ", 4)) return ZB_ERR_INVALID_PROOF; // readHeader, serialization.zig:184-207
+    r.p += 4;
+    if (r.u32() != 1) return ZB_ERR_INVALID_PROOF;
+    if (r.u64() != P) return ZB_ERR_INVALID_PROOF; // FieldMismatch :108-110
+    const uint64_t num_steps = r.u64();
+    const uint32_t v = r.u32();
+    r.u32();
+    if (v > 63 || v != log2_ceil_u64(num_steps)) return ZB_ERR_INVALID_PROOF; // Proof.init derives num_vars from num_steps (:113)
+    if (!r.need(52)) return ZB_ERR_INVALID_PROOF;
+    const uint8_t *ph = r.p;
+    r.p += 32;
+    r.u64(); r.u64();
+    for (int part = 0; part < 2; part++) { // initial / final registers
+        const uint32_t n = r.u32();
+        if (!r.need(8 * (size_t)n + 12)) return ZB_ERR_INVALID_PROOF;
+        r.p += 8 * (size_t)n;
+    }
+    r.u64();
+    const uint32_t n_out = r.u32();
+    if (!r.need(8 * (size_t)n_out)) return ZB_ERR_INVALID_PROOF;
+    r.p += 8 * (size_t)n_out;
+    uint8_t hash[32];
+    Sha256::hash(program, program_len, hash);
+    if (memcmp(hash, ph, 32)) return ZB_ERR_PROGRAM_HASH_MISMATCH; // bindPublicInputs, verifier.zig:101-107
+    *verdict = 0;
+    // verifySumcheckProof: only round 0 is checked, g(0) + g(1) == final_eval (verifier.zig:196-214)
+    auto sumcheck = [&](uint32_t nv, int ncoef, bool *ok) -> bool {
+        if (!r.need((size_t)nv * (ncoef + 1) * 8 + 8)) return false;
+        uint64_t g0 = 0, g1 = 0;
+        for (uint32_t rd = 0; rd < nv; rd++)
+            for (int k = 0; k < ncoef; k++) {
+                const uint64_t c = r.u64() % P;
+                if (rd == 0) {
+                    if (k == 0) g0 = c;
+                    g1 = f_add(g1, c);
+                }
+            }
+        r.p += (size_t)nv * 8;
+        const uint64_t fe = r.u64() % P;
+        *ok = nv == 0 || f_add(g0, g1) == fe;
+        return true;
+    };
+    bool ok = true;
+    if (!sumcheck(v, 4, &ok)) return ZB_ERR_INVALID_PROOF;
+    if (!ok) {
+        *verdict = 1;
+        return ZB_OK;
+    }
+    if (!r.need(4)) return ZB_ERR_INVALID_PROOF;
+    const uint32_t n_lasso = r.u32();
+    for (uint32_t k = 0; k < n_lasso; k++) { // verifyLassoProof :233-262
+        if (!r.need(16)) return ZB_ERR_INVALID_PROOF;
+        r.u32(); r.u64();
+        const uint32_t lv = r.u32();
+        if (!sumcheck(lv, 3, &ok)) return ZB_ERR_INVALID_PROOF;
+        if (!ok && *verdict == 0) *verdict = 2;
+    }
+    for (int i = 0; i < 43; i++) { // verifyOpening :270-294
+        if (!r.need(32 + (size_t)v * 8 + 36)) return ZB_ERR_INVALID_PROOF;
+        const uint8_t *root = r.p;
+        r.p += 32 + (size_t)v * 8;
+        const uint64_t value = r.u64() % P, pvalue = r.u64() % P;
+        r.u64();
+        const uint64_t leaf = r.u64() % P;
+        const uint32_t plen = r.u32();
+        if (!r.need((size_t)plen * 33)) return ZB_ERR_INVALID_PROOF;
+        const uint8_t *sibs = r.p, *dirs = r.p + (size_t)plen * 32;
+        r.p += (size_t)plen * 33;
+        if (*verdict == 0 && (value != pvalue || !zh_merkle_verify(root, leaf, sibs, dirs, plen))) *verdict = 3;
+    }
+    return ZB_OK;
+}
+
 /* ------------------------------------------------------------------ Lasso */
 
 void zh_flat_commit(const uint64_t *evals, uint64_t n, uint8_t out[32]) { // lasso_prover.zig:242-252
