@@ -401,6 +401,22 @@ def run_extras(args, z, ctx, peak):
                                       "note": "pack = H2D of 43 u64 columns + k_witness_pack; commitments = one batched build + 43 x (eval + open)"}
     for m in wpolys:
         m.deinit()
+    # the whole post-VM part of `zigz prove` (pack, placeholder sumcheck/Lasso transcript, commitments, openings, ZIGZ v1
+    # bytes) at 2^18 steps, the largest trace the reference's own serializer buffer can hold
+    lgp = min(18, args.log2n)
+    pcols = np.ascontiguousarray(cols[:, : (1 << lgp)])
+    pcols[33] = 0x13  # every step an OP_IMM: one lookup constraint per step would overflow the reference buffer, so ...
+    pcols[33, 2048:] = 0x37  # ... only the first 2048 steps carry a lookup (LUI has no table)
+    program = bytes(1024)
+    zero32 = [0] * 32
+    z.prove_from_trace(ctx, program, 0x1000, zero32, pcols, 0x2000, zero32, [1, 2, 3], compat_buffer=True)
+    t0 = time.perf_counter()
+    proof = z.prove_from_trace(ctx, program, 0x1000, zero32, pcols, 0x2000, zero32, [1, 2, 3], compat_buffer=True)
+    pv_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    verdict = z.verify_proof(proof, program)
+    out[f"C4_prove_from_trace_2^{lgp}_steps"] = {"prove_ms": pv_ms, "proof_bytes": len(proof), "verify_ms": (time.perf_counter() - t0) * 1e3,
+                                                 "verdict": verdict}
     # C2: Lasso over the 8-bit ADD/AND/XOR subtables, 2^22 lookups each (host rows -> proof)
     lgq = min(22, args.log2n)
     rng = np.random.default_rng(1)
