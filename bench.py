@@ -406,7 +406,7 @@ def run_extras(args, z, ctx, peak):
     lgp = min(18, args.log2n)
     pcols = np.ascontiguousarray(cols[:, : (1 << lgp)])
     pcols[33] = 0x13  # every step an OP_IMM: one lookup constraint per step would overflow the reference buffer, so ...
-    pcols[33, 2048:] = 0x37  # ... only the first 2048 steps carry a lookup (LUI has no table)
+    pcols[33, 128:] = 0x37  # ... only the first 128 steps carry a lookup (LUI has no table): 774 bytes of slack at num_vars = 18
     program = bytes(1024)
     zero32 = [0] * 32
     z.prove_from_trace(ctx, program, 0x1000, zero32, pcols, 0x2000, zero32, [1, 2, 3], compat_buffer=True)
