@@ -83,9 +83,9 @@ __device__ __forceinline__ bool xchg_allreduce(unsigned long long (&tot)[NS], co
 // Block-reduce NS u64 partial sums, add them to the global accumulators; the last CTA converts the totals with
 // `fin` (canonical field elements), optionally sums them over all GPUs (mb.xchg) and publishes payload + sequence
 // number to the mailbox.
-template <int NS, typename Fin>
+template <int NS, typename Fin, int TPB = THREADS>
 __device__ __forceinline__ void publish_sums(unsigned long long (&s)[NS], const Mailbox &mb, Fin fin) {
-    __shared__ unsigned long long sm[NS][THREADS / 32];
+    __shared__ unsigned long long sm[NS][TPB / 32];
     __shared__ unsigned long long s_tot[NS];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -100,7 +100,7 @@ __device__ __forceinline__ void publish_sums(unsigned long long (&s)[NS], const 
         for (int k = 0; k < NS; k++) {
             unsigned long long v = 0;
 #pragma unroll
-            for (int w = 0; w < THREADS / 32; w++) v += sm[k][w];
+            for (int w = 0; w < TPB / 32; w++) v += sm[k][w];
             atomicAdd(&mb.acc[k], v);
         }
         __threadfence();
@@ -529,28 +529,28 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <int D, int FV, int STAGES_>
+template <int D, int FV, int STAGES_, int TPB>
 struct GridAsync {
     static constexpr int NT = 1 << FV;
     static constexpr int NSLOT = D * 4 * NT;
-    static constexpr int STAGE_BYTES = NSLOT * THREADS * 8;
+    static constexpr int STAGE_BYTES = NSLOT * TPB * 8;
     static constexpr int STAGES = STAGES_;
     static constexpr int SMEM = STAGES * STAGE_BYTES;
-    static_assert(STAGES >= 2 && SMEM <= 200 * 1024, "ring depth");
+    static_assert(STAGES >= 2 && SMEM <= 222 * 1024, "ring depth");
 };
 
-template <int D, int FV, int STAGES_>
-__global__ void __launch_bounds__(THREADS) k_fold_grid_async(PolySet ps, uint64_t mq, uint32_t r1, uint32_t rp1, uint32_t r2,
+template <int D, int FV, int STAGES_, int TPB>
+__global__ void __launch_bounds__(TPB) k_fold_grid_async(PolySet ps, uint64_t mq, uint32_t r1, uint32_t rp1, uint32_t r2,
                                                              uint32_t rp2, Mailbox mb) {
-    using G = GridAsync<D, FV, STAGES_>;
+    using G = GridAsync<D, FV, STAGES_, TPB>;
     constexpr int NP = NPts<D>::value, NS = NP * NP, NT = G::NT, NSLOT = G::NSLOT, STAGES = G::STAGES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2 *ring = reinterpret_cast<uint2 *>(smem_raw); // [STAGES][NSLOT][THREADS]
     unsigned long long s[NS];
 #pragma unroll
     for (int k = 0; k < NS; k++) s[k] = 0;
-    const uint64_t stride = (uint64_t)gridDim.x * THREADS;
-    const uint64_t i0 = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * TPB;
+    const uint64_t i0 = (uint64_t)blockIdx.x * TPB + threadIdx.x;
     const uint64_t cnt = i0 < mq ? (mq - i0 + stride - 1) / stride : 0;
     auto issue = [&](int stage, uint64_t i) {
 #pragma unroll
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(THREADS) k_fold_grid_async(PolySet ps, uint64_
             for (int j = 0; j < 4; j++)
 #pragma unroll
                 for (int t = 0; t < NT; t++)
-                    cp_async8(&ring[((size_t)stage * NSLOT + (k * 4 + j) * NT + t) * THREADS + threadIdx.x], p + i + j * mq + t * (4 * mq));
+                    cp_async8(&ring[((size_t)stage * NSLOT + (k * 4 + j) * NT + t) * TPB + threadIdx.x], p + i + j * mq + t * (4 * mq));
         }
     };
 #pragma unroll
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(THREADS) k_fold_grid_async(PolySet ps, uint64_
 #pragma unroll
             for (int j = 0; j < 4; j++)
 #pragma unroll
-                for (int t = 0; t < NT; t++) a[j][t] = ring[((size_t)stage * NSLOT + (k * 4 + j) * NT + t) * THREADS + threadIdx.x];
+                for (int t = 0; t < NT; t++) a[j][t] = ring[((size_t)stage * NSLOT + (k * 4 + j) * NT + t) * TPB + threadIdx.x];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 if constexpr (FV == 0) {
@@ -626,38 +626,42 @@ __global__ void __launch_bounds__(THREADS) k_fold_grid_async(PolySet ps, uint64_
         }
     }
     cp_async_wait<0>();
-    publish_sums<NS>(s, mb, FinishGrid<D, NS>());
+    publish_sums<NS, FinishGrid<D, NS>, TPB>(s, mb, FinishGrid<D, NS>());
 }
 
-template <int D, int FV, int STAGES_>
+template <int D, int FV, int STAGES_, int TPB>
 static void fold_grid_async_launch_s(const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
-    using G = GridAsync<D, FV, STAGES_>;
+    using G = GridAsync<D, FV, STAGES_, TPB>;
     static const bool once = [] {
-        cudaFuncSetAttribute(k_fold_grid_async<D, FV, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        cudaFuncSetAttribute(k_fold_grid_async<D, FV, STAGES_, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         return true;
     }();
     (void)once;
     const uint64_t mq = m / 8;
-    const int per_sm = (227 * 1024) / (G::SMEM + 2048) < 1 ? 1 : (227 * 1024) / (G::SMEM + 2048);
-    const int grid = grid_for(mq, sm, per_sm > 4 ? 4 : per_sm);
-    k_fold_grid_async<D, FV, STAGES_><<<grid, THREADS, G::SMEM, st>>>(ps, mq, r1, bb::shoup_pre(r1), r2, bb::shoup_pre(r2), mb);
+    int per_sm = (227 * 1024) / (G::SMEM + 2048);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    uint64_t need = (mq + TPB - 1) / TPB, cap = (uint64_t)sm * per_sm;
+    const int grid = (int)(need < cap ? (need ? need : 1) : cap);
+    k_fold_grid_async<D, FV, STAGES_, TPB><<<grid, TPB, G::SMEM, st>>>(ps, mq, r1, bb::shoup_pre(r1), r2, bb::shoup_pre(r2), mb);
 }
 
-// ring depth per (D, FV): the slots of one iteration are D*4*2^FV*8 bytes per thread; the default keeps ~100-200 KB per SM
+// Ring shape per (D, FV): the slots of one iteration are D*4*2^FV*8 bytes per thread. Measured for d = 3
+// (profiles/r01_grid_sweep.txt, tools/sweep3.sh): one folded variable: 384 threads x 2 stages 6488 GB/s, 512 x 2 6286,
+// 128 x 4 6261, 256 x 3 6118, 256 x 4 5925, 384 x 3 4754; two folded variables: 256 x 2 5648, 128 x 4 5369, 192 x 2 4787.
+// ZB_GRID_CFG_F1=803 selects 256 x 3 for one folded variable.
 template <int D, int FV>
 static void fold_grid_async_launch(const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
-    constexpr int SB = D * 4 * (1 << FV) * THREADS * 8;
-    constexpr int MAXS = (196608 / SB) > 4 ? 4 : (196608 / SB);
-    // measured (profiles/r01_grid_sweep.txt): d = 3, one folded variable: 3 stages 5978 GB/s, 4 stages 5816, 2 stages (2 CTAs/SM) 4738
-    static const int want = tune(FV == 2 ? "ZB_GRID_STAGES_F2" : FV == 1 ? "ZB_GRID_STAGES_F1" : "ZB_GRID_STAGES_F0",
-                                 (FV == 1 && MAXS >= 3) ? 3 : MAXS);
-    if constexpr (MAXS >= 4) {
-        if (want >= 4) return fold_grid_async_launch_s<D, FV, 4>(ps, m, r1, r2, mb, sm, st);
+    constexpr int SLOT_BYTES = D * 4 * (1 << FV) * 8; // per thread and stage
+    if constexpr (FV == 1) {
+        static const int cfg = tune("ZB_GRID_CFG_F1", 1202);
+        if (cfg == 803) return fold_grid_async_launch_s<D, FV, 3, 256>(ps, m, r1, r2, mb, sm, st);
+        return fold_grid_async_launch_s<D, FV, 2, 384>(ps, m, r1, r2, mb, sm, st);
+    } else if constexpr (SLOT_BYTES * 256 * 3 <= 222 * 1024) {
+        return fold_grid_async_launch_s<D, FV, 3, 256>(ps, m, r1, r2, mb, sm, st);
+    } else {
+        return fold_grid_async_launch_s<D, FV, 2, 256>(ps, m, r1, r2, mb, sm, st);
     }
-    if constexpr (MAXS >= 3) {
-        if (want >= 3) return fold_grid_async_launch_s<D, FV, 3>(ps, m, r1, r2, mb, sm, st);
-    }
-    return fold_grid_async_launch_s<D, FV, 2>(ps, m, r1, r2, mb, sm, st);
 }
 
 template <int D, int VEC>
