@@ -429,8 +429,8 @@ struct FinishGrid {
     }
 };
 
-// VEC = consecutive elements per thread and load (2: 8-byte loads, one polynomial at a time; 1: 4-byte loads with the
-// loads of ALL polynomials issued before any arithmetic — more bytes in flight per register)
+// Plain-load version (used below 2^16 entries, where the pass is not bandwidth-bound): 8-byte loads, one polynomial at a
+// time. (A 4-byte-load variant with all polynomials prefetched was measured at 2.3-3.2 TB/s and dropped, r01_grid_sweep.txt.)
 template <int D, int FV, int VEC>
 __global__ void __launch_bounds__(THREADS) k_fold_grid(PolySet ps, uint64_t mq, uint32_t r1, uint32_t rp1, uint32_t r2, uint32_t rp2,
                                                        Mailbox mb) {
@@ -442,7 +442,8 @@ __global__ void __launch_bounds__(THREADS) k_fold_grid(PolySet ps, uint64_t mq, 
     const uint64_t stride = (uint64_t)gridDim.x * THREADS;
     for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < mq; i += stride) {
         uint32_t f[D][4][VEC]; // [poly][quarter (b1 b2)][vector lane]
-        if constexpr (VEC == 2) {
+        static_assert(VEC == 2, "8-byte vectors");
+        {
 #pragma unroll
             for (int k = 0; k < D; k++) {
                 const uint2 *p = reinterpret_cast<const uint2 *>(ps.src[k]);
@@ -472,24 +473,6 @@ __global__ void __launch_bounds__(THREADS) k_fold_grid(PolySet ps, uint64_t mq, 
                     for (int j = 0; j < 4; j++) o[i + j * mq] = make_uint2(f[k][j][0], f[k][j][1]);
                 }
             }
-        } else {
-            uint32_t a[D][4][NT];
-#pragma unroll
-            for (int k = 0; k < D; k++)
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-#pragma unroll
-                    for (int t = 0; t < NT; t++) a[k][j][t] = ps.src[k][i + j * mq + t * (4 * mq)];
-#pragma unroll
-            for (int k = 0; k < D; k++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if constexpr (FV == 0) f[k][j][0] = a[k][j][0];
-                    else if constexpr (FV == 1) f[k][j][0] = bb::lerp(a[k][j][0], a[k][j][1], r1, rp1);
-                    else
-                        f[k][j][0] = bb::lerp(bb::lerp(a[k][j][0], a[k][j][2], r1, rp1), bb::lerp(a[k][j][1], a[k][j][3], r1, rp1), r2, rp2);
-                    if constexpr (FV > 0) ps.dst[k][i + j * mq] = f[k][j][0];
-                }
         }
 #pragma unroll
         for (int c = 0; c < VEC; c++) {
@@ -685,9 +668,7 @@ static void fold_grid_t(int nfold, const PolySet &ps, uint64_t m, uint32_t r1, u
         else fold_grid_async_launch<D, 2>(ps, m, r1, r2, mb, sm, st);
         return;
     }
-    static const int VEC = tune("ZB_GRID_VEC", 2);
-    if (VEC == 1) fold_grid_v<D, 1>(nfold, ps, m, r1, r2, mb, sm, st);
-    else fold_grid_v<D, 2>(nfold, ps, m, r1, r2, mb, sm, st);
+    fold_grid_v<D, 2>(nfold, ps, m, r1, r2, mb, sm, st);
 }
 
 void launch_fold_grid(int d, int nfold, const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm,
