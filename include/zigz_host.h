@@ -43,7 +43,7 @@ uint64_t zh_eval_univariate(const uint64_t *coeffs, uint32_t n, uint64_t x);
 /* ---- SumcheckProver(BabyBear): src/proofs/sumcheck_prover.zig ---- */
 /* Tuning: tables of at least 2^v entries are proved two rounds per pass over the data (zb_prod_grid / zb_prod_fold_grid:
  * ~10.7 instead of 16 bytes of HBM traffic per element and polynomial, half the host round trips); smaller ones one round per
- * kernel. 0 disables the two-round path. Default 18 (env ZB_GRID_MIN_LOG2). Returns the previous value. Process-wide. */
+ * kernel. 0 disables the two-round path. Default 15 (env ZB_GRID_MIN_LOG2). Returns the previous value. Process-wide. */
 int32_t zh_set_grid_min_log2(int32_t v);
 /* prove :26-91. `poly` is left untouched (the reference copies it, :47). round_polys: v*2 coefficients [s0, s1-s0],
  * final_point: v challenges, final_eval: current_poly.evaluations[0], claimed_sum: sumOverHypercube (:40).

@@ -120,7 +120,7 @@ static int g_grid_min_log2 = -1;
 static int grid_min_log2() { // tables below 2^this use one kernel per round (and the persistent tail); 0 disables the grid path
     if (g_grid_min_log2 < 0) {
         const char *e = getenv("ZB_GRID_MIN_LOG2");
-        int x = e && *e ? atoi(e) : 18;
+        int x = e && *e ? atoi(e) : 15;
         g_grid_min_log2 = x < 0 ? 0 : x;
     }
     return g_grid_min_log2;
