@@ -454,26 +454,49 @@ int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32
         if (rc0) return rc0;
     }
     // Hybrid: the pack threads are the bottleneck (~70-80 GB/s of source on 16 cores) while PCIe still has headroom at
-    // 4 bytes per element, so every `raw_every`-th chunk of a PINNED source skips the CPU: it is copied as 8-byte words
-    // by the DMA engine while the threads pack the following chunks, and narrowed by a kernel (k_narrow).
+    // 4 bytes per element, so some chunks of a PINNED source skip the CPU: they are copied as 8-byte words by the DMA
+    // engine while the threads pack the following chunks, and narrowed by a kernel (k_narrow). Which chunks go raw is
+    // decided on the fly from a model of the copy queue: a chunk goes raw when the copies already queued would finish
+    // before the threads could pack it (the DMA engine would idle otherwise). ZB_UPLOAD_RAW_EVERY=k (k > 0) forces the
+    // fixed pattern "every k-th chunk raw", 0 turns raw chunks off.
     static const int raw_every_cfg = [] {
         const char *e = getenv("ZB_UPLOAD_RAW_EVERY");
-        return e && *e ? atoi(e) : 6;
+        return e && *e ? atoi(e) : -1;
+    }();
+    static const double pcie_bps = [] {
+        const char *e = getenv("ZB_UPLOAD_PCIE_GBS"); // H2D rate the queue model assumes
+        return (e && *e ? atof(e) : 53.0) * 1e9;
     }();
     const int raw_every = pinned ? raw_every_cfg : 0;
     BufRef raw_stage;
-    if (raw_every > 0 && n > PACK_CHUNK * (uint64_t)raw_every) {
+    if (raw_every != 0 && n > PACK_CHUNK * 4) {
         int32_t rc = dev_alloc(ctx, PACK_CHUNK * sizeof(uint64_t), &raw_stage);
         if (rc) return rc;
     }
+    using clk = std::chrono::steady_clock;
+    const auto t_start = clk::now();
+    auto now_s = [&] { return std::chrono::duration<double>(clk::now() - t_start).count(); };
+    double dma_free_at = 0.0; // model: when the copies queued so far will have drained
+    double pack_s = 0.0;      // duration of the last full-chunk pack
+    auto queued = [&](uint64_t bytes) {
+        const double t = now_s();
+        dma_free_at = (dma_free_at > t ? dma_free_at : t) + (double)bytes / pcie_bps;
+    };
     const int T = ctx->pool->size();
     std::vector<char> bad(T, 0);
     int buf = ctx->pack_next;
     uint64_t chunk_idx = 0;
     for (uint64_t off = 0; off < n; off += PACK_CHUNK, chunk_idx++) {
         const uint64_t m = n - off < PACK_CHUNK ? n - off : PACK_CHUNK;
-        if (raw_stage && (chunk_idx % raw_every) == (uint64_t)(raw_every - 1)) {
+        bool raw = false;
+        if (raw_stage && raw_every > 0) raw = (chunk_idx % raw_every) == (uint64_t)(raw_every - 1);
+        else if (raw_stage) {
+            const double est = pack_s > 0 ? pack_s : (double)m * 8 / (4.0e9 * T);
+            raw = dma_free_at - now_s() < est;
+        }
+        if (raw) {
             CK(cudaMemcpyAsync(raw_stage->ptr, host + off, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+            queued(m * sizeof(uint64_t));
             {
                 ProfScope _ps(ctx, "narrow_u64", m * 12);
                 launch_narrow_u64((const uint64_t *)raw_stage->ptr, dst + off, m, ctx->d_err, ctx->stream);
@@ -484,12 +507,15 @@ int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32
         CK(cudaEventSynchronize(ctx->pack_done[buf])); // the copy that last used this staging buffer has finished
         uint32_t *stage = ctx->pack_buf[buf];
         const uint64_t *src = host + off;
+        const double t_pack = now_s();
         ctx->pool->run([&](int tid) {
             const uint64_t per = ((m + T - 1) / T + 15) & ~15ull;
             const uint64_t lo = per * tid < m ? per * tid : m, hi = lo + per < m ? lo + per : m;
             if (hi > lo && zigz::narrow_u64_to_u32(src + lo, stage + lo, hi - lo, bb::P)) bad[tid] = 1;
         });
+        if (m == PACK_CHUNK) pack_s = now_s() - t_pack;
         CK(cudaMemcpyAsync(dst + off, stage, m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        queued(m * sizeof(uint32_t));
         CK(cudaEventRecord(ctx->pack_done[buf], ctx->stream));
         buf = (buf + 1) % PACK_BUFS;
     }
