@@ -171,6 +171,15 @@ int32_t zb_merkle_free(zb_ctx *ctx, zb_tree t);
  * h = 0; for x in row: h ^= x; h = XXH3_64(seed 0, le64(h)); eval = h % p. Rows beyond n_rows up to n_padded are zero
  * (lasso_prover.zig:140-142). Result is a Multilinear of n_padded (power of two) evaluations. */
 int32_t zb_xxh3_rows(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, zb_mle *out);
+/* The same, streamed: rows go up, are hashed and come back down into `host_mirror` (n_padded canonical u32, from
+ * zb_host_mirror) chunk by chunk; after each chunk *avail (release store) is the number of leading evaluations that are
+ * final in host_mirror. A second host thread can consume the mirror while the call is still running — this is how
+ * LassoProver.prove hides the upload and the sumcheck behind the sequential commitToPolynomial sponge
+ * (lasso_prover.zig:160-164, 242-252). On return *avail == n_padded (or the status is an error). */
+int32_t zb_xxh3_rows_stream(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, zb_mle *out,
+                            uint32_t *host_mirror, uint64_t *avail);
+/* a second context-owned pinned buffer (independent of zb_host_scratch) of at least `bytes` bytes */
+int32_t zb_host_mirror(zb_ctx *ctx, size_t bytes, void **out);
 /* buildAddTable (op 0) / buildXorTable (1) / buildAndTable (2) hashed directly on the device:
  * entry index = a * 2^bits + b -> hashEntry((a, b) -> op(a, b)) */
 int32_t zb_table_mle(zb_ctx *ctx, int32_t op, uint32_t bits, zb_mle *out);

@@ -117,6 +117,12 @@ int32_t zh_verify_proof(const uint8_t *proof, size_t len, const uint8_t *program
 /* std.crypto.hash.sha2.Sha256 one-shot (program hash, prover.zig:98-99) */
 void zh_sha256(const void *data, size_t n, uint8_t out[32]);
 
+/* Tuning: query lists that pad to at least 2^v evaluations run the query commitment (the sequential SHA3 sponge,
+ * lasso_prover.zig:242-252) on a second host thread, fed chunk by chunk through zb_xxh3_rows_stream while the rows are still
+ * being uploaded and the sumcheck runs. -1 = never. Default 18 (env ZB_LASSO_PIPELINE_MIN_LOG2). Returns the previous value.
+ * Process-wide. Chunk size: zb_set_option(ctx, "lasso_chunk_log2", rows_log2), default 19. */
+int32_t zh_set_lasso_pipeline_min_log2(int32_t v);
+
 /* ---- LassoProver(BabyBear): src/lookups/lasso_prover.zig ---- */
 /* prove :103-173. Rows are flattened (inputs || outputs), `arity` u64 each (the reference's TableEntry / LookupQuery
  * hold separately allocated slices, table_builder.zig:14-35, lasso_prover.zig:65-86).

@@ -108,3 +108,62 @@ def test_full_size_lookup_properties(zlib, ctx, po):
     assert ok and final_claim == pr.sumcheck_proof.final_eval
     want_small = po.lasso_prove(BB, po.build_table(BB, po.TABLE_XOR, 8), blk)
     assert pr.table_commitment == want_small.table_commitment
+
+
+@pytest.mark.parametrize("nq,chunk_log2", [(3 * 1024, 8), (4096, 10), (1000, 4), (5, 4)])
+def test_pipelined_commitment_matches_oracle(zlib, ctx, po, nq, chunk_log2):
+    """The two-thread schedule (query sponge fed by zb_xxh3_rows_stream) forced on small inputs with tiny chunks: same
+    proof as the oracle's sequential lasso_prover.zig:103-173, including chunks that end inside a sponge block."""
+    table = po.build_table(BB, po.TABLE_XOR, 8)
+    q = lasso_queries("xor", 8, nq)
+    want = po.lasso_prove(BB, table, q)
+    old = zlib.lib().zh_set_lasso_pipeline_min_log2(0)
+    ctx.set_option("lasso_chunk_log2", chunk_log2)
+    try:
+        _same(zlib.LassoProver.prove(ctx, table, q), want)
+        _same(zlib.LassoProver.prove_builtin(ctx, po.TABLE_XOR, 8, q), want)
+    finally:
+        zlib.lib().zh_set_lasso_pipeline_min_log2(old)
+        ctx.set_option("lasso_chunk_log2", 19)
+
+
+def test_pipelined_error_paths(zlib, ctx):
+    """A non-canonical row in a late chunk stops the sponge thread and surfaces as the upload's error."""
+    old = zlib.lib().zh_set_lasso_pipeline_min_log2(0)
+    ctx.set_option("lasso_chunk_log2", 4)
+    try:
+        q = lasso_queries("xor", 8, 100).copy()
+        q[90, 2] = BB  # == p: not canonical
+        with pytest.raises(zlib.ZigzError) as e:
+            zlib.LassoProver.prove_builtin(ctx, zlib.TABLE_XOR, 8, q)
+        assert e.value.name == "NotCanonical"
+        ok = zlib.LassoProver.prove_builtin(ctx, zlib.TABLE_XOR, 8, lasso_queries("xor", 8, 100))
+        assert ok.num_lookups == 100
+    finally:
+        zlib.lib().zh_set_lasso_pipeline_min_log2(old)
+        ctx.set_option("lasso_chunk_log2", 19)
+
+
+def test_full_size_commitments_vs_hashlib(zlib, ctx):
+    """2^22-entry query polynomial (3 * 2^20 lookups, zero padded): both schedules give the digest hashlib computes over
+    the le64 encodings of the downloaded evaluations (commitToPolynomial, lasso_prover.zig:242-252)."""
+    import ctypes as C
+    import hashlib
+    q = np.tile(lasso_queries("and", 8, 3 << 10), (1 << 10, 1))
+    h = C.c_uint64(0)
+    ctx.check(zlib.lib().zb_xxh3_rows(ctx.handle, q.reshape(-1).ctypes.data_as(C.POINTER(C.c_uint64)), q.shape[0], 3, 1 << 22,
+                                      C.byref(h)))
+    poly = zlib.Multilinear(ctx, h.value)
+    evals = poly.evaluations
+    poly.deinit()
+    assert not evals[3 << 20:].any()
+    want = hashlib.sha3_256(np.ascontiguousarray(evals, dtype="<u8").tobytes()).digest()
+    piped = zlib.LassoProver.prove_builtin(ctx, zlib.TABLE_AND, 8, q)
+    old = zlib.lib().zh_set_lasso_pipeline_min_log2(-1)
+    try:
+        serial = zlib.LassoProver.prove_builtin(ctx, zlib.TABLE_AND, 8, q)
+    finally:
+        zlib.lib().zh_set_lasso_pipeline_min_log2(old)
+    assert piped.query_commitment == want and serial.query_commitment == want
+    assert piped.table_commitment == serial.table_commitment
+    assert piped.sumcheck_proof.to_bytes() == serial.sumcheck_proof.to_bytes()

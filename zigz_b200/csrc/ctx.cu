@@ -120,6 +120,9 @@ struct zb_ctx {
     int tail_log2 = 14; // tables of <= 2^tail_log2 entries finish inside the persistent kernel (0 = never)
     void *scratch = nullptr; // zb_host_scratch
     size_t scratch_bytes = 0;
+    void *mirror = nullptr; // zb_host_mirror
+    size_t mirror_bytes = 0;
+    int lasso_chunk_log2 = 19; // rows per chunk of zb_xxh3_rows_stream
     // host-narrowing upload path
     std::unique_ptr<zigz::HostPool> pool;
     uint32_t *pack_buf[3] = {nullptr, nullptr, nullptr};
@@ -667,6 +670,7 @@ void zb_ctx_destroy(zb_ctx *ctx) {
     cudaFree(ctx->d_tail_status);
     cudaFree(ctx->d_bcast);
     if (ctx->scratch) cudaFreeHost(ctx->scratch);
+    if (ctx->mirror) cudaFreeHost(ctx->mirror);
     for (int b = 0; b < 3; b++) {
         if (ctx->pack_buf[b]) cudaFreeHost(ctx->pack_buf[b]);
         if (ctx->pack_done[b]) cudaEventDestroy(ctx->pack_done[b]);
@@ -700,6 +704,11 @@ int32_t zb_set_option(zb_ctx *ctx, const char *key, int64_t value) {
     }
     if (key && !strcmp(key, "tail_test_starve")) {
         ctx->tail_test_starve = value != 0;
+        return ZB_OK;
+    }
+    if (key && !strcmp(key, "lasso_chunk_log2")) {
+        if (value < 4 || value > 30) return ZB_ERR_BAD_ARGUMENT;
+        ctx->lasso_chunk_log2 = (int)value;
         return ZB_OK;
     }
     if (key && !strcmp(key, "starved")) {
@@ -977,6 +986,21 @@ int32_t zb_host_scratch(zb_ctx *ctx, size_t bytes, void **out) {
         ctx->scratch_bytes = bytes;
     }
     *out = ctx->scratch;
+    return ZB_OK;
+}
+
+int32_t zb_host_mirror(zb_ctx *ctx, size_t bytes, void **out) {
+    if (!out) return ZB_ERR_BAD_ARGUMENT;
+    if (bytes > ctx->mirror_bytes) {
+        tail_quiesce(ctx);
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->mirror) cudaFreeHost(ctx->mirror);
+        ctx->mirror = nullptr;
+        ctx->mirror_bytes = 0;
+        CK(cudaHostAlloc(&ctx->mirror, bytes, cudaHostAllocDefault));
+        ctx->mirror_bytes = bytes;
+    }
+    *out = ctx->mirror;
     return ZB_OK;
 }
 
@@ -1766,6 +1790,57 @@ int32_t zb_xxh3_rows(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint32_
         LAUNCHED("fill");
     }
     return zb_sync(ctx);
+}
+
+int32_t zb_xxh3_rows_stream(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, zb_mle *out,
+                            uint32_t *host_mirror, uint64_t *avail) {
+    tail_quiesce(ctx);
+    int32_t rc = check_pow2(n_padded);
+    if (rc) return rc;
+    if (n_rows > n_padded || arity == 0 || (!rows && n_rows) || !out || !host_mirror || !avail) return ZB_ERR_BAD_ARGUMENT;
+    Mle *m = nullptr;
+    rc = new_mle(ctx, n_padded, out, &m);
+    if (rc) return rc;
+    auto fail = [&](int32_t e) {
+        cudaStreamSynchronize(ctx->stream);
+        ctx->mles.erase(*out);
+        *out = 0;
+        return e;
+    };
+    const uint64_t CH = 1ull << ctx->lasso_chunk_log2; // rows per streamed chunk (option "lasso_chunk_log2")
+    if (n_rows) {
+        BufRef drows;
+        rc = dev_alloc(ctx, n_rows * arity * sizeof(uint32_t), &drows);
+        if (rc) return fail(rc);
+        uint32_t *d_rows = (uint32_t *)drows->ptr;
+        for (uint64_t r0 = 0; r0 < n_rows; r0 += CH) {
+            const uint64_t r1 = r0 + CH < n_rows ? r0 + CH : n_rows;
+            // drains the stream: the previous chunk's hashes have landed in the mirror when this returns
+            rc = upload_narrow(ctx, rows + r0 * arity, (r1 - r0) * arity, d_rows + r0 * arity);
+            if (rc) return fail(rc);
+            __atomic_store_n(avail, r0, __ATOMIC_RELEASE);
+            const uint64_t n_out = r1 == n_rows ? n_padded - r0 : r1 - r0; // the last chunk also writes the zero padding
+            {
+                ProfScope _ps(ctx, "xxh3_rows", (r1 - r0) * (4ull * arity) + n_out * 4);
+                launch_xxh3_rows(d_rows + r0 * arity, r1 - r0, arity, n_out, m->d() + r0, ctx->stream);
+            }
+            LAUNCHED("xxh3_rows");
+            CK(cudaMemcpyAsync(host_mirror + r0, m->d() + r0, n_out * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        rc = zb_sync(ctx); // before drows goes back to the pool
+        if (rc) return fail(rc);
+    } else {
+        {
+            ProfScope _ps(ctx, "fill", n_padded * 4);
+            launch_fill(m->d(), n_padded, 0, ctx->stream);
+        }
+        LAUNCHED("fill");
+        memset(host_mirror, 0, n_padded * sizeof(uint32_t));
+        rc = zb_sync(ctx);
+        if (rc) return fail(rc);
+    }
+    __atomic_store_n(avail, n_padded, __ATOMIC_RELEASE);
+    return ZB_OK;
 }
 
 int32_t zb_table_mle(zb_ctx *ctx, int32_t op, uint32_t bits, zb_mle *out) {

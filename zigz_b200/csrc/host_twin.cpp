@@ -6,7 +6,9 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <immintrin.h>
 #include <new>
+#include <thread>
 #include <vector>
 
 using zigz::Sha3_256;
@@ -809,6 +811,79 @@ static uint64_t ceil_pow2(uint64_t n) {
     return r;
 }
 
+// The sumcheck proof and the two commitments of a Lasso proof do not depend on one another (lasso_prover.zig:160-164),
+// and the query commitment — one sequential SHA3 sponge over every padded query evaluation, :242-252 — is by far the
+// longest step. For long query lists it therefore runs on a second host thread over a pinned mirror of the query
+// polynomial that fills chunk by chunk (zb_xxh3_rows_stream) while this thread uploads the remaining rows, proves the
+// sumcheck and commits to the table. Same digests, same proof; zh_set_lasso_pipeline_min_log2(-1) keeps it on one thread.
+static int g_lasso_pipeline_min_log2 = -2; // -2: not read yet, -1: never
+static int lasso_pipeline_min_log2() {
+    if (g_lasso_pipeline_min_log2 == -2) {
+        const char *e = getenv("ZB_LASSO_PIPELINE_MIN_LOG2");
+        g_lasso_pipeline_min_log2 = e && *e ? atoi(e) : 18;
+        if (g_lasso_pipeline_min_log2 < -1) g_lasso_pipeline_min_log2 = -1;
+    }
+    return g_lasso_pipeline_min_log2;
+}
+static bool lasso_pipeline(uint64_t n_padded) {
+    const int v = lasso_pipeline_min_log2();
+    return v >= 0 && v < 63 && n_padded >= (1ull << v);
+}
+
+// query rows -> query polynomial, sumcheck, both commitments (table_poly is consumed: freed on return)
+static int32_t lasso_run(zb_ctx *ctx, zb_mle table_poly, const uint64_t *query_rows, uint64_t n_queries, uint32_t arity,
+                         uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars, uint8_t qc[32],
+                         uint8_t tc[32]) {
+    const uint64_t n_padded = ceil_pow2(n_queries);
+    zb_mle query_poly = 0;
+    int32_t rc;
+    if (!lasso_pipeline(n_padded)) {
+        rc = zb_xxh3_rows(ctx, query_rows, n_queries, arity, n_padded, &query_poly); // :131-142
+        if (rc == ZB_OK) rc = lasso_finish(ctx, table_poly, query_poly, round_polys, final_point, final_eval, num_vars, qc, tc);
+    } else {
+        uint32_t *mirror = nullptr;
+        rc = zb_host_mirror(ctx, n_padded * sizeof(uint32_t), (void **)&mirror);
+        if (rc) {
+            zb_mle_free(ctx, table_poly);
+            return rc;
+        }
+        uint64_t avail = 0;
+        int stop = 0;
+        Sha3_256 hq;
+        std::thread sponge([&] {
+            uint64_t done = 0;
+            while (done < n_padded) {
+                const uint64_t a = __atomic_load_n(&avail, __ATOMIC_ACQUIRE);
+                if (a == done) {
+                    if (__atomic_load_n(&stop, __ATOMIC_ACQUIRE)) return;
+                    _mm_pause();
+                    continue;
+                }
+                hq.update_words_u32(mirror + done, a - done);
+                done = a;
+            }
+        });
+        rc = zb_xxh3_rows_stream(ctx, query_rows, n_queries, arity, n_padded, &query_poly, mirror, &avail);
+        if (rc == ZB_OK) {
+            if (num_vars) zb_mle_len(ctx, query_poly, nullptr, num_vars);
+            rc = zh_sumcheck_prove(ctx, query_poly, round_polys, final_point, final_eval, nullptr); // :160
+        }
+        if (rc == ZB_OK) rc = zh_lasso_commit_poly(ctx, table_poly, tc); // :164
+        if (rc) __atomic_store_n(&stop, 1, __ATOMIC_RELEASE);
+        sponge.join();
+        if (rc == ZB_OK) hq.peek(qc); // :163
+    }
+    if (query_poly) zb_mle_free(ctx, query_poly);
+    zb_mle_free(ctx, table_poly);
+    return rc;
+}
+
+int32_t zh_set_lasso_pipeline_min_log2(int32_t v) {
+    const int32_t old = lasso_pipeline_min_log2();
+    g_lasso_pipeline_min_log2 = v < -1 ? -1 : v;
+    return old;
+}
+
 int32_t zh_lasso_prove(zb_ctx *ctx, const uint64_t *table_rows, uint64_t n_table, const uint64_t *query_rows,
                        uint64_t n_queries, uint32_t arity, uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval,
                        uint32_t *num_vars, uint8_t qc[32], uint8_t tc[32]) {
@@ -816,14 +891,10 @@ int32_t zh_lasso_prove(zb_ctx *ctx, const uint64_t *table_rows, uint64_t n_table
     // Multilinear.init(table_evals) :124 -> EmptyEvaluations / LengthNotPowerOfTwo
     if (n_table == 0) return ZB_ERR_EMPTY_EVALUATIONS;
     if (n_table & (n_table - 1)) return ZB_ERR_LENGTH_NOT_POW2;
-    zb_mle table_poly = 0, query_poly = 0;
+    zb_mle table_poly = 0;
     int32_t rc = zb_xxh3_rows(ctx, table_rows, n_table, arity, n_table, &table_poly); // :119-122
     if (rc) return rc;
-    rc = zb_xxh3_rows(ctx, query_rows, n_queries, arity, ceil_pow2(n_queries), &query_poly); // :131-142
-    if (rc == ZB_OK) rc = lasso_finish(ctx, table_poly, query_poly, round_polys, final_point, final_eval, num_vars, qc, tc);
-    if (query_poly) zb_mle_free(ctx, query_poly);
-    zb_mle_free(ctx, table_poly);
-    return rc;
+    return lasso_run(ctx, table_poly, query_rows, n_queries, arity, round_polys, final_point, final_eval, num_vars, qc, tc);
 }
 
 int32_t zh_lasso_prove_with_mapping(zb_ctx *ctx, const uint64_t *table_rows, uint64_t n_table, const uint64_t *query_rows,
@@ -845,14 +916,10 @@ int32_t zh_lasso_prove_builtin(zb_ctx *ctx, int32_t op, uint32_t bits, const uin
                                uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars,
                                uint8_t qc[32], uint8_t tc[32]) {
     if (n_queries == 0) return ZB_ERR_NO_QUERIES;
-    zb_mle table_poly = 0, query_poly = 0;
+    zb_mle table_poly = 0;
     int32_t rc = zb_table_mle(ctx, op, bits, &table_poly);
     if (rc) return rc;
-    rc = zb_xxh3_rows(ctx, query_rows, n_queries, 3, ceil_pow2(n_queries), &query_poly);
-    if (rc == ZB_OK) rc = lasso_finish(ctx, table_poly, query_poly, round_polys, final_point, final_eval, num_vars, qc, tc);
-    if (query_poly) zb_mle_free(ctx, query_poly);
-    zb_mle_free(ctx, table_poly);
-    return rc;
+    return lasso_run(ctx, table_poly, query_rows, n_queries, 3, round_polys, final_point, final_eval, num_vars, qc, tc);
 }
 
 } // extern "C"
