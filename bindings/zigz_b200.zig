@@ -58,6 +58,8 @@ pub extern fn zb_merkle_info(ctx: *Ctx, t: Tree, n_values: ?*u64, height: ?*u32,
 pub extern fn zb_merkle_open(ctx: *Ctx, t: Tree, index: u64, siblings: [*]u8, dirs: [*]u8, leaf_value: ?*u64) i32;
 pub extern fn zb_merkle_free(ctx: *Ctx, t: Tree) i32;
 pub extern fn zb_xxh3_rows(ctx: *Ctx, rows: ?[*]const u64, n_rows: u64, arity: u32, n_padded: u64, out: *Mle) i32;
+pub extern fn zb_xxh3_rows_stream(ctx: *Ctx, rows: ?[*]const u64, n_rows: u64, arity: u32, n_padded: u64, out: *Mle, host_mirror: [*]u32, avail: *u64) i32;
+pub extern fn zb_host_mirror(ctx: *Ctx, bytes: usize, out: *?*anyopaque) i32;
 pub extern fn zb_table_mle(ctx: *Ctx, op: i32, bits: u32, out: *Mle) i32;
 
 // ---- host twin (include/zigz_host.h): only needed if the Zig bodies are not kept ----
