@@ -66,6 +66,8 @@ pub extern fn zb_table_mle(ctx: *Ctx, op: i32, bits: u32, out: *Mle) i32;
 pub extern fn zh_sumcheck_prove(ctx: *Ctx, poly: Mle, round_polys: [*]u64, final_point: [*]u64, final_eval: *u64, claimed_sum: ?*u64) i32;
 pub extern fn zh_commit_open(ctx: *Ctx, poly: Mle, tree: Tree, point: ?[*]const u64, npoint: u32, value: *u64, leaf_index: *u64, leaf_value: *u64, siblings: [*]u8, dirs: [*]u8) i32;
 pub extern fn zh_lasso_prove(ctx: *Ctx, table_rows: [*]const u64, n_table: u64, query_rows: [*]const u64, n_queries: u64, arity: u32, round_polys: [*]u64, final_point: [*]u64, final_eval: *u64, num_vars: *u32, query_commitment: *[32]u8, table_commitment: *[32]u8) i32;
+pub extern fn zh_lasso_prove_builtin(ctx: *Ctx, op: i32, bits: u32, query_rows: [*]const u64, n_queries: u64, round_polys: [*]u64, final_point: [*]u64, final_eval: *u64, num_vars: *u32, query_commitment: *[32]u8, table_commitment: *[32]u8) i32;
+pub extern fn zh_lasso_prove_builtin_batch(ctx: *Ctx, n_jobs: u32, ops: [*]const i32, bits: [*]const u32, query_rows: [*]const [*]const u64, n_queries: [*]const u64, round_polys: [*]const [*]u64, final_points: [*]const [*]u64, final_evals: [*]u64, num_vars: [*]u32, query_commitments: [*]u8, table_commitments: [*]u8, statuses: [*]i32) i32;
 
 /// Drop-in body for `SumcheckProver(BabyBear).prove` (src/proofs/sumcheck_prover.zig:26-91): the transcript,
 /// the proof container and the challenge derivation stay exactly as in the reference; only the two hot loops

@@ -142,6 +142,15 @@ int32_t zh_lasso_prove_with_mapping(zb_ctx *ctx, const uint64_t *table_rows, uin
 int32_t zh_lasso_prove_builtin(zb_ctx *ctx, int32_t op, uint32_t bits, const uint64_t *query_rows, uint64_t n_queries,
                                uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars,
                                uint8_t query_commitment[32], uint8_t table_commitment[32]);
+/* n_jobs independent proofs of that kind in one call — e.g. the per-lookup-kind proofs of one execution trace. Same
+ * outputs as n_jobs calls of zh_lasso_prove_builtin (per-job arrays; commitments are n_jobs x 32 bytes; statuses[j] is job
+ * j's status and the return value the first non-zero one). The query commitments, each one sequential SHA3 sponge
+ * (:242-252) and ~98 % of a proof's time, run concurrently on one host thread per proof while the calling thread drives the
+ * GPU work of the next proof. Not in the reference, whose prover is single-threaded: an extension for throughput. */
+int32_t zh_lasso_prove_builtin_batch(zb_ctx *ctx, uint32_t n_jobs, const int32_t *ops, const uint32_t *bits,
+                                     const uint64_t *const *query_rows, const uint64_t *n_queries, uint64_t *const *round_polys,
+                                     uint64_t *const *final_points, uint64_t *final_evals, uint32_t *num_vars,
+                                     uint8_t *query_commitments, uint8_t *table_commitments, int32_t *statuses);
 /* commitToPolynomial :242-252 over host evaluations: SHA3-256 of le64(e[0]) || ... || le64(e[n-1]) (8-byte elements,
  * or canonical 4-byte elements that are absorbed zero-extended) */
 void zh_flat_commit(const uint64_t *evals, uint64_t n, uint8_t out[32]);

@@ -167,3 +167,30 @@ def test_full_size_commitments_vs_hashlib(zlib, ctx):
     assert piped.query_commitment == want and serial.query_commitment == want
     assert piped.table_commitment == serial.table_commitment
     assert piped.sumcheck_proof.to_bytes() == serial.sumcheck_proof.to_bytes()
+
+
+def test_batch_matches_single_proofs(zlib, ctx, po):
+    """zh_lasso_prove_builtin_batch: three tables, ragged query counts, both schedules in one batch — the proofs are
+    those of the one-at-a-time calls (and therefore of the oracle, see above)."""
+    jobs = [(po.TABLE_ADD, 8, lasso_queries("add", 8, 3000)), (po.TABLE_XOR, 8, lasso_queries("xor", 8, 17)),
+            (po.TABLE_AND, 8, lasso_queries("and", 8, 4096)), (po.TABLE_XOR, 4, lasso_queries("xor", 4, 700))]
+    singles = [zlib.LassoProver.prove_builtin(ctx, *j) for j in jobs]
+    old = zlib.lib().zh_set_lasso_pipeline_min_log2(10)  # jobs 0, 2 and 3 pipelined, job 1 sequential
+    ctx.set_option("lasso_chunk_log2", 9)
+    try:
+        batch = zlib.LassoProver.prove_builtin_batch(ctx, jobs)
+        bad = list(jobs)
+        q = jobs[2][2].copy()
+        q[4000, 0] = BB
+        bad[2] = (po.TABLE_AND, 8, q)
+        with pytest.raises(zlib.ZigzError) as e:
+            zlib.LassoProver.prove_builtin_batch(ctx, bad)
+        assert e.value.name == "NotCanonical"
+    finally:
+        zlib.lib().zh_set_lasso_pipeline_min_log2(old)
+        ctx.set_option("lasso_chunk_log2", 19)
+    for got, want in zip(batch, singles):
+        assert got.sumcheck_proof.to_bytes() == want.sumcheck_proof.to_bytes()
+        assert got.query_commitment == want.query_commitment and got.table_commitment == want.table_commitment
+        assert got.num_lookups == want.num_lookups
+    assert zlib.LassoProver.prove_builtin_batch(ctx, []) == []

@@ -719,3 +719,28 @@ class LassoProver:
         q = _a64(queries)
         nq = q.shape[0]
         return LassoProver._run(ctx, lambda *o: lib().zh_lasso_prove_builtin(ctx.handle, op, bits, _p64(q.reshape(-1)), nq, *o), nq)
+
+    @staticmethod
+    def prove_builtin_batch(ctx: Context, jobs) -> List[LassoProof]:
+        """jobs = [(op, bits, queries), ...]: the proofs `prove_builtin` returns one by one, with the sequential query
+        commitments of all jobs running concurrently (zh_lasso_prove_builtin_batch). Raises the first job's error."""
+        k = len(jobs)
+        if k == 0:
+            return []
+        qs = [_a64(q) for _, _, q in jobs]
+        nqs = [q.shape[0] if q.ndim == 2 else 0 for q in qs]
+        vmax = [max(int(max(n, 1) - 1).bit_length(), 1) for n in nqs]
+        rps = [np.zeros((v, 2), np.uint64) for v in vmax]
+        fps = [np.zeros(v, np.uint64) for v in vmax]
+        P64 = C.POINTER(u64)
+        ops = (C.c_int32 * k)(*[int(op) for op, _, _ in jobs])
+        bits = (u32 * k)(*[int(b) for _, b, _ in jobs])
+        qptr = (P64 * k)(*[_p64(q.reshape(-1)) if q.size else P64() for q in qs])
+        nq = (u64 * k)(*nqs)
+        rpp = (P64 * k)(*[_p64(r) for r in rps])
+        fpp = (P64 * k)(*[_p64(f) for f in fps])
+        fe, nv, st = (u64 * k)(), (u32 * k)(), (C.c_int32 * k)()
+        qc, tc = np.zeros((k, 32), np.uint8), np.zeros((k, 32), np.uint8)
+        ctx.check(lib().zh_lasso_prove_builtin_batch(ctx.handle, k, ops, bits, qptr, nq, rpp, fpp, fe, nv, _p8(qc), _p8(tc), st))
+        return [LassoProof(SumcheckProof(nv[j], rps[j][:nv[j]], fps[j][:nv[j]], fe[j]), qc[j].tobytes(), tc[j].tobytes(), nqs[j])
+                for j in range(k)]

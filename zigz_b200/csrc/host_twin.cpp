@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <immintrin.h>
+#include <memory>
 #include <new>
 #include <thread>
 #include <vector>
@@ -830,50 +831,75 @@ static bool lasso_pipeline(uint64_t n_padded) {
     return v >= 0 && v < 63 && n_padded >= (1ull << v);
 }
 
-// query rows -> query polynomial, sumcheck, both commitments (table_poly is consumed: freed on return)
-static int32_t lasso_run(zb_ctx *ctx, zb_mle table_poly, const uint64_t *query_rows, uint64_t n_queries, uint32_t arity,
-                         uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars, uint8_t qc[32],
-                         uint8_t tc[32]) {
-    const uint64_t n_padded = ceil_pow2(n_queries);
-    zb_mle query_poly = 0;
-    int32_t rc;
-    if (!lasso_pipeline(n_padded)) {
-        rc = zb_xxh3_rows(ctx, query_rows, n_queries, arity, n_padded, &query_poly); // :131-142
-        if (rc == ZB_OK) rc = lasso_finish(ctx, table_poly, query_poly, round_polys, final_point, final_eval, num_vars, qc, tc);
-    } else {
-        uint32_t *mirror = nullptr;
-        rc = zb_host_mirror(ctx, n_padded * sizeof(uint32_t), (void **)&mirror);
-        if (rc) {
-            zb_mle_free(ctx, table_poly);
-            return rc;
-        }
-        uint64_t avail = 0;
-        int stop = 0;
-        Sha3_256 hq;
-        std::thread sponge([&] {
+// The sponge thread of one query commitment: absorbs mirror[0, n) as le64 words while `avail` grows.
+struct SpongeFeed {
+    const uint32_t *mirror = nullptr;
+    uint64_t n = 0;
+    uint64_t avail = 0; // written by the producer (release), read here (acquire)
+    int stop = 0;
+    Sha3_256 h;
+    std::thread th;
+    void start(const uint32_t *m, uint64_t count) {
+        mirror = m;
+        n = count;
+        th = std::thread([this] {
             uint64_t done = 0;
-            while (done < n_padded) {
+            while (done < n) {
                 const uint64_t a = __atomic_load_n(&avail, __ATOMIC_ACQUIRE);
                 if (a == done) {
                     if (__atomic_load_n(&stop, __ATOMIC_ACQUIRE)) return;
                     _mm_pause();
                     continue;
                 }
-                hq.update_words_u32(mirror + done, a - done);
+                h.update_words_u32(mirror + done, a - done);
                 done = a;
             }
         });
-        rc = zb_xxh3_rows_stream(ctx, query_rows, n_queries, arity, n_padded, &query_poly, mirror, &avail);
-        if (rc == ZB_OK) {
-            if (num_vars) zb_mle_len(ctx, query_poly, nullptr, num_vars);
-            rc = zh_sumcheck_prove(ctx, query_poly, round_polys, final_point, final_eval, nullptr); // :160
-        }
-        if (rc == ZB_OK) rc = zh_lasso_commit_poly(ctx, table_poly, tc); // :164
-        if (rc) __atomic_store_n(&stop, 1, __ATOMIC_RELEASE);
-        sponge.join();
-        if (rc == ZB_OK) hq.peek(qc); // :163
     }
+    void finish(bool ok, uint8_t out[32]) {
+        if (!ok) __atomic_store_n(&stop, 1, __ATOMIC_RELEASE);
+        if (th.joinable()) th.join();
+        if (ok) h.peek(out);
+    }
+};
+
+// the calling thread's share of a pipelined proof; `feed` has been started on `mirror` and is finished by the caller
+static int32_t lasso_piped_body(zb_ctx *ctx, zb_mle table_poly, const uint64_t *query_rows, uint64_t n_queries, uint32_t arity,
+                                uint64_t n_padded, uint32_t *mirror, SpongeFeed &feed, uint64_t *round_polys,
+                                uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars, uint8_t tc[32]) {
+    zb_mle query_poly = 0;
+    int32_t rc = zb_xxh3_rows_stream(ctx, query_rows, n_queries, arity, n_padded, &query_poly, mirror, &feed.avail); // :131-142
+    if (rc == ZB_OK) {
+        if (num_vars) zb_mle_len(ctx, query_poly, nullptr, num_vars);
+        rc = zh_sumcheck_prove(ctx, query_poly, round_polys, final_point, final_eval, nullptr); // :160
+    }
+    if (rc == ZB_OK) rc = zh_lasso_commit_poly(ctx, table_poly, tc); // :164
     if (query_poly) zb_mle_free(ctx, query_poly);
+    return rc;
+}
+
+// query rows -> query polynomial, sumcheck, both commitments (table_poly is consumed: freed on return)
+static int32_t lasso_run(zb_ctx *ctx, zb_mle table_poly, const uint64_t *query_rows, uint64_t n_queries, uint32_t arity,
+                         uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint32_t *num_vars, uint8_t qc[32],
+                         uint8_t tc[32]) {
+    const uint64_t n_padded = ceil_pow2(n_queries);
+    int32_t rc;
+    if (!lasso_pipeline(n_padded)) {
+        zb_mle query_poly = 0;
+        rc = zb_xxh3_rows(ctx, query_rows, n_queries, arity, n_padded, &query_poly); // :131-142
+        if (rc == ZB_OK) rc = lasso_finish(ctx, table_poly, query_poly, round_polys, final_point, final_eval, num_vars, qc, tc);
+        if (query_poly) zb_mle_free(ctx, query_poly);
+    } else {
+        uint32_t *mirror = nullptr;
+        rc = zb_host_mirror(ctx, n_padded * sizeof(uint32_t), (void **)&mirror);
+        if (rc == ZB_OK) {
+            SpongeFeed feed;
+            feed.start(mirror, n_padded);
+            rc = lasso_piped_body(ctx, table_poly, query_rows, n_queries, arity, n_padded, mirror, feed, round_polys, final_point,
+                                  final_eval, num_vars, tc);
+            feed.finish(rc == ZB_OK, qc); // :163
+        }
+    }
     zb_mle_free(ctx, table_poly);
     return rc;
 }
@@ -920,6 +946,61 @@ int32_t zh_lasso_prove_builtin(zb_ctx *ctx, int32_t op, uint32_t bits, const uin
     int32_t rc = zb_table_mle(ctx, op, bits, &table_poly);
     if (rc) return rc;
     return lasso_run(ctx, table_poly, query_rows, n_queries, 3, round_polys, final_point, final_eval, num_vars, qc, tc);
+}
+
+int32_t zh_lasso_prove_builtin_batch(zb_ctx *ctx, uint32_t n_jobs, const int32_t *ops, const uint32_t *bits,
+                                     const uint64_t *const *query_rows, const uint64_t *n_queries, uint64_t *const *round_polys,
+                                     uint64_t *const *final_points, uint64_t *final_evals, uint32_t *num_vars,
+                                     uint8_t *query_commitments, uint8_t *table_commitments, int32_t *statuses) {
+    if (n_jobs == 0) return ZB_OK;
+    if (!ops || !bits || !query_rows || !n_queries || !round_polys || !final_points || !final_evals || !num_vars ||
+        !query_commitments || !table_commitments || !statuses)
+        return ZB_ERR_BAD_ARGUMENT;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const uint32_t wave = hw > 2 ? hw - 1 : 1; // one sponge thread per proof in flight, this thread drives the GPU
+    int32_t first = ZB_OK;
+    for (uint32_t base = 0; base < n_jobs; base += wave) {
+        const uint32_t cnt = n_jobs - base < wave ? n_jobs - base : wave;
+        std::vector<uint64_t> padded(cnt), off(cnt);
+        std::vector<char> piped(cnt);
+        uint64_t total = 0;
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint64_t nq = n_queries[base + k];
+            padded[k] = ceil_pow2(nq);
+            piped[k] = nq > 0 && lasso_pipeline(padded[k]);
+            off[k] = total;
+            if (piped[k]) total += padded[k];
+        }
+        uint32_t *mirror = nullptr;
+        int32_t mrc = total ? zb_host_mirror(ctx, total * sizeof(uint32_t), (void **)&mirror) : ZB_OK;
+        std::vector<std::unique_ptr<SpongeFeed>> feeds(cnt);
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint32_t j = base + k;
+            uint8_t *qc = query_commitments + 32 * (size_t)j, *tc = table_commitments + 32 * (size_t)j;
+            if (!piped[k]) {
+                statuses[j] = zh_lasso_prove_builtin(ctx, ops[j], bits[j], query_rows[j], n_queries[j], round_polys[j],
+                                                     final_points[j], final_evals + j, num_vars + j, qc, tc);
+                continue;
+            }
+            statuses[j] = mrc;
+            if (mrc) continue;
+            zb_mle table_poly = 0;
+            statuses[j] = zb_table_mle(ctx, ops[j], bits[j], &table_poly);
+            if (statuses[j]) continue;
+            feeds[k].reset(new SpongeFeed);
+            feeds[k]->start(mirror + off[k], padded[k]);
+            statuses[j] = lasso_piped_body(ctx, table_poly, query_rows[j], n_queries[j], 3, padded[k], mirror + off[k], *feeds[k],
+                                           round_polys[j], final_points[j], final_evals + j, num_vars + j, tc);
+            zb_mle_free(ctx, table_poly);
+            if (statuses[j]) feeds[k]->finish(false, nullptr); // stop this sponge now; the others keep running
+        }
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint32_t j = base + k;
+            if (feeds[k] && statuses[j] == ZB_OK) feeds[k]->finish(true, query_commitments + 32 * (size_t)j);
+            if (statuses[j] && first == ZB_OK) first = statuses[j];
+        }
+    }
+    return first;
 }
 
 } // extern "C"
