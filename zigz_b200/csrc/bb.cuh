@@ -59,4 +59,31 @@ __device__ __forceinline__ uint32_t lerp(uint32_t lo, uint32_t hi, uint32_t r, u
     return add(lo, mul_shoup(sub_lazy(hi, lo), r, rp)); // Shoup accepts any x < 2^32: no reduction of hi - lo needed
 }
 
+// Two variables bound in one step: w0*a0 + w1*a1 + w2*a2 + w3*a3 with the four bilinear weights
+// ((1-r1)(1-r2), (1-r1)r2, r1(1-r2), r1 r2) given in Montgomery form (bilinear_weights). The four 62-bit products are
+// summed in 64 bits (4 P^2 < 2^64) and reduced once: 11 instructions against 27 for three nested lerps, same canonical
+// value (exact field arithmetic, field.zig:112-147).
+constexpr uint32_t P_INV = 0x88000001u; // P^{-1} mod 2^32
+__device__ __forceinline__ uint32_t dot4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t w0, uint32_t w1, uint32_t w2,
+                                         uint32_t w3) {
+    const uint64_t t = (uint64_t)a0 * w0 + (uint64_t)a1 * w1 + (uint64_t)a2 * w2 + (uint64_t)a3 * w3;
+    uint32_t hi = (uint32_t)(t >> 32); // < 1.875 P
+    hi = min(hi, hi - P);              // < P
+    const uint32_t m = (uint32_t)t * P_INV;
+    const uint32_t u = hi - __umulhi(m, P); // (t' - m P) / 2^32, exact; in (-P, P)
+    return min(u, u + P);
+}
+struct BilinearWeights {
+    uint32_t w[4];
+};
+__host__ inline BilinearWeights bilinear_weights(uint32_t r1, uint32_t r2) {
+    const uint32_t n1 = sub(1u, r1), n2 = sub(1u, r2);
+    BilinearWeights b;
+    b.w[0] = mul(mul(n1, n2), R_MOD_P);
+    b.w[1] = mul(mul(n1, r2), R_MOD_P);
+    b.w[2] = mul(mul(r1, n2), R_MOD_P);
+    b.w[3] = mul(mul(r1, r2), R_MOD_P);
+    return b;
+}
+
 } // namespace bb

@@ -429,6 +429,24 @@ struct FinishGrid {
     }
 };
 
+// Kernel arguments of the fold step: one folded variable takes (r1, shoup(r1), r2, shoup(r2)) and interpolates; two folded
+// variables take the four bilinear weights in Montgomery form and bind both in one dot product (bb::dot4).
+struct FoldArgs {
+    uint32_t a[4];
+};
+template <int FV>
+static FoldArgs fold_args(uint32_t r1, uint32_t r2) {
+    FoldArgs f;
+    if (FV == 2) {
+        const bb::BilinearWeights w = bb::bilinear_weights(r1, r2);
+        // quarter t = 2 b1 + b2 (b1 = the variable bound by r1): weights in the order a[j][0..3]
+        f.a[0] = w.w[0], f.a[1] = w.w[1], f.a[2] = w.w[2], f.a[3] = w.w[3];
+    } else {
+        f.a[0] = r1, f.a[1] = bb::shoup_pre(r1), f.a[2] = r2, f.a[3] = bb::shoup_pre(r2);
+    }
+    return f;
+}
+
 // Plain-load version (used below 2^16 entries, where the pass is not bandwidth-bound): 8-byte loads, one polynomial at a
 // time. (A 4-byte-load variant with all polynomials prefetched was measured at 2.3-3.2 TB/s and dropped, r01_grid_sweep.txt.)
 template <int D, int FV, int VEC>
@@ -461,10 +479,9 @@ __global__ void __launch_bounds__(THREADS) k_fold_grid(PolySet ps, uint64_t mq, 
                         f[k][j][0] = bb::lerp(a[j][0].x, a[j][1].x, r1, rp1);
                         f[k][j][1] = bb::lerp(a[j][0].y, a[j][1].y, r1, rp1);
                     } else {
-                        const uint32_t lx = bb::lerp(a[j][0].x, a[j][2].x, r1, rp1), hx = bb::lerp(a[j][1].x, a[j][3].x, r1, rp1);
-                        const uint32_t ly = bb::lerp(a[j][0].y, a[j][2].y, r1, rp1), hy = bb::lerp(a[j][1].y, a[j][3].y, r1, rp1);
-                        f[k][j][0] = bb::lerp(lx, hx, r2, rp2);
-                        f[k][j][1] = bb::lerp(ly, hy, r2, rp2);
+                        // FV == 2: (r1, rp1, r2, rp2) carry the four bilinear weights (fold_weights)
+                        f[k][j][0] = bb::dot4(a[j][0].x, a[j][1].x, a[j][2].x, a[j][3].x, r1, rp1, r2, rp2);
+                        f[k][j][1] = bb::dot4(a[j][0].y, a[j][1].y, a[j][2].y, a[j][3].y, r1, rp1, r2, rp2);
                     }
                 }
                 if constexpr (FV > 0) {
@@ -575,10 +592,9 @@ __global__ void __launch_bounds__(TPB) k_fold_grid_async(PolySet ps, uint64_t mq
                     f[k][j][0] = bb::lerp(a[j][0].x, a[j][1].x, r1, rp1);
                     f[k][j][1] = bb::lerp(a[j][0].y, a[j][1].y, r1, rp1);
                 } else {
-                    const uint32_t lx = bb::lerp(a[j][0].x, a[j][2].x, r1, rp1), hx = bb::lerp(a[j][1].x, a[j][3].x, r1, rp1);
-                    const uint32_t ly = bb::lerp(a[j][0].y, a[j][2].y, r1, rp1), hy = bb::lerp(a[j][1].y, a[j][3].y, r1, rp1);
-                    f[k][j][0] = bb::lerp(lx, hx, r2, rp2);
-                    f[k][j][1] = bb::lerp(ly, hy, r2, rp2);
+                    // FV == 2: (r1, rp1, r2, rp2) carry the four bilinear weights (fold_weights)
+                    f[k][j][0] = bb::dot4(a[j][0].x, a[j][1].x, a[j][2].x, a[j][3].x, r1, rp1, r2, rp2);
+                    f[k][j][1] = bb::dot4(a[j][0].y, a[j][1].y, a[j][2].y, a[j][3].y, r1, rp1, r2, rp2);
                 }
             }
             if constexpr (FV > 0) {
@@ -626,7 +642,8 @@ static void fold_grid_async_launch_s(const PolySet &ps, uint64_t m, uint32_t r1,
     if (per_sm > 4) per_sm = 4;
     uint64_t need = (mq + TPB - 1) / TPB, cap = (uint64_t)sm * per_sm;
     const int grid = (int)(need < cap ? (need ? need : 1) : cap);
-    k_fold_grid_async<D, FV, STAGES_, TPB><<<grid, TPB, G::SMEM, st>>>(ps, mq, r1, bb::shoup_pre(r1), r2, bb::shoup_pre(r2), mb);
+    const FoldArgs fa = fold_args<FV>(r1, r2);
+    k_fold_grid_async<D, FV, STAGES_, TPB><<<grid, TPB, G::SMEM, st>>>(ps, mq, fa.a[0], fa.a[1], fa.a[2], fa.a[3], mb);
 }
 
 // Ring shape per (D, FV): the slots of one iteration are D*4*2^FV*8 bytes per thread. Measured for d = 3
@@ -652,10 +669,10 @@ static void fold_grid_v(int nfold, const PolySet &ps, uint64_t m, uint32_t r1, u
     static const int CPS = tune("ZB_GRID_CPS", 4);
     const uint64_t mq = m / (4 * VEC);
     const int grid = grid_for(mq, sm, CPS);
-    const uint32_t rp1 = bb::shoup_pre(r1), rp2 = bb::shoup_pre(r2);
-    if (nfold == 0) k_fold_grid<D, 0, VEC><<<grid, THREADS, 0, st>>>(ps, mq, r1, rp1, r2, rp2, mb);
-    else if (nfold == 1) k_fold_grid<D, 1, VEC><<<grid, THREADS, 0, st>>>(ps, mq, r1, rp1, r2, rp2, mb);
-    else k_fold_grid<D, 2, VEC><<<grid, THREADS, 0, st>>>(ps, mq, r1, rp1, r2, rp2, mb);
+    const FoldArgs f1 = fold_args<1>(r1, r2), f2 = fold_args<2>(r1, r2);
+    if (nfold == 0) k_fold_grid<D, 0, VEC><<<grid, THREADS, 0, st>>>(ps, mq, f1.a[0], f1.a[1], f1.a[2], f1.a[3], mb);
+    else if (nfold == 1) k_fold_grid<D, 1, VEC><<<grid, THREADS, 0, st>>>(ps, mq, f1.a[0], f1.a[1], f1.a[2], f1.a[3], mb);
+    else k_fold_grid<D, 2, VEC><<<grid, THREADS, 0, st>>>(ps, mq, f2.a[0], f2.a[1], f2.a[2], f2.a[3], mb);
 }
 
 template <int D>
