@@ -43,12 +43,14 @@ __device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b) {
 // Lazy forms (fewer instructions in the HBM-bound kernels, which otherwise brush the issue limit under the power cap):
 //   sub_lazy  : a - b + P in [1, 2P) for canonical a, b (2P < 2^32)
 //   mont_mul_lazy : a*b*2^-32 mod P in [0, 2P), valid for a < 2^32 (lazy allowed) and b < P (canonical):
-//                   t = a*b < 2^32 P, m P < 2^32 P, so t + m P < 2^64 and the quotient is < 2P
+//                   t = a*b < 2^32 P so hi(t) < P
 __host__ __device__ __forceinline__ uint32_t sub_lazy(uint32_t a, uint32_t b) { return a - b + P; }
 __device__ __forceinline__ uint32_t mont_mul_lazy(uint32_t a, uint32_t b) {
-    uint64_t t = (uint64_t)a * b;
-    uint32_t m = (uint32_t)t * P_NEG_INV;
-    return (uint32_t)((t + (uint64_t)m * P) >> 32);
+    // subtractive form: with m = lo(t) * P^{-1}, t - m P is an exact multiple of 2^32 and (t - m P) / 2^32 = hi(t) - hi(m P),
+    // no carry to propagate. hi(t) < P and hi(m P) < P, so adding P lands in [1, 2P).
+    const uint64_t t = (uint64_t)a * b;
+    const uint32_t m = (uint32_t)t * 0x88000001u; // P^{-1} mod 2^32
+    return (uint32_t)(t >> 32) + P - __umulhi(m, P);
 }
 
 // plain a*b mod P via two Montgomery steps is wasteful; for a one-off product use this
