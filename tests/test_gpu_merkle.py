@@ -141,10 +141,11 @@ def test_config_c3_size_tree(zlib, ctx, po):
         m.deinit()
 
 
-def test_full_size_tree_properties(zlib, ctx, po):
-    """2^22 leaves: every opened path must verify against the root with the HOST verifier, leaf digests must equal
-    SHA3(le64(value)), and the root must equal the root of the two half-trees hashed together (subtree sharding)."""
-    lg = 22
+@pytest.mark.parametrize("lg", [22, 26])
+def test_full_size_tree_properties(zlib, ctx, po, lg):
+    """2^22 and 2^26 leaves (BASELINE config C3): every opened path must verify against the root with the HOST verifier,
+    leaf digests must equal SHA3(le64(value)), and the root must equal the root of the two half-trees hashed together
+    (subtree sharding)."""
     poly = zlib.Multilinear.synthetic(ctx, 0xC0FFEE, 1 << lg)
     com, tree = zlib.CommitmentScheme.commit(poly)
     from _cases import splitmix64

@@ -119,6 +119,29 @@ def test_full_size_properties(zlib, ctx, po, d, lg):
         p.deinit()
 
 
+@pytest.mark.parametrize("d,lg", [(3, 30), (1, 28)])
+def test_baseline_size_fold_chain_agrees_with_eval_kernel(zlib, ctx, po, d, lg):
+    """BASELINE config C5 at its full size (three 2^30-entry tables) and the d=1 prover at 2^28: besides the verifier's
+    round checks, every final evaluation must equal Multilinear.eval of the untouched table at the challenge point —
+    computed by a different kernel family (k_eval_*), LSB-first (multilinear.zig:110-144) where the prover binds the
+    top index bit first (:154-180), hence the reversed point."""
+    info = ctx.device_info()  # free memory counts the context's own cached blocks as used: compare against the total
+    if info["total_mem"] < (2 * d + 2) * (4 << lg):
+        pytest.skip("not enough free device memory for this size")
+    polys = [zlib.Multilinear.synthetic(ctx, 500 + k, 1 << lg) for k in range(d)]
+    pr = zlib.ProductSumcheckProver.prove(polys, consume=False)
+    ok, final_claim = po.sumcheck_verify_rounds(BB, pr.round_polynomials, pr.claimed_sum)
+    assert ok
+    prod = 1
+    for x in pr.final_evals:
+        prod = prod * x % BB
+    assert final_claim == prod
+    point = [int(x) for x in pr.final_point][::-1]
+    for k, p in enumerate(polys):
+        assert p.eval(point) == pr.final_evals[k], k
+        p.deinit()
+
+
 # ---------------------------------------------------------------- persistent tail kernel (zb_set_option "tail_log2")
 @pytest.mark.parametrize("prelaunch", [1, 0])
 @pytest.mark.parametrize("tail_log2", [0, 2, 3, 10, 14, 20])
