@@ -1,6 +1,7 @@
 //! Zig bindings for libzigz_b200.so — the reference-side glue a zigz maintainer would add.
-//! NOT compiled in this repo's image (no Zig toolchain there); it mirrors include/zigz_b200.h and
-//! include/zigz_host.h one to one and is checked against them by tests/test_cabi_cpu.py (same names).
+//! NOT compiled in this repo's image (no Zig toolchain there). It declares every function of include/zigz_b200.h and
+//! include/zigz_host.h: the ones the wrappers below use are written by hand, the rest is derived from the headers by
+//! tools/gen_zig_externs.py (section at the end); tests/test_cabi_cpu.py fails when the two drift apart.
 //! Link with: exe.linkSystemLibrary("zigz_b200"); exe.addLibraryPath(...); exe.linkLibC();
 const std = @import("std");
 
@@ -107,3 +108,70 @@ pub fn sumcheckProve(comptime F: type, comptime protocol: type, ctx: *Ctx, evalu
     proof.final_eval = F.init(s[0]); // after the last fold s[0] is current_poly.evaluations[0] (:88)
     return proof;
 }
+
+// ---- generated from include/*.h by tools/gen_zig_externs.py (do not edit below) ----
+pub extern fn zb_status_name(status: i32) [*:0]const u8;
+pub extern fn zb_kernel_launches(ctx: *Ctx) u64;
+pub extern fn zb_host_alloc(ctx: *Ctx, bytes: usize, out: [*c]?*anyopaque) i32;
+pub extern fn zb_host_free(ctx: *Ctx, p: ?*anyopaque) i32;
+pub extern fn zb_device_info(ctx: *Ctx, sm_count: [*c]i32, total_mem: [*c]u64, free_mem: [*c]u64) i32;
+pub extern fn zb_int_pipe_peak(ctx: *Ctx, lop3_per_s: [*c]f64, shf_per_s: [*c]f64, keccak_mix_per_s: [*c]f64) i32;
+pub extern fn zb_stream(ctx: *Ctx) ?*anyopaque;
+pub extern fn zb_sync(ctx: *Ctx) i32;
+pub extern fn zb_set_option(ctx: *Ctx, key: [*:0]const u8, value: i64) i32;
+pub extern fn zb_get_option(ctx: *Ctx, key: [*:0]const u8, value: [*c]i64) i32;
+pub extern fn zb_timer_start(ctx: *Ctx) i32;
+pub extern fn zb_timer_stop(ctx: *Ctx, ms: [*c]f32) i32;
+pub extern fn zb_profile_enable(ctx: *Ctx, on: i32) i32;
+pub extern fn zb_profile_count(ctx: *Ctx) u32;
+pub extern fn zb_profile_entry(ctx: *Ctx, i: u32, name: [*c]u8, name_cap: u32, launches: [*c]u64, total_ms: [*c]f64, algorithmic_bytes: [*c]u64) i32;
+pub extern fn zb_mle_upload_u32(ctx: *Ctx, evals: [*c]const u32, n: u64, out: [*c]Mle) i32;
+pub extern fn zb_mle_constant(ctx: *Ctx, num_vars: u32, value: u64, out: [*c]Mle) i32;
+pub extern fn zb_mle_synthetic(ctx: *Ctx, seed: u64, start: u64, stride: u64, n: u64, out: [*c]Mle) i32;
+pub extern fn zb_mle_clone(ctx: *Ctx, src: Mle, out: [*c]Mle) i32;
+pub extern fn zb_mle_download_range(ctx: *Ctx, m: Mle, offset: u64, out: [*c]u64, n: u64) i32;
+pub extern fn zb_mle_download_u32(ctx: *Ctx, m: Mle, offset: u64, out: [*c]u32, n: u64) i32;
+pub extern fn zb_host_scratch(ctx: *Ctx, bytes: usize, out: [*c]?*anyopaque) i32;
+pub extern fn zb_merkle_leaf_hashes(ctx: *Ctx, t: Tree, out: [*c]u8, n_digests: u64) i32;
+pub extern fn zb_comm_unique_id(nccl_path: [*:0]const u8, out: *[128]u8) i32;
+pub extern fn zb_comm_init(ctx: *Ctx, nccl_path: [*:0]const u8, unique_id: *const [128]u8, rank: i32, world: i32) i32;
+pub extern fn zb_comm_info(ctx: *Ctx, rank: [*c]i32, world: [*c]i32) i32;
+pub extern fn zb_comm_allreduce_u64(ctx: *Ctx, vals: [*c]u64, n: u32) i32;
+pub extern fn zb_comm_p2p_handle(ctx: *Ctx, out: *[64]u8) i32;
+pub extern fn zb_comm_p2p_attach(ctx: *Ctx, handles: [*c]const u8) i32;
+pub extern fn zb_comm_allgather_cyclic(ctx: *Ctx, local: Mle, out: [*c]Mle) i32;
+pub extern fn zb_comm_destroy(ctx: *Ctx) i32;
+pub extern fn zh_transcript_new() *Transcript;
+pub extern fn zh_transcript_clone(t: *const Transcript) *Transcript;
+pub extern fn zh_transcript_free(t: *Transcript) void;
+pub extern fn zh_transcript_append_field(t: *Transcript, value: u64) void;
+pub extern fn zh_transcript_append_fields(t: *Transcript, v: [*c]const u64, n: usize) void;
+pub extern fn zh_transcript_append_bytes(t: *Transcript, data: ?*const anyopaque, n: usize) void;
+pub extern fn zh_transcript_challenge(t: *Transcript) u64;
+pub extern fn zh_transcript_finalize(t: *Transcript, out: *[32]u8) void;
+pub extern fn zh_sha3_256(data: ?*const anyopaque, n: usize, out: *[32]u8) void;
+pub extern fn zh_digest_to_field(digest: *const [32]u8) u64;
+pub extern fn zh_f_add(a: u64, b: u64) u64;
+pub extern fn zh_f_sub(a: u64, b: u64) u64;
+pub extern fn zh_f_mul(a: u64, b: u64) u64;
+pub extern fn zh_eval_univariate(coeffs: [*c]const u64, n: u32, x: u64) u64;
+pub extern fn zh_set_grid_min_log2(v: i32) i32;
+pub extern fn zh_sumcheck_prove_interactive(ctx: *Ctx, poly: Mle, challenges: [*c]const u64, n_challenges: u32, round_polys: [*c]u64, final_point: [*c]u64, final_eval: [*c]u64) i32;
+pub extern fn zh_sumcheck_proof_to_bytes(num_vars: u32, round_polys: [*c]const u64, final_point: [*c]const u64, final_eval: u64, out: [*c]u8) usize;
+pub extern fn zh_prodcheck_prove(ctx: *Ctx, polys: [*c]const Mle, d: u32, round_polys: [*c]u64, final_point: [*c]u64, final_evals: [*c]u64, claimed_sum: [*c]u64) i32;
+pub extern fn zh_prodcheck_prove_consume(ctx: *Ctx, polys: [*c]const Mle, d: u32, round_polys: [*c]u64, final_point: [*c]u64, final_evals: [*c]u64, claimed_sum: [*c]u64) i32;
+pub extern fn zh_commit(ctx: *Ctx, poly: Mle, tree: [*c]Tree, root: *[32]u8, num_vars: [*c]u32) i32;
+pub extern fn zh_batch_commit(ctx: *Ctx, polys: [*c]const Mle, count: u32, trees: [*c]Tree, roots: [*c]u8) i32;
+pub extern fn zh_commit_sharded(ctx: *Ctx, local_poly: Mle, tree: [*c]Tree, local_root: *[32]u8, root: *[32]u8) i32;
+pub extern fn zh_point_to_index(point: [*c]const u64, npoint: u32) u64;
+pub extern fn zh_merkle_verify(root: *const [32]u8, value: u64, siblings: [*c]const u8, dirs: [*c]const u8, height: u32) i32;
+pub extern fn zh_commit_verify(root: *const [32]u8, leaf_value: u64, siblings: [*c]const u8, dirs: [*c]const u8, height: u32) i32;
+pub extern fn zh_generate_commitments(ctx: *Ctx, tr: *Transcript, polys: [*c]const Mle, count: u32, roots: [*c]u8, points: [*c]u64, values: [*c]u64, leaf_indices: [*c]u64, leaf_values: [*c]u64, siblings: [*c]u8, dirs: [*c]u8) i32;
+pub extern fn zh_prove_from_trace(ctx: *Ctx, program: [*c]const u8, program_len: usize, entry_pc: u64, initial_regs: [*c]const u64, n_initial_regs: u32, trace_cols: [*c]const u64, num_steps: u64, final_pc: u64, final_regs: [*c]const u64, outputs: [*c]const u64, n_outputs: u32, compat_buffer: i32, out: [*c]u8, out_cap: usize, out_len: [*c]usize) i32;
+pub extern fn zh_verify_proof(proof: [*c]const u8, len: usize, program: [*c]const u8, program_len: usize, verdict: [*c]i32) i32;
+pub extern fn zh_sha256(data: ?*const anyopaque, n: usize, out: *[32]u8) void;
+pub extern fn zh_set_lasso_pipeline_min_log2(v: i32) i32;
+pub extern fn zh_lasso_prove_with_mapping(ctx: *Ctx, table_rows: [*c]const u64, n_table: u64, query_rows: [*c]const u64, n_queries: u64, mapping: [*c]const u64, n_mapping: u64, arity: u32, round_polys: [*c]u64, final_point: [*c]u64, final_eval: [*c]u64, num_vars: [*c]u32, query_commitment: *[32]u8, table_commitment: *[32]u8) i32;
+pub extern fn zh_flat_commit(evals: [*c]const u64, n: u64, out: *[32]u8) void;
+pub extern fn zh_flat_commit_u32(evals: [*c]const u32, n: u64, out: *[32]u8) void;
+pub extern fn zh_lasso_commit_poly(ctx: *Ctx, poly: Mle, out: *[32]u8) i32;

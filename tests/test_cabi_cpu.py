@@ -58,3 +58,14 @@ def test_no_cpu_fallback_without_a_device(zlib):
     with pytest.raises(zlib.ZigzError) as e:
         zlib.Context(0)
     assert e.value.name == "NoCudaDevice"
+
+
+def test_zig_binding_declares_the_whole_c_abi():
+    """bindings/zigz_b200.zig (what a zigz maintainer links against) must declare exactly the functions the headers
+    declare: hand-written externs plus the section tools/gen_zig_externs.py derives from include/*.h."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_zig_externs.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
