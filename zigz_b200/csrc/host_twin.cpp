@@ -839,10 +839,19 @@ struct SpongeFeed {
     int stop = 0;
     Sha3_256 h;
     std::thread th;
-    void start(const uint32_t *m, uint64_t count) {
+    // false when no thread could be started (the caller then commits sequentially)
+    bool start(const uint32_t *m, uint64_t count) {
         mirror = m;
         n = count;
-        th = std::thread([this] {
+        try {
+            th = std::thread([this] { run(); });
+        } catch (...) {
+            return false;
+        }
+        return true;
+    }
+    void run() {
+        {
             uint64_t done = 0;
             while (done < n) {
                 const uint64_t a = __atomic_load_n(&avail, __ATOMIC_ACQUIRE);
@@ -854,7 +863,7 @@ struct SpongeFeed {
                 h.update_words_u32(mirror + done, a - done);
                 done = a;
             }
-        });
+        }
     }
     void finish(bool ok, uint8_t out[32]) {
         if (!ok) __atomic_store_n(&stop, 1, __ATOMIC_RELEASE);
@@ -894,10 +903,11 @@ static int32_t lasso_run(zb_ctx *ctx, zb_mle table_poly, const uint64_t *query_r
         rc = zb_host_mirror(ctx, n_padded * sizeof(uint32_t), (void **)&mirror);
         if (rc == ZB_OK) {
             SpongeFeed feed;
-            feed.start(mirror, n_padded);
+            const bool threaded = feed.start(mirror, n_padded);
             rc = lasso_piped_body(ctx, table_poly, query_rows, n_queries, arity, n_padded, mirror, feed, round_polys, final_point,
                                   final_eval, num_vars, tc);
-            feed.finish(rc == ZB_OK, qc); // :163
+            if (!threaded && rc == ZB_OK) feed.run(); // the mirror is complete: absorb it here
+            feed.finish(rc == ZB_OK, qc);             // :163
         }
     }
     zb_mle_free(ctx, table_poly);
@@ -988,10 +998,11 @@ int32_t zh_lasso_prove_builtin_batch(zb_ctx *ctx, uint32_t n_jobs, const int32_t
             statuses[j] = zb_table_mle(ctx, ops[j], bits[j], &table_poly);
             if (statuses[j]) continue;
             feeds[k].reset(new SpongeFeed);
-            feeds[k]->start(mirror + off[k], padded[k]);
+            const bool threaded = feeds[k]->start(mirror + off[k], padded[k]);
             statuses[j] = lasso_piped_body(ctx, table_poly, query_rows[j], n_queries[j], 3, padded[k], mirror + off[k], *feeds[k],
                                            round_polys[j], final_points[j], final_evals + j, num_vars + j, tc);
             zb_mle_free(ctx, table_poly);
+            if (!threaded && statuses[j] == ZB_OK) feeds[k]->run();
             if (statuses[j]) feeds[k]->finish(false, nullptr); // stop this sponge now; the others keep running
         }
         for (uint32_t k = 0; k < cnt; k++) {
