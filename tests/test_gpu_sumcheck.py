@@ -119,9 +119,10 @@ def test_full_size_properties(zlib, ctx, po, d, lg):
         p.deinit()
 
 
-@pytest.mark.parametrize("d,lg", [(3, 30), (1, 28)])
+@pytest.mark.parametrize("d,lg", [(3, 30), (1, 28), (1, 32), (2, 31)])
 def test_baseline_size_fold_chain_agrees_with_eval_kernel(zlib, ctx, po, d, lg):
-    """BASELINE config C5 at its full size (three 2^30-entry tables) and the d=1 prover at 2^28: besides the verifier's
+    """BASELINE config C5 at its full size (three 2^30-entry tables), the d=1 prover at 2^28, and tables of 2^31 / 2^32
+    entries (element indices and byte offsets beyond 32 bits — the largest single tables 180 GB hold twice): besides the verifier's
     round checks, every final evaluation must equal Multilinear.eval of the untouched table at the challenge point —
     computed by a different kernel family (k_eval_*), LSB-first (multilinear.zig:110-144) where the prover binds the
     top index bit first (:154-180), hence the reversed point."""
