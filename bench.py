@@ -304,6 +304,7 @@ def run_e2e(args, z, ctx, comm, dist, local, rank, world, polys):
             m.deinit()
         return pr
 
+    barrier(dist)  # pinning 24 GiB per rank takes seconds and differs between ranks
     step()  # warm-up (allocator cache, page tables)
     steps = max(1, min(args.steps, args.e2e_steps))
     barrier(dist)

@@ -2021,6 +2021,17 @@ int32_t zb_comm_p2p_attach(zb_ctx *ctx, const uint8_t *handles) {
     XchgView view{};
     view.rank = ctx->rank;
     view.world = ctx->world;
+    {
+        // how long the last CTA waits for the other ranks' rows. Ranks are only loosely coupled: each one uploads its own
+        // shard before it proves, and those uploads share the host's cores and memory, so seconds of skew are normal.
+        const char *e = getenv("ZB_XCHG_PATIENCE_S");
+        double sec = e && *e ? atof(e) : 30.0;
+        if (sec < 0.1) sec = 0.1;
+        if (sec > 100.0) sec = 100.0; // stays below the host's 120 s wait for the kernel
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+        view.patience = (long long)(sec * 1e3 * (khz > 0 ? khz : 1965000));
+    }
     for (int q = 0; q < ctx->world; q++) {
         if (q == ctx->rank) {
             view.peer[q] = ctx->d_xchg;

@@ -21,6 +21,7 @@ constexpr int XCHG_SET_WORDS = XCHG_MAX_RANKS * XCHG_ROW + XCHG_MAX_RANKS;
 struct XchgView {
     unsigned long long *peer[XCHG_MAX_RANKS]; // peer[q] = rank q's exchange buffer as seen from this GPU (peer[rank] = own)
     int rank, world;
+    long long patience; // SM cycles a rank waits for its peers' rows before it reports a starved exchange
 };
 
 struct Mailbox {

@@ -40,7 +40,8 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 // point of the same round: lane q stores this rank's words into rank q's exchange buffer (NVLink P2P store) and
 // raises this rank's flag there; then lane q waits for rank q's flag in the LOCAL buffer and reads its words; a warp
 // shuffle adds the rows. No NCCL call, no extra launch: the reduction rides in the tail of the kernel that produced
-// the partial sums. Returns false on a ~2 s starvation (a peer never arrived).
+// the partial sums. Returns false when a peer's row has not arrived after xv->patience cycles (default ~30 s: ranks
+// that upload their own shards first can be seconds apart; ZB_XCHG_PATIENCE_S).
 template <int NS>
 __device__ __forceinline__ bool xchg_allreduce(unsigned long long (&tot)[NS], const XchgView *xv, unsigned long long seq) {
     const int lane = threadIdx.x & 31;
@@ -59,9 +60,9 @@ __device__ __forceinline__ bool xchg_allreduce(unsigned long long (&tot)[NS], co
     for (int k = 0; k < NS; k++) v[k] = 0;
     if (lane < world) {
         volatile unsigned long long *mine = xv->peer[rank] + set;
-        const long long t0 = clock64();
+        const long long t0 = clock64(), patience = xv->patience;
         while (mine[XCHG_MAX_RANKS * XCHG_ROW + lane] != seq) {
-            if (clock64() - t0 > 4000000000ll) {
+            if (clock64() - t0 > patience) {
                 ok = false;
                 break;
             }
