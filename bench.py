@@ -232,11 +232,24 @@ def run_ours(args):
                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
 
     # ---- e2e: host u64 buffers -> C ABI -> proof on the host
+    # A failure here (host RAM, a rank that never arrives) must not take the device-timed line above with it: every
+    # rank records it, the ranks agree that it happened, and the secondary measurements are skipped.
     e2e = None
+    e2e_failed = 0.0
     if not args.skip_e2e:
-        e2e = run_e2e(args, z, ctx, comm, dist, local, rank, world, polys)
+        try:
+            e2e = run_e2e(args, z, ctx, comm, dist, local, rank, world, polys)
+        except Exception as exc:  # noqa: BLE001 - reported in the JSON line
+            e2e = {"value": None, "unit": UNIT, "error": f"{type(exc).__name__}: {exc}"[:300]}
+            e2e_failed = 1.0
+        if world > 1:
+            e2e_failed = max_over_ranks(dist, e2e_failed, local)
+            if e2e_failed and e2e.get("value") is not None:
+                e2e = {"value": None, "unit": UNIT, "error": "another rank failed in the end-to-end leg"}
     for p in polys:
         p.deinit()
+    if e2e_failed:
+        args.skip_extras = True
 
     extras = None
     cpu = None
@@ -299,6 +312,8 @@ def run_e2e(args, z, ctx, comm, dist, local, rank, world, polys):
 
     def step():
         ms_ = [z.Multilinear.init(ctx, h) for h in host]
+        if comm is not None:
+            barrier(dist)  # the ranks' uploads share the host; meet before the first in-kernel exchange
         pr = z.ProductSumcheckProver.prove(ms_, consume=True) if comm is None else comm.prodcheck_prove(ms_, consume=True)
         for m in ms_:
             m.deinit()
