@@ -75,6 +75,13 @@ __device__ __forceinline__ uint32_t dot4(uint32_t a0, uint32_t a1, uint32_t a2, 
     const uint32_t u = hi - __umulhi(m, P); // (t' - m P) / 2^32, exact; in (-P, P)
     return min(u, u + P);
 }
+// One variable bound as a dot product: w0*a0 + w1*a1 with ((1-r) R, r R); 2 P^2 < P 2^32, so hi(t) < P needs no correction.
+__device__ __forceinline__ uint32_t dot2(uint32_t a0, uint32_t a1, uint32_t w0, uint32_t w1) {
+    const uint64_t t = (uint64_t)a0 * w0 + (uint64_t)a1 * w1;
+    const uint32_t m = (uint32_t)t * P_INV;
+    const uint32_t u = (uint32_t)(t >> 32) - __umulhi(m, P);
+    return min(u, u + P);
+}
 struct BilinearWeights {
     uint32_t w[4];
 };

@@ -540,7 +540,9 @@ struct GridAsync {
     static_assert(STAGES >= 2 && SMEM <= 222 * 1024, "ring depth");
 };
 
-template <int D, int FV, int STAGES_, int TPB>
+// DOT (FV == 1 only): (r1, rp1) carry the Montgomery weights ((1-r) R, r R) and the variable is bound as a two-term dot
+// product (bb::dot2) instead of an interpolation with a Shoup product (ZB_GRID_DOT2)
+template <int D, int FV, int STAGES_, int TPB, bool DOT = false>
 __global__ void __launch_bounds__(TPB) k_fold_grid_async(PolySet ps, uint64_t mq, uint32_t r1, uint32_t rp1, uint32_t r2,
                                                              uint32_t rp2, Mailbox mb) {
     using G = GridAsync<D, FV, STAGES_, TPB>;
@@ -590,8 +592,13 @@ __global__ void __launch_bounds__(TPB) k_fold_grid_async(PolySet ps, uint64_t mq
                     f[k][j][0] = a[j][0].x;
                     f[k][j][1] = a[j][0].y;
                 } else if constexpr (FV == 1) {
-                    f[k][j][0] = bb::lerp(a[j][0].x, a[j][1].x, r1, rp1);
-                    f[k][j][1] = bb::lerp(a[j][0].y, a[j][1].y, r1, rp1);
+                    if constexpr (DOT) {
+                        f[k][j][0] = bb::dot2(a[j][0].x, a[j][1].x, r1, rp1);
+                        f[k][j][1] = bb::dot2(a[j][0].y, a[j][1].y, r1, rp1);
+                    } else {
+                        f[k][j][0] = bb::lerp(a[j][0].x, a[j][1].x, r1, rp1);
+                        f[k][j][1] = bb::lerp(a[j][0].y, a[j][1].y, r1, rp1);
+                    }
                 } else {
                     // FV == 2: (r1, rp1, r2, rp2) carry the four bilinear weights (fold_weights)
                     f[k][j][0] = bb::dot4(a[j][0].x, a[j][1].x, a[j][2].x, a[j][3].x, r1, rp1, r2, rp2);
@@ -629,11 +636,11 @@ __global__ void __launch_bounds__(TPB) k_fold_grid_async(PolySet ps, uint64_t mq
     publish_sums<NS, FinishGrid<D, NS>, TPB>(s, mb, FinishGrid<D, NS>());
 }
 
-template <int D, int FV, int STAGES_, int TPB>
+template <int D, int FV, int STAGES_, int TPB, bool DOT = false>
 static void fold_grid_async_launch_s(const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
     using G = GridAsync<D, FV, STAGES_, TPB>;
     static const bool once = [] {
-        cudaFuncSetAttribute(k_fold_grid_async<D, FV, STAGES_, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        cudaFuncSetAttribute(k_fold_grid_async<D, FV, STAGES_, TPB, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         return true;
     }();
     (void)once;
@@ -643,8 +650,12 @@ static void fold_grid_async_launch_s(const PolySet &ps, uint64_t m, uint32_t r1,
     if (per_sm > 4) per_sm = 4;
     uint64_t need = (mq + TPB - 1) / TPB, cap = (uint64_t)sm * per_sm;
     const int grid = (int)(need < cap ? (need ? need : 1) : cap);
-    const FoldArgs fa = fold_args<FV>(r1, r2);
-    k_fold_grid_async<D, FV, STAGES_, TPB><<<grid, TPB, G::SMEM, st>>>(ps, mq, fa.a[0], fa.a[1], fa.a[2], fa.a[3], mb);
+    FoldArgs fa = fold_args<FV>(r1, r2);
+    if (DOT) {
+        fa.a[0] = bb::mul(bb::sub(1u, r1), bb::R_MOD_P);
+        fa.a[1] = bb::mul(r1, bb::R_MOD_P);
+    }
+    k_fold_grid_async<D, FV, STAGES_, TPB, DOT><<<grid, TPB, G::SMEM, st>>>(ps, mq, fa.a[0], fa.a[1], fa.a[2], fa.a[3], mb);
 }
 
 // Ring shape per (D, FV): the slots of one iteration are D*4*2^FV*8 bytes per thread. Measured for d = 3
@@ -656,7 +667,9 @@ static void fold_grid_async_launch(const PolySet &ps, uint64_t m, uint32_t r1, u
     constexpr int SLOT_BYTES = D * 4 * (1 << FV) * 8; // per thread and stage
     if constexpr (FV == 1) {
         static const int cfg = tune("ZB_GRID_CFG_F1", 1202);
+        static const int dot = tune("ZB_GRID_DOT2", 0);
         if (cfg == 803) return fold_grid_async_launch_s<D, FV, 3, 256>(ps, m, r1, r2, mb, sm, st);
+        if (dot) return fold_grid_async_launch_s<D, FV, 2, 384, true>(ps, m, r1, r2, mb, sm, st);
         return fold_grid_async_launch_s<D, FV, 2, 384>(ps, m, r1, r2, mb, sm, st);
     } else if constexpr (SLOT_BYTES * 256 * 3 <= 222 * 1024) {
         return fold_grid_async_launch_s<D, FV, 3, 256>(ps, m, r1, r2, mb, sm, st);
