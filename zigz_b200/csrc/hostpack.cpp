@@ -49,27 +49,35 @@ HostPool::HostPool(int threads) : nthreads_(threads < 1 ? 1 : threads) {
 HostPool::~HostPool() {
     {
         std::lock_guard<std::mutex> lk(mu_);
-        stop_ = true;
+        stop_.store(true, std::memory_order_release);
     }
     cv_start_.notify_all();
     for (auto &t : threads_) t.join();
 }
 
+namespace {
+constexpr int SPIN_LIMIT = 2000; // x _mm_pause (~40-140 cycles each): tens of microseconds
+}
+
 void HostPool::worker(int tid) {
     uint64_t seen = 0;
     for (;;) {
-        const std::function<void(int)> *job;
-        {
+        uint64_t e;
+        int spins = 0;
+        while ((e = epoch_.load(std::memory_order_acquire)) == seen && !stop_.load(std::memory_order_acquire)) {
+            if (++spins < SPIN_LIMIT) {
+                _mm_pause();
+                continue;
+            }
             std::unique_lock<std::mutex> lk(mu_);
-            cv_start_.wait(lk, [&] { return stop_ || epoch_ != seen; });
-            if (stop_) return;
-            seen = epoch_;
-            job = job_;
+            cv_start_.wait(lk, [&] { return stop_.load(std::memory_order_acquire) || epoch_.load(std::memory_order_acquire) != seen; });
         }
-        (*job)(tid);
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            if (--pending_ == 0) cv_done_.notify_one();
+        if (e == seen) return; // stop
+        seen = e;
+        (*job_)(tid); // published before the epoch moved
+        if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+            std::lock_guard<std::mutex> lk(mu_); // the caller is either before its predicate check or waiting
+            cv_done_.notify_one();
         }
     }
 }
@@ -79,16 +87,23 @@ void HostPool::run(const std::function<void(int)> &fn) {
         fn(0);
         return;
     }
+    job_ = &fn;
+    pending_.store(nthreads_ - 1, std::memory_order_relaxed);
     {
         std::lock_guard<std::mutex> lk(mu_);
-        job_ = &fn;
-        pending_ = nthreads_ - 1;
-        epoch_++;
+        epoch_.fetch_add(1, std::memory_order_release);
     }
     cv_start_.notify_all();
     fn(0);
-    std::unique_lock<std::mutex> lk(mu_);
-    cv_done_.wait(lk, [&] { return pending_ == 0; });
+    int spins = 0;
+    while (pending_.load(std::memory_order_acquire) != 0) {
+        if (++spins < SPIN_LIMIT) {
+            _mm_pause();
+            continue;
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return pending_.load(std::memory_order_acquire) == 0; });
+    }
 }
 
 } // namespace zigz
