@@ -168,3 +168,18 @@ def test_verifier_twin_on_oracle_proofs(zlib, po, golden):
     out = np.zeros(32, np.uint8)
     zlib.lib().zh_sha256(b"abc", 3, out.ctypes.data_as(zlib.api.P8))
     assert out.tobytes() == hashlib.sha256(b"abc").digest()
+
+
+def test_host_pool_and_narrowing_cpp():
+    """tests/cpp/test_hostpool.cpp: the upload path's fork-join pool (spin-then-sleep) and the AVX2 u64 -> u32 narrowing
+    with its canonical check, compiled and run on the host."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "tests", "cpp", "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "test_hostpool")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-pthread", os.path.join(root, "tests", "cpp", "test_hostpool.cpp"),
+                    os.path.join(root, "zigz_b200", "csrc", "hostpack.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "hostpool ok" in r.stdout, r.stdout + r.stderr
