@@ -34,11 +34,32 @@ class OracleError(Exception):
         super().__init__(f"error.{self.name}")
 
 
+def _host_tag() -> str:
+    """Identifies the CPU the library was compiled for (-march=native): model name + feature flags."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            txt = f.read()
+        model = next((ln.split(":", 1)[1].strip() for ln in txt.splitlines() if ln.startswith("model name")), "?")
+        flags = next((ln.split(":", 1)[1].strip() for ln in txt.splitlines() if ln.startswith("flags")), "")
+        return model + " " + hashlib.sha1(flags.encode()).hexdigest()[:12]
+    except OSError:
+        return "unknown"
+
+
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("zo_hash.c", "zigz_oracle.c", "zo_hash.h", "zigz_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("zo_hash.c", "zigz_oracle.c", "zo_hash.h", "zigz_oracle.h", "Makefile")]
+    tag_file = os.path.join(_HERE, "_build", "host.txt")
+    tag = _host_tag()
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
-    if force or stale:
-        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    try:
+        other_host = open(tag_file).read() != tag  # built with -march=native on another CPU (snapshot from the build container)
+    except OSError:
+        other_host = True
+    if force or stale or other_host:
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+        with open(tag_file, "w") as f:
+            f.write(tag)
     return _SO
 
 
@@ -302,6 +323,19 @@ def merkle_open(tree: MerkleTree, index: int):
     _chk(lib().zo_merkle_open(_p(tree.values), tree.values.size, _p8(tree.leaf_hashes), index, _p8(sib), _p8(dirs),
                               C.byref(val)))
     return val.value, sib[:tree.height].copy(), dirs[:tree.height].copy()
+
+
+def merkle_open_many(tree: MerkleTree, indices):
+    """[(value, siblings, dirs)] for every index, with one recomputation of the levels."""
+    idx = _a(indices)
+    k, h = idx.size, max(tree.height, 1)
+    sib = np.zeros((k, h, 32), np.uint8)
+    dirs = np.zeros((k, h), np.uint8)
+    vals = np.zeros(k, np.uint64)
+    L = lib()
+    L.zo_merkle_open_many.argtypes = [P64, u64, P8, P64, u32, P8, P8, P64]
+    _chk(L.zo_merkle_open_many(_p(tree.values), tree.values.size, _p8(tree.leaf_hashes), _p(idx), k, _p8(sib), _p8(dirs), _p(vals)))
+    return [(int(vals[j]), sib[j, :tree.height].copy(), dirs[j, :tree.height].copy()) for j in range(k)]
 
 
 def merkle_verify(root: bytes, value: int, siblings, dirs) -> bool:

@@ -429,6 +429,39 @@ int zo_merkle_open(const uint64_t *values, uint64_t n, const uint8_t *leaf_hashe
     return ZO_OK;
 }
 
+/* `k` openings with ONE recomputation of the levels: exactly zo_merkle_open's walk (merkle_tree.zig:335-353) for every
+ * index, sharing the level arrays — a test convenience for large trees (the reference recomputes all levels per open).
+ * siblings: k x height x 32 bytes, dirs: k x height, values: k. */
+int zo_merkle_open_many(const uint64_t *values, uint64_t n, const uint8_t *leaf_hashes, const uint64_t *indices, uint32_t k,
+                        uint8_t *siblings, uint8_t *dirs, uint64_t *out_values) {
+    for (uint32_t j = 0; j < k; j++)
+        if (indices[j] >= n) return ZO_ERR_INDEX_OUT_OF_BOUNDS;
+    uint64_t count = zo_ceil_pow2(n);
+    uint32_t height = (uint32_t)__builtin_ctzll(count);
+    uint8_t *cur = malloc(count * 32);
+    if (!cur) return ZO_ERR_OOM;
+    memcpy(cur, leaf_hashes, count * 32);
+    for (uint32_t level = 0; level < height; level++) {
+        for (uint32_t j = 0; j < k; j++) {
+            uint64_t ci = indices[j] >> level;
+            int is_right = (ci % 2) == 1;
+            uint64_t sib = is_right ? ci - 1 : ci + 1;
+            memcpy(siblings + ((size_t)j * height + level) * 32, cur + 32 * sib, 32);
+            dirs[(size_t)j * height + level] = (uint8_t)is_right;
+        }
+        uint64_t next_size = count / 2;
+        uint8_t *next = malloc(next_size * 32);
+        if (!next) { free(cur); return ZO_ERR_OOM; }
+        for (uint64_t i = 0; i < next_size; i++) zo_merge_hashes(cur + 64 * i, cur + 64 * i + 32, next + 32 * i);
+        free(cur);
+        cur = next;
+        count = next_size;
+    }
+    free(cur);
+    for (uint32_t j = 0; j < k; j++) out_values[j] = values[indices[j]];
+    return ZO_OK;
+}
+
 int zo_merkle_verify(const uint8_t root[32], uint64_t value, const uint8_t *siblings, const uint8_t *dirs, uint32_t height) {
     /* :362-373 */
     uint8_t cur[32], nxt[32];
@@ -664,7 +697,8 @@ int zo_verify_proof(uint64_t p, const uint8_t *proof, size_t len, const uint8_t 
     n = get32(&r); NEED(8 * (size_t)n + 12); r += 8 * (size_t)n;
     (void)get64(&r);
     n = get32(&r); NEED(8 * (size_t)n); r += 8 * (size_t)n;
-    if (memcmp(hash, ph, 32)) return ZO_ERR_PROGRAM_HASH_MISMATCH; /* verifier.zig:101-107 */
+    /* deserialize (serialization.zig:98-127) reads EVERY section before verify runs: structural errors anywhere come
+     * first, then the program-hash error (verifier.zig:101-107), then the verdicts in the verifier's order */
     /* constraint sumcheck: only round 0 is checked (verifier.zig:209-214) */
     NEED((size_t)v * 40 + 8);
     uint64_t g0 = 0, g1 = 0;
@@ -676,7 +710,7 @@ int zo_verify_proof(uint64_t p, const uint8_t *proof, size_t len, const uint8_t 
     r += (size_t)v * 8;
     uint64_t final_eval = zo_f_init(p, get64(&r));
     *result = 0;
-    if (v > 0 && zo_f_add(p, g0, g1) != final_eval) { *result = 1; return ZO_OK; }
+    if (v > 0 && zo_f_add(p, g0, g1) != final_eval) *result = 1;
     NEED(4);
     uint32_t n_lasso = get32(&r);
     for (uint32_t k = 0; k < n_lasso; k++) {
@@ -709,6 +743,7 @@ int zo_verify_proof(uint64_t p, const uint8_t *proof, size_t len, const uint8_t 
         if (*result == 0 && (value != pvalue || !zo_merkle_verify(root, leaf, sibs, dirs, plen))) *result = 3;
     }
 #undef NEED
+    if (memcmp(hash, ph, 32)) { *result = 0; return ZO_ERR_PROGRAM_HASH_MISMATCH; } /* verifier.zig:101-107 */
     return ZO_OK;
 }
 

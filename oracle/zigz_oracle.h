@@ -105,6 +105,9 @@ int zo_merkle_build(const uint64_t *values, uint64_t n, uint8_t *leaf_hashes, ui
 /* open :324-360 — recomputes every level like the reference. siblings: height*32, dirs: height. */
 int zo_merkle_open(const uint64_t *values, uint64_t n, const uint8_t *leaf_hashes, uint64_t index, uint8_t *siblings,
                    uint8_t *dirs, uint64_t *value);
+/* k openings sharing one recomputation of the levels (test convenience for large trees; same walk as zo_merkle_open) */
+int zo_merkle_open_many(const uint64_t *values, uint64_t n, const uint8_t *leaf_hashes, const uint64_t *indices, uint32_t k,
+                        uint8_t *siblings, uint8_t *dirs, uint64_t *out_values);
 /* verify :362-373 */
 int zo_merkle_verify(const uint8_t root[32], uint64_t value, const uint8_t *siblings, const uint8_t *dirs, uint32_t height);
 

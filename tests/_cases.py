@@ -77,3 +77,22 @@ def prove_inputs(steps, seed, n_init, n_out):
     outputs = [splitmix64(seed + 90 + i) for i in range(n_out)]
     return dict(program=program, entry_pc=0x1000, initial_regs=init, cols=cols, final_pc=0x1000 + 4 * steps, final_regs=final_regs,
                 outputs=outputs)
+
+
+def splitmix64_np(x):
+    """Vectorised splitmix64 over a uint64 array (wrap-around arithmetic)."""
+    x = np.asarray(x, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def lasso_queries_np(op, bits, n):
+    """lasso_queries for large n: a = splitmix(3j) & mask, b = splitmix(3j+1) & mask, out = op(a, b)."""
+    m = np.uint64((1 << bits) - 1)
+    j = np.arange(n, dtype=np.uint64)
+    a, b = splitmix64_np(np.uint64(3) * j) & m, splitmix64_np(np.uint64(3) * j + np.uint64(1)) & m
+    out = {"add": (a + b) & m, "xor": a ^ b, "and": a & b}[op]
+    return np.ascontiguousarray(np.stack([a, b, out], axis=1))

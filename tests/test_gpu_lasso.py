@@ -93,9 +93,9 @@ def test_errors(zlib, ctx):  # lasso_prover.zig:108-110, 186-201, 352-412
 
 
 def test_full_size_lookup_properties(zlib, ctx, po):
-    """2^22 lookups (BASELINE config 2): commitments are checked against hashlib over the downloaded evaluations
-    is too slow for the oracle's sumcheck, so use structure: the proof of 2^22 queries that repeat a 2^12 block must
-    (a) pass the verifier's round checks and (b) have claimed sum = 2^10 * sum of the block's hashes."""
+    """2^22 lookups (BASELINE config 2) through structure (the bit-for-bit oracle comparison at this size lives in
+    test_gpu_baseline_sizes.py): the proof of 2^22 queries that repeat a 2^12 block must (a) pass the verifier's round
+    checks and (b) have claimed sum = 2^10 * sum of the block's hashes."""
     blk = lasso_queries("xor", 8, 1 << 12)
     q = np.tile(blk, (1 << 10, 1))
     pr = zlib.LassoProver.prove_builtin(ctx, zlib.TABLE_XOR, 8, q)

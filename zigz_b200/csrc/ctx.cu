@@ -40,7 +40,7 @@ struct Mle {
 };
 
 struct Tree {
-    BufRef values;      // u32 values (shared with the Multilinear it was built from)
+    BufRef values;      // u32 values: the tree's own copy (merkle_tree.zig:291)
     uint64_t n_values;  // unpadded
     uint64_t padded;
     uint32_t height;
@@ -170,7 +170,7 @@ int32_t cuda_fail(zb_ctx *c, cudaError_t e, const char *what) {
 
 size_t round_size(size_t b) {
     if (b < 512) return 512;
-    // round to 1/8 of the leading power of two so the cache reuses blocks across rounds
+    // round to 1/16 of the enclosing power of two so the cache reuses blocks across rounds
     size_t p = 1;
     while (p < b) p <<= 1;
     size_t step = p / 16;
@@ -223,8 +223,16 @@ DevBuf::~DevBuf() {
 
 namespace {
 
+void rearm(zb_ctx *c);
+
 // Wait for the mailbox sequence number published by the last CTA of the most recent launch.
+int32_t wait_mail_raw(zb_ctx *ctx, unsigned long long seq);
 int32_t wait_mail(zb_ctx *ctx, unsigned long long seq) {
+    const int32_t rc = wait_mail_raw(ctx, seq);
+    if (rc) rearm(ctx);
+    return rc;
+}
+int32_t wait_mail_raw(zb_ctx *ctx, unsigned long long seq) {
     volatile unsigned long long *flag = ctx->h_mail + MAIL_WORDS;
     auto t0 = std::chrono::steady_clock::now();
     uint64_t spins = 0;
@@ -344,7 +352,26 @@ struct ProfScope {
 
 // Ends a running persistent tail kernel (abort tag) so that other work can use the stream. The tables stay
 // consistent: every round it completed was written back in place and the handle lengths were updated per round.
+// Every public entry runs this first (directly or through tail_quiesce): the context's device becomes the calling
+// thread's current device, so two contexts on different GPUs can be driven from one thread, and a host (or torch) that
+// switched devices in between cannot send our launches and allocations to the wrong GPU.
+inline void ensure_device(zb_ctx *c) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != c->device) cudaSetDevice(c->device);
+}
+
+// After a timeout or a CUDA error the kernel that should have re-armed the accumulators may never have published:
+// drain the stream and zero them so that the next launch starts clean instead of adding to stale partial sums.
+void rearm(zb_ctx *c) {
+    cudaStreamSynchronize(c->stream);
+    cudaGetLastError();
+    cudaMemsetAsync(c->d_acc, 0, MAIL_WORDS * sizeof(unsigned long long), c->stream);
+    cudaMemsetAsync(c->d_ticket, 0, 2 * sizeof(unsigned int), c->stream); // ticket + err flag
+    cudaStreamSynchronize(c->stream);
+}
+
 void tail_quiesce(zb_ctx *c) {
+    ensure_device(c);
     if (!c->tail.active && !c->pre.active) return;
     __atomic_store_n(c->h_chal, (unsigned long long)0xFFFFFFFFu << 32, __ATOMIC_RELEASE);
     cudaStreamSynchronize(c->stream);
@@ -618,7 +645,8 @@ int32_t zb_ctx_create(int32_t device, zb_ctx **out) {
     ctx->device = device;
     auto fail = [&](cudaError_t err, const char *what) {
         fprintf(stderr, "zigz_b200: %s: %s\n", what, cudaGetErrorString(err));
-        delete ctx;
+        cudaGetLastError();
+        zb_ctx_destroy(ctx); // releases whatever had been created (every member starts out null)
         return (int32_t)ZB_ERR_CUDA;
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
@@ -654,9 +682,9 @@ int32_t zb_ctx_create(int32_t device, zb_ctx **out) {
 
 void zb_ctx_destroy(zb_ctx *ctx) {
     if (!ctx) return;
-    tail_quiesce(ctx);
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->h_chal && ctx->stream) tail_quiesce(ctx);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->mles.clear();
     ctx->trees.clear();
     release_cache(ctx);
@@ -675,9 +703,10 @@ void zb_ctx_destroy(zb_ctx *ctx) {
         if (ctx->pack_buf[b]) cudaFreeHost(ctx->pack_buf[b]);
         if (ctx->pack_done[b]) cudaEventDestroy(ctx->pack_done[b]);
     }
-    cudaFreeHost(ctx->h_chal);
-    cudaFreeHost(ctx->h_mail);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->h_chal) cudaFreeHost(ctx->h_chal);
+    if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
     delete ctx;
 }
 
@@ -924,8 +953,13 @@ int32_t zb_mle_clone(zb_ctx *ctx, zb_mle src, zb_mle *out) {
     Mle *m = nullptr;
     int32_t rc = new_mle(ctx, n, out, &m);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(m->d(), sb->ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    return zb_sync(ctx);
+    const cudaError_t ce = cudaMemcpyAsync(m->d(), sb->ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
+    rc = ce == cudaSuccess ? zb_sync(ctx) : cuda_fail(ctx, ce, "cudaMemcpyAsync(clone)");
+    if (rc) {
+        ctx->mles.erase(*out);
+        *out = 0;
+    }
+    return rc;
 }
 
 int32_t zb_mle_free(zb_ctx *ctx, zb_mle h) {
@@ -1251,7 +1285,11 @@ static int32_t wait_polling_kernel(zb_ctx *ctx, unsigned long long seq, bool *go
     while (*flag != seq) {
         if ((++spins & 0x3FFF) == 0) {
             cudaError_t q = cudaStreamQuery(ctx->stream);
-            if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(ctx, q, "polling kernel");
+            if (q != cudaSuccess && q != cudaErrorNotReady) {
+                const int32_t e = cuda_fail(ctx, q, "polling kernel");
+                rearm(ctx);
+                return e;
+            }
             if (q == cudaSuccess) { // drained: give the mapped write 2 ms to land, then decide
                 auto t1 = std::chrono::steady_clock::now();
                 while (*flag != seq && std::chrono::steady_clock::now() - t1 < std::chrono::milliseconds(2)) {
@@ -1261,6 +1299,7 @@ static int32_t wait_polling_kernel(zb_ctx *ctx, unsigned long long seq, bool *go
             }
             if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
                 tail_quiesce(ctx);
+                rearm(ctx);
                 ctx->last_error = "timeout waiting for a polling kernel";
                 return ZB_ERR_TIMEOUT;
             }
@@ -1270,6 +1309,7 @@ static int32_t wait_polling_kernel(zb_ctx *ctx, unsigned long long seq, bool *go
     if (!*gone && ctx->comm_reduce == 2 && ctx->d_xchg_view && ctx->h_mail[MAIL_WORDS - 1] == 1ull) {
         ctx->h_mail[MAIL_WORDS - 1] = 0;
         ctx->last_error = "peer exchange: a rank never arrived";
+        rearm(ctx);
         return ZB_ERR_TIMEOUT;
     }
     return ZB_OK;
@@ -1344,6 +1384,7 @@ static int32_t fold_inplace_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, u
         in_pre = in_pre && ctx->pre.h[k] == polys[k];
     }
     if (!in_tail && !in_pre) tail_quiesce(ctx);
+    else ensure_device(ctx);
     Mle *ms[MAX_POLYS];
     int32_t rc = gather_polys(ctx, polys, d, ms);
     if (rc) return rc;
@@ -1662,24 +1703,43 @@ int32_t zb_merkle_build(zb_ctx *ctx, const zb_mle *polys, uint32_t count, zb_tre
         if (i == 0) n0 = m->n;
         else if (m->n != n0) return ZB_ERR_DIFFERENT_NUM_VARS;
     }
+    // a failure in a later batch must not leave the trees of the completed batches behind
+    auto undo = [&](uint32_t done, int32_t rc) {
+        cudaStreamSynchronize(ctx->stream);
+        for (uint32_t j = 0; j < done; j++) {
+            ctx->trees.erase(trees[j]);
+            trees[j] = 0;
+        }
+        return rc;
+    };
     for (uint32_t base = 0; base < count; base += MAX_BATCH) {
         uint32_t c = count - base < (uint32_t)MAX_BATCH ? count - base : MAX_BATCH;
         std::vector<zb_tree> hs(c);
         for (uint32_t t = 0; t < c; t++) {
             Mle *m = get_mle(ctx, polys[base + t]);
+            // the tree keeps its OWN copy of the values, like SimpleMerkleTree.build (merkle_tree.zig:291): the polynomial
+            // may be folded in place afterwards (consuming sumcheck) without changing what `open` reports
+            BufRef vals;
+            int32_t rc = dev_alloc(ctx, m->n * sizeof(uint32_t), &vals);
+            cudaError_t ce = cudaSuccess;
+            if (rc == ZB_OK)
+                ce = cudaMemcpyAsync(vals->ptr, m->d(), m->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
+            if (rc == ZB_OK && ce != cudaSuccess) rc = cuda_fail(ctx, ce, "cudaMemcpyAsync(tree values)");
             Tree *tp = nullptr;
-            int32_t rc = new_tree(ctx, m->buf, m->n, &hs[t], &tp);
+            if (rc == ZB_OK) rc = new_tree(ctx, vals, m->n, &hs[t], &tp);
             if (rc) {
+                cudaStreamSynchronize(ctx->stream);
                 for (uint32_t j = 0; j < t; j++) ctx->trees.erase(hs[j]);
-                return rc;
+                return undo(base, rc);
             }
         }
         Tree *ts[MAX_BATCH];
         for (uint32_t t = 0; t < c; t++) ts[t] = get_tree(ctx, hs[t]); // map is stable now
         int32_t rc = build_batch(ctx, ts, c, roots ? roots + 32 * (size_t)base : nullptr);
         if (rc) {
+            cudaStreamSynchronize(ctx->stream);
             for (uint32_t t = 0; t < c; t++) ctx->trees.erase(hs[t]);
-            return rc;
+            return undo(base, rc);
         }
         for (uint32_t t = 0; t < c; t++) trees[base + t] = hs[t];
     }
@@ -1824,8 +1884,10 @@ int32_t zb_xxh3_rows_stream(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, 
                 ProfScope _ps(ctx, "xxh3_rows", (r1 - r0) * (4ull * arity) + n_out * 4);
                 launch_xxh3_rows(d_rows + r0 * arity, r1 - r0, arity, n_out, m->d() + r0, ctx->stream);
             }
-            LAUNCHED("xxh3_rows");
-            CK(cudaMemcpyAsync(host_mirror + r0, m->d() + r0, n_out * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            rc = check_launch(ctx, "xxh3_rows");
+            if (rc) return fail(rc);
+            const cudaError_t ce = cudaMemcpyAsync(host_mirror + r0, m->d() + r0, n_out * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+            if (ce != cudaSuccess) return fail(cuda_fail(ctx, ce, "cudaMemcpyAsync(mirror)"));
         }
         rc = zb_sync(ctx); // before drows goes back to the pool
         if (rc) return fail(rc);
@@ -1834,7 +1896,8 @@ int32_t zb_xxh3_rows_stream(zb_ctx *ctx, const uint64_t *rows, uint64_t n_rows, 
             ProfScope _ps(ctx, "fill", n_padded * 4);
             launch_fill(m->d(), n_padded, 0, ctx->stream);
         }
-        LAUNCHED("fill");
+        rc = check_launch(ctx, "fill");
+        if (rc) return fail(rc);
         memset(host_mirror, 0, n_padded * sizeof(uint32_t));
         rc = zb_sync(ctx);
         if (rc) return fail(rc);

@@ -4,6 +4,7 @@
 #include "../../include/zigz_host.h"
 #include "sha3_host.hpp"
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <immintrin.h>
@@ -119,14 +120,18 @@ static void grid_round_b(uint32_t d, const uint64_t *grid, uint64_t r, uint64_t 
     evals_to_coeffs(d, ey, coeffs);
 }
 
-static int g_grid_min_log2 = -1;
+// process-wide tuning knob (test hook zh_set_grid_min_log2): atomic, so that host threads driving different contexts
+// (one per GPU of a device-mask context) can read it while a test thread sets it
+static std::atomic<int> g_grid_min_log2{-1};
 static int grid_min_log2() { // tables below 2^this use one kernel per round (and the persistent tail); 0 disables the grid path
-    if (g_grid_min_log2 < 0) {
+    int v = g_grid_min_log2.load(std::memory_order_relaxed);
+    if (v < 0) {
         const char *e = getenv("ZB_GRID_MIN_LOG2");
         int x = e && *e ? atoi(e) : 15;
-        g_grid_min_log2 = x < 0 ? 0 : x;
+        v = x < 0 ? 0 : x;
+        g_grid_min_log2.store(v, std::memory_order_relaxed);
     }
-    return g_grid_min_log2;
+    return v;
 }
 
 static int gather_log2() {
@@ -354,7 +359,7 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
 
 int32_t zh_set_grid_min_log2(int32_t v) {
     const int32_t old = grid_min_log2();
-    g_grid_min_log2 = v < 0 ? 0 : v;
+    g_grid_min_log2.store(v < 0 ? 0 : v, std::memory_order_relaxed);
     return old;
 }
 
@@ -702,9 +707,9 @@ int32_t zh_verify_proof(const uint8_t *proof, size_t len, const uint8_t *program
     const uint32_t n_out = r.u32();
     if (!r.need(8 * (size_t)n_out)) return ZB_ERR_INVALID_PROOF;
     r.p += 8 * (size_t)n_out;
-    uint8_t hash[32];
-    Sha256::hash(program, program_len, hash);
-    if (memcmp(hash, ph, 32)) return ZB_ERR_PROGRAM_HASH_MISMATCH; // bindPublicInputs, verifier.zig:101-107
+    // The reference deserializes the WHOLE proof before it verifies anything (serialization.zig:98-127), so a truncated or
+    // garbled later section is a deserialize error even when an earlier check would reject: walk every section first and
+    // decide afterwards, in the verifier's order (program hash, constraint sumcheck, Lasso proofs, openings).
     *verdict = 0;
     // verifySumcheckProof: only round 0 is checked, g(0) + g(1) == final_eval (verifier.zig:196-214)
     auto sumcheck = [&](uint32_t nv, int ncoef, bool *ok) -> bool {
@@ -725,10 +730,7 @@ int32_t zh_verify_proof(const uint8_t *proof, size_t len, const uint8_t *program
     };
     bool ok = true;
     if (!sumcheck(v, 4, &ok)) return ZB_ERR_INVALID_PROOF;
-    if (!ok) {
-        *verdict = 1;
-        return ZB_OK;
-    }
+    if (!ok) *verdict = 1;
     if (!r.need(4)) return ZB_ERR_INVALID_PROOF;
     const uint32_t n_lasso = r.u32();
     for (uint32_t k = 0; k < n_lasso; k++) { // verifyLassoProof :233-262
@@ -750,6 +752,12 @@ int32_t zh_verify_proof(const uint8_t *proof, size_t len, const uint8_t *program
         const uint8_t *sibs = r.p, *dirs = r.p + (size_t)plen * 32;
         r.p += (size_t)plen * 33;
         if (*verdict == 0 && (value != pvalue || !zh_merkle_verify(root, leaf, sibs, dirs, plen))) *verdict = 3;
+    }
+    uint8_t hash[32];
+    Sha256::hash(program, program_len, hash);
+    if (memcmp(hash, ph, 32)) { // bindPublicInputs, verifier.zig:101-107: an error, raised before any verdict
+        *verdict = 0;
+        return ZB_ERR_PROGRAM_HASH_MISMATCH;
     }
     return ZB_OK;
 }
@@ -817,14 +825,16 @@ static uint64_t ceil_pow2(uint64_t n) {
 // longest step. For long query lists it therefore runs on a second host thread over a pinned mirror of the query
 // polynomial that fills chunk by chunk (zb_xxh3_rows_stream) while this thread uploads the remaining rows, proves the
 // sumcheck and commits to the table. Same digests, same proof; zh_set_lasso_pipeline_min_log2(-1) keeps it on one thread.
-static int g_lasso_pipeline_min_log2 = -2; // -2: not read yet, -1: never
+static std::atomic<int> g_lasso_pipeline_min_log2{-2}; // -2: not read yet, -1: never
 static int lasso_pipeline_min_log2() {
-    if (g_lasso_pipeline_min_log2 == -2) {
+    int v = g_lasso_pipeline_min_log2.load(std::memory_order_relaxed);
+    if (v == -2) {
         const char *e = getenv("ZB_LASSO_PIPELINE_MIN_LOG2");
-        g_lasso_pipeline_min_log2 = e && *e ? atoi(e) : 18;
-        if (g_lasso_pipeline_min_log2 < -1) g_lasso_pipeline_min_log2 = -1;
+        v = e && *e ? atoi(e) : 18;
+        if (v < -1) v = -1;
+        g_lasso_pipeline_min_log2.store(v, std::memory_order_relaxed);
     }
-    return g_lasso_pipeline_min_log2;
+    return v;
 }
 static bool lasso_pipeline(uint64_t n_padded) {
     const int v = lasso_pipeline_min_log2();
@@ -916,7 +926,7 @@ static int32_t lasso_run(zb_ctx *ctx, zb_mle table_poly, const uint64_t *query_r
 
 int32_t zh_set_lasso_pipeline_min_log2(int32_t v) {
     const int32_t old = lasso_pipeline_min_log2();
-    g_lasso_pipeline_min_log2 = v < -1 ? -1 : v;
+    g_lasso_pipeline_min_log2.store(v < -1 ? -1 : v, std::memory_order_relaxed);
     return old;
 }
 
