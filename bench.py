@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 SEED = 0x5A49475A
+MERKLE_ALU_OPS = 4308.0  # ALU-pipe instructions per Keccak-f[1600] + SHA3 framing in k_merkle_*: 24 x (122 LOP3 + 58 SHF) - folded constants
 METRIC = "babybear_sumcheck_melem_per_s"
 UNIT = "Melem/s"
 
@@ -116,6 +117,40 @@ def max_over_ranks(dist, x, local):
 
 
 # ----------------------------------------------------------------------------- reference arm (CPU)
+def cpu_prodcheck(po, es):
+    return po.prodcheck_prove(po.BABYBEAR_P, es)
+
+
+_CORE_JOB = """
+import sys, time
+sys.path.insert(0, %r)
+from oracle import pyoracle as po
+BB, n, seed = po.BABYBEAR_P, 1 << %d, %d
+es = [po.fill_synthetic(BB, seed + k, 0, n) for k in range(3)]
+po.prodcheck_prove(BB, [e[: n >> 4] for e in es])
+while time.time() < %r:  # common start, so that the timed proves really run side by side
+    time.sleep(0.001)
+t0 = time.perf_counter()
+po.prodcheck_prove(BB, es)
+print(time.perf_counter() - t0)
+"""
+
+
+def all_cores_rate(po, lg):
+    """Aggregate Melem/s of one independent single-threaded prove per host core, each in its own process (the reference has
+    no threads of its own — src/ has no spawn/atomic/@Vector, SURVEY.md — so the only way it fills a host is one job per core;
+    separate processes because its per-round allocations would serialise threads of one process on the address-space lock)."""
+    import subprocess
+    cores = os.cpu_count() or 1
+    start_at = time.time() + 2.0 + (1 << lg) * 3 * 2.5e-7  # import + fill + warm-up of the slowest child
+    procs = [subprocess.Popen([sys.executable, "-c", _CORE_JOB % (ROOT, lg, SEED + 16 * c, start_at)], stdout=subprocess.PIPE, text=True)
+             for c in range(cores)]
+    secs = [float(p.communicate()[0].strip().splitlines()[-1]) for p in procs]
+    n = 1 << lg
+    return {"value": sum(n / t for t in secs) / 1e6, "unit": UNIT, "cores": cores, "seconds_max": max(secs),
+            "what": f"{cores} independent proves of three 2^{lg}-entry tables, one process per core, concurrently; sum of the per-process rates"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -132,12 +167,19 @@ def run_reference(args):
         po.prodcheck_prove(BB, es)
     dt = (time.perf_counter() - t0) / args.steps
     val = n / dt / 1e6
-    sample = f"degree-3 product sumcheck over three 2^{lg}-entry tables per step (same generator, same algorithm; the 2^{args.log2n} job is out of reach for one CPU thread in minutes)"
+    sample = (f"each step = one degree-3 product sumcheck over three 2^{lg}-entry tables (same generator, same algorithm: a bounded "
+              f"sample, 1/{1 << (args.log2n - lg)} of the 2^{args.log2n} job, which is out of reach for one CPU thread in minutes); "
+              "the metric is size-normalised (elements per second)")
+    cfg = workload_config(args, 1)
+    cfg.update({"sample": True, "sample_log2_n": lg, "sample_note": "the reference arm proves 2^%d-entry tables per step, not 2^%d" % (lg, args.log2n)})
+    allc = all_cores_rate(po, lg)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 (canonical BabyBear, u128 % reduction like the reference)", "data": "synthetic",
-            "config": workload_config(args, 1),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "config": cfg,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                             "threads_note": "the reference prover is single-threaded (no thread/SIMD code in src/), so one prove can use one core",
+                             "all_cores": allc, "host_cores_available": os.cpu_count()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
     return 0
@@ -151,10 +193,51 @@ def workload_config(args, world):
 
 
 # ----------------------------------------------------------------------------- our arm (GPU)
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def sharded_selfcheck(z, ctx, comm, local, rank, world):
+    """Before anything is timed at N > 1: a small sharded prove (2^20 entries per GPU) must equal, bit for bit, the proof one GPU
+    computes for the same global tables (every rank checks on its own GPU, with a second context that has no communicator)."""
+    n_local = 1 << 20
+    shards = [z.Multilinear.synthetic(ctx, SEED + k, n_local, start=rank, stride=world) for k in range(3)]
+    got = comm.prodcheck_prove(shards)
+    for p in shards:
+        p.deinit()
+    with z.Context(local) as solo:
+        full = [z.Multilinear.synthetic(solo, SEED + k, n_local * world) for k in range(3)]
+        want = z.ProductSumcheckProver.prove(full, consume=True)
+    same = (got.round_polynomials.tolist() == want.round_polynomials.tolist() and got.final_point.tolist() == want.final_point.tolist()
+            and list(got.final_evals) == list(want.final_evals) and got.claimed_sum == want.claimed_sum)
+    if not same:
+        raise SystemExit(f"rank {rank}: sharded proof differs from the single-GPU proof of the same tables")
+    return {"log2_n_total": 20 + (world - 1).bit_length(), "equal_to_single_gpu_proof": True}
+
+
+def timed_proves(ctx, dist, local, prove, polys, steps):
+    """K proves with device events on the context's stream, per-kernel accounting on; max over ranks."""
+    ctx.profile(True)
+    launches0 = ctx.kernel_launches
+    barrier(dist)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(steps):
+        pr = prove(polys)
+    ms = ctx.timer_stop()
+    barrier(dist)
+    launches = ctx.kernel_launches - launches0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    return max_over_ranks(dist, ms, local), prof, launches, pr
+
+
 def run_ours(args):
     rank, world, local, dist = dist_setup(args.gpus)
     import zigz_b200 as z
-    BB = z.BABYBEAR_P
     ctx = z.Context(local)
     n = 1 << args.log2n
     d = 3
@@ -163,39 +246,36 @@ def run_ours(args):
         comm = sharded.Comm(ctx, dist, rank, world)
     else:
         comm = None
+    selfcheck = None
+    if comm is not None:
+        selfcheck = sharded_selfcheck(z, ctx, comm, local, rank, world)
+        log("sharded self-check passed")
 
-    def make_polys():
+    def make_polys(n_local):
         # cyclic shard: local element j is global index rank + world*j
-        return [z.Multilinear.synthetic(ctx, SEED + k, n, start=rank, stride=world) for k in range(d)]
+        return [z.Multilinear.synthetic(ctx, SEED + k, n_local, start=rank, stride=world) for k in range(d)]
 
     def prove(polys):
         if comm is None:
             return z.ProductSumcheckProver.prove(polys)
         return comm.prodcheck_prove(polys)
 
-    polys = make_polys()
+    polys = make_polys(n)
     for _ in range(args.warmup):
         pr = prove(polys)
+    log("warm-up done")
     # ---- value: device-resident inputs, device events, max over ranks
     sampler = ClockSampler(local)
-    ctx.profile(True)
-    launches0 = ctx.kernel_launches
-    barrier(dist)
-    ctx.sync()
+    if comm is not None:
+        ctx.set_option("xchg_stats_reset", 1)
     sampler.start()
-    ctx.timer_start()
-    for _ in range(args.steps):
-        pr = prove(polys)
-    ms = ctx.timer_stop()
-    barrier(dist)
+    ms, prof, launches, pr = timed_proves(ctx, dist, local, prove, polys, args.steps)
     clocks = sampler.stop()
-    launches = ctx.kernel_launches - launches0
-    prof = ctx.profile_read()
-    ctx.profile(False)
-    ms = max_over_ranks(dist, ms, local)
+    xchg = exchange_stats(ctx, comm, args.steps, ms, prof)
     ms_per_step = ms / args.steps
     total_elems = n * world
     value = total_elems / (ms_per_step * 1e-3) / 1e6
+    log(f"timed region done: {ms_per_step:.3f} ms per prove")
 
     # roofline of the dominant kernel family, from the events recorded live in the timed region
     peak, peak_src = peaks()
@@ -222,23 +302,42 @@ def run_ours(args):
                 "launches": dom_cnt, "avg_launch_ms": dom_ms / dom_cnt if dom_cnt else None,
                 "algorithmic_bytes_per_step": dom_bytes // max(args.steps, 1),
                 "kernel_share_of_step": dom_ms / ms if ms else None, "all_kernels_share_of_step": kernel_ms / ms if ms else None,
-                # whole prove: bytes the kernels of one prove actually have to move (two rounds per pass: ~32 B per element
+                # whole prove: bytes the kernels of one prove actually have to move (two rounds per pass: ~40 B per element
                 # and step for d = 3) over the step time; and the same time against the one-round-per-pass model of
                 # SURVEY.md §8d (48 B per element), which the two-round schedule undercuts — that ratio may exceed 1
                 "whole_prove_bytes_per_step": bytes_moved,
                 "whole_prove_frac": bytes_moved / (ms_per_step * 1e-3) / 1e9 / peak,
                 "vs_one_round_per_pass_model_48B_per_elem": (48.0 * n) / (ms_per_step * 1e-3) / 1e9 / peak}
-    by_kernel = {k: {"launches": v[0], "ms": round(v[1], 4), "GBps": round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] else None}
-                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    by_kernel = kernel_table(prof)
+
+    # ---- C5 as BASELINE.json words it: ONE 2^30-entry job sharded across the GPUs (strong scaling)
+    strong = None
+    if comm is not None and not args.skip_extras:
+        lgs = args.log2n - (world - 1).bit_length()
+        sp = make_polys(1 << lgs)
+        for _ in range(args.warmup):
+            prove(sp)
+        ctx.set_option("xchg_stats_reset", 1)
+        sms, sprof, _, _ = timed_proves(ctx, dist, local, prove, sp, args.steps)
+        for p in sp:
+            p.deinit()
+        s_step = sms / args.steps
+        strong = {"log2_n_total": args.log2n, "log2_n_per_gpu": lgs, "ms_per_step": s_step,
+                  "melem_per_s": (1 << args.log2n) / (s_step * 1e-3) / 1e6, "kernels": kernel_table(sprof),
+                  "exchange": exchange_stats(ctx, comm, args.steps, sms, sprof),
+                  "hbm_frac_of_bytes_moved": sum(v[2] for v in sprof.values()) / args.steps / (s_step * 1e-3) / 1e9 / peak,
+                  "note": "the driver computes strong-scaling efficiency from the N=1 value (same total size) and this line"}
+        log(f"strong-scaling leg done: {s_step:.3f} ms per prove of 2^{args.log2n} total")
 
     # ---- e2e: host u64 buffers -> C ABI -> proof on the host
     # A failure here (host RAM, a rank that never arrives) must not take the device-timed line above with it: every
     # rank records it, the ranks agree that it happened, and the secondary measurements are skipped.
     e2e = None
+    e2e_pageable = None
     e2e_failed = 0.0
     if not args.skip_e2e:
         try:
-            e2e = run_e2e(args, z, ctx, comm, dist, local, rank, world, polys)
+            e2e, e2e_pageable = run_e2e(args, z, ctx, comm, dist, local, rank, world, polys)
         except Exception as exc:  # noqa: BLE001 - reported in the JSON line
             e2e = {"value": None, "unit": UNIT, "error": f"{type(exc).__name__}: {exc}"[:300]}
             e2e_failed = 1.0
@@ -246,6 +345,7 @@ def run_ours(args):
             e2e_failed = max_over_ranks(dist, e2e_failed, local)
             if e2e_failed and e2e.get("value") is not None:
                 e2e = {"value": None, "unit": UNIT, "error": "another rank failed in the end-to-end leg"}
+        log("end-to-end legs done")
     for p in polys:
         p.deinit()
     if e2e_failed:
@@ -271,8 +371,16 @@ def run_ours(args):
                                                                   "keccak_per_s": (2 * leaves - 1) / dt, "root": com.commitment.hex()}}
     if rank == 0 and world == 1 and not args.skip_extras:
         extras = run_extras(args, z, ctx, peak)
+        log("extras done")
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_baseline(args)
+        log("cpu baseline done")
+    if extras is None:
+        extras = {}
+    if strong is not None:
+        extras[f"C5_strong_2^{args.log2n}_total"] = strong
+    extras["lasso_grand_product_memory_checking"] = ("absent in the reference (lasso_prover.zig:147-158 only describes the constraint in "
+                                                     "comments; SURVEY.md §0): not built, nothing to be bit-exact with")
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -280,6 +388,12 @@ def run_ours(args):
                 "dtype": "u32 (canonical BabyBear in registers; u64 accumulators)", "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "kernels": by_kernel}
+        if e2e_pageable is not None:
+            line["e2e_pageable"] = e2e_pageable
+        if xchg is not None:
+            line["exchange"] = xchg
+        if selfcheck is not None:
+            line["selfcheck"] = selfcheck
         if cpu:
             line["cpu_baseline"] = cpu
         if extras:
@@ -292,10 +406,30 @@ def run_ours(args):
     return 0
 
 
+def kernel_table(prof):
+    return {k: {"launches": v[0], "ms": round(v[1], 4), "GBps": round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] else None}
+            for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+
+
+def exchange_stats(ctx, comm, steps, ms, prof):
+    """Per-round exchange cost at N > 1: the time the publishing CTA spent waiting for the other ranks' partial sums
+    inside the kernels (skew between GPUs + NVLink latency; counted by the kernels themselves) and the host gap (step time
+    not covered by any kernel)."""
+    if comm is None or not getattr(comm, "p2p", False):
+        return None
+    rounds, wait_ns = ctx.get_option("xchg_rounds"), ctx.get_option("xchg_wait_ns")
+    kernel_ms = sum(v[1] for v in prof.values())
+    return {"mode": "in-kernel NVLink peer exchange", "exchanged_rounds_per_step": rounds / steps if steps else None,
+            "wait_in_kernel_us_per_round": wait_ns / 1e3 / rounds if rounds else None,
+            "wait_in_kernel_ms_per_step": wait_ns / 1e6 / steps if steps else None,
+            "host_gap_ms_per_step": (ms - kernel_ms) / steps if steps else None, "rank": 0}
+
+
 def run_e2e(args, z, ctx, comm, dist, local, rank, world, polys):
-    """Same prove, inputs in pinned HOST memory as the reference's u64 field elements."""
+    """Same prove, inputs in HOST memory as the reference's u64 field elements: once from pinned buffers (the contract's e2e)
+    and once from ordinary pageable allocations, which is what a Zig caller's allocator hands over."""
     n = 1 << args.log2n
-    # host-memory guard: every rank pins 3 tables of 8-byte elements
+    # host-memory guard: every rank holds 3 tables of 8-byte elements, pinned and (N = 1) pageable
     try:
         import psutil
         avail = psutil.virtual_memory().available
@@ -303,38 +437,60 @@ def run_e2e(args, z, ctx, comm, dist, local, rank, world, polys):
         avail = None
     need = 3 * n * 8 * world
     if avail is not None and need * 1.25 > avail:
-        return {"value": None, "unit": UNIT, "skipped": f"host RAM: need {need >> 30} GiB pinned for {world} ranks, {avail >> 30} GiB available"}
+        return {"value": None, "unit": UNIT, "skipped": f"host RAM: need {need >> 30} GiB pinned for {world} ranks, {avail >> 30} GiB available"}, None
     host = []
     for p in polys:  # untimed: materialise this rank's shard on the host
         h = ctx.pinned(n, np.uint64)
         ctx.check(z.lib().zb_mle_download(ctx.handle, p.handle, h.ctypes.data_as(z.api.P64), n))
         host.append(h)
+    log("host copies of the tables materialised")
+    h2d_rate = ctx.h2d_rate(1 << 30) if rank == 0 else None  # measured link rate (pinned source, 1 GiB)
 
-    def step():
-        ms_ = [z.Multilinear.init(ctx, h) for h in host]
-        if comm is not None:
-            barrier(dist)  # the ranks' uploads share the host; meet before the first in-kernel exchange
-        pr = z.ProductSumcheckProver.prove(ms_, consume=True) if comm is None else comm.prodcheck_prove(ms_, consume=True)
-        for m in ms_:
-            m.deinit()
-        return pr
+    def measure(bufs, label):
+        def step():
+            ms_ = [z.Multilinear.init(ctx, h) for h in bufs]
+            if comm is not None:
+                barrier(dist)  # the ranks' uploads share the host; meet before the first in-kernel exchange
+            pr = z.ProductSumcheckProver.prove(ms_, consume=True) if comm is None else comm.prodcheck_prove(ms_, consume=True)
+            for m in ms_:
+                m.deinit()
+            return pr
 
-    barrier(dist)  # pinning 24 GiB per rank takes seconds and differs between ranks
-    step()  # warm-up (allocator cache, page tables)
-    steps = max(1, min(args.steps, args.e2e_steps))
-    barrier(dist)
-    ctx.sync()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        pr = step()
-    ctx.sync()
-    dt = time.perf_counter() - t0
-    dt = max_over_ranks(dist, dt, local)
-    v = pr.num_vars
-    d2h = (v * 4 + v + 3) * 8
-    return {"value": n * world / (dt / steps) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 3 * n * 8 * world,
-            "d2h_bytes_per_step": d2h * world, "steps": steps, "ms_per_step": dt / steps * 1e3,
-            "api": "zb_mle_upload x3 + zh_prodcheck_prove_consume (include/zigz_b200.h, zigz_host.h)"}
+        barrier(dist)  # pinning 24 GiB per rank takes seconds and differs between ranks
+        step()  # warm-up (allocator cache, page tables)
+        steps = max(1, min(args.steps, args.e2e_steps))
+        link0 = ctx.get_option("h2d_bytes")
+        barrier(dist)
+        ctx.sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pr = step()
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        dt = max_over_ranks(dist, dt, local)
+        link = (ctx.get_option("h2d_bytes") - link0) / steps
+        v = pr.num_vars
+        d2h = (v * 4 + v + 3) * 8
+        out = {"value": n * world / (dt / steps) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 3 * n * 8 * world,
+               "d2h_bytes_per_step": d2h * world, "steps": steps, "ms_per_step": dt / steps * 1e3, "source": label,
+               "link_bytes_per_step_per_gpu": link,
+               "api": "zb_mle_upload x3 + zh_prodcheck_prove_consume (include/zigz_b200.h, zigz_host.h)"}
+        if h2d_rate:
+            out["h2d_rate_measured_GBps"] = h2d_rate / 1e9
+            # bytes that actually crossed the link (u64 -> u32 narrowing on the host halves most of them) / time / link rate
+            out["pcie_frac"] = link / (dt / steps) / h2d_rate
+            out["pcie_floor_ms_4B_per_elem"] = 3 * n * 4 / h2d_rate * 1e3
+        return out
+
+    pinned = measure(host, "pinned host buffers (cudaHostAlloc)")
+    pageable = None
+    if world == 1 and (avail is None or need * 2.5 < avail):
+        pg = [np.empty(n, np.uint64) for _ in host]
+        for a, b in zip(pg, host):
+            np.copyto(a, b)
+        log("pageable copies made")
+        pageable = measure(pg, "pageable host buffers (ordinary allocations, as a Zig allocator returns)")
+    return pinned, pageable
 
 
 def timed(ctx, fn, reps, warm=2):
@@ -347,30 +503,65 @@ def timed(ctx, fn, reps, warm=2):
     return ctx.timer_stop() / reps
 
 
+def wall(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def bytes_of(ctx, fn):
+    """Algorithmic HBM bytes the kernels of one call move (per-kernel accounting, outside any timing)."""
+    ctx.profile(True)
+    fn()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    return sum(v[2] for v in prof.values()), {k: v[0] for k, v in prof.items()}
+
+
 def run_extras(args, z, ctx, peak):
-    """Secondary numbers for the other BASELINE configs (single GPU)."""
+    """Secondary numbers for the other BASELINE configs (single GPU), each with the CPU port beside it (1 core, like the
+    reference) on the same input or a stated bounded sample, and the fraction of the bound that applies (HBM / INT pipe / host)."""
+    from oracle import pyoracle as po
+    BB = z.BABYBEAR_P
     out = {}
     # C1: d=1 sumcheck over 2^20 (the reference's own API, SumcheckProver.prove)
     p20 = z.Multilinear.synthetic(ctx, SEED, 1 << 20)
-    t0 = time.perf_counter()
-    reps = 20
-    for _ in range(3):
-        z.SumcheckProver.prove(p20)
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        z.SumcheckProver.prove(p20)
-    dt = (time.perf_counter() - t0) / reps
-    out["C1_sumcheck_d1_2^20"] = {"ms": dt * 1e3, "melem_per_s": (1 << 20) / dt / 1e6, "note": "latency-bound: 20 host round trips"}
+    dt = wall(lambda: z.SumcheckProver.prove(p20), 50, warm=5)
+    moved, launches = bytes_of(ctx, lambda: z.SumcheckProver.prove(p20))
+    e20 = po.fill_synthetic(BB, SEED, 0, 1 << 20)
+    cdt = min(wall(lambda: po.sumcheck_prove(BB, e20), 1, warm=1) for _ in range(3))
+    out["C1_sumcheck_d1_2^20"] = {"ms": dt * 1e3, "melem_per_s": (1 << 20) / dt / 1e6, "kernel_launches": sum(launches.values()),
+                                  "hbm_frac_of_bytes_moved": moved / dt / 1e9 / peak, "hbm_frac_16B_per_elem": 16.0 * (1 << 20) / dt / 1e9 / peak,
+                                  "bound": "latency (one host round trip per pass; the table is L2-resident)",
+                                  "cpu_baseline": {"ms": cdt * 1e3, "melem_per_s": (1 << 20) / cdt / 1e6, "cores": 1, "kind": "port",
+                                                   "sample": "the same 2^20-entry table"},
+                                  "note": "several rounds per pass through linearity: block sums, 5-variable folds, last <= 10 rounds from a published table"}
     p20.deinit()
     # d=1 sumcheck over 2^28: HBM-bound regime of the reference's own prover
     lg = min(28, args.log2n)
     pb = z.Multilinear.synthetic(ctx, SEED, 1 << lg)
-    ms = timed(ctx, lambda: z.SumcheckProver.prove(pb), 5)
-    out[f"sumcheck_d1_2^{lg}"] = {"ms": ms, "melem_per_s": (1 << lg) / ms / 1e3, "hbm_frac_16B_per_elem": 16.0 * (1 << lg) / (ms * 1e-3) / 1e9 / peak}
+    ms = timed(ctx, lambda: z.SumcheckProver.prove(pb), 10)
+    moved, _ = bytes_of(ctx, lambda: z.SumcheckProver.prove(pb))
+    lgc = min(24, lg)
+    ec = po.fill_synthetic(BB, SEED, 0, 1 << lgc)
+    cdt = wall(lambda: po.sumcheck_prove(BB, ec), 1, warm=0)
+    out[f"sumcheck_d1_2^{lg}"] = {"ms": ms, "melem_per_s": (1 << lg) / ms / 1e3, "hbm_frac_of_bytes_moved": moved / (ms * 1e-3) / 1e9 / peak,
+                                  "bytes_moved_per_elem": moved / (1 << lg), "hbm_frac_16B_per_elem": 16.0 * (1 << lg) / (ms * 1e-3) / 1e9 / peak,
+                                  "cpu_baseline": {"melem_per_s": (1 << lgc) / cdt / 1e6, "cores": 1, "kind": "port",
+                                                   "sample": f"one prove of a 2^{lgc}-entry table (size-normalised)"}}
     # MLE eval at 2^lg
     pt = np.arange(1, lg + 1, dtype=np.uint64) * 7919 % z.BABYBEAR_P
-    ms = timed(ctx, lambda: pb.eval(pt), 5)
-    out[f"mle_eval_2^{lg}"] = {"ms": ms, "hbm_frac_4B_per_elem": 4.0 * (1 << lg) / (ms * 1e-3) / 1e9 / peak}
+    ms = timed(ctx, lambda: pb.eval(pt), 10)
+    lge = min(18, lg)
+    ee = po.fill_synthetic(BB, SEED, 0, 1 << lge)
+    cdt = wall(lambda: po.mle_eval(BB, ee, pt[:lge]), 1, warm=0)
+    out[f"mle_eval_2^{lg}"] = {"ms": ms, "hbm_frac_4B_per_elem": 4.0 * (1 << lg) / (ms * 1e-3) / 1e9 / peak,
+                               "cpu_baseline": {"melem_per_s": (1 << lge) / cdt / 1e6, "cores": 1, "kind": "port",
+                                                "sample": f"Multilinear.eval of a 2^{lge}-entry table, the reference's O(N v) loop (multilinear.zig:110-144)"},
+                               "melem_per_s": (1 << lg) / ms / 1e3}
     pb.deinit()
     # C3: Merkle commitment of a 2^26-entry witness polynomial + 16 openings
     lgm = min(26, args.log2n)
@@ -391,11 +582,21 @@ def run_extras(args, z, ctx, peak):
         opens.append((time.perf_counter() - t0) * 1e3)
     open_ms = float(np.median(opens[1:]))  # 16 openings, first call excluded (warm-up)
     ip = ctx.int_pipe_peak()  # measured LOP3/SHF ceiling of this GPU (zb_int_pipe_peak)
-    alu_ops = 4308.0  # ALU-pipe instructions per Keccak-f[1600] + SHA3 framing in k_merkle_*: 24 x (122 LOP3 + 58 SHF) - folded constants
+    alu_ops = MERKLE_ALU_OPS
+    lgmc = min(20, lgm)
+    em = po.fill_synthetic(BB, SEED + 9, 0, 1 << lgmc)
+    t0 = time.perf_counter()
+    tc = po.merkle_build(em)
+    cdt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    po.merkle_open(tc, 12345)
+    codt = time.perf_counter() - t0
     out[f"C3_merkle_commit_2^{lgm}"] = {"ms": ms, "keccak_per_s": hashes / (ms * 1e-3), "hbm_frac_68B_per_leaf": 68.0 * (1 << lgm) / (ms * 1e-3) / 1e9 / peak,
                                          "open_ms": open_ms, "int_pipe_measured": ip,
-                                         "int_pipe_frac": hashes * alu_ops / (ms * 1e-3) / ip["keccak_mix_per_s"],
-                                         "bound": "integer ALU pipe (LOP3/SHF); frac = hashes x 4308 ALU ops / time / measured Keccak-mix lane-ops/s"}
+                                         "int_pipe_frac": hashes * alu_ops / (ms * 1e-3) / ip["keccak_mix_per_s"], "alu_ops_per_hash": alu_ops,
+                                         "bound": f"integer ALU pipe (LOP3/SHF); int_pipe_frac = hashes x {alu_ops:.0f} ALU ops / time / measured Keccak-mix lane-ops/s",
+                                         "cpu_baseline": {"keccak_per_s": (2 * (1 << lgmc) - 1) / cdt, "open_ms": codt * 1e3, "cores": 1, "kind": "port",
+                                                          "sample": f"build of a 2^{lgmc}-leaf tree and one open (the reference recomputes every level per open, merkle_tree.zig:335-353)"}}
     trees.pop().deinit()
     pm.deinit()
     # C4 (the device part of `zigz prove`): 43 witness polynomials of 2^20 steps: pack from SoA trace columns, then
@@ -403,36 +604,69 @@ def run_extras(args, z, ctx, peak):
     lgw = min(20, args.log2n)
     rngw = np.random.default_rng(2)
     cols = rngw.integers(0, 1 << 63, size=(43, (1 << lgw) - 7), dtype=np.uint64)
-    for m in z.witness_pack(ctx, cols):  # warm-up (allocator cache, staging buffers)
-        m.deinit()
+
+    def c4(columns):
+        for m in z.witness_pack(ctx, columns):  # warm-up (allocator cache, staging buffers)
+            m.deinit()
+        t0 = time.perf_counter()
+        wp = z.witness_pack(ctx, columns)
+        pack_ms = (time.perf_counter() - t0) * 1e3
+        z.generate_commitments(z.FiatShamirTranscript(), wp)  # warm-up
+        t0 = time.perf_counter()
+        z.generate_commitments(z.FiatShamirTranscript(), wp)
+        gc_ms = (time.perf_counter() - t0) * 1e3
+        for m in wp:
+            m.deinit()
+        return pack_ms, gc_ms
+    pack_ms, gc_ms = c4(cols)
+    lgs = min(14, lgw)
+    cols_s = np.ascontiguousarray(cols[:, : (1 << lgs) - 7])
+    spack_ms, sgc_ms = c4(cols_s)
     t0 = time.perf_counter()
-    wpolys = z.witness_pack(ctx, cols)
-    pack_ms = (time.perf_counter() - t0) * 1e3
-    z.generate_commitments(z.FiatShamirTranscript(), wpolys)  # warm-up
+    ws = po.witness_pack(BB, cols_s)
+    cpack = time.perf_counter() - t0
     t0 = time.perf_counter()
-    z.generate_commitments(z.FiatShamirTranscript(), wpolys)
-    gc_ms = (time.perf_counter() - t0) * 1e3
-    out[f"C4_witness_43x2^{lgw}"] = {"witness_pack_ms": pack_ms, "generate_commitments_ms": gc_ms,
-                                      "keccak_per_s": 43 * (2 * (1 << lgw) - 1) / (gc_ms * 1e-3),
-                                      "note": "pack = H2D of 43 u64 columns + k_witness_pack; commitments = one batched build + 43 x (eval + open)"}
-    for m in wpolys:
-        m.deinit()
+    po.generate_commitments(BB, po.Transcript(), ws)
+    cgc = time.perf_counter() - t0
+    kec = 43 * (2 * (1 << lgw) - 1)
+    out[f"C4_witness_43x2^{lgw}"] = {"witness_pack_ms": pack_ms, "generate_commitments_ms": gc_ms, "keccak_per_s": kec / (gc_ms * 1e-3),
+                                      "int_pipe_frac": kec * alu_ops / (gc_ms * 1e-3) / ip["keccak_mix_per_s"],
+                                      "same_at_sample_size": {"log2_steps": lgs, "witness_pack_ms": spack_ms, "generate_commitments_ms": sgc_ms},
+                                      "cpu_baseline": {"witness_pack_ms": cpack * 1e3, "generate_commitments_ms": cgc * 1e3, "cores": 1, "kind": "port",
+                                                       "sample": f"43 polynomials of 2^{lgs} steps (the reference evaluates in O(N v) and recomputes the tree per open, "
+                                                                 "so its cost grows faster than linearly with the trace length)"},
+                                      "note": "pack = H2D of 43 u64 columns + k_witness_pack; commitments = one batched build + batched evaluations and openings"}
     # the whole post-VM part of `zigz prove` (pack, placeholder sumcheck/Lasso transcript, commitments, openings, ZIGZ v1
     # bytes) at 2^18 steps, the largest trace the reference's own serializer buffer can hold
     lgp = min(18, args.log2n)
-    pcols = np.ascontiguousarray(cols[:, : (1 << lgp)])
-    pcols[33] = 0x13  # every step an OP_IMM: one lookup constraint per step would overflow the reference buffer, so ...
-    pcols[33, 128:] = 0x37  # ... only the first 128 steps carry a lookup (LUI has no table): 774 bytes of slack at num_vars = 18
     program = bytes(1024)
     zero32 = [0] * 32
+
+    def trace_cols(lgx):
+        pc_ = np.ascontiguousarray(cols[:, : (1 << lgx)])
+        pc_[33] = 0x13  # every step an OP_IMM: one lookup constraint per step would overflow the reference buffer, so ...
+        pc_[33, 128:] = 0x37  # ... only the first 128 steps carry a lookup (LUI has no table): 774 bytes of slack at num_vars = 18
+        return pc_
+    pcols = trace_cols(lgp)
     z.prove_from_trace(ctx, program, 0x1000, zero32, pcols, 0x2000, zero32, [1, 2, 3], compat_buffer=True)
     t0 = time.perf_counter()
     proof = z.prove_from_trace(ctx, program, 0x1000, zero32, pcols, 0x2000, zero32, [1, 2, 3], compat_buffer=True)
     pv_ms = (time.perf_counter() - t0) * 1e3
     t0 = time.perf_counter()
     verdict = z.verify_proof(proof, program)
-    out[f"C4_prove_from_trace_2^{lgp}_steps"] = {"prove_ms": pv_ms, "proof_bytes": len(proof), "verify_ms": (time.perf_counter() - t0) * 1e3,
-                                                 "verdict": verdict}
+    vf_ms = (time.perf_counter() - t0) * 1e3
+    lgps = min(12, lgp)
+    scols = trace_cols(lgps)
+    z.prove_from_trace(ctx, program, 0x1000, zero32, scols, 0x2000, zero32, [1, 2, 3], compat_buffer=True)
+    t0 = time.perf_counter()
+    sproof = z.prove_from_trace(ctx, program, 0x1000, zero32, scols, 0x2000, zero32, [1, 2, 3], compat_buffer=True)
+    spv_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    cproof = po.prove_from_trace(BB, program, 0x1000, zero32, scols, 0x2000, zero32, [1, 2, 3], compat_buffer=True)
+    cpv = time.perf_counter() - t0
+    out[f"C4_prove_from_trace_2^{lgp}_steps"] = {"prove_ms": pv_ms, "proof_bytes": len(proof), "verify_ms": vf_ms, "verdict": verdict,
+                                                 "same_at_sample_size": {"log2_steps": lgps, "prove_ms": spv_ms, "bytes_equal_to_cpu_port": sproof == cproof},
+                                                 "cpu_baseline": {"prove_ms": cpv * 1e3, "cores": 1, "kind": "port", "sample": f"the same trace cut to 2^{lgps} steps"}}
     # C2: Lasso over the 8-bit ADD/AND/XOR subtables, 2^22 lookups each (host rows -> proof)
     lgq = min(22, args.log2n)
     rng = np.random.default_rng(1)
@@ -452,7 +686,25 @@ def run_extras(args, z, ctx, peak):
     t0 = time.perf_counter()
     z.LassoProver.prove_builtin_batch(ctx, jobs)
     batch_ms = (time.perf_counter() - t0) * 1e3
-    out[f"C2_lasso_2^{lgq}_lookups"] = {"ms_per_table": res, "ms_three_tables_one_batch_call": batch_ms, "note": "= the query commitment: one sequential host SHA3 sponge over 2^22 le64 words (lasso_prover.zig:242-252, ~225 ns per Keccak-f on one core); upload, XXH3, sumcheck and the table commitment run in its shadow on the GPU and a second thread"}
+    # the host-bound part alone: one SHA3 sponge over 2^lgq le64 words (commitToPolynomial, lasso_prover.zig:242-252)
+    import ctypes as C
+    words = np.arange(1 << lgq, dtype=np.uint32)
+    dig = (C.c_uint8 * 32)()
+    z.lib().zh_flat_commit_u32(words.ctypes.data_as(C.POINTER(C.c_uint32)), words.size, dig)
+    t0 = time.perf_counter()
+    z.lib().zh_flat_commit_u32(words.ctypes.data_as(C.POINTER(C.c_uint32)), words.size, dig)
+    sponge_ms = (time.perf_counter() - t0) * 1e3
+    qx = jobs[2][2]
+    tab = po.build_table(BB, po.TABLE_XOR, 8)
+    t0 = time.perf_counter()
+    po.lasso_prove(BB, tab, qx)
+    classo = time.perf_counter() - t0
+    out[f"C2_lasso_2^{lgq}_lookups"] = {"ms_per_table": res, "ms_three_tables_one_batch_call": batch_ms,
+                                        "host_sponge_ms": sponge_ms, "host_frac": sponge_ms / res["xor"],
+                                        "bound": "host: ONE sequential SHA3 sponge over the query polynomial (lasso_prover.zig:242-252); host_frac = that sponge alone / prove time",
+                                        "cpu_baseline": {"ms": classo * 1e3, "cores": 1, "kind": "port", "sample": "the same XOR proof: 2^%d lookups, 65536-entry table" % lgq},
+                                        "note": "upload, XXH3, sumcheck and the table commitment run in the sponge's shadow on the GPU and a second thread; the GPU buys "
+                                                "little here because the reference's commitment is sequential by construction"}
     return out
 
 

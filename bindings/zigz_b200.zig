@@ -91,6 +91,9 @@ pub fn sumcheckProve(comptime F: type, comptime protocol: type, ctx: *Ctx, evalu
     defer state.deinit();
 
     var cur: Mle = 0;
+    defer if (cur != 0) {
+        _ = zb_mle_free(ctx, cur); // registered before the loop: a failing `try` inside it must not leak the folded table
+    };
     for (0..num_vars) |round| {
         const coeffs = [2]F{ F.init(s[0]), F.init(s[1]).sub(F.init(s[0])) }; // [s0, s1 - s0] (multilinear.zig:227-230)
         proof.round_polynomials[round][0] = coeffs[0];
@@ -103,7 +106,6 @@ pub fn sumcheckProve(comptime F: type, comptime protocol: type, ctx: *Ctx, evalu
             try check(zb_mle_fold_inplace(ctx, cur, challenge.value, &s));
         }
     }
-    defer _ = zb_mle_free(ctx, cur);
     for (state.challenges, 0..) |c, i| proof.final_point[i] = c;
     proof.final_eval = F.init(s[0]); // after the last fold s[0] is current_poly.evaluations[0] (:88)
     return proof;
@@ -116,6 +118,7 @@ pub extern fn zb_host_alloc(ctx: *Ctx, bytes: usize, out: [*c]?*anyopaque) i32;
 pub extern fn zb_host_free(ctx: *Ctx, p: ?*anyopaque) i32;
 pub extern fn zb_device_info(ctx: *Ctx, sm_count: [*c]i32, total_mem: [*c]u64, free_mem: [*c]u64) i32;
 pub extern fn zb_int_pipe_peak(ctx: *Ctx, lop3_per_s: [*c]f64, shf_per_s: [*c]f64, keccak_mix_per_s: [*c]f64) i32;
+pub extern fn zb_h2d_rate(ctx: *Ctx, bytes: usize, bytes_per_s: [*c]f64) i32;
 pub extern fn zb_stream(ctx: *Ctx) ?*anyopaque;
 pub extern fn zb_sync(ctx: *Ctx) i32;
 pub extern fn zb_set_option(ctx: *Ctx, key: [*:0]const u8, value: i64) i32;
@@ -132,6 +135,9 @@ pub extern fn zb_mle_clone(ctx: *Ctx, src: Mle, out: [*c]Mle) i32;
 pub extern fn zb_mle_download_range(ctx: *Ctx, m: Mle, offset: u64, out: [*c]u64, n: u64) i32;
 pub extern fn zb_mle_download_u32(ctx: *Ctx, m: Mle, offset: u64, out: [*c]u32, n: u64) i32;
 pub extern fn zb_host_scratch(ctx: *Ctx, bytes: usize, out: [*c]?*anyopaque) i32;
+pub extern fn zb_mle_block_sums(ctx: *Ctx, m: Mle, k: u32, sums: [*c]u64) i32;
+pub extern fn zb_mle_fold_multi(ctx: *Ctx, m: Mle, k_fold: u32, r: [*c]const u64, out: [*c]Mle, k_next: u32, sums: [*c]u64) i32;
+pub extern fn zb_mle_collapse(ctx: *Ctx, m: Mle, value: u64) i32;
 pub extern fn zb_merkle_leaf_hashes(ctx: *Ctx, t: Tree, out: [*c]u8, n_digests: u64) i32;
 pub extern fn zb_comm_unique_id(nccl_path: [*:0]const u8, out: *[128]u8) i32;
 pub extern fn zb_comm_init(ctx: *Ctx, nccl_path: [*:0]const u8, unique_id: *const [128]u8, rank: i32, world: i32) i32;

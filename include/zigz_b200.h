@@ -73,6 +73,9 @@ int32_t zb_device_info(zb_ctx *ctx, int32_t *sm_count, uint64_t *total_mem, uint
 /* measured integer-pipe ceiling of this GPU for the hashing kernels: 32-bit lane-operations per second of independent
  * LOP3 chains, SHF chains, and the Keccak mix (122 LOP3 : 58 SHF), each timed with CUDA events over ~ms-long launches */
 int32_t zb_int_pipe_peak(zb_ctx *ctx, double *lop3_per_s, double *shf_per_s, double *keccak_mix_per_s);
+/* measured host->device copy rate of this GPU's link (pinned source, one `bytes`-sized cudaMemcpyAsync, best of 3, CUDA
+ * events): the denominator of bench.py's pcie_frac */
+int32_t zb_h2d_rate(zb_ctx *ctx, size_t bytes, double *bytes_per_s);
 /* raw stream handle (cudaStream_t) the context launches on: for CUDA-event timing by a harness */
 void *zb_stream(zb_ctx *ctx);
 int32_t zb_sync(zb_ctx *ctx);
@@ -152,6 +155,22 @@ int32_t zb_prod_partial_eval(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint6
 int32_t zb_prod_grid(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *grid);
 int32_t zb_prod_fold_grid(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint32_t nfold, const uint64_t *r, zb_mle *out,
                           uint64_t *grid);
+
+/* ---- several rounds per pass for ONE polynomial (d = 1, SumcheckProver.prove sumcheck_prover.zig:50-77) ----
+ * roundPolynomial (multilinear.zig:205-232) is linear in the table, so the 2^k sums over the blocks selected by the top k
+ * index bits hold the next k round polynomials (the host folds the 2^k sums with each challenge exactly as partialEval
+ * folds the table), and the k partialEval steps (:154-180) that follow collapse into one pass:
+ *   new[i] = sum_b w_b e[b m + i],  w_b = prod_j (b_j ? r_j : 1 - r_j),  m = n / 2^k  — the same canonical values.
+ * zb_mle_block_sums: sums[b], b < 2^k (1 <= k <= 5, n >= 2^(k+2)).
+ * zb_mle_fold_multi: binds the top k_fold (1..5) variables with r[0..k_fold) (r[0] = the top bit, as partialEval would), in
+ * place when out == NULL (the handle shrinks to m entries) or into a NEW table, and returns 2^k_next sums over the blocks of
+ * the folded table. k_next == log2(m) (allowed up to 10) returns the folded table itself — the host can then finish
+ * the remaining <= 10 rounds without another device round trip. Otherwise k_next <= 5 and m >= 2^(k_next+2). */
+int32_t zb_mle_block_sums(zb_ctx *ctx, zb_mle m, uint32_t k, uint64_t *sums);
+int32_t zb_mle_fold_multi(zb_ctx *ctx, zb_mle m, uint32_t k_fold, const uint64_t *r, zb_mle *out, uint32_t k_next, uint64_t *sums);
+/* replaces the table by the single value `value` (length 1): how a consuming prove leaves its polynomial when the last
+ * rounds were finished from a published table */
+int32_t zb_mle_collapse(zb_ctx *ctx, zb_mle m, uint64_t value);
 
 /* ---- SimpleMerkleTree(F, SHA3Hasher): src/commitments/merkle_tree.zig:273-402 ---- */
 /* build :283-318 for `count` polynomials of equal length in one batch (CommitmentScheme.batchCommit,

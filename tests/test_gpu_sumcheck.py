@@ -152,6 +152,7 @@ def test_tail_kernel_settings_give_identical_proofs(zlib, ctx, po, tail_log2, pr
     try:
         ctx.set_option("tail_log2", tail_log2)
         ctx.set_option("prelaunch", prelaunch)
+        ctx.set_option("linear_d1", prelaunch)  # d = 1: several-rounds-per-pass prover on / off as well
         for d, lg in ((1, 1), (1, 2), (1, 9), (1, 16), (3, 2), (3, 11), (2, 13), (3, 17)):
             es = [po.fill_synthetic(BB, 900 + k, 0, 1 << lg) for k in range(d)]
             polys = [zlib.Multilinear.init(ctx, e) for e in es]
@@ -163,6 +164,7 @@ def test_tail_kernel_settings_give_identical_proofs(zlib, ctx, po, tail_log2, pr
     finally:
         ctx.set_option("tail_log2", old)
         ctx.set_option("prelaunch", oldp)
+        ctx.set_option("linear_d1", 1)
     assert ctx.get_option("starved") == 0  # no polling kernel ever left without its challenge
 
 
@@ -225,6 +227,7 @@ def test_tail_kernel_starvation_falls_back_to_launches(zlib, po):
     with zlib.Context(0) as c2:
         c2.set_option("tail_log2", 14)  # the default, unless ZB_TAIL_LOG2 overrides it
         c2.set_option("prelaunch", 1)
+        c2.set_option("linear_d1", 0)  # the one-round-per-kernel prover is the one with polling kernels
         for lg in (12, 18):  # 2^12: the tail kernel starves; 2^18: a pre-launched fold kernel starves
             e = po.fill_synthetic(BB, 4242, 0, 1 << lg)
             poly = zlib.Multilinear.init(c2, e)
@@ -321,3 +324,63 @@ def test_grid_entry_points_directly(zlib, ctx, po):
         with pytest.raises(zlib.ZigzError):  # too small for the vector kernel: the caller must use the single-round entries
             small = zlib.Multilinear.init(ctx, [1, 2, 3, 4])
             ctx.check(L.zb_prod_grid(ctx.handle, (C.c_uint64 * 1)(small.handle), 1, grid))
+
+
+# ---------------------------------------------------------------- d = 1: several rounds per pass (zb_mle_block_sums / zb_mle_fold_multi)
+@pytest.mark.parametrize("lg", [11, 12, 13, 15, 16, 17, 19, 21, 22])
+@pytest.mark.parametrize("host_tail", [10, 7, 2])
+def test_linear_prover_matches_one_round_per_kernel_and_oracle(zlib, ctx, po, lg, host_tail):
+    """SumcheckProver.prove (sumcheck_prover.zig:26-91) through block sums + multi-variable folds: every pass shape
+    (first pass of 5, folds of 5, published tables of 2^2..2^10 entries, left-over variable counts) against the oracle,
+    the interactive variant, and the consuming variant (the polynomial ends as its final evaluation)."""
+    e = po.fill_synthetic(BB, 0xC0FFEE + lg, 0, 1 << lg)
+    want = po.sumcheck_prove(BB, e)
+    ctx.set_option("host_tail_log2", host_tail)
+    try:
+        poly = zlib.Multilinear.init(ctx, e)
+        assert zlib.SumcheckProver.prove(poly).to_bytes() == want.to_bytes()
+        assert np.array_equal(poly.evaluations[:33], e[:33]) and len(poly) == 1 << lg  # untouched
+        ch = po.fill_synthetic(BB, 99, 0, lg)
+        wi = po.sumcheck_prove_interactive(BB, e, ch)
+        pi = zlib.SumcheckProver.prove_interactive(poly, ch)
+        assert pi.round_polynomials.tolist() == wi.round_polys.tolist() and pi.final_eval == wi.final_eval
+        pc = zlib.ProductSumcheckProver.prove([poly], consume=True)
+        assert pc.round_polynomials.tolist() == want.round_polys.tolist() and pc.final_evals[0] == want.final_eval
+        assert len(poly) == 1 and int(poly.evaluations[0]) == want.final_eval
+    finally:
+        ctx.set_option("host_tail_log2", 10)
+
+
+def test_block_sums_and_fold_multi_entry_points(zlib, ctx, po):
+    """zb_mle_block_sums / zb_mle_fold_multi against partialEval applied k times (multilinear.zig:154-180) and plain block sums."""
+    import ctypes as C
+    L = zlib.lib()
+    rng = np.random.default_rng(11)
+    for lg, k, k_next in ((7, 1, 2), (9, 2, 5), (12, 3, 4), (13, 5, 5), (14, 4, 10), (12, 5, 7), (16, 5, 1), (8, 5, 3)):
+        e = po.fill_synthetic(BB, 7000 + lg, 0, 1 << lg)
+        poly = zlib.Multilinear.init(ctx, e)
+        kk = min(k, 5)
+        sums = np.zeros(1 << kk, np.uint64)
+        ctx.check(L.zb_mle_block_sums(ctx.handle, poly.handle, kk, sums.ctypes.data_as(zlib.api.P64)))
+        blocks = e.reshape(1 << kk, -1)
+        assert sums.tolist() == [int(b.astype(object).sum() % BB) for b in blocks]
+        r = rng.integers(0, BB, size=k, dtype=np.uint64)
+        folded = e
+        for x in r:
+            folded = po.mle_partial_eval(BB, folded, int(x))
+        for inplace in (False, True):
+            out = C.c_uint64(0)
+            got = np.zeros(1 << k_next, np.uint64)
+            ctx.check(L.zb_mle_fold_multi(ctx.handle, poly.handle, k, r.ctypes.data_as(zlib.api.P64), None if inplace else C.byref(out),
+                                          k_next, got.ctypes.data_as(zlib.api.P64)))
+            res = poly if inplace else zlib.Multilinear(ctx, out.value)
+            assert np.array_equal(res.evaluations, folded), (lg, k, inplace)
+            assert got.tolist() == [int(b.astype(object).sum() % BB) for b in folded.reshape(1 << k_next, -1)]
+            if not inplace:
+                assert np.array_equal(poly.evaluations, e)
+                res.deinit()
+        poly.deinit()
+    small = zlib.Multilinear.init(ctx, [1, 2, 3, 4, 5, 6, 7, 8])
+    buf = np.zeros(32, np.uint64)
+    assert L.zb_mle_block_sums(ctx.handle, small.handle, 2, buf.ctypes.data_as(zlib.api.P64)) == -22  # n < 4 * 2^k: BadArgument
+    assert L.zb_mle_fold_multi(ctx.handle, small.handle, 1, buf.ctypes.data_as(zlib.api.P64), None, 1, buf.ctypes.data_as(zlib.api.P64)) == -22

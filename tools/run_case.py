@@ -16,6 +16,7 @@ ap.add_argument("case")
 ap.add_argument("--log2n", type=int, default=24)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--count", type=int, default=1, help="merkle: polynomials per batch")
+ap.add_argument("--noprofile", action="store_true", help="no per-kernel events (latency measurements)")
 a = ap.parse_args()
 n = 1 << a.log2n
 with z.Context(0) as ctx:
@@ -44,7 +45,8 @@ with z.Context(0) as ctx:
     else:
         raise SystemExit("unknown case")
     fn()
-    ctx.profile(True)
+    fn()
+    ctx.profile(not a.noprofile)
     ctx.sync()
     t0 = time.perf_counter()
     ctx.timer_start()

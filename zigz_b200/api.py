@@ -124,6 +124,12 @@ class Context:
         self.check(lib().zb_int_pipe_peak(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"lop3_per_s": a.value, "shf_per_s": b.value, "keccak_mix_per_s": c.value}
 
+    def h2d_rate(self, nbytes: int = 1 << 30) -> float:
+        """Measured host->device copy rate (bytes/s) from pinned memory on this GPU's link."""
+        v = C.c_double(0)
+        self.check(lib().zb_h2d_rate(self._h, nbytes, C.byref(v)))
+        return v.value
+
     def device_info(self):
         sm, tot, free = C.c_int32(0), u64(0), u64(0)
         self.check(lib().zb_device_info(self._h, C.byref(sm), C.byref(tot), C.byref(free)))

@@ -48,8 +48,11 @@ struct Tree {
     uint8_t root[32];
 };
 
-constexpr size_t BULK_OFFSET = 256;          // bytes into the mapped mailbox page
+constexpr size_t BULK_OFFSET = 512;          // bytes into the mapped mailbox page (payload words + sequence number come first)
 constexpr size_t BULK_BYTES = 64 * 32 * 2;   // 64 digests for paths / roots (x2 slack)
+constexpr size_t DUMP_OFFSET = BULK_OFFSET + BULK_BYTES; // published tables of zb_mle_fold_multi (u64 per value)
+constexpr size_t DUMP_BYTES = sizeof(unsigned long long) << LIN_DUMP_MAX_LOG2;
+static_assert((MAIL_WORDS + 1) * sizeof(unsigned long long) <= BULK_OFFSET, "mailbox payload overlaps the bulk area");
 constexpr size_t STAGE_ELEMS = 32ull << 20;  // upload staging chunk (u64 elements)
 
 } // namespace
@@ -66,6 +69,7 @@ struct zb_ctx {
     unsigned int *d_err = nullptr;
     unsigned long long seq = 0;
     uint64_t launches = 0;
+    uint64_t h2d_bytes = 0; // bytes handed to host->device copies by the upload paths (bench.py: pcie_frac)
     // allocator cache
     std::multimap<size_t, void *> free_blocks;
     size_t cached_bytes = 0;
@@ -118,6 +122,11 @@ struct zb_ctx {
     unsigned long long *d_bcast = nullptr; // device word the polling CTA republishes the challenge in
     unsigned int *d_claim = nullptr;
     int tail_log2 = 14; // tables of <= 2^tail_log2 entries finish inside the persistent kernel (0 = never)
+    // d = 1 provers: several rounds per pass through linearity (zb_mle_block_sums / zb_mle_fold_multi); once the folded
+    // table has <= 2^host_tail_log2 entries it is published whole and the host finishes the (latency-bound) last rounds
+    bool linear_d1 = true;
+    int host_tail_log2 = LIN_DUMP_MAX_LOG2;
+    int linear_k = LIN_MAX_K; // variables bound per pass
     void *scratch = nullptr; // zb_host_scratch
     size_t scratch_bytes = 0;
     void *mirror = nullptr; // zb_host_mirror
@@ -138,6 +147,7 @@ struct zb_ctx {
     unsigned long long *d_xchg = nullptr;
     void *xchg_peer[16] = {nullptr};
     XchgView *d_xchg_view = nullptr;
+    unsigned long long *d_xchg_stats = nullptr; // {wait cycles, exchanged rounds}
     unsigned long long xchg_seq = 0;
 
     Mailbox mailbox() {
@@ -431,7 +441,7 @@ int upload_threads(zb_ctx *ctx) {
     if (const char *e = getenv("ZB_UPLOAD_THREADS")) return atoi(e) < 1 ? 1 : atoi(e);
     int hw = (int)std::thread::hardware_concurrency();
     int t = hw / (ctx->world > 0 ? ctx->world : 1);
-    return t > 16 ? 16 : (t < 1 ? 1 : t);
+    return t > 32 ? 32 : (t < 1 ? 1 : t); // packing is memory-bound on the pool's hosts well before 32 threads
 }
 
 int32_t ensure_pack(zb_ctx *ctx) {
@@ -454,6 +464,7 @@ int32_t staged_h2d(zb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
     cudaGetLastError();
     if (pinned || bytes < (1u << 20)) {
         CK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += bytes;
         return ZB_OK;
     }
     int32_t rc = ensure_pack(ctx);
@@ -473,6 +484,7 @@ int32_t staged_h2d(zb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
             if (hi > lo) memcpy(stage + lo, src + lo, hi - lo);
         });
         CK(cudaMemcpyAsync((char *)d_dst + off, stage, m, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += m;
         CK(cudaEventRecord(ctx->pack_done[buf], ctx->stream));
     }
     return ZB_OK;
@@ -526,6 +538,7 @@ int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32
         }
         if (raw) {
             CK(cudaMemcpyAsync(raw_stage->ptr, host + off, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d_bytes += m * sizeof(uint64_t);
             queued(m * sizeof(uint64_t));
             {
                 ProfScope _ps(ctx, "narrow_u64", m * 12);
@@ -545,6 +558,7 @@ int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32
         });
         if (m == PACK_CHUNK) pack_s = now_s() - t_pack;
         CK(cudaMemcpyAsync(dst + off, stage, m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += m * sizeof(uint32_t);
         queued(m * sizeof(uint32_t));
         CK(cudaEventRecord(ctx->pack_done[buf], ctx->stream));
         buf = (buf + 1) % PACK_BUFS;
@@ -586,6 +600,7 @@ int32_t upload_narrow(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32_t *d
     for (uint64_t off = 0; off < n; off += chunk) {
         uint64_t m = n - off < chunk ? n - off : chunk;
         CK(cudaMemcpyAsync(stage->ptr, host + off, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += m * sizeof(uint64_t);
         {
             ProfScope _ps(ctx, "narrow_u64", m * 12);
             launch_narrow_u64((const uint64_t *)stage->ptr, dst + off, m, ctx->d_err, ctx->stream);
@@ -654,7 +669,7 @@ int32_t zb_ctx_create(int32_t device, zb_ctx **out) {
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
-    size_t mail_bytes = BULK_OFFSET + BULK_BYTES;
+    size_t mail_bytes = DUMP_OFFSET + DUMP_BYTES;
     if ((e = cudaHostAlloc((void **)&ctx->h_mail, mail_bytes, cudaHostAllocMapped)) != cudaSuccess) return fail(e, "cudaHostAlloc");
     memset(ctx->h_mail, 0, mail_bytes);
     if ((e = cudaHostGetDevicePointer((void **)&ctx->d_mail, ctx->h_mail, 0)) != cudaSuccess) return fail(e, "cudaHostGetDevicePointer");
@@ -668,6 +683,15 @@ int32_t zb_ctx_create(int32_t device, zb_ctx **out) {
     cudaMemsetAsync(ctx->d_tail_status, 0, sizeof(unsigned int), ctx->stream);
     if (const char *t = getenv("ZB_TAIL_LOG2")) ctx->tail_log2 = atoi(t);
     if (const char *t = getenv("ZB_PRELAUNCH")) ctx->prelaunch = atoi(t) != 0;
+    if (const char *t = getenv("ZB_LINEAR_D1")) ctx->linear_d1 = atoi(t) != 0;
+    if (const char *t = getenv("ZB_LINEAR_K")) {
+        const int x = atoi(t);
+        ctx->linear_k = x < 1 ? 1 : (x > LIN_MAX_K ? LIN_MAX_K : x);
+    }
+    if (const char *t = getenv("ZB_HOST_TAIL_LOG2")) {
+        const int x = atoi(t);
+        ctx->host_tail_log2 = x < 2 ? 2 : (x > LIN_DUMP_MAX_LOG2 ? LIN_DUMP_MAX_LOG2 : x);
+    }
     if ((e = cudaMalloc(&ctx->d_bcast, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
     ctx->d_claim = (unsigned int *)(ctx->d_bcast + 1);
     cudaMemsetAsync(ctx->d_bcast, 0, 2 * sizeof(unsigned long long), ctx->stream);
@@ -744,6 +768,24 @@ int32_t zb_set_option(zb_ctx *ctx, const char *key, int64_t value) {
         ctx->starved = (int)value;
         return ZB_OK;
     }
+    if (key && !strcmp(key, "xchg_stats_reset")) {
+        if (ctx->d_xchg_stats) CK(cudaMemset(ctx->d_xchg_stats, 0, 2 * sizeof(unsigned long long)));
+        return ZB_OK;
+    }
+    if (key && !strcmp(key, "linear_d1")) {
+        ctx->linear_d1 = value != 0;
+        return ZB_OK;
+    }
+    if (key && !strcmp(key, "host_tail_log2")) {
+        if (value < 2 || value > LIN_DUMP_MAX_LOG2) return ZB_ERR_BAD_ARGUMENT;
+        ctx->host_tail_log2 = (int)value;
+        return ZB_OK;
+    }
+    if (key && !strcmp(key, "linear_k")) {
+        if (value < 1 || value > LIN_MAX_K) return ZB_ERR_BAD_ARGUMENT;
+        ctx->linear_k = (int)value;
+        return ZB_OK;
+    }
     if (key && !strcmp(key, "comm_reduce")) {
         if (value < 0 || value > 2 || (value == 2 && !ctx->d_xchg_view)) return ZB_ERR_BAD_ARGUMENT;
         ctx->comm_reduce = (int)value;
@@ -767,6 +809,35 @@ int32_t zb_get_option(zb_ctx *ctx, const char *key, int64_t *value) {
     }
     if (key && value && !strcmp(key, "starved")) {
         *value = ctx->starved;
+        return ZB_OK;
+    }
+    if (key && value && !strcmp(key, "linear_d1")) {
+        *value = ctx->linear_d1 ? 1 : 0;
+        return ZB_OK;
+    }
+    if (key && value && !strcmp(key, "host_tail_log2")) {
+        *value = ctx->host_tail_log2;
+        return ZB_OK;
+    }
+    if (key && value && !strcmp(key, "linear_k")) {
+        *value = ctx->linear_k;
+        return ZB_OK;
+    }
+    if (key && value && !strcmp(key, "h2d_bytes")) {
+        *value = (int64_t)ctx->h2d_bytes;
+        return ZB_OK;
+    }
+    if (key && value && (!strcmp(key, "xchg_wait_ns") || !strcmp(key, "xchg_rounds"))) {
+        // in-kernel peer exchange: time the last CTA spent waiting for the other ranks' rows (skew between GPUs + NVLink
+        // latency), summed over the exchanged rounds since the last reset, and the number of those rounds
+        unsigned long long st[2] = {0, 0};
+        if (ctx->d_xchg_stats) {
+            tail_quiesce(ctx);
+            CK(cudaMemcpy(st, ctx->d_xchg_stats, sizeof(st), cudaMemcpyDeviceToHost));
+        }
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+        *value = !strcmp(key, "xchg_rounds") ? (int64_t)st[1] : (int64_t)((double)st[0] * 1e6 / (khz > 0 ? khz : 1965000));
         return ZB_OK;
     }
     if (key && value && !strcmp(key, "p2p_attached")) {
@@ -846,6 +917,36 @@ int32_t zb_int_pipe_peak(zb_ctx *ctx, double *lop3, double *shf, double *mix) {
     }
     cudaEventDestroy(a);
     cudaEventDestroy(b);
+    return ZB_OK;
+}
+
+int32_t zb_h2d_rate(zb_ctx *ctx, size_t bytes, double *bytes_per_s) {
+    tail_quiesce(ctx);
+    if (!bytes_per_s || bytes < (1u << 20)) return ZB_ERR_BAD_ARGUMENT;
+    void *h = nullptr;
+    BufRef d;
+    int32_t rc = dev_alloc(ctx, bytes, &d);
+    if (rc) return rc;
+    CK(cudaHostAlloc(&h, bytes, cudaHostAllocDefault));
+    memset(h, 1, bytes);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) { // the first repetition warms up
+        cudaEventRecord(a, ctx->stream);
+        cudaMemcpyAsync(d->ptr, h, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        cudaEventRecord(b, ctx->stream);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFreeHost(h);
+    CK(cudaGetLastError());
+    *bytes_per_s = (double)bytes / (best * 1e-3);
     return ZB_OK;
 }
 
@@ -1146,6 +1247,21 @@ int32_t zb_mle_eval(zb_ctx *ctx, zb_mle h, const uint64_t *point, uint32_t npoin
     // through the block kernel, up to 12 variables per pass; the last pass publishes the value
     do {
         const bool big = (n >= (1ull << 20));
+        if (!big && v - done <= 20) { // everything that is left in ONE launch (tiles per CTA, then the last CTA finishes)
+            const int nv = (int)(v - done < 12 ? v - done : 12), nv2 = (int)(v - done) - nv;
+            EvalPoint pt{}, pt2{};
+            for (int k = 0; k < nv; k++) pt.r[k] = (uint32_t)point[done + k], pt.rp[k] = bb::shoup_pre(pt.r[k]);
+            for (int k = 0; k < nv2; k++) pt2.r[k] = (uint32_t)point[done + nv + k], pt2.rp[k] = bb::shoup_pre(pt2.r[k]);
+            const uint64_t n_out = n >> nv;
+            int32_t rc = dev_alloc(ctx, (n_out < 128 ? 128 : n_out) * sizeof(uint32_t), &scratch[which]);
+            if (rc) return rc;
+            {
+                ProfScope _ps(ctx, "eval_finish", (n + n_out) * 4);
+                launch_eval_finish(src, n, nv, pt, (uint32_t *)scratch[which]->ptr, nv2, pt2, mb, ctx->sm_count, ctx->stream);
+            }
+            LAUNCHED("eval_finish");
+            break;
+        }
         int nv = big ? 10 : (int)(v - done < 12 ? v - done : 12);
         EvalPoint pt{};
         for (int k = 0; k < nv; k++) {
@@ -1624,6 +1740,93 @@ int32_t zb_prod_fold_grid(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint32_t
                           uint64_t *grid) {
     if (nfold < 1) return ZB_ERR_BAD_ARGUMENT;
     return fold_grid_impl(ctx, polys, d, nfold, r, out, grid);
+}
+
+/* ------------------------------------------------------------------ d = 1: several rounds per pass (linearity) */
+
+int32_t zb_mle_block_sums(zb_ctx *ctx, zb_mle h, uint32_t k, uint64_t *sums) {
+    tail_quiesce(ctx);
+    Mle *m = get_mle(ctx, h);
+    if (!m) return ZB_ERR_BAD_HANDLE;
+    if (!sums || k < 1 || k > (uint32_t)LIN_MAX_K || m->n < (4ull << k)) return ZB_ERR_BAD_ARGUMENT;
+    Mailbox mb = ctx->mailbox();
+    {
+        ProfScope _ps(ctx, "block_sums_d1", m->n * 4);
+        launch_block_sums(m->d(), m->n, (int)k, mb, ctx->sm_count, ctx->stream);
+    }
+    LAUNCHED("block_sums");
+    int32_t rc = wait_mail(ctx, mb.seq);
+    if (rc) return rc;
+    for (uint32_t b = 0; b < (1u << k); b++) sums[b] = ctx->h_mail[b];
+    return ZB_OK;
+}
+
+int32_t zb_mle_fold_multi(zb_ctx *ctx, zb_mle h, uint32_t k_fold, const uint64_t *r, zb_mle *out, uint32_t k_next, uint64_t *sums) {
+    tail_quiesce(ctx);
+    Mle *m = get_mle(ctx, h);
+    if (!m) return ZB_ERR_BAD_HANDLE;
+    if (!r || !sums || k_fold < 1 || k_fold > (uint32_t)LIN_MAX_K) return ZB_ERR_BAD_ARGUMENT;
+    const uint64_t n = m->n, mm = n >> k_fold;
+    if (mm < 4 || (mm << k_fold) != n) return ZB_ERR_BAD_ARGUMENT;
+    const bool dump = (1ull << k_next) == mm;
+    if (dump ? k_next > (uint32_t)LIN_DUMP_MAX_LOG2 : (k_next < 1 || k_next > (uint32_t)LIN_MAX_K || mm < (4ull << k_next)))
+        return ZB_ERR_BAD_ARGUMENT;
+    for (uint32_t j = 0; j < k_fold; j++)
+        if (r[j] >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    // eq weights, index = the k_fold top index bits with r[0] <-> the most significant one, in Montgomery form
+    FoldWeights fw{};
+    fw.w[0] = bb::R_MOD_P; // 1 in Montgomery form
+    for (uint32_t j = 0; j < k_fold; j++) { // after step j: w[0 .. 2^(j+1)) for the bits b_0..b_j (b_0 = MSB so far)
+        const uint32_t rj = (uint32_t)r[j], nj = bb::sub(1u, rj);
+        for (int t = (1 << j) - 1; t >= 0; t--) {
+            const uint32_t base = fw.w[t];
+            fw.w[2 * t] = bb::mul(base, nj);
+            fw.w[2 * t + 1] = bb::mul(base, rj);
+        }
+    }
+    const uint32_t *src = m->d();
+    uint32_t *dst = m->d();
+    BufRef keep = m->buf;
+    if (out) {
+        Mle *o = nullptr;
+        int32_t rc = new_mle(ctx, mm, out, &o);
+        if (rc) return rc;
+        dst = o->d();
+    }
+    Mailbox mb = ctx->mailbox();
+    unsigned long long *d_dump = dump ? (unsigned long long *)((uint8_t *)ctx->d_mail + DUMP_OFFSET) : nullptr;
+    {
+        ProfScope _ps(ctx, "foldk_d1", (n + mm) * 4);
+        launch_foldk_sums(src, dst, n, (int)k_fold, fw, (int)k_next, d_dump, mb, ctx->sm_count, ctx->stream);
+    }
+    int32_t rc = check_launch(ctx, "foldk_sums");
+    if (rc == ZB_OK) rc = wait_mail(ctx, mb.seq);
+    if (rc) {
+        if (out) {
+            ctx->mles.erase(*out);
+            *out = 0;
+        }
+        return rc;
+    }
+    if (!out) get_mle(ctx, h)->n = mm;
+    if (dump) memcpy(sums, (uint8_t *)ctx->h_mail + DUMP_OFFSET, mm * sizeof(uint64_t));
+    else
+        for (uint32_t b = 0; b < (1u << k_next); b++) sums[b] = ctx->h_mail[b];
+    return ZB_OK;
+}
+
+int32_t zb_mle_collapse(zb_ctx *ctx, zb_mle h, uint64_t value) {
+    tail_quiesce(ctx);
+    Mle *m = get_mle(ctx, h);
+    if (!m) return ZB_ERR_BAD_HANDLE;
+    if (value >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    {
+        ProfScope _ps(ctx, "fill", 4);
+        launch_fill(m->d(), 1, (uint32_t)value, ctx->stream);
+    }
+    LAUNCHED("fill");
+    m->n = 1;
+    return zb_sync(ctx);
 }
 
 /* ------------------------------------------------------------------ Merkle */
@@ -2105,6 +2308,9 @@ int32_t zb_comm_p2p_attach(zb_ctx *ctx, const uint8_t *handles) {
         CK(cudaIpcOpenMemHandle(&ctx->xchg_peer[q], h, cudaIpcMemLazyEnablePeerAccess));
         view.peer[q] = (unsigned long long *)ctx->xchg_peer[q];
     }
+    CK(cudaMalloc(&ctx->d_xchg_stats, 2 * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->d_xchg_stats, 0, 2 * sizeof(unsigned long long)));
+    view.stats = ctx->d_xchg_stats;
     CK(cudaMalloc(&ctx->d_xchg_view, sizeof(XchgView)));
     CK(cudaMemcpy(ctx->d_xchg_view, &view, sizeof(XchgView), cudaMemcpyHostToDevice));
     return ZB_OK;
@@ -2175,6 +2381,8 @@ int32_t zb_comm_destroy(zb_ctx *ctx) {
             }
         if (ctx->d_xchg_view) cudaFree(ctx->d_xchg_view);
         ctx->d_xchg_view = nullptr;
+        if (ctx->d_xchg_stats) cudaFree(ctx->d_xchg_stats);
+        ctx->d_xchg_stats = nullptr;
         cudaFree(ctx->d_xchg);
         ctx->d_xchg = nullptr;
     }

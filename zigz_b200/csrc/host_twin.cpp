@@ -23,7 +23,9 @@ inline uint64_t f_add(uint64_t a, uint64_t b) { // field.zig:73-88
     return s >= P ? s - P : s;
 }
 inline uint64_t f_sub(uint64_t a, uint64_t b) { return a >= b ? a - b : P - (b - a); } // field.zig:91-98
-inline uint64_t f_mul(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) % P); } // field.zig:112-147
+// field.zig:112-147 computes (u128)a*b % p; for canonical operands (< p < 2^31) the product fits 62 bits, so the same
+// canonical value comes out of a plain 64-bit remainder (a multiply-by-reciprocal, ~10x faster than the __umodti3 call)
+inline uint64_t f_mul(uint64_t a, uint64_t b) { return (a * b) % P; }
 
 inline uint64_t digest_to_field(const uint8_t d[32]) { // hash.zig:228-242: first 8 bytes LE, then F.init = mod p
     uint64_t v;
@@ -61,8 +63,9 @@ uint64_t zh_f_mul(uint64_t a, uint64_t b) { return f_mul(a % P, b % P); }
 
 uint64_t zh_eval_univariate(const uint64_t *c, uint32_t n, uint64_t x) { // sumcheck_protocol.zig:113-123 (Horner)
     if (n == 0) return 0;
-    uint64_t r = c[n - 1];
-    for (uint32_t i = n - 1; i > 0; i--) r = f_add(f_mul(r, x), c[i - 1]);
+    x %= P; // F.init
+    uint64_t r = c[n - 1] % P;
+    for (uint32_t i = n - 1; i > 0; i--) r = f_add(f_mul(r, x), c[i - 1] % P);
     return r;
 }
 
@@ -143,6 +146,74 @@ static int gather_log2() {
     return v;
 }
 
+// d = 1 on one GPU, tables of more than 2^10 entries: several rounds per pass over the data (zb_mle_block_sums /
+// zb_mle_fold_multi). The 2^k block sums S in hand ARE a 2^k-entry multilinear table whose sumcheck rounds equal the next k
+// rounds of the big table (roundPolynomial is linear, multilinear.zig:205-232), so the host runs those rounds on S exactly as
+// sumcheck_prover.zig:50-77 does — roundPolynomial, transcript, partialEval — while the device only sees one launch per k
+// rounds. When the folded table is small enough to be published whole, S is the table itself and the host finishes the proof.
+static int32_t prove_linear(zb_ctx *ctx, zb_mle poly, uint32_t v, bool consume, const uint64_t *fixed_challenges,
+                            uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint64_t *claimed_sum) {
+    int64_t dump_log2 = 10, kk = 5;
+    zb_get_option(ctx, "host_tail_log2", &dump_log2);
+    zb_get_option(ctx, "linear_k", &kk);
+    const uint32_t K = (uint32_t)kk;    // variables per device pass
+    uint64_t S[1u << 10];
+    uint64_t rs[10];
+    uint32_t u = v;                     // log2 of the current device table
+    uint32_t have = u - 2 < K ? u - 2 : K; // S holds 2^have block sums (blocks of >= 4 entries)
+    int32_t rc = zb_mle_block_sums(ctx, poly, have, S);
+    if (rc) return rc;
+    zh_transcript tr; // State.init -> FiatShamirTranscript.init (sumcheck_protocol.zig:149-164)
+    zb_mle cur = poly;
+    bool owned = false;
+    uint32_t round = 0;
+    for (;;) {
+        uint64_t len = 1ull << have;
+        for (uint32_t t = 0; t < have; t++, round++) {
+            const uint64_t h = len / 2;
+            uint64_t s0 = 0, s1 = 0; // roundPolynomial :216-224 on the block sums
+            for (uint64_t i = 0; i < h; i++) {
+                s0 = f_add(s0, S[i]);
+                s1 = f_add(s1, S[i + h]);
+            }
+            const uint64_t c[2] = {s0, f_sub(s1, s0)}; // :229
+            round_polys[2 * (size_t)round] = c[0];
+            round_polys[2 * (size_t)round + 1] = c[1];
+            if (round == 0 && claimed_sum) *claimed_sum = f_add(s0, s1); // sumOverHypercube, sumcheck_prover.zig:40
+            uint64_t r;
+            if (fixed_challenges) {
+                r = fixed_challenges[round]; // proveInteractive :127
+            } else {
+                zh_transcript_append_fields(&tr, c, 2); // generateChallenge, sumcheck_protocol.zig:176-184
+                r = zh_transcript_challenge(&tr);
+            }
+            final_point[round] = r;
+            rs[t < 10 ? t : 9] = r;
+            for (uint64_t i = 0; i < h; i++) S[i] = f_add(S[i], f_mul(r, f_sub(S[i + h], S[i]))); // partialEval :166-173
+            len = h;
+        }
+        if (u == have) break; // S was the (published) table itself: S[0] is current_poly.evaluations[0] (:88)
+        // the device binds the same `have` variables in one pass and returns the sums for the next rounds
+        const uint32_t u_next = u - have;
+        const uint32_t k_next = u_next <= (uint32_t)dump_log2 ? u_next : (u_next - 2 < K ? u_next - 2 : K);
+        zb_mle next = 0;
+        rc = zb_mle_fold_multi(ctx, cur, have, rs, (consume || owned) ? nullptr : &next, k_next, S);
+        if (rc) break;
+        if (next) {
+            cur = next;
+            owned = true;
+        }
+        u = u_next;
+        have = k_next;
+    }
+    if (rc == ZB_OK) {
+        *final_eval = S[0];
+        if (consume) rc = zb_mle_collapse(ctx, poly, S[0]); // the caller's table ends as its final evaluation, as after v folds
+    }
+    if (owned) zb_mle_free(ctx, cur);
+    return rc;
+}
+
 static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool consume, const uint64_t *fixed_challenges,
                             uint64_t *round_polys, uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum) {
     if (d < 1 || d > 3 || !polys) return ZB_ERR_BAD_ARGUMENT;
@@ -152,6 +223,11 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
     if (rc) return rc;
     int32_t rank = 0, world = 1;
     zb_comm_info(ctx, &rank, &world);
+    if (d == 1 && world == 1 && v_local > 10) {
+        int64_t lin = 0;
+        zb_get_option(ctx, "linear_d1", &lin);
+        if (lin) return prove_linear(ctx, polys[0], v_local, consume, fixed_challenges, round_polys, final_point, final_evals, claimed_sum);
+    }
     uint32_t v_tail = 0;
     while ((1 << v_tail) < world) v_tail++;
     const uint32_t v = v_local + v_tail;

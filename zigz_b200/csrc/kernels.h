@@ -9,7 +9,7 @@ namespace zk {
 
 constexpr int MAX_POLYS = 3;    // product sumcheck degree
 constexpr int MAX_BATCH = 64;   // trees per batched Merkle launch
-constexpr int MAIL_WORDS = 24;  // u64 payload words per mailbox (16-word round grids + a status word)
+constexpr int MAIL_WORDS = 40;  // u64 payload words per mailbox (16-word round grids, 32 block sums, a status word)
 
 // Completion mailbox. `acc`/`ticket` live in device memory; `mail` is mapped pinned host memory.
 // mail[0..MAIL_WORDS) payload, mail[MAIL_WORDS] = sequence number written last (release, system scope).
@@ -22,6 +22,7 @@ struct XchgView {
     unsigned long long *peer[XCHG_MAX_RANKS]; // peer[q] = rank q's exchange buffer as seen from this GPU (peer[rank] = own)
     int rank, world;
     long long patience; // SM cycles a rank waits for its peers' rows before it reports a starved exchange
+    unsigned long long *stats; // device: {cycles spent waiting for peers, exchanged rounds}, accumulated (nullptr: off)
 };
 
 struct Mailbox {
@@ -86,6 +87,25 @@ void launch_fold_grid(int d, int nfold, const PolySet &ps, uint64_t m, uint32_t 
                       cudaStream_t st);
 inline bool fold_grid_ok(uint64_t m) { return m >= 8 && (m % 8) == 0; }
 
+// ---- d = 1 (the reference's own prover): several rounds per pass through LINEARITY ----
+// roundPolynomial of one multilinear table is linear in the table: s0/s1 of round t are sums of the 2^k block sums
+// S[b] = sum of e over block b (top k index bits = b) folded with the challenges so far. So 2^k block sums serve the next k
+// rounds on the host, and the device then binds those k variables in ONE pass as a 2^k-term dot product with the eq weights
+// w_b = prod_j (b_j ? r_j : 1 - r_j) — exactly partialEval applied k times (exact field arithmetic) — emitting the next
+// block sums on the way: 2^28 entries take 5 passes (8.3 B per element) instead of 28 rounds (13.3-16 B per element).
+constexpr int LIN_MAX_K = 5;          // variables per pass (32 block sums / 32-term dot product)
+constexpr int LIN_DUMP_MAX_LOG2 = 10; // a folded table of <= 2^10 entries is published whole (block length 1)
+struct FoldWeights {
+    uint32_t w[1 << LIN_MAX_K]; // Montgomery form (w R mod p), index = the K top index bits (first-bound variable = MSB)
+};
+// payload[b] = sum of src over block b of nb = 2^k (1..5) equal blocks, canonical; n % (4 nb) == 0
+void launch_block_sums(const uint32_t *src, uint64_t n, int k, const Mailbox &mb, int sm_count, cudaStream_t st);
+// dst[i] = sum_t w[t] src[t m + i] (m = n >> k, i < m; dst may equal src). k_next >= 0 with m >> k_next >= 4: payload =
+// 2^k_next block sums of dst. dump != nullptr (needs m <= 2^LIN_DUMP_MAX_LOG2, m % 4 == 0): the folded values themselves go to
+// dump[0..m) as u64 (host-mapped) instead, and the payload is empty.
+void launch_foldk_sums(const uint32_t *src, uint32_t *dst, uint64_t n, int k, const FoldWeights &w, int k_next,
+                       unsigned long long *dump, const Mailbox &mb, int sm_count, cudaStream_t st);
+
 // Plain sum of all n evaluations: payload {sum mod p}
 void launch_sum(const uint32_t *src, uint64_t n, const Mailbox &mb, int sm_count, cudaStream_t st);
 
@@ -97,6 +117,11 @@ struct EvalPoint {
 };
 void launch_eval_stage(const uint32_t *src, uint64_t n, int nvars, const EvalPoint &pt, uint32_t *out, const Mailbox *mb,
                        int sm_count, cudaStream_t st);
+
+// The remaining nv + nv2 (nv <= 12, nv2 <= 8) variables of n = 2^(nv + nv2) values in one launch: tiles of 2^nv per CTA into
+// out[0 .. 2^nv2), then the last CTA folds those with pt2 and publishes the value.
+void launch_eval_finish(const uint32_t *src, uint64_t n, int nv, const EvalPoint &pt, uint32_t *out, int nv2, const EvalPoint &pt2,
+                        const Mailbox &mb, int sm_count, cudaStream_t st);
 
 // Large stage: folds the 10 low variables of `src` (n a multiple of 1024): out[j] = fold of src[1024 j ..). pt.r[0..10).
 void launch_eval_warp10(const uint32_t *src, uint64_t n, const EvalPoint &pt, uint32_t *out, int sm_count, cudaStream_t st);

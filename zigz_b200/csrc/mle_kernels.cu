@@ -11,6 +11,7 @@
 #include "kernels.h"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace zk {
 
@@ -70,6 +71,18 @@ __device__ __forceinline__ bool xchg_allreduce(unsigned long long (&tot)[NS], co
         __threadfence_system();
 #pragma unroll
         for (int k = 0; k < NS; k++) v[k] = mine[lane * XCHG_ROW + k];
+        if (xv->stats != nullptr) { // the slowest peer's row sets this rank's wait
+            long long waited = clock64() - t0;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                const long long other = __shfl_xor_sync(__activemask(), waited, o, 16);
+                waited = other > waited ? other : waited;
+            }
+            if (lane == 0) {
+                atomicAdd(&xv->stats[0], (unsigned long long)waited);
+                atomicAdd(&xv->stats[1], 1ull);
+            }
+        }
     }
 #pragma unroll
     for (int k = 0; k < NS; k++) {
@@ -547,7 +560,7 @@ __global__ void __launch_bounds__(TPB) k_fold_grid_async(PolySet ps, uint64_t mq
                                                              uint32_t rp2, Mailbox mb) {
     using G = GridAsync<D, FV, STAGES_, TPB>;
     constexpr int NP = NPts<D>::value, NS = NP * NP, NT = G::NT, NSLOT = G::NSLOT, STAGES = G::STAGES;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint2 *ring = reinterpret_cast<uint2 *>(smem_raw); // [STAGES][NSLOT][THREADS]
     unsigned long long s[NS];
 #pragma unroll
@@ -636,6 +649,191 @@ __global__ void __launch_bounds__(TPB) k_fold_grid_async(PolySet ps, uint64_t mq
     publish_sums<NS, FinishGrid<D, NS>, TPB>(s, mb, FinishGrid<D, NS>());
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bulk asynchronous copies (cp.async.bulk, SASS UBLKCP) completing on shared-memory mbarriers (SYNCS): ONE instruction
+// moves a KB-sized contiguous slab global -> shared without touching the register file or the LSU issue slots of the
+// consumer warps. The streaming kernels below use them as a producer/consumer ring: a `full` barrier per stage carries
+// the expected byte count (expect_tx), an `empty` barrier hands the stage back to the producer.
+// ---------------------------------------------------------------------------------------------
+namespace blk {
+__device__ __forceinline__ uint32_t saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { // arrives once and arms the byte count
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(saddr(bar)),
+        "r"(parity)
+        : "memory");
+}
+// bytes: multiple of 16; both addresses 16-byte aligned
+__device__ __forceinline__ void g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(saddr(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(saddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+} // namespace blk
+
+// k_fold_grid_async with the per-thread LDGSTS ring (24-48 8-byte copies per thread and iteration) replaced by a CTA-wide
+// ring of bulk copies: a tile is TPB consecutive vector units; each of the D*4*2^FV operand streams of the tile is one
+// contiguous TPB*8-byte slab, fetched by ONE cp.async.bulk issued from the producer warp. The consumer warps wait on the
+// stage's `full` mbarrier, read their operands with conflict-free 8-byte LDS and hand the stage back through `empty`.
+template <int D, int FV, int STAGES_, int TPB>
+struct GridBulk {
+    static constexpr int NT = 1 << FV;
+    static constexpr int NSLOT = D * 4 * NT;
+    static constexpr int SLAB_BYTES = TPB * 8;
+    static constexpr int STAGE_BYTES = NSLOT * SLAB_BYTES;
+    static constexpr int STAGES = STAGES_;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128; // + barriers (+ alignment slack)
+    static constexpr int THREADS_ALL = TPB + 32; // consumers + one producer warp
+    static_assert(STAGES >= 2 && SMEM <= 227 * 1024, "ring depth");
+};
+
+template <int D, int FV, int STAGES_, int TPB>
+__global__ void __launch_bounds__(TPB + 32, 1) k_fold_grid_bulk(PolySet ps, uint64_t mq, uint32_t r1, uint32_t rp1, uint32_t r2,
+                                                                uint32_t rp2, Mailbox mb) {
+    using G = GridBulk<D, FV, STAGES_, TPB>;
+    constexpr int NP = NPts<D>::value, NS = NP * NP, NT = G::NT, NSLOT = G::NSLOT, STAGES = G::STAGES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint2 *ring = reinterpret_cast<uint2 *>(smem_raw); // [STAGES][NSLOT][TPB]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * G::STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int st = 0; st < STAGES; st++) {
+            blk::mbar_init(&full[st], 1);          // the producer's arrive.expect_tx
+            blk::mbar_init(&empty[st], TPB / 32);  // one arrival per consumer warp
+        }
+        blk::fence_barrier_init();
+    }
+    __syncthreads();
+    const uint64_t n_tiles = mq / TPB; // mq is a multiple of TPB (launcher)
+    const uint64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    unsigned long long s[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) s[k] = 0;
+    if (tid >= TPB) {
+        // ---- producer warp ----
+        const int lane = tid - TPB;
+        for (uint64_t it = 0; it < my_tiles; it++) {
+            const int stage = (int)(it % STAGES);
+            const uint32_t use = (uint32_t)(it / STAGES);
+            if (use > 0) blk::mbar_wait(&empty[stage], (use - 1) & 1); // the consumers have drained the previous tile of this stage
+            if (lane == 0) blk::mbar_expect_tx(&full[stage], G::STAGE_BYTES);
+            __syncwarp();
+            const uint64_t i0 = (blockIdx.x + it * gridDim.x) * TPB;
+            for (int slot = lane; slot < NSLOT; slot += 32) {
+                const int k = slot / (4 * NT), j = (slot / NT) % 4, t = slot % NT;
+                const uint2 *src = reinterpret_cast<const uint2 *>(ps.src[k]) + i0 + (uint64_t)j * mq + (uint64_t)t * (4 * mq);
+                blk::g2s(&ring[((size_t)stage * NSLOT + slot) * TPB], src, G::SLAB_BYTES, &full[stage]);
+            }
+        }
+    } else {
+        // ---- consumer warps ----
+        for (uint64_t it = 0; it < my_tiles; it++) {
+            const int stage = (int)(it % STAGES);
+            blk::mbar_wait(&full[stage], (uint32_t)(it / STAGES) & 1);
+            const uint64_t i = (blockIdx.x + it * gridDim.x) * TPB + tid;
+            uint32_t f[D][4][2];
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                uint2 a[4][NT];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int t = 0; t < NT; t++) a[j][t] = ring[((size_t)stage * NSLOT + (k * 4 + j) * NT + t) * TPB + tid];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if constexpr (FV == 0) {
+                        f[k][j][0] = a[j][0].x;
+                        f[k][j][1] = a[j][0].y;
+                    } else if constexpr (FV == 1) {
+                        f[k][j][0] = bb::lerp(a[j][0].x, a[j][1].x, r1, rp1);
+                        f[k][j][1] = bb::lerp(a[j][0].y, a[j][1].y, r1, rp1);
+                    } else {
+                        f[k][j][0] = bb::dot4(a[j][0].x, a[j][1].x, a[j][2].x, a[j][3].x, r1, rp1, r2, rp2);
+                        f[k][j][1] = bb::dot4(a[j][0].y, a[j][1].y, a[j][2].y, a[j][3].y, r1, rp1, r2, rp2);
+                    }
+                }
+                if (k == D - 1) { // every operand of this tile is in registers: hand the stage back before the arithmetic
+                    __syncwarp();
+                    if ((tid & 31) == 0) blk::mbar_arrive(&empty[stage]);
+                }
+                if constexpr (FV > 0) {
+                    uint2 *o = reinterpret_cast<uint2 *>(ps.dst[k]);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) o[i + j * mq] = make_uint2(f[k][j][0], f[k][j][1]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                uint32_t val[D][NP][NP];
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    uint32_t x0[NP], x1[NP];
+                    expand_line<D>(f[k][0][c], f[k][2][c], x0);
+                    expand_line<D>(f[k][1][c], f[k][3][c], x1);
+#pragma unroll
+                    for (int ix = 0; ix < NP; ix++) expand_line<D>(x0[ix], x1[ix], val[k][ix]);
+                }
+#pragma unroll
+                for (int ix = 0; ix < NP; ix++)
+#pragma unroll
+                    for (int iy = 0; iy < NP; iy++) {
+                        if constexpr (D == 1) s[ix * NP + iy] += val[0][ix][iy];
+                        else if constexpr (D == 2) s[ix * NP + iy] += bb::mont_mul_lazy(val[0][ix][iy], val[1][ix][iy]);
+                        else s[ix * NP + iy] += bb::mont_mul_lazy(bb::mont_mul_lazy(val[0][ix][iy], val[1][ix][iy]), val[2][ix][iy]);
+                    }
+            }
+        }
+    }
+    publish_sums<NS, FinishGrid<D, NS>, TPB + 32>(s, mb, FinishGrid<D, NS>());
+}
+
+template <int D, int FV, int STAGES_, int TPB>
+static void fold_grid_bulk_launch_s(const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
+    using G = GridBulk<D, FV, STAGES_, TPB>;
+    static const bool once = [] {
+        cudaFuncSetAttribute(k_fold_grid_bulk<D, FV, STAGES_, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        return true;
+    }();
+    (void)once;
+    const uint64_t mq = m / 8, n_tiles = mq / TPB;
+    const int grid = (int)(n_tiles < (uint64_t)sm ? n_tiles : (uint64_t)sm);
+    const FoldArgs fa = fold_args<FV>(r1, r2);
+    k_fold_grid_bulk<D, FV, STAGES_, TPB><<<grid, G::THREADS_ALL, G::SMEM, st>>>(ps, mq, fa.a[0], fa.a[1], fa.a[2], fa.a[3], mb);
+}
+
+// ring shape of the bulk version: the deepest ring that fits 227 KB with 256-unit (2 KB) slabs; 128-unit slabs when that
+// would leave fewer than 2 stages... (D = 3, two folded variables: 48 slabs = 96 KB per stage, 2 stages)
+template <int D, int FV>
+static void fold_grid_bulk_launch(const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
+    constexpr int NSLOT = D * 4 * (1 << FV);
+    static const int cfg = tune("ZB_GRID_BULK_TPB", 256);
+    if (cfg == 128) {
+        constexpr int ST = (220 * 1024) / (NSLOT * 128 * 8) > 8 ? 8 : (220 * 1024) / (NSLOT * 128 * 8);
+        return fold_grid_bulk_launch_s<D, FV, ST, 128>(ps, m, r1, r2, mb, sm, st);
+    }
+    constexpr int ST = (220 * 1024) / (NSLOT * 256 * 8) > 6 ? 6 : (220 * 1024) / (NSLOT * 256 * 8);
+    return fold_grid_bulk_launch_s<D, FV, ST, 256>(ps, m, r1, r2, mb, sm, st);
+}
+
 template <int D, int FV, int STAGES_, int TPB, bool DOT = false>
 static void fold_grid_async_launch_s(const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
     using G = GridAsync<D, FV, STAGES_, TPB>;
@@ -693,6 +891,16 @@ template <int D>
 static void fold_grid_t(int nfold, const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
     static const int ASYNC = tune("ZB_GRID_ASYNC", 1);
     static const int ASYNC_MIN = tune("ZB_GRID_ASYNC_MIN_LOG2", 16);
+    // bulk-copy ring (cp.async.bulk + mbarrier): default for two folded variables, where the per-thread LDGSTS ring spends
+    // 48 copy instructions per thread and iteration (ZB_GRID_BULK: bit 0 = nfold 0, bit 1 = nfold 1, bit 2 = nfold 2)
+    static const int BULK = tune("ZB_GRID_BULK", 4);
+    static const int BULK_MIN = tune("ZB_GRID_BULK_MIN_LOG2", 18);
+    if (((BULK >> nfold) & 1) && m >= (1ull << BULK_MIN) && (m / 8) % 256 == 0) {
+        if (nfold == 0) fold_grid_bulk_launch<D, 0>(ps, m, r1, r2, mb, sm, st);
+        else if (nfold == 1) fold_grid_bulk_launch<D, 1>(ps, m, r1, r2, mb, sm, st);
+        else fold_grid_bulk_launch<D, 2>(ps, m, r1, r2, mb, sm, st);
+        return;
+    }
     if (ASYNC && m >= (1ull << ASYNC_MIN)) { // the ring pays off once the pass is bandwidth-bound
         if (nfold == 0) fold_grid_async_launch<D, 0>(ps, m, r1, r2, mb, sm, st);
         else if (nfold == 1) fold_grid_async_launch<D, 1>(ps, m, r1, r2, mb, sm, st);
@@ -952,6 +1160,179 @@ void launch_sum(const uint32_t *src, uint64_t n, const Mailbox &mb, int sm, cuda
 }
 
 // ---------------------------------------------------------------------------------------------
+// d = 1: several rounds per pass through linearity (see kernels.h). The CTAs sweep the table in grid-stride order (all
+// CTAs next to each other in every operand stream: one DRAM/TLB hot spot per stream, like the other fold kernels — a first
+// version that gave every CTA its own output block kept 32 x 32 spots open and reached 4.4-5.2 TB/s). Block sums: a
+// warp's 32 consecutive vectors always lie in one block (block length >= 128 elements), so the warp adds its running sum to
+// a shared-memory accumulator whenever its block changes; one global atomicAdd per CTA and block at the end.
+// ---------------------------------------------------------------------------------------------
+constexpr int LIN_NB = 1 << LIN_MAX_K;
+
+struct BlockAcc {
+    unsigned long long *sacc; // shared: LIN_NB accumulators
+    __device__ __forceinline__ void init(unsigned long long *sm) {
+        sacc = sm;
+        if (threadIdx.x < LIN_NB) sacc[threadIdx.x] = 0;
+        __syncthreads();
+    }
+    // warp-uniform block index
+    __device__ __forceinline__ void flush_warp(uint64_t b, unsigned long long s) {
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&sacc[b], s);
+    }
+    __device__ __forceinline__ void flush_lane(uint64_t b, unsigned long long s) {
+        if (s) atomicAdd(&sacc[b], s);
+    }
+    // all threads: CTA totals -> global accumulators; the last CTA publishes nb canonical sums (nb == 0: only the sequence number)
+    __device__ __forceinline__ void publish(int nb, const Mailbox &mb) {
+        __shared__ bool is_last;
+        __syncthreads();
+        if ((int)threadIdx.x < nb && sacc[threadIdx.x]) atomicAdd(&mb.acc[threadIdx.x], sacc[threadIdx.x]);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = (atomicAdd(mb.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (is_last && threadIdx.x < 32) {
+            __threadfence();
+            const int lane = threadIdx.x;
+            volatile unsigned long long *mail = (volatile unsigned long long *)mb.mail;
+            if (lane < nb) {
+                mail[lane] = atomicExch(&mb.acc[lane], 0ull) % bb::P; // read + re-arm
+                __threadfence_system();
+            }
+            __syncwarp();
+            if (lane == 0) {
+                *mb.ticket = 0u;
+                __threadfence_system();
+                mail[MAIL_WORDS] = mb.seq;
+            }
+        }
+    }
+};
+
+constexpr int LIN_TPB = 256;
+
+// n4 uint4 in the table, blocks of 2^logL4 uint4 each
+__global__ void __launch_bounds__(LIN_TPB) k_block_sums(const uint32_t *__restrict__ src, uint64_t n4, int logL4, int nb, Mailbox mb) {
+    __shared__ unsigned long long sm[LIN_NB];
+    BlockAcc acc;
+    acc.init(sm);
+    const uint4 *p = reinterpret_cast<const uint4 *>(src);
+    const uint64_t stride = (uint64_t)gridDim.x * LIN_TPB;
+    uint64_t i = (uint64_t)blockIdx.x * LIN_TPB + threadIdx.x;
+    while (i < n4) {
+        const uint64_t b = i >> logL4;
+        const uint64_t end = (b + 1) << logL4; // <= n4
+        unsigned long long s = 0;
+#pragma unroll 8
+        for (; i < end; i += stride) {
+            const uint4 v = p[i];
+            s += (unsigned long long)(v.x + v.y) + (unsigned long long)(v.z + v.w); // each pair < 2^32
+        }
+        if (logL4 >= 5) acc.flush_warp(b, s);
+        else acc.flush_lane(b, s);
+    }
+    acc.publish(nb, mb);
+}
+
+void launch_block_sums(const uint32_t *src, uint64_t n, int k, const Mailbox &mb, int sm, cudaStream_t st) {
+    static const int CPS = tune("ZB_BSUM_CPS", 8);
+    const uint64_t n4 = n / 4;
+    int logL4 = 0;
+    while ((1ull << (logL4 + k)) < n4) logL4++;
+    k_block_sums<<<grid_for(n4, sm, CPS), LIN_TPB, 0, st>>>(src, n4, logL4, 1 << k, mb);
+}
+
+// sum of <= 8 canonical values -> canonical: q = x >> 31 never exceeds floor(x / P) and x - q P < 2 P
+__device__ __forceinline__ uint32_t reduce_small(unsigned long long x) {
+    const uint32_t q = (uint32_t)(x >> 31);
+    const uint32_t r = (uint32_t)x - q * bb::P;
+    return min(r, r - bb::P);
+}
+
+template <int K, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_foldk_sums(const uint32_t *src, uint32_t *dst, uint64_t m4, int logL4, int nb,
+                                                          FoldWeights fw, unsigned long long *dump, Mailbox mb) {
+    constexpr int NT = 1 << K;
+    __shared__ unsigned long long sm[LIN_NB];
+    BlockAcc acc;
+    acc.init(sm);
+    const uint4 *p = reinterpret_cast<const uint4 *>(src);
+    uint4 *o = reinterpret_cast<uint4 *>(dst);
+    const uint64_t stride = (uint64_t)gridDim.x * TPB;
+    uint64_t i4 = (uint64_t)blockIdx.x * TPB + threadIdx.x;
+    while (i4 < m4) {
+        const uint64_t b = dump ? 0 : i4 >> logL4;
+        const uint64_t end = dump ? m4 : (b + 1) << logL4;
+        unsigned long long s = 0;
+        for (; i4 < end; i4 += stride) {
+            uint4 v[NT];
+#pragma unroll
+            for (int t = 0; t < NT; t++) v[t] = p[(uint64_t)t * m4 + i4];
+            uint32_t r[4];
+            if constexpr (K == 1) {
+                r[0] = bb::dot2(v[0].x, v[1].x, fw.w[0], fw.w[1]);
+                r[1] = bb::dot2(v[0].y, v[1].y, fw.w[0], fw.w[1]);
+                r[2] = bb::dot2(v[0].z, v[1].z, fw.w[0], fw.w[1]);
+                r[3] = bb::dot2(v[0].w, v[1].w, fw.w[0], fw.w[1]);
+            } else {
+                unsigned long long a[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int g = 0; g < NT / 4; g++) {
+                    const uint32_t w0 = fw.w[4 * g], w1 = fw.w[4 * g + 1], w2 = fw.w[4 * g + 2], w3 = fw.w[4 * g + 3];
+                    a[0] += bb::dot4(v[4 * g].x, v[4 * g + 1].x, v[4 * g + 2].x, v[4 * g + 3].x, w0, w1, w2, w3);
+                    a[1] += bb::dot4(v[4 * g].y, v[4 * g + 1].y, v[4 * g + 2].y, v[4 * g + 3].y, w0, w1, w2, w3);
+                    a[2] += bb::dot4(v[4 * g].z, v[4 * g + 1].z, v[4 * g + 2].z, v[4 * g + 3].z, w0, w1, w2, w3);
+                    a[3] += bb::dot4(v[4 * g].w, v[4 * g + 1].w, v[4 * g + 2].w, v[4 * g + 3].w, w0, w1, w2, w3);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) r[q] = NT == 4 ? (uint32_t)a[q] : reduce_small(a[q]);
+            }
+            o[i4] = make_uint4(r[0], r[1], r[2], r[3]);
+            if (dump != nullptr) {
+                volatile unsigned long long *d = (volatile unsigned long long *)dump + 4 * i4;
+                d[0] = r[0], d[1] = r[1], d[2] = r[2], d[3] = r[3];
+                __threadfence_system();
+            } else {
+                s += (unsigned long long)(r[0] + r[1]) + (unsigned long long)(r[2] + r[3]);
+            }
+        }
+        if (dump == nullptr) {
+            if (logL4 >= 5) acc.flush_warp(b, s);
+            else acc.flush_lane(b, s);
+        }
+    }
+    acc.publish(nb, mb);
+}
+
+template <int K>
+static void foldk_launch(const uint32_t *src, uint32_t *dst, uint64_t n, const FoldWeights &w, int k_next, unsigned long long *dump,
+                         const Mailbox &mb, int sm, cudaStream_t st) {
+    // K = 5 keeps 32 128-bit loads per thread in flight (128 data registers): 128 threads x 3 CTAs per SM
+    constexpr int TPB = K >= 5 ? 128 : 256, MINB = K >= 5 ? 3 : 2;
+    static const int CPS = tune("ZB_FOLDK_CPS", 2); // measured at 2^28 (r02_sweep2.txt): 2 -> 5228 GB/s, 3 -> 5082, 4 -> 4791
+    const uint64_t m4 = (n >> K) / 4;
+    const int nb = dump ? 0 : (1 << k_next);
+    int logL4 = 0;
+    if (!dump)
+        while ((1ull << (logL4 + k_next)) < m4) logL4++;
+    uint64_t need = (m4 + TPB - 1) / TPB, cap = (uint64_t)sm * CPS;
+    const int grid = (int)(need < cap ? need : cap);
+    k_foldk_sums<K, TPB, MINB><<<grid, TPB, 0, st>>>(src, dst, m4, logL4, nb, w, dump, mb);
+}
+
+void launch_foldk_sums(const uint32_t *src, uint32_t *dst, uint64_t n, int k, const FoldWeights &w, int k_next,
+                       unsigned long long *dump, const Mailbox &mb, int sm, cudaStream_t st) {
+    switch (k) {
+    case 1: foldk_launch<1>(src, dst, n, w, k_next, dump, mb, sm, st); break;
+    case 2: foldk_launch<2>(src, dst, n, w, k_next, dump, mb, sm, st); break;
+    case 3: foldk_launch<3>(src, dst, n, w, k_next, dump, mb, sm, st); break;
+    case 4: foldk_launch<4>(src, dst, n, w, k_next, dump, mb, sm, st); break;
+    default: foldk_launch<5>(src, dst, n, w, k_next, dump, mb, sm, st); break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Multilinear.eval, LSB-first. One stage folds NV <= 12 variables: a CTA folds a tile of 2^NV consecutive
 // elements to one value: 16 elements per thread in registers (4 variables), 5 variables by warp shuffle,
 // 3 variables through shared memory.
@@ -1028,6 +1409,102 @@ __global__ void __launch_bounds__(THREADS) k_eval_stage(const uint32_t *src, uin
     }
 }
 
+// The last stage(s) in ONE launch: every CTA folds tiles of 2^nv elements (as k_eval_stage does), and the last CTA to finish
+// (atomic ticket) folds the n_tiles = 2^nv2 (<= 256) partial results with the remaining variables and publishes the value —
+// instead of two launches of ~10 us each for the 2^18 leftovers of a 2^28-entry evaluation.
+__device__ __forceinline__ uint32_t cta_fold_tile(const uint32_t *base, uint64_t tile_elems, int nv, const EvalPoint &pt, uint32_t *sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t v = 0;
+    int var = 0;
+    if (nv >= 4) {
+        const uint64_t chunk = (uint64_t)threadIdx.x * 16;
+        uint32_t e[16];
+        if (chunk < tile_elems) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(base + chunk);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint4 q = __ldcg(p + j);
+                e[4 * j] = q.x;
+                e[4 * j + 1] = q.y;
+                e[4 * j + 2] = q.z;
+                e[4 * j + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) e[j] = 0;
+        }
+#pragma unroll
+        for (int lv = 0; lv < 4; lv++) {
+#pragma unroll
+            for (int j = 0; j < (8 >> lv); j++) e[j] = bb::lerp(e[2 * j], e[2 * j + 1], pt.r[lv], pt.rp[lv]);
+        }
+        v = e[0];
+        var = 4;
+    } else {
+        v = (threadIdx.x < tile_elems) ? __ldcg(base + threadIdx.x) : 0;
+    }
+#pragma unroll
+    for (int step = 0; step < 5; step++) {
+        uint32_t other = __shfl_down_sync(0xffffffffu, v, 1 << step);
+        if (var < nv) {
+            v = bb::lerp(v, other, pt.r[var], pt.rp[var]);
+            var++;
+        }
+    }
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    uint32_t res = 0;
+    if (threadIdx.x == 0) {
+        uint32_t w[THREADS / 32];
+#pragma unroll
+        for (int j = 0; j < THREADS / 32; j++) w[j] = sm[j];
+        int vv = var;
+#pragma unroll
+        for (int lv = 0; lv < 3; lv++) {
+            if (vv < nv) {
+#pragma unroll
+                for (int j = 0; j < (4 >> lv); j++) w[j] = bb::lerp(w[2 * j], w[2 * j + 1], pt.r[vv], pt.rp[vv]);
+                vv++;
+            }
+        }
+        res = w[0];
+    }
+    __syncthreads();
+    return res; // valid in thread 0
+}
+
+__global__ void __launch_bounds__(THREADS) k_eval_finish(const uint32_t *src, uint64_t n_tiles, int nv, EvalPoint pt, uint32_t *out, int nv2,
+                                                         EvalPoint pt2, Mailbox mb) {
+    __shared__ uint32_t sm[THREADS / 32];
+    __shared__ bool is_last;
+    const uint64_t tile_elems = 1ull << nv;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t v = cta_fold_tile(src + tile * tile_elems, tile_elems, nv, pt, sm);
+        if (threadIdx.x == 0) out[tile] = v;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = (atomicAdd(mb.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const uint32_t v = cta_fold_tile(out, n_tiles, nv2, pt2, sm);
+    if (threadIdx.x == 0) {
+        *mb.ticket = 0u;
+        ((volatile unsigned long long *)mb.mail)[0] = v;
+        __threadfence_system();
+        ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
+    }
+}
+
+void launch_eval_finish(const uint32_t *src, uint64_t n, int nv, const EvalPoint &pt, uint32_t *out, int nv2, const EvalPoint &pt2,
+                        const Mailbox &mb, int sm, cudaStream_t st) {
+    const uint64_t n_tiles = n >> nv;
+    const uint64_t cap = (uint64_t)sm * 8;
+    k_eval_finish<<<(int)(n_tiles < cap ? n_tiles : cap), THREADS, 0, st>>>(src, n_tiles, nv, pt, out, nv2, pt2, mb);
+}
+
 // Big stages: one WARP folds a tile of 1024 consecutive elements (10 variables) with fully coalesced 512-byte
 // loads and no block barrier. The multilinear extension is symmetric in the order variables are bound (exact
 // arithmetic), so the kernel binds them in the order the data arrives: bits 0,1 (inside a uint4), bits 7,8,9 (the
@@ -1075,8 +1552,87 @@ __global__ void __launch_bounds__(THREADS) k_eval_warp10(const uint32_t *__restr
     }
 }
 
+// The same stage with the tile fetched by ONE bulk copy per warp (cp.async.bulk, 4 KB) into a per-warp ring of shared-memory
+// stages; every warp is its own producer (lane 0 issues the copy for the tile ES stages ahead) and consumer (all lanes wait
+// on the stage's mbarrier, then read their 8 uint4 with conflict-free LDS.128): no register-staged loads, no block barrier,
+// ES x 4 KB per warp in flight at all times.
+template <int EVB_WARPS, int EVB_STAGES>
+__global__ void __launch_bounds__(EVB_WARPS * 32) k_eval_warp10_bulk(const uint32_t *__restrict__ src, uint64_t n_tiles, EvalPoint pt,
+                                                                        uint32_t *__restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint4 *ring = reinterpret_cast<uint4 *>(smem_raw) + (size_t)wib * EVB_STAGES * 256; // [stage][256 uint4]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)EVB_WARPS * EVB_STAGES * 4096) + wib * EVB_STAGES;
+    if (lane == 0) {
+        for (int st = 0; st < EVB_STAGES; st++) blk::mbar_init(&full[st], 1);
+        blk::fence_barrier_init();
+    }
+    __syncwarp();
+    const uint64_t warp = (uint64_t)blockIdx.x * EVB_WARPS + wib, n_warps = (uint64_t)gridDim.x * EVB_WARPS;
+    const uint64_t cnt = warp < n_tiles ? (n_tiles - warp + n_warps - 1) / n_warps : 0;
+    auto issue = [&](uint64_t it) { // lane 0 only
+        const int st = (int)(it % EVB_STAGES);
+        blk::mbar_expect_tx(&full[st], 4096);
+        blk::g2s(ring + (size_t)st * 256, src + (warp + it * n_warps) * 1024, 4096, &full[st]);
+    };
+    if (lane == 0)
+        for (uint64_t it = 0; it < (uint64_t)(EVB_STAGES - 1) && it < cnt; it++) issue(it);
+    for (uint64_t it = 0; it < cnt; it++) {
+        const int st = (int)(it % EVB_STAGES);
+        if (lane == 0 && it + EVB_STAGES - 1 < cnt) {
+            blk::fence_proxy_async(); // the stage being refilled was read (generic proxy) one iteration ago
+            issue(it + EVB_STAGES - 1);
+        }
+        blk::mbar_wait(&full[st], (uint32_t)(it / EVB_STAGES) & 1);
+        const uint4 *tile = ring + (size_t)st * 256 + lane;
+        uint32_t e[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint4 v = tile[32 * j];
+            const uint32_t a = bb::lerp(v.x, v.y, pt.r[0], pt.rp[0]);
+            const uint32_t b = bb::lerp(v.z, v.w, pt.r[0], pt.rp[0]);
+            e[j] = bb::lerp(a, b, pt.r[1], pt.rp[1]);
+        }
+#pragma unroll
+        for (int lv = 0; lv < 3; lv++) {
+#pragma unroll
+            for (int j = 0; j < (4 >> lv); j++) e[j] = bb::lerp(e[2 * j], e[2 * j + 1], pt.r[7 + lv], pt.rp[7 + lv]);
+        }
+        uint32_t x = e[0];
+#pragma unroll
+        for (int step = 0; step < 5; step++) {
+            uint32_t other = __shfl_down_sync(0xffffffffu, x, 1 << step);
+            x = bb::lerp(x, other, pt.r[2 + step], pt.rp[2 + step]);
+        }
+        if (lane == 0) out[warp + it * n_warps] = x;
+        // the shuffles above are warp-wide: every lane has consumed its LDS results before lane 0 refills this stage
+    }
+}
+
 void launch_eval_warp10(const uint32_t *src, uint64_t n, const EvalPoint &pt, uint32_t *out, int sm, cudaStream_t st) {
     const uint64_t n_tiles = n >> 10;
+    // measured at 2^28 (profiles/r02_sweep2.txt): plain loads 6250 GB/s; bulk ring 8 warps x 6 stages 4698, 16 x 3 6654,
+    // 4 x 6 (2 CTAs/SM) 4753, 8 x 3 (2 CTAs/SM) 6444, 32 x 1 6705, 16 x 2 6848 <- default
+    static const int BULK = tune("ZB_EVAL_BULK", 6);
+    auto bulk = [&](auto warps_c, auto stages_c, int per_sm) {
+        constexpr int W = decltype(warps_c)::value, S = decltype(stages_c)::value;
+        constexpr int SMEM = W * S * 4096 + W * S * 8;
+        static const bool once = [] {
+            cudaFuncSetAttribute(k_eval_warp10_bulk<W, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+            return true;
+        }();
+        (void)once;
+        uint64_t ctas = (n_tiles + W - 1) / W;
+        if (ctas > (uint64_t)sm * per_sm) ctas = (uint64_t)sm * per_sm;
+        k_eval_warp10_bulk<W, S><<<(int)(ctas ? ctas : 1), W * 32, SMEM, st>>>(src, n_tiles, pt, out);
+    };
+    using std::integral_constant;
+    if (BULK == 1) return bulk(integral_constant<int, 8>{}, integral_constant<int, 6>{}, 1);
+    if (BULK == 2) return bulk(integral_constant<int, 16>{}, integral_constant<int, 3>{}, 1);
+    if (BULK == 3) return bulk(integral_constant<int, 4>{}, integral_constant<int, 6>{}, 2);
+    if (BULK == 4) return bulk(integral_constant<int, 8>{}, integral_constant<int, 3>{}, 2);
+    if (BULK == 5) return bulk(integral_constant<int, 32>{}, integral_constant<int, 1>{}, 1);
+    if (BULK == 6) return bulk(integral_constant<int, 16>{}, integral_constant<int, 2>{}, 1);
     static const int UT = tune("ZB_EVAL_UT", 2);
     static const int CPS = tune("ZB_EVAL_CPS", 2);
     const uint64_t warps_needed = (n_tiles + UT - 1) / UT;
