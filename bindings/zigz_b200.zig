@@ -112,6 +112,11 @@ pub fn sumcheckProve(comptime F: type, comptime protocol: type, ctx: *Ctx, evalu
 }
 
 // ---- generated from include/*.h by tools/gen_zig_externs.py (do not edit below) ----
+pub extern fn zb_ctx_create_mask(device_mask: u32, out: [*c]*Ctx) i32;
+pub extern fn zb_group_size(ctx: *Ctx) i32;
+pub extern fn zb_group_run(ctx: *Ctx, fn_: *const fn (*Ctx, i32, i32, ?*anyopaque) callconv(.C) i32, user: ?*anyopaque) i32;
+pub extern fn zb_group_mle(ctx: *Ctx, h: Mle, rank: i32, out: [*c]Mle) i32;
+pub extern fn zb_group_mle_set_len(ctx: *Ctx, h: Mle, n: u64) i32;
 pub extern fn zb_status_name(status: i32) [*:0]const u8;
 pub extern fn zb_kernel_launches(ctx: *Ctx) u64;
 pub extern fn zb_host_alloc(ctx: *Ctx, bytes: usize, out: [*c]?*anyopaque) i32;

@@ -61,7 +61,24 @@ enum zb_status {
 
 /* ---- context ---- */
 int32_t zb_ctx_create(int32_t device, zb_ctx **out);
+/* One context over SEVERAL GPUs of this process (`device_mask` selects 1/2/4/8 GPUs; bit d = device d).
+ * No NCCL, no CUDA IPC, no second process: the library enables peer access between the devices, runs one host thread per
+ * device, and the kernels exchange their per-round partial sums through each other's memory over NVLink.
+ * On such a context zb_mle_upload / _upload_u32 / _synthetic / _constant create SHARDED tables (cyclic layout: GPU = low index
+ * bits, so every MSB-first fold pair is local), and zb_mle_free / _len / _download / _sum / _eval, zb_merkle_build / _open /
+ * _info / _free, zh_sumcheck_prove*, zh_prodcheck_prove*, zh_commit*, zh_generate_commitments accept them: same results, bit for
+ * bit, as on one GPU. Tables need >= world^2 entries. Every other entry point keeps working on plain (single-GPU) handles of
+ * the first selected device. A mask with one bit is zb_ctx_create. */
+int32_t zb_ctx_create_mask(uint32_t device_mask, zb_ctx **out);
 void zb_ctx_destroy(zb_ctx *ctx);
+/* number of devices behind ctx (1 for an ordinary context) */
+int32_t zb_group_size(zb_ctx *ctx);
+/* for host twins: run fn(rank's context, rank, world, user) once per device, concurrently, each on its own host thread;
+ * returns the first failing status. zb_group_mle: rank's shard of a sharded table, as a handle of that rank's context. */
+typedef int32_t (*zb_rank_fn)(zb_ctx *rank_ctx, int32_t rank, int32_t world, void *user);
+int32_t zb_group_run(zb_ctx *ctx, zb_rank_fn fn, void *user);
+int32_t zb_group_mle(zb_ctx *ctx, zb_mle h, int32_t rank, zb_mle *out);
+int32_t zb_group_mle_set_len(zb_ctx *ctx, zb_mle h, uint64_t n);
 const char *zb_last_error(zb_ctx *ctx);
 const char *zb_status_name(int32_t status);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */

@@ -17,7 +17,8 @@ from zigz_b200 import _cabi  # noqa: E402
 ZIG = os.path.join(ROOT, "bindings", "zigz_b200.zig")
 MARK = "// ---- generated from include/*.h by tools/gen_zig_externs.py (do not edit below) ----"
 BASE = {"int32_t": "i32", "int64_t": "i64", "uint32_t": "u32", "uint64_t": "u64", "size_t": "usize", "int": "c_int",
-        "uint8_t": "u8", "zb_mle": "Mle", "zb_tree": "Tree", "float": "f32", "double": "f64", "char": "u8"}
+        "uint8_t": "u8", "zb_mle": "Mle", "zb_tree": "Tree", "float": "f32", "double": "f64", "char": "u8",
+        "zb_rank_fn": "*const fn (*Ctx, i32, i32, ?*anyopaque) callconv(.C) i32"}
 OPAQUE = {"zb_ctx": "Ctx", "zh_transcript": "Transcript"}
 KEYWORDS = {"error", "type", "test", "var", "const", "fn", "align", "union", "struct", "enum", "opaque", "export", "extern"}
 

@@ -19,7 +19,7 @@ HEADERS = [os.path.join(ROOT, "include", "zigz_b200.h"), os.path.join(ROOT, "inc
 _CTYPES = {
     "int32_t": C.c_int32, "int64_t": C.c_int64, "uint32_t": C.c_uint32, "uint64_t": C.c_uint64, "size_t": C.c_size_t, "int": C.c_int,
     "uint8_t": C.c_uint8, "zb_mle": C.c_uint64, "zb_tree": C.c_uint64, "void": None, "char": C.c_char, "float": C.c_float,
-    "double": C.c_double,
+    "double": C.c_double, "zb_rank_fn": C.c_void_p,  # callback pointer (host twins only)
 }
 _OPAQUE = {"zb_ctx", "zh_transcript"}
 

@@ -44,12 +44,21 @@ def _b8(b: bytes):
 class Context:
     """One GPU + one stream; calls are synchronous and serialized like the single-threaded reference."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, device_mask: Optional[int] = None):
+        """device: one GPU. device_mask (bit d = GPU d, 2/4/8 bits): ONE context over several GPUs of this process
+        (zb_ctx_create_mask): tables are sharded, provers and commitments run on all of them, results are unchanged."""
         self._h = C.c_void_p()
-        rc = lib().zb_ctx_create(device, C.byref(self._h))
+        if device_mask is not None:
+            rc = lib().zb_ctx_create_mask(device_mask, C.byref(self._h))
+        else:
+            rc = lib().zb_ctx_create(device, C.byref(self._h))
         if rc != 0:
             self._h = None
             raise ZigzError(rc, "zb_ctx_create: a CUDA device is required, there is no CPU fallback")
+
+    @property
+    def n_devices(self) -> int:
+        return int(lib().zb_group_size(self._h))
 
     def check(self, rc: int):
         if rc != 0:

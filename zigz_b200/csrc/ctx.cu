@@ -6,10 +6,15 @@
 #include "bb.cuh"
 #include "hostpack.hpp"
 #include "kernels.h"
+#include "sha3_host.hpp"
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <functional>
+#include <immintrin.h>
+#include <mutex>
 #include <cstdlib>
 #include <dlfcn.h>
 #include <cstring>
@@ -148,6 +153,11 @@ struct zb_ctx {
     void *xchg_peer[16] = {nullptr};
     XchgView *d_xchg_view = nullptr;
     unsigned long long *d_xchg_stats = nullptr; // {wait cycles, exchanged rounds}
+    // single-process multi-GPU (zb_ctx_create_mask): the contexts of one process that form a communicator without NCCL
+    // or CUDA IPC share a LocalComm (host barrier + pointer exchange for the peer-memory collectives); the FRONT context
+    // (rank 0, the one handed to the caller) additionally owns the group: children, worker threads, sharded handles
+    std::shared_ptr<struct LocalComm> local;
+    struct Group *group = nullptr;
     unsigned long long xchg_seq = 0;
 
     Mailbox mailbox() {
@@ -163,6 +173,56 @@ struct zb_ctx {
     uint8_t *h_bulk() { return (uint8_t *)h_mail + BULK_OFFSET; }
     uint8_t *d_bulk() { return (uint8_t *)d_mail + BULK_OFFSET; }
 };
+
+// ---- single-process multi-GPU ----
+struct LocalComm {
+    int world = 1;
+    std::atomic<int> count{0};
+    std::atomic<int> sense{0};
+    const void *ptr[XCHG_MAX_RANKS] = {nullptr};
+    // sense-reversing barrier between the ranks' host threads (every rank calls it the same number of times)
+    void barrier() {
+        const int s = sense.load(std::memory_order_acquire);
+        if (count.fetch_add(1, std::memory_order_acq_rel) == world - 1) {
+            count.store(0, std::memory_order_relaxed);
+            sense.store(s ^ 1, std::memory_order_release);
+        } else {
+            while (sense.load(std::memory_order_acquire) == s) _mm_pause();
+        }
+    }
+};
+struct GMle { // one table sharded CYCLICALLY over the group's GPUs (rank = low index bits)
+    zb_mle child[XCHG_MAX_RANKS];
+    uint64_t n; // total length
+};
+struct GTree { // one Merkle tree sharded by contiguous subtree
+    zb_tree child[XCHG_MAX_RANKS];
+    uint64_t n_values;
+    uint32_t height;
+    std::vector<uint8_t> top; // the top log2(world) levels: (2 world - 1) digests, level l (width world >> l) at offset 2 world - (2 world >> l)
+    uint8_t root[32];
+};
+struct Group {
+    int world = 1;
+    zb_ctx *child[XCHG_MAX_RANKS] = {nullptr}; // child[0] is the front context itself
+    std::vector<std::thread> workers;          // ranks 1 .. world-1; rank 0 runs on the calling thread
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    std::function<int32_t(int)> job;
+    uint64_t epoch = 0;
+    int pending = 0;
+    bool stop = false;
+    int32_t status[XCHG_MAX_RANKS] = {0};
+    std::unordered_map<uint64_t, GMle> mles;
+    std::unordered_map<uint64_t, GTree> trees;
+    uint64_t next_handle = 1;
+};
+constexpr uint64_t GROUP_HANDLE_BIT = 1ull << 63;
+static thread_local bool t_in_group_job = false; // inside a per-rank job the front context is just rank 0's context
+static inline bool group_front(const zb_ctx *c) { return c->group != nullptr && !t_in_group_job; }
+static inline bool is_group_handle(uint64_t h) { return (h & GROUP_HANDLE_BIT) != 0; }
+// runs job(rank) once per rank, concurrently (rank 0 on the calling thread); returns the first failing status
+static int32_t group_run(zb_ctx *front, const std::function<int32_t(int)> &job);
 
 namespace {
 
@@ -276,7 +336,7 @@ int32_t comm_publish(zb_ctx *ctx, unsigned long long seq, int nwords); // define
 
 // Mailbox for a kernel whose payload must be summed over the ranks: the kernel writes into the device exchange
 // buffer, comm_publish() then all-reduces it in stream order and publishes the reduced words to the host mailbox.
-inline bool reduce_on_device(const zb_ctx *c) { return c->comm_reduce && c->world > 1 && c->nccl_comm; }
+inline bool reduce_on_device(const zb_ctx *c) { return c->comm_reduce && c->world > 1 && (c->nccl_comm || c->local); }
 inline bool reduce_p2p(const zb_ctx *c) { return c->comm_reduce == 2 && c->d_xchg_view; }
 inline Mailbox round_mailbox(zb_ctx *c, bool reduce) {
     Mailbox m = c->mailbox();
@@ -612,6 +672,20 @@ int32_t upload_narrow(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32_t *d
 
 } // namespace
 
+// multi-device context: operations on sharded tables / trees (defined at the end of this file)
+template <typename T>
+static int32_t zg_upload(zb_ctx *front, const T *evals, uint64_t n, zb_mle *out);
+static int32_t group_make_mle(zb_ctx *front, uint64_t n_total, zb_mle *out, const std::function<int32_t(int, zb_ctx *, zb_mle *)> &make);
+static int32_t zg_mle_free(zb_ctx *front, zb_mle h);
+static int32_t zg_mle_download(zb_ctx *front, zb_mle h, uint64_t offset, uint64_t *out, uint64_t n);
+static int32_t zg_mle_eval(zb_ctx *front, zb_mle h, const uint64_t *point, uint32_t npoint, uint64_t *out);
+static int32_t zg_mle_sum(zb_ctx *front, zb_mle h, uint64_t *out);
+static int32_t zg_merkle_build(zb_ctx *front, const zb_mle *polys, uint32_t count, zb_tree *trees, uint8_t *roots);
+static int32_t zg_merkle_open(zb_ctx *front, zb_tree h, uint64_t index, uint8_t *siblings, uint8_t *dirs, uint64_t *leaf_value);
+static int32_t zg_merkle_free(zb_ctx *front, zb_tree h);
+static GMle *get_gmle(zb_ctx *front, zb_mle h);
+static GTree *get_gtree(zb_ctx *front, zb_tree h);
+
 extern "C" {
 
 const char *zb_status_name(int32_t s) {
@@ -706,6 +780,19 @@ int32_t zb_ctx_create(int32_t device, zb_ctx **out) {
 
 void zb_ctx_destroy(zb_ctx *ctx) {
     if (!ctx) return;
+    if (ctx->group) { // multi-device front: stop the rank threads, then the other ranks' contexts, then this one
+        Group *g = ctx->group;
+        ctx->group = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g->mu);
+            g->stop = true;
+        }
+        g->cv_go.notify_all();
+        for (auto &t : g->workers) t.join();
+        for (int r = 0; r < g->world; r++) cudaStreamSynchronize(g->child[r]->stream);
+        for (int r = g->world - 1; r >= 1; r--) zb_ctx_destroy(g->child[r]);
+        delete g;
+    }
     cudaSetDevice(ctx->device);
     if (ctx->h_chal && ctx->stream) tail_quiesce(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -735,16 +822,32 @@ void zb_ctx_destroy(zb_ctx *ctx) {
 }
 
 const char *zb_last_error(zb_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
-uint64_t zb_kernel_launches(zb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t zb_kernel_launches(zb_ctx *ctx) {
+    if (!ctx) return 0;
+    uint64_t n = ctx->launches;
+    if (group_front(ctx))
+        for (int r = 1; r < ctx->group->world; r++) n += ctx->group->child[r]->launches;
+    return n;
+}
 void *zb_stream(zb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int32_t zb_sync(zb_ctx *ctx) {
+    if (group_front(ctx))
+        for (int r = 1; r < ctx->group->world; r++) {
+            const int32_t rc = zb_sync(ctx->group->child[r]);
+            if (rc) return rc;
+        }
     tail_quiesce(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     return ZB_OK;
 }
 
 int32_t zb_set_option(zb_ctx *ctx, const char *key, int64_t value) {
+    if (group_front(ctx)) // the same setting on every rank's context
+        for (int r = 1; r < ctx->group->world; r++) {
+            const int32_t rc = zb_set_option(ctx->group->child[r], key, value);
+            if (rc) return rc;
+        }
     tail_quiesce(ctx);
     if (key && !strcmp(key, "tail_log2")) {
         if (value < 0 || value > 20) return ZB_ERR_BAD_ARGUMENT;
@@ -974,6 +1077,7 @@ int32_t zb_device_info(zb_ctx *ctx, int32_t *sm_count, uint64_t *total_mem, uint
 /* ------------------------------------------------------------------ Multilinear */
 
 int32_t zb_mle_upload(zb_ctx *ctx, const uint64_t *evals, uint64_t n, zb_mle *out) {
+    if (group_front(ctx)) return zg_upload<uint64_t>(ctx, evals, n, out);
     tail_quiesce(ctx);
     int32_t rc = check_pow2(n);
     if (rc) return rc;
@@ -990,6 +1094,7 @@ int32_t zb_mle_upload(zb_ctx *ctx, const uint64_t *evals, uint64_t n, zb_mle *ou
 }
 
 int32_t zb_mle_upload_u32(zb_ctx *ctx, const uint32_t *evals, uint64_t n, zb_mle *out) {
+    if (group_front(ctx)) return zg_upload<uint32_t>(ctx, evals, n, out);
     tail_quiesce(ctx);
     int32_t rc = check_pow2(n);
     if (rc) return rc;
@@ -1017,6 +1122,13 @@ int32_t zb_mle_upload_u32(zb_ctx *ctx, const uint32_t *evals, uint64_t n, zb_mle
 }
 
 int32_t zb_mle_constant(zb_ctx *ctx, uint32_t num_vars, uint64_t value, zb_mle *out) {
+    if (group_front(ctx)) {
+        uint32_t k = 0;
+        while ((1 << k) < ctx->group->world) k++;
+        if (num_vars < 2 * k || num_vars > 40 || !out) return ZB_ERR_BAD_ARGUMENT;
+        return group_make_mle(ctx, 1ull << num_vars, out,
+                              [&](int, zb_ctx *c, zb_mle *h) { return zb_mle_constant(c, num_vars - k, value, h); });
+    }
     tail_quiesce(ctx);
     if (num_vars > 40 || value >= bb::P || !out) return value >= bb::P ? ZB_ERR_NOT_CANONICAL : ZB_ERR_BAD_ARGUMENT;
     Mle *m = nullptr;
@@ -1031,6 +1143,13 @@ int32_t zb_mle_constant(zb_ctx *ctx, uint32_t num_vars, uint64_t value, zb_mle *
 }
 
 int32_t zb_mle_synthetic(zb_ctx *ctx, uint64_t seed, uint64_t start, uint64_t stride, uint64_t n, zb_mle *out) {
+    if (group_front(ctx)) { // rank r generates its cyclic shard: global elements r, r + P, r + 2 P, ...
+        const uint64_t P = (uint64_t)ctx->group->world;
+        if (check_pow2(n) || n < P * P || !out) return check_pow2(n) ? check_pow2(n) : ZB_ERR_BAD_ARGUMENT;
+        return group_make_mle(ctx, n, out, [&](int r, zb_ctx *c, zb_mle *h) {
+            return zb_mle_synthetic(c, seed, start + (uint64_t)r * stride, stride * P, n / P, h);
+        });
+    }
     tail_quiesce(ctx);
     int32_t rc = check_pow2(n);
     if (rc) return rc;
@@ -1064,12 +1183,20 @@ int32_t zb_mle_clone(zb_ctx *ctx, zb_mle src, zb_mle *out) {
 }
 
 int32_t zb_mle_free(zb_ctx *ctx, zb_mle h) {
+    if (group_front(ctx) && is_group_handle(h)) return zg_mle_free(ctx, h);
     tail_quiesce(ctx);
     if (!ctx->mles.erase(h)) return ZB_ERR_BAD_HANDLE;
     return ZB_OK;
 }
 
 int32_t zb_mle_len(zb_ctx *ctx, zb_mle h, uint64_t *n, uint32_t *num_vars) {
+    if (group_front(ctx) && is_group_handle(h)) {
+        GMle *gm = get_gmle(ctx, h);
+        if (!gm) return ZB_ERR_BAD_HANDLE;
+        if (n) *n = gm->n;
+        if (num_vars) *num_vars = (uint32_t)__builtin_ctzll(gm->n);
+        return ZB_OK;
+    }
     Mle *m = get_mle(ctx, h);
     if (!m) return ZB_ERR_BAD_HANDLE;
     if (n) *n = m->n;
@@ -1080,6 +1207,7 @@ int32_t zb_mle_len(zb_ctx *ctx, zb_mle h, uint64_t *n, uint32_t *num_vars) {
 int32_t zb_mle_download(zb_ctx *ctx, zb_mle h, uint64_t *out, uint64_t n) { return zb_mle_download_range(ctx, h, 0, out, n); }
 
 int32_t zb_mle_download_range(zb_ctx *ctx, zb_mle h, uint64_t offset, uint64_t *out, uint64_t n) {
+    if (group_front(ctx) && is_group_handle(h)) return zg_mle_download(ctx, h, offset, out, n);
     tail_quiesce(ctx);
     Mle *m = get_mle(ctx, h);
     if (!m) return ZB_ERR_BAD_HANDLE;
@@ -1140,6 +1268,7 @@ int32_t zb_host_mirror(zb_ctx *ctx, size_t bytes, void **out) {
 }
 
 int32_t zb_mle_sum(zb_ctx *ctx, zb_mle h, uint64_t *out) {
+    if (group_front(ctx) && is_group_handle(h)) return zg_mle_sum(ctx, h, out);
     tail_quiesce(ctx);
     Mle *m = get_mle(ctx, h);
     if (!m) return ZB_ERR_BAD_HANDLE;
@@ -1230,6 +1359,7 @@ int32_t zb_mle_fold_inplace(zb_ctx *ctx, zb_mle h, uint64_t r, uint64_t next[2])
 }
 
 int32_t zb_mle_eval(zb_ctx *ctx, zb_mle h, const uint64_t *point, uint32_t npoint, uint64_t *out) {
+    if (group_front(ctx) && is_group_handle(h)) return zg_mle_eval(ctx, h, point, npoint, out);
     tail_quiesce(ctx);
     Mle *m = get_mle(ctx, h);
     if (!m) return ZB_ERR_BAD_HANDLE;
@@ -1897,6 +2027,7 @@ static int32_t new_tree(zb_ctx *ctx, BufRef values, uint64_t n_values, zb_tree *
 }
 
 int32_t zb_merkle_build(zb_ctx *ctx, const zb_mle *polys, uint32_t count, zb_tree *trees, uint8_t *roots) {
+    if (group_front(ctx) && polys && count && is_group_handle(polys[0])) return zg_merkle_build(ctx, polys, count, trees, roots);
     tail_quiesce(ctx);
     if (!polys || !trees || count == 0) return ZB_ERR_BAD_ARGUMENT;
     uint64_t n0 = 0;
@@ -1970,6 +2101,14 @@ int32_t zb_merkle_build_values(zb_ctx *ctx, const uint64_t *values, uint64_t n, 
 }
 
 int32_t zb_merkle_info(zb_ctx *ctx, zb_tree h, uint64_t *n_values, uint32_t *height, uint8_t root[32]) {
+    if (group_front(ctx) && is_group_handle(h)) {
+        GTree *gt = get_gtree(ctx, h);
+        if (!gt) return ZB_ERR_BAD_HANDLE;
+        if (n_values) *n_values = gt->n_values;
+        if (height) *height = gt->height;
+        if (root) memcpy(root, gt->root, 32);
+        return ZB_OK;
+    }
     Tree *t = get_tree(ctx, h);
     if (!t) return ZB_ERR_BAD_HANDLE;
     if (n_values) *n_values = t->n_values;
@@ -1979,6 +2118,7 @@ int32_t zb_merkle_info(zb_ctx *ctx, zb_tree h, uint64_t *n_values, uint32_t *hei
 }
 
 int32_t zb_merkle_open(zb_ctx *ctx, zb_tree h, uint64_t index, uint8_t *siblings, uint8_t *dirs, uint64_t *leaf_value) {
+    if (group_front(ctx) && is_group_handle(h)) return zg_merkle_open(ctx, h, index, siblings, dirs, leaf_value);
     tail_quiesce(ctx);
     Tree *t = get_tree(ctx, h);
     if (!t) return ZB_ERR_BAD_HANDLE;
@@ -2015,6 +2155,7 @@ int32_t zb_merkle_leaf_hashes(zb_ctx *ctx, zb_tree h, uint8_t *out, uint64_t n_d
 }
 
 int32_t zb_merkle_free(zb_ctx *ctx, zb_tree h) {
+    if (group_front(ctx) && is_group_handle(h)) return zg_merkle_free(ctx, h);
     tail_quiesce(ctx);
     if (!ctx->trees.erase(h)) return ZB_ERR_BAD_HANDLE;
     return ZB_OK;
@@ -2246,6 +2387,28 @@ int32_t zb_comm_allgather_cyclic(zb_ctx *ctx, zb_mle local, zb_mle *out) {
     Mle *m = get_mle(ctx, local);
     if (!m || !out) return m ? ZB_ERR_BAD_ARGUMENT : ZB_ERR_BAD_HANDLE;
     if (ctx->world == 1) return zb_mle_clone(ctx, local, out);
+    if (ctx->local) { // same process: every rank reads the peers' shards directly over NVLink
+        const uint64_t n = m->n;
+        const uint32_t *mine = m->d();
+        BufRef keep = m->buf;
+        Mle *o = nullptr;
+        int32_t rc = new_mle(ctx, n * ctx->world, out, &o);
+        ctx->local->ptr[ctx->rank] = mine;
+        ctx->local->barrier();
+        if (rc == ZB_OK) {
+            PeerSrc ps{};
+            for (int q = 0; q < ctx->world; q++) ps.p[q] = (const uint32_t *)ctx->local->ptr[q];
+            launch_interleave_peers(ps, o->d(), n, (uint32_t)ctx->world, ctx->sm_count, ctx->stream);
+            rc = check_launch(ctx, "interleave_peers");
+            if (rc == ZB_OK) rc = zb_sync(ctx);
+        }
+        ctx->local->barrier(); // the peers have finished reading this rank's shard
+        if (rc && *out) {
+            ctx->mles.erase(*out);
+            *out = 0;
+        }
+        return rc;
+    }
     if (!ctx->nccl_comm) return ZB_ERR_BAD_ARGUMENT;
     const uint64_t n = m->n;
     BufRef src = m->buf, tmp;
@@ -2349,8 +2512,11 @@ int32_t zb_comm_init(zb_ctx *ctx, const char *nccl_path, const uint8_t unique_id
 }
 
 int32_t zb_comm_info(zb_ctx *ctx, int32_t *rank, int32_t *world) {
-    if (rank) *rank = ctx->rank;
-    if (world) *world = ctx->world;
+    // the front of a multi-device context acts as an ordinary one-GPU context for plain handles; it is rank 0 of the
+    // group only inside a per-rank job
+    const bool plain = group_front(ctx);
+    if (rank) *rank = plain ? 0 : ctx->rank;
+    if (world) *world = plain ? 1 : ctx->world;
     return ZB_OK;
 }
 
@@ -2397,6 +2563,426 @@ int32_t zb_comm_destroy(zb_ctx *ctx) {
         ctx->rank = 0;
         ctx->world = 1;
     }
+    return ZB_OK;
+}
+
+/* ------------------------------------------------------------------ single-process multi-GPU (zb_ctx_create_mask) */
+
+} // extern "C"
+
+static void group_worker(Group *g, int rank) {
+    cudaSetDevice(g->child[rank]->device);
+    t_in_group_job = true;
+    uint64_t seen = 0;
+    for (;;) {
+        std::unique_lock<std::mutex> lk(g->mu);
+        g->cv_go.wait(lk, [&] { return g->stop || g->epoch != seen; });
+        if (g->stop) return;
+        seen = g->epoch;
+        lk.unlock();
+        const int32_t rc = g->job(rank);
+        lk.lock();
+        g->status[rank] = rc;
+        if (--g->pending == 0) g->cv_done.notify_one();
+    }
+}
+
+static int32_t group_run(zb_ctx *front, const std::function<int32_t(int)> &job) {
+    Group *g = front->group;
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->job = job;
+        g->pending = g->world - 1;
+        g->epoch++;
+    }
+    g->cv_go.notify_all();
+    t_in_group_job = true;
+    const int32_t rc0 = job(0);
+    t_in_group_job = false;
+    {
+        std::unique_lock<std::mutex> lk(g->mu);
+        g->cv_done.wait(lk, [&] { return g->pending == 0; });
+    }
+    ensure_device(front);
+    if (rc0) return rc0;
+    for (int r = 1; r < g->world; r++)
+        if (g->status[r]) {
+            front->last_error = "rank " + std::to_string(r) + ": " + g->child[r]->last_error;
+            return g->status[r];
+        }
+    return ZB_OK;
+}
+
+static GMle *get_gmle(zb_ctx *front, zb_mle h) {
+    auto it = front->group->mles.find(h);
+    return it == front->group->mles.end() ? nullptr : &it->second;
+}
+static GTree *get_gtree(zb_ctx *front, zb_tree h) {
+    auto it = front->group->trees.find(h);
+    return it == front->group->trees.end() ? nullptr : &it->second;
+}
+static int32_t group_unsupported(zb_ctx *front, const char *what) {
+    front->last_error = std::string(what) + ": not available on a multi-device context (use one context per device for it)";
+    return ZB_ERR_BAD_ARGUMENT;
+}
+static uint32_t log2_world(int world) {
+    uint32_t k = 0;
+    while ((1 << k) < world) k++;
+    return k;
+}
+// registers a sharded table made of per-rank tables h[r]
+static zb_mle group_new_mle(zb_ctx *front, const zb_mle *h, uint64_t n_total) {
+    GMle gm{};
+    for (int r = 0; r < front->group->world; r++) gm.child[r] = h[r];
+    gm.n = n_total;
+    const uint64_t id = GROUP_HANDLE_BIT | front->group->next_handle++;
+    front->group->mles[id] = gm;
+    return id;
+}
+static void group_free_children(zb_ctx *front, const zb_mle *h) {
+    Group *g = front->group;
+    group_run(front, [&](int r) { return h[r] ? zb_mle_free(g->child[r], h[r]) : ZB_OK; });
+}
+
+// Every rank creates its cyclic shard with `make(rank, child ctx, &handle)`
+static int32_t group_make_mle(zb_ctx *front, uint64_t n_total, zb_mle *out, const std::function<int32_t(int, zb_ctx *, zb_mle *)> &make) {
+    Group *g = front->group;
+    zb_mle h[XCHG_MAX_RANKS] = {0};
+    const int32_t rc = group_run(front, [&](int r) { return make(r, g->child[r], &h[r]); });
+    if (rc) {
+        group_free_children(front, h);
+        return rc;
+    }
+    *out = group_new_mle(front, h, n_total);
+    return ZB_OK;
+}
+
+// Host order -> cyclic shards: rank b uploads the CONTIGUOUS slice [b B, (b+1) B) of the host table over its own PCIe link
+// (every link carries 1/world of the table exactly once, narrowed to 4 bytes on the way), then deals it out over NVLink:
+// element j P + q of the slice is local element b B/P + j of rank q's shard (push, 128-byte coalesced peer stores).
+template <typename T>
+static int32_t zg_upload(zb_ctx *front, const T *evals, uint64_t n, zb_mle *out) {
+    Group *g = front->group;
+    const uint64_t P = (uint64_t)g->world;
+    int32_t rc = check_pow2(n);
+    if (rc) return rc;
+    if (!evals || !out) return ZB_ERR_BAD_ARGUMENT;
+    if (n < P * P) return group_unsupported(front, "a table with fewer than world^2 entries");
+    const uint64_t B = n / P;
+    zb_mle shard[XCHG_MAX_RANKS] = {0};
+    rc = group_run(front, [&](int r) -> int32_t {
+        zb_ctx *ctx = g->child[r];
+        tail_quiesce(ctx);
+        Mle *m = nullptr;
+        int32_t e = new_mle(ctx, B, &shard[r], &m); // (no early return below: every rank must reach both barriers)
+        BufRef slice;
+        if (e == ZB_OK) e = dev_alloc(ctx, B * sizeof(uint32_t), &slice);
+        if (e == ZB_OK) {
+            if constexpr (sizeof(T) == 8) e = upload_narrow(ctx, (const uint64_t *)evals + (uint64_t)r * B, B, (uint32_t *)slice->ptr);
+            else {
+                e = staged_h2d(ctx, slice->ptr, evals + (uint64_t)r * B, B * sizeof(uint32_t));
+                if (e == ZB_OK) {
+                    launch_check_u32((const uint32_t *)slice->ptr, B, ctx->d_err, ctx->stream);
+                    e = check_launch(ctx, "check");
+                }
+                if (e == ZB_OK) e = read_err_flag(ctx);
+            }
+        }
+        ctx->local->ptr[r] = m ? m->d() : nullptr;
+        ctx->local->barrier(); // every rank's shard exists and its address is known (also on a failure: keep the ranks in step)
+        bool all = true;
+        for (uint64_t q = 0; q < P; q++) all = all && ctx->local->ptr[q] != nullptr;
+        if (e == ZB_OK && !all) e = ZB_ERR_OOM; // a peer could not allocate its shard: nobody deals
+        if (e == ZB_OK) {
+            PeerDst pd{};
+            for (uint64_t q = 0; q < P; q++) pd.p[q] = (uint32_t *)ctx->local->ptr[q] + (uint64_t)r * (B / P);
+            launch_deal_peers((const uint32_t *)slice->ptr, pd, B / P, (uint32_t)P, ctx->sm_count, ctx->stream);
+            e = check_launch(ctx, "deal_peers");
+            if (e == ZB_OK) e = zb_sync(ctx);
+        }
+        ctx->local->barrier(); // all pushes have landed before anybody uses (or frees) a shard
+        return e;
+    });
+    if (rc) {
+        group_free_children(front, shard);
+        return rc;
+    }
+    *out = group_new_mle(front, shard, n);
+    return ZB_OK;
+}
+
+static int32_t zg_mle_free(zb_ctx *front, zb_mle h) {
+    GMle *gm = get_gmle(front, h);
+    if (!gm) return ZB_ERR_BAD_HANDLE;
+    zb_mle c[XCHG_MAX_RANKS];
+    memcpy(c, gm->child, sizeof(c));
+    front->group->mles.erase(h);
+    group_free_children(front, c);
+    return ZB_OK;
+}
+
+static int32_t zg_mle_download(zb_ctx *front, zb_mle h, uint64_t offset, uint64_t *out, uint64_t n) {
+    GMle *gm = get_gmle(front, h);
+    if (!gm) return ZB_ERR_BAD_HANDLE;
+    if (offset > gm->n || n > gm->n - offset || !out) return ZB_ERR_BAD_ARGUMENT;
+    Group *g = front->group;
+    const uint64_t P = (uint64_t)g->world, nl = gm->n / P;
+    std::vector<std::vector<uint64_t>> tmp(P);
+    int32_t rc = group_run(front, [&](int r) {
+        tmp[r].resize(nl);
+        return zb_mle_download(g->child[r], gm->child[r], tmp[r].data(), nl);
+    });
+    if (rc) return rc;
+    for (uint64_t i = 0; i < n; i++) out[i] = tmp[(offset + i) % P][(offset + i) / P];
+    return ZB_OK;
+}
+
+// Multilinear.eval on cyclic shards (LSB-first: the rank is index bits 0 .. log2 P - 1, bound by point[0 .. log2 P)):
+// value = sum_r eq(point[0..k), r) * eval_r(point[k..v))
+static int32_t zg_mle_eval(zb_ctx *front, zb_mle h, const uint64_t *point, uint32_t npoint, uint64_t *out) {
+    GMle *gm = get_gmle(front, h);
+    if (!gm) return ZB_ERR_BAD_HANDLE;
+    Group *g = front->group;
+    const uint32_t v = (uint32_t)__builtin_ctzll(gm->n), k = log2_world(g->world);
+    if (npoint != v) return ZB_ERR_WRONG_NUM_VARS;
+    for (uint32_t i = 0; i < v; i++)
+        if (point[i] >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    uint64_t part[XCHG_MAX_RANKS] = {0};
+    int32_t rc = group_run(front, [&](int r) { return zb_mle_eval(g->child[r], gm->child[r], point + k, v - k, &part[r]); });
+    if (rc) return rc;
+    uint32_t acc = 0;
+    for (int r = 0; r < g->world; r++) {
+        uint32_t w = 1;
+        for (uint32_t b = 0; b < k; b++) w = bb::mul(w, ((r >> b) & 1) ? (uint32_t)point[b] : bb::sub(1u, (uint32_t)point[b]));
+        acc = bb::add(acc, bb::mul(w, (uint32_t)part[r]));
+    }
+    *out = acc;
+    return ZB_OK;
+}
+
+static int32_t zg_mle_sum(zb_ctx *front, zb_mle h, uint64_t *out) {
+    GMle *gm = get_gmle(front, h);
+    if (!gm || !out) return gm ? ZB_ERR_BAD_ARGUMENT : ZB_ERR_BAD_HANDLE;
+    Group *g = front->group;
+    uint64_t part[XCHG_MAX_RANKS] = {0};
+    int32_t rc = group_run(front, [&](int r) { return zb_mle_sum(g->child[r], gm->child[r], &part[r]); });
+    if (rc) return rc;
+    uint64_t s = 0;
+    for (int r = 0; r < g->world; r++) s += part[r];
+    *out = s % bb::P;
+    return ZB_OK;
+}
+
+// SimpleMerkleTree.build for sharded tables: rank r gathers the CONTIGUOUS block [r B, (r+1) B) out of the cyclic shards
+// over NVLink (the tree's own copy of the values, merkle_tree.zig:291), builds that subtree, and the host hashes the
+// log2(world) levels above the world subtree roots (mergeHashesSHA3, hash.zig:187-195).
+static int32_t zg_merkle_build(zb_ctx *front, const zb_mle *polys, uint32_t count, zb_tree *trees, uint8_t *roots) {
+    Group *g = front->group;
+    const uint64_t P = (uint64_t)g->world;
+    if (!polys || !trees || count == 0) return ZB_ERR_BAD_ARGUMENT;
+    std::vector<GMle *> gms(count);
+    for (uint32_t i = 0; i < count; i++) {
+        gms[i] = is_group_handle(polys[i]) ? get_gmle(front, polys[i]) : nullptr;
+        if (!gms[i]) return ZB_ERR_BAD_HANDLE;
+        if (gms[i]->n != gms[0]->n) return ZB_ERR_DIFFERENT_NUM_VARS;
+    }
+    const uint64_t n = gms[0]->n, B = n / P;
+    if (B < P) return group_unsupported(front, "a table with fewer than world^2 entries");
+    std::vector<std::vector<zb_tree>> ct(P, std::vector<zb_tree>(count, 0));
+    std::vector<std::vector<uint8_t>> croots(P, std::vector<uint8_t>(32 * (size_t)count));
+    int32_t rc = group_run(front, [&](int r) -> int32_t {
+        zb_ctx *ctx = g->child[r];
+        int32_t e = ZB_OK;
+        std::vector<zb_mle> blocks(count, 0);
+        for (uint32_t i = 0; i < count; i++) {
+            tail_quiesce(ctx);
+            Mle *bm = nullptr;
+            if (e == ZB_OK) e = new_mle(ctx, B, &blocks[i], &bm);
+            Mle *mine = get_mle(ctx, gms[i]->child[r]);
+            ctx->local->ptr[r] = mine ? mine->d() : nullptr;
+            ctx->local->barrier();
+            if (e == ZB_OK && !mine) e = ZB_ERR_BAD_HANDLE;
+            if (e == ZB_OK) {
+                PeerSrc ps{};
+                for (uint64_t q = 0; q < P; q++) ps.p[q] = (const uint32_t *)ctx->local->ptr[q] + (uint64_t)r * (B / P);
+                launch_interleave_peers(ps, bm->d(), B / P, (uint32_t)P, ctx->sm_count, ctx->stream);
+                e = check_launch(ctx, "interleave_peers");
+                if (e == ZB_OK) e = zb_sync(ctx);
+            }
+            ctx->local->barrier(); // nobody's shard pointer slot is overwritten while a peer still reads it
+        }
+        if (e == ZB_OK) e = zb_merkle_build(ctx, blocks.data(), count, ct[r].data(), croots[r].data());
+        for (uint32_t i = 0; i < count; i++)
+            if (blocks[i]) zb_mle_free(ctx, blocks[i]); // the trees hold their own copies
+        return e;
+    });
+    if (rc) {
+        group_run(front, [&](int r) {
+            for (uint32_t i = 0; i < count; i++)
+                if (ct[r][i]) zb_merkle_free(g->child[r], ct[r][i]);
+            return ZB_OK;
+        });
+        return rc;
+    }
+    const uint32_t k = log2_world(g->world);
+    for (uint32_t i = 0; i < count; i++) {
+        GTree gt{};
+        gt.n_values = n;
+        gt.height = (uint32_t)__builtin_ctzll(n);
+        gt.top.assign((2 * P - 1) * 32, 0);
+        for (uint64_t r = 0; r < P; r++) {
+            gt.child[r] = ct[r][i];
+            memcpy(&gt.top[32 * r], &croots[r][32 * (size_t)i], 32);
+        }
+        for (uint32_t l = 0; l < k; l++) {
+            const uint64_t in = 2 * P - (2 * P >> l), outo = 2 * P - (2 * P >> (l + 1));
+            for (uint64_t j = 0; j < (P >> (l + 1)); j++) zigz::Sha3_256::hash(&gt.top[32 * (in + 2 * j)], 64, &gt.top[32 * (outo + j)]);
+        }
+        memcpy(gt.root, &gt.top[32 * (2 * P - 2)], 32);
+        if (roots) memcpy(roots + 32 * (size_t)i, gt.root, 32);
+        const uint64_t id = GROUP_HANDLE_BIT | g->next_handle++;
+        g->trees[id] = gt;
+        trees[i] = id;
+    }
+    return ZB_OK;
+}
+
+static int32_t zg_merkle_open(zb_ctx *front, zb_tree h, uint64_t index, uint8_t *siblings, uint8_t *dirs, uint64_t *leaf_value) {
+    GTree *gt = get_gtree(front, h);
+    if (!gt) return ZB_ERR_BAD_HANDLE;
+    if (index >= gt->n_values) return ZB_ERR_INDEX_OUT_OF_BOUNDS; // merkle_tree.zig:325
+    Group *g = front->group;
+    const uint64_t P = (uint64_t)g->world, B = gt->n_values / P;
+    const uint32_t k = log2_world(g->world), hl = gt->height - k;
+    const uint64_t owner = index / B;
+    // the owner's context serves the path inside its subtree (a plain call from this thread: contexts are thread-agnostic)
+    int32_t rc = zb_merkle_open(g->child[owner], gt->child[owner], index % B, siblings, dirs, leaf_value);
+    ensure_device(front);
+    if (rc) return rc;
+    for (uint32_t l = 0; l < k; l++) { // :341-345 continued above the subtree roots
+        const uint64_t pos = owner >> l, off = 2 * P - (2 * P >> l);
+        memcpy(siblings + 32 * (size_t)(hl + l), &gt->top[32 * (off + (pos ^ 1))], 32);
+        dirs[hl + l] = (uint8_t)(pos & 1);
+    }
+    return ZB_OK;
+}
+
+static int32_t zg_merkle_free(zb_ctx *front, zb_tree h) {
+    GTree *gt = get_gtree(front, h);
+    if (!gt) return ZB_ERR_BAD_HANDLE;
+    Group *g = front->group;
+    zb_tree c[XCHG_MAX_RANKS];
+    memcpy(c, gt->child, sizeof(c));
+    g->trees.erase(h);
+    group_run(front, [&](int r) { return zb_merkle_free(g->child[r], c[r]); });
+    return ZB_OK;
+}
+
+extern "C" {
+
+int32_t zb_ctx_create_mask(uint32_t device_mask, zb_ctx **out) {
+    if (!out) return ZB_ERR_BAD_ARGUMENT;
+    *out = nullptr;
+    int devs[XCHG_MAX_RANKS], world = 0;
+    for (int d = 0; d < 32; d++)
+        if ((device_mask >> d) & 1u) {
+            if (world == XCHG_MAX_RANKS) return ZB_ERR_BAD_ARGUMENT;
+            devs[world++] = d;
+        }
+    if (world == 0 || (world & (world - 1))) return ZB_ERR_BAD_ARGUMENT; // 1, 2, 4, 8 or 16 devices
+    if (world == 1) return zb_ctx_create(devs[0], out);
+    zb_ctx *c[XCHG_MAX_RANKS] = {nullptr};
+    auto fail = [&](int32_t rc) {
+        for (int r = world - 1; r >= 0; r--)
+            if (c[r]) {
+                c[r]->group = nullptr;
+                zb_ctx_destroy(c[r]);
+            }
+        return rc;
+    };
+    for (int r = 0; r < world; r++) {
+        const int32_t rc = zb_ctx_create(devs[r], &c[r]);
+        if (rc) return fail(rc);
+    }
+    // peer access between every pair (NVLink / NVSwitch): kernels of one GPU read and write the others' memory directly
+    for (int r = 0; r < world; r++) {
+        cudaSetDevice(devs[r]);
+        for (int q = 0; q < world; q++) {
+            if (q == r) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devs[r], devs[q]);
+            if (!can) {
+                c[0]->last_error = "no peer access between the selected devices";
+                fprintf(stderr, "zigz_b200: device %d cannot access device %d\n", devs[r], devs[q]);
+                return fail(ZB_ERR_CUDA);
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devs[q], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ZB_ERR_CUDA);
+            cudaGetLastError();
+        }
+    }
+    auto lc = std::make_shared<LocalComm>();
+    lc->world = world;
+    const size_t xbytes = 2 * XCHG_SET_WORDS * sizeof(unsigned long long);
+    for (int r = 0; r < world; r++) {
+        cudaSetDevice(devs[r]);
+        c[r]->local = lc;
+        c[r]->rank = r;
+        c[r]->world = world;
+        if (cudaMalloc(&c[r]->d_xchg, xbytes) != cudaSuccess || cudaMemset(c[r]->d_xchg, 0, xbytes) != cudaSuccess) return fail(ZB_ERR_OOM);
+        if (cudaMalloc(&c[r]->d_xchg_stats, 2 * sizeof(unsigned long long)) != cudaSuccess) return fail(ZB_ERR_OOM);
+        cudaMemset(c[r]->d_xchg_stats, 0, 2 * sizeof(unsigned long long));
+    }
+    for (int r = 0; r < world; r++) {
+        cudaSetDevice(devs[r]);
+        XchgView view{};
+        view.rank = r;
+        view.world = world;
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, devs[r]);
+        view.patience = (long long)(30.0 * 1e3 * (khz > 0 ? khz : 1965000));
+        view.stats = c[r]->d_xchg_stats;
+        for (int q = 0; q < world; q++) view.peer[q] = c[q]->d_xchg; // plain device pointers: one address space, peer access on
+        if (cudaMalloc(&c[r]->d_xchg_view, sizeof(XchgView)) != cudaSuccess) return fail(ZB_ERR_OOM);
+        cudaMemcpy(c[r]->d_xchg_view, &view, sizeof(XchgView), cudaMemcpyHostToDevice);
+    }
+    Group *g = new Group();
+    g->world = world;
+    for (int r = 0; r < world; r++) g->child[r] = c[r];
+    c[0]->group = g;
+    for (int r = 1; r < world; r++) g->workers.emplace_back(group_worker, g, r);
+    cudaSetDevice(devs[0]);
+    *out = c[0];
+    return ZB_OK;
+}
+
+/* how many device contexts stand behind ctx (1 for an ordinary context) */
+int32_t zb_group_size(zb_ctx *ctx) { return ctx && ctx->group ? ctx->group->world : 1; }
+
+/* host twins: run fn(rank's context, rank, world, user) once per device of a multi-device context, concurrently, each on
+ * the thread that owns that device; returns the first failing status. On an ordinary context: fn(ctx, 0, 1, user). */
+int32_t zb_group_run(zb_ctx *ctx, zb_rank_fn fn, void *user) {
+    if (!ctx || !fn) return ZB_ERR_BAD_ARGUMENT;
+    if (!group_front(ctx)) return fn(ctx, ctx->rank, ctx->world, user);
+    Group *g = ctx->group;
+    return group_run(ctx, [&](int r) { return fn(g->child[r], r, g->world, user); });
+}
+
+/* rank's shard of a sharded table (a handle of that rank's context) */
+int32_t zb_group_mle(zb_ctx *ctx, zb_mle h, int32_t rank, zb_mle *out) {
+    if (!ctx || !ctx->group || !out || rank < 0 || rank >= ctx->group->world) return ZB_ERR_BAD_ARGUMENT;
+    auto it = ctx->group->mles.find(h);
+    if (it == ctx->group->mles.end()) return ZB_ERR_BAD_HANDLE;
+    *out = it->second.child[rank];
+    return ZB_OK;
+}
+
+/* after a consuming prove the shards have been folded away: the sharded table shrinks to `n` entries in total */
+int32_t zb_group_mle_set_len(zb_ctx *ctx, zb_mle h, uint64_t n) {
+    if (!ctx || !ctx->group) return ZB_ERR_BAD_ARGUMENT;
+    auto it = ctx->group->mles.find(h);
+    if (it == ctx->group->mles.end()) return ZB_ERR_BAD_HANDLE;
+    it->second.n = n;
     return ZB_OK;
 }
 

@@ -433,6 +433,54 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
     return ZB_OK;
 }
 
+// Multi-device context (zb_ctx_create_mask): the tables are sharded cyclically over the GPUs; every rank's host thread
+// runs the SAME round loop on its own shard (prove_rounds with world > 1: per-round partial sums exchanged inside the
+// kernels over NVLink, identical transcripts on every rank), rank 0 writes the caller's buffers.
+namespace {
+constexpr uint64_t GROUP_HANDLE_BIT = 1ull << 63;
+struct GroupProve {
+    zb_ctx *front;
+    const zb_mle *polys;
+    uint32_t d, v;
+    bool consume;
+    const uint64_t *fixed;
+    uint64_t *round_polys, *final_point, *final_evals, *claimed_sum;
+};
+int32_t group_prove_rank(zb_ctx *c, int32_t rank, int32_t, void *user) {
+    GroupProve *j = static_cast<GroupProve *>(user);
+    zb_mle h[3] = {0, 0, 0};
+    for (uint32_t k = 0; k < j->d; k++) {
+        const int32_t rc = zb_group_mle(j->front, j->polys[k], rank, &h[k]);
+        if (rc) return rc;
+    }
+    if (rank == 0) return prove_rounds(c, h, j->d, j->consume, j->fixed, j->round_polys, j->final_point, j->final_evals, j->claimed_sum);
+    std::vector<uint64_t> rp((size_t)j->v * (j->d + 1)), fp(j->v);
+    uint64_t fe[3], cs = 0;
+    return prove_rounds(c, h, j->d, j->consume, j->fixed, rp.data(), fp.data(), fe, &cs);
+}
+bool on_group(zb_ctx *ctx, const zb_mle *polys) { return zb_group_size(ctx) > 1 && polys && (polys[0] & GROUP_HANDLE_BIT); }
+int32_t group_prove(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool consume, const uint64_t *fixed, uint64_t *round_polys,
+                    uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum) {
+    if (d < 1 || d > 3) return ZB_ERR_BAD_ARGUMENT;
+    uint64_t n = 0;
+    uint32_t v = 0;
+    int32_t rc = zb_mle_len(ctx, polys[0], &n, &v);
+    if (rc) return rc;
+    if (v == 0) return ZB_ERR_NO_VARIABLES;
+    for (uint32_t k = 1; k < d; k++) {
+        uint64_t nk = 0;
+        rc = zb_mle_len(ctx, polys[k], &nk, nullptr);
+        if (rc) return rc;
+        if (nk != n) return ZB_ERR_DIFFERENT_NUM_VARS;
+    }
+    GroupProve job{ctx, polys, d, v, consume, fixed, round_polys, final_point, final_evals, claimed_sum};
+    rc = zb_group_run(ctx, group_prove_rank, &job);
+    if (rc == ZB_OK && consume) // the shards were folded away in place; what is left of them is not a table of the caller's any more
+        for (uint32_t k = 0; k < d; k++) zb_group_mle_set_len(ctx, polys[k], (uint64_t)zb_group_size(ctx));
+    return rc;
+}
+} // namespace
+
 int32_t zh_set_grid_min_log2(int32_t v) {
     const int32_t old = grid_min_log2();
     g_grid_min_log2.store(v < 0 ? 0 : v, std::memory_order_relaxed);
@@ -441,6 +489,7 @@ int32_t zh_set_grid_min_log2(int32_t v) {
 
 int32_t zh_sumcheck_prove(zb_ctx *ctx, zb_mle poly, uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval,
                           uint64_t *claimed_sum) {
+    if (on_group(ctx, &poly)) return group_prove(ctx, &poly, 1, false, nullptr, round_polys, final_point, final_eval, claimed_sum);
     return prove_rounds(ctx, &poly, 1, false, nullptr, round_polys, final_point, final_eval, claimed_sum);
 }
 
@@ -454,6 +503,7 @@ int32_t zh_sumcheck_prove_interactive(zb_ctx *ctx, zb_mle poly, const uint64_t *
     if (n_challenges != v) return ZB_ERR_WRONG_NUM_CHALLENGES;    // :105-107
     for (uint32_t i = 0; i < v; i++)
         if (challenges[i] >= P) return ZB_ERR_NOT_CANONICAL;
+    if (on_group(ctx, &poly)) return group_prove(ctx, &poly, 1, false, challenges, round_polys, final_point, final_eval, nullptr);
     return prove_rounds(ctx, &poly, 1, false, challenges, round_polys, final_point, final_eval, nullptr);
 }
 
@@ -472,11 +522,13 @@ size_t zh_sumcheck_proof_to_bytes(uint32_t v, const uint64_t *round_polys, const
 
 int32_t zh_prodcheck_prove(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *round_polys, uint64_t *final_point,
                            uint64_t *final_evals, uint64_t *claimed_sum) {
+    if (on_group(ctx, polys)) return group_prove(ctx, polys, d, false, nullptr, round_polys, final_point, final_evals, claimed_sum);
     return prove_rounds(ctx, polys, d, false, nullptr, round_polys, final_point, final_evals, claimed_sum);
 }
 
 int32_t zh_prodcheck_prove_consume(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *round_polys, uint64_t *final_point,
                                    uint64_t *final_evals, uint64_t *claimed_sum) {
+    if (on_group(ctx, polys)) return group_prove(ctx, polys, d, true, nullptr, round_polys, final_point, final_evals, claimed_sum);
     return prove_rounds(ctx, polys, d, true, nullptr, round_polys, final_point, final_evals, claimed_sum);
 }
 

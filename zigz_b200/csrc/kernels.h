@@ -76,6 +76,18 @@ void launch_publish_reduced(const unsigned long long *src, int n, unsigned long 
 // multi-GPU: all-gathered cyclic shards [rank][j] -> global order out[rank + world * j]
 void launch_interleave(const uint32_t *gathered, uint32_t *out, uint64_t n_local, uint32_t world, cudaStream_t st);
 
+// single-process multi-GPU: peer-memory transposes between the cyclic (sumcheck) and contiguous (host order / Merkle) layouts
+struct PeerSrc {
+    const uint32_t *p[XCHG_MAX_RANKS];
+};
+struct PeerDst {
+    uint32_t *p[XCHG_MAX_RANKS];
+};
+// out[j * world + q] = src.p[q][j], j < n_local (reads the peers)
+void launch_interleave_peers(const PeerSrc &src, uint32_t *out, uint64_t n_local, uint32_t world, int sm_count, cudaStream_t st);
+// dst.p[q][j] = src[j * world + q], j < n_out (writes into the peers)
+void launch_deal_peers(const uint32_t *src, const PeerDst &dst, uint64_t n_out, uint32_t world, int sm_count, cudaStream_t st);
+
 // Two rounds per pass. With the top two index bits of the (possibly folded) tables as variables (X, Y), the bivariate
 //   G(X, Y) = sum_i prod_k B_k,i(X, Y),   B bilinear through the four quarter elements,
 // holds BOTH next round polynomials: g(X) = G(X, 0) + G(X, 1) and, once r is known, g'(Y) = G(r, Y). One pass over the

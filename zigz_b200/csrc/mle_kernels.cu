@@ -10,6 +10,7 @@
 #include "bb.cuh"
 #include "kernels.h"
 
+#include <atomic>
 #include <cstdlib>
 #include <type_traits>
 
@@ -23,6 +24,19 @@ static int tune(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
 }
+
+// Opt-in dynamic shared memory is a per-DEVICE function attribute: a process that drives several GPUs (zb_ctx_create_mask)
+// must set it once on each of them.
+#define ENSURE_DYN_SMEM(kernel, bytes)                                                                 \
+    do {                                                                                               \
+        static std::atomic<unsigned> done_{0};                                                         \
+        int dev_ = 0;                                                                                  \
+        cudaGetDevice(&dev_);                                                                          \
+        if (!((done_.load(std::memory_order_acquire) >> (dev_ & 31)) & 1u)) {                          \
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);          \
+            done_.fetch_or(1u << (dev_ & 31), std::memory_order_release);                              \
+        }                                                                                              \
+    } while (0)
 
 static inline int grid_for(uint64_t work_items, int sm_count, int ctas_per_sm) {
     uint64_t need = (work_items + THREADS - 1) / THREADS;
@@ -809,11 +823,7 @@ __global__ void __launch_bounds__(TPB + 32, 1) k_fold_grid_bulk(PolySet ps, uint
 template <int D, int FV, int STAGES_, int TPB>
 static void fold_grid_bulk_launch_s(const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
     using G = GridBulk<D, FV, STAGES_, TPB>;
-    static const bool once = [] {
-        cudaFuncSetAttribute(k_fold_grid_bulk<D, FV, STAGES_, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-        return true;
-    }();
-    (void)once;
+    ENSURE_DYN_SMEM((k_fold_grid_bulk<D, FV, STAGES_, TPB>), G::SMEM);
     const uint64_t mq = m / 8, n_tiles = mq / TPB;
     const int grid = (int)(n_tiles < (uint64_t)sm ? n_tiles : (uint64_t)sm);
     const FoldArgs fa = fold_args<FV>(r1, r2);
@@ -837,11 +847,7 @@ static void fold_grid_bulk_launch(const PolySet &ps, uint64_t m, uint32_t r1, ui
 template <int D, int FV, int STAGES_, int TPB, bool DOT = false>
 static void fold_grid_async_launch_s(const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, const Mailbox &mb, int sm, cudaStream_t st) {
     using G = GridAsync<D, FV, STAGES_, TPB>;
-    static const bool once = [] {
-        cudaFuncSetAttribute(k_fold_grid_async<D, FV, STAGES_, TPB, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-        return true;
-    }();
-    (void)once;
+    ENSURE_DYN_SMEM((k_fold_grid_async<D, FV, STAGES_, TPB, DOT>), G::SMEM);
     const uint64_t mq = m / 8;
     int per_sm = (227 * 1024) / (G::SMEM + 2048);
     if (per_sm < 1) per_sm = 1;
@@ -1086,6 +1092,45 @@ void launch_interleave(const uint32_t *gathered, uint32_t *out, uint64_t n_local
 }
 
 
+// ---- single-process multi-GPU (zb_ctx_create_mask): tables move between the GPUs' layouts through peer memory ----
+// pull: out[j * world + q] = src_q[j] (j < n_local): every warp reads 128 contiguous bytes from each peer over NVLink,
+// the interleave happens in shared memory, the local writes are fully coalesced. Serves the all-gather of cyclic shards
+// and the cyclic -> contiguous-block transpose in front of a sharded Merkle build.
+constexpr int PEER_J = 256;
+__global__ void __launch_bounds__(PEER_J) k_interleave_peers(PeerSrc ps, uint32_t *out, uint64_t n_local, uint32_t world) {
+    extern __shared__ uint32_t sm_peer[]; // [PEER_J * world]
+    for (uint64_t j0 = (uint64_t)blockIdx.x * PEER_J; j0 < n_local; j0 += (uint64_t)gridDim.x * PEER_J) {
+        const uint64_t j = j0 + threadIdx.x;
+        for (uint32_t q = 0; q < world; q++) sm_peer[threadIdx.x * world + q] = j < n_local ? ps.p[q][j] : 0u;
+        __syncthreads();
+        const uint64_t cnt = (n_local - j0 < PEER_J ? n_local - j0 : PEER_J) * world;
+        for (uint64_t k = threadIdx.x; k < cnt; k += PEER_J) out[j0 * world + k] = sm_peer[k];
+        __syncthreads();
+    }
+}
+void launch_interleave_peers(const PeerSrc &ps, uint32_t *out, uint64_t n_local, uint32_t world, int sm, cudaStream_t st) {
+    uint64_t g = (n_local + PEER_J - 1) / PEER_J, cap = (uint64_t)sm * 8;
+    k_interleave_peers<<<(int)(g < cap ? (g ? g : 1) : cap), PEER_J, PEER_J * world * sizeof(uint32_t), st>>>(ps, out, n_local, world);
+}
+// push: dst_q[j] = src[j * world + q] (j < n_out): coalesced local reads, 128-byte coalesced stores into every peer.
+// Serves the host-order (contiguous block per GPU) -> cyclic-shard deal after an upload.
+__global__ void __launch_bounds__(PEER_J) k_deal_peers(const uint32_t *src, PeerDst pd, uint64_t n_out, uint32_t world) {
+    extern __shared__ uint32_t sm_peer[];
+    for (uint64_t j0 = (uint64_t)blockIdx.x * PEER_J; j0 < n_out; j0 += (uint64_t)gridDim.x * PEER_J) {
+        const uint64_t cnt = (n_out - j0 < PEER_J ? n_out - j0 : PEER_J) * world;
+        for (uint64_t k = threadIdx.x; k < cnt; k += PEER_J) sm_peer[k] = src[j0 * world + k];
+        __syncthreads();
+        const uint64_t j = j0 + threadIdx.x;
+        if (j < n_out)
+            for (uint32_t q = 0; q < world; q++) pd.p[q][j] = sm_peer[threadIdx.x * world + q];
+        __syncthreads();
+    }
+}
+void launch_deal_peers(const uint32_t *src, const PeerDst &pd, uint64_t n_out, uint32_t world, int sm, cudaStream_t st) {
+    uint64_t g = (n_out + PEER_J - 1) / PEER_J, cap = (uint64_t)sm * 8;
+    k_deal_peers<<<(int)(g < cap ? (g ? g : 1) : cap), PEER_J, PEER_J * world * sizeof(uint32_t), st>>>(src, pd, n_out, world);
+}
+
 template <int D>
 static void round_sums_t(const PolySet &ps, uint64_t n, const Mailbox &mb, int sm, cudaStream_t st) {
     uint64_t h = n / 2;
@@ -1184,28 +1229,31 @@ struct BlockAcc {
         if (s) atomicAdd(&sacc[b], s);
     }
     // all threads: CTA totals -> global accumulators; the last CTA publishes nb canonical sums (nb == 0: only the sequence number)
+    // nb == 0 (a table was published instead of sums): the CTA's host-mapped stores are made visible by ONE system
+    // fence of thread 0 behind the CTA barrier (fences are cumulative) instead of one per thread.
     __device__ __forceinline__ void publish(int nb, const Mailbox &mb) {
         __shared__ bool is_last;
         __syncthreads();
-        if ((int)threadIdx.x < nb && sacc[threadIdx.x]) atomicAdd(&mb.acc[threadIdx.x], sacc[threadIdx.x]);
-        __threadfence();
+        if ((int)threadIdx.x < nb && sacc[threadIdx.x]) {
+            atomicAdd(&mb.acc[threadIdx.x], sacc[threadIdx.x]);
+            __threadfence();
+        }
         __syncthreads();
-        if (threadIdx.x == 0) is_last = (atomicAdd(mb.ticket, 1u) == gridDim.x - 1);
+        if (threadIdx.x == 0) {
+            if (nb == 0) __threadfence_system();
+            else __threadfence();
+            is_last = (atomicAdd(mb.ticket, 1u) == gridDim.x - 1);
+        }
         __syncthreads();
         if (is_last && threadIdx.x < 32) {
             __threadfence();
             const int lane = threadIdx.x;
             volatile unsigned long long *mail = (volatile unsigned long long *)mb.mail;
-            if (lane < nb) {
-                mail[lane] = atomicExch(&mb.acc[lane], 0ull) % bb::P; // read + re-arm
-                __threadfence_system();
-            }
+            if (lane < nb) mail[lane] = atomicExch(&mb.acc[lane], 0ull) % bb::P; // read + re-arm
+            if (lane == 0) *mb.ticket = 0u;
+            __threadfence_system(); // one fence: payload (all lanes) before the sequence number
             __syncwarp();
-            if (lane == 0) {
-                *mb.ticket = 0u;
-                __threadfence_system();
-                mail[MAIL_WORDS] = mb.seq;
-            }
+            if (lane == 0) mail[MAIL_WORDS] = mb.seq;
         }
     }
 };
@@ -1213,16 +1261,21 @@ struct BlockAcc {
 constexpr int LIN_TPB = 256;
 
 // n4 uint4 in the table, blocks of 2^logL4 uint4 each
-__global__ void __launch_bounds__(LIN_TPB) k_block_sums(const uint32_t *__restrict__ src, uint64_t n4, int logL4, int nb, Mailbox mb) {
+// chunk4 == 0: grid-stride order (large tables). chunk4 > 0 (small, L2-resident tables): CTA c owns the contiguous vectors
+// [c chunk4, (c+1) chunk4), so a thread's loads stay inside one block and are all in flight together.
+__global__ void __launch_bounds__(LIN_TPB) k_block_sums(const uint32_t *__restrict__ src, uint64_t n4, int logL4, int nb, uint64_t chunk4,
+                                                        Mailbox mb) {
     __shared__ unsigned long long sm[LIN_NB];
     BlockAcc acc;
     acc.init(sm);
     const uint4 *p = reinterpret_cast<const uint4 *>(src);
-    const uint64_t stride = (uint64_t)gridDim.x * LIN_TPB;
-    uint64_t i = (uint64_t)blockIdx.x * LIN_TPB + threadIdx.x;
-    while (i < n4) {
+    const uint64_t stride = chunk4 ? LIN_TPB : (uint64_t)gridDim.x * LIN_TPB;
+    uint64_t i = (chunk4 ? (uint64_t)blockIdx.x * chunk4 : (uint64_t)blockIdx.x * LIN_TPB) + threadIdx.x;
+    const uint64_t limit = chunk4 && (blockIdx.x + 1) * chunk4 < n4 ? (blockIdx.x + 1) * chunk4 : n4;
+    while (i < limit) {
         const uint64_t b = i >> logL4;
-        const uint64_t end = (b + 1) << logL4; // <= n4
+        const uint64_t bend = (b + 1) << logL4; // <= n4
+        const uint64_t end = bend < limit ? bend : limit;
         unsigned long long s = 0;
 #pragma unroll 8
         for (; i < end; i += stride) {
@@ -1240,7 +1293,14 @@ void launch_block_sums(const uint32_t *src, uint64_t n, int k, const Mailbox &mb
     const uint64_t n4 = n / 4;
     int logL4 = 0;
     while ((1ull << (logL4 + k)) < n4) logL4++;
-    k_block_sums<<<grid_for(n4, sm, CPS), LIN_TPB, 0, st>>>(src, n4, logL4, 1 << k, mb);
+    // small tables: at least 8 loads per thread (all in flight together) instead of one CTA per 256 vectors — the pass is
+    // latency-bound there and every CTA costs a ticket atomic
+    const uint64_t cap = (uint64_t)sm * CPS, chunk4 = 8 * LIN_TPB;
+    if (n4 <= cap * chunk4) {
+        k_block_sums<<<(int)((n4 + chunk4 - 1) / chunk4), LIN_TPB, 0, st>>>(src, n4, logL4, 1 << k, chunk4, mb);
+    } else {
+        k_block_sums<<<(int)cap, LIN_TPB, 0, st>>>(src, n4, logL4, 1 << k, 0, mb);
+    }
 }
 
 // sum of <= 8 canonical values -> canonical: q = x >> 31 never exceeds floor(x / P) and x - q P < 2 P
@@ -1292,7 +1352,6 @@ __global__ void __launch_bounds__(TPB, MINB) k_foldk_sums(const uint32_t *src, u
             if (dump != nullptr) {
                 volatile unsigned long long *d = (volatile unsigned long long *)dump + 4 * i4;
                 d[0] = r[0], d[1] = r[1], d[2] = r[2], d[3] = r[3];
-                __threadfence_system();
             } else {
                 s += (unsigned long long)(r[0] + r[1]) + (unsigned long long)(r[2] + r[3]);
             }
@@ -1617,11 +1676,7 @@ void launch_eval_warp10(const uint32_t *src, uint64_t n, const EvalPoint &pt, ui
     auto bulk = [&](auto warps_c, auto stages_c, int per_sm) {
         constexpr int W = decltype(warps_c)::value, S = decltype(stages_c)::value;
         constexpr int SMEM = W * S * 4096 + W * S * 8;
-        static const bool once = [] {
-            cudaFuncSetAttribute(k_eval_warp10_bulk<W, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-            return true;
-        }();
-        (void)once;
+        ENSURE_DYN_SMEM((k_eval_warp10_bulk<W, S>), SMEM);
         uint64_t ctas = (n_tiles + W - 1) / W;
         if (ctas > (uint64_t)sm * per_sm) ctas = (uint64_t)sm * per_sm;
         k_eval_warp10_bulk<W, S><<<(int)(ctas ? ctas : 1), W * 32, SMEM, st>>>(src, n_tiles, pt, out);
