@@ -140,9 +140,12 @@ pub extern fn zb_mle_clone(ctx: *Ctx, src: Mle, out: [*c]Mle) i32;
 pub extern fn zb_mle_download_range(ctx: *Ctx, m: Mle, offset: u64, out: [*c]u64, n: u64) i32;
 pub extern fn zb_mle_download_u32(ctx: *Ctx, m: Mle, offset: u64, out: [*c]u32, n: u64) i32;
 pub extern fn zb_host_scratch(ctx: *Ctx, bytes: usize, out: [*c]?*anyopaque) i32;
+pub extern fn zb_mle_eval_batch(ctx: *Ctx, polys: [*c]const Mle, count: u32, points: [*c]const u64, npoint: u32, out: [*c]u64) i32;
+pub extern fn zb_mle_eq(ctx: *Ctx, tau: [*c]const u64, num_vars: u32, out: [*c]Mle) i32;
 pub extern fn zb_mle_block_sums(ctx: *Ctx, m: Mle, k: u32, sums: [*c]u64) i32;
 pub extern fn zb_mle_fold_multi(ctx: *Ctx, m: Mle, k_fold: u32, r: [*c]const u64, out: [*c]Mle, k_next: u32, sums: [*c]u64) i32;
 pub extern fn zb_mle_collapse(ctx: *Ctx, m: Mle, value: u64) i32;
+pub extern fn zb_merkle_open_batch(ctx: *Ctx, trees: [*c]const Tree, count: u32, indices: [*c]const u64, siblings: [*c]u8, dirs: [*c]u8, leaf_values: [*c]u64) i32;
 pub extern fn zb_merkle_leaf_hashes(ctx: *Ctx, t: Tree, out: [*c]u8, n_digests: u64) i32;
 pub extern fn zb_comm_unique_id(nccl_path: [*:0]const u8, out: *[128]u8) i32;
 pub extern fn zb_comm_init(ctx: *Ctx, nccl_path: [*:0]const u8, unique_id: *const [128]u8, rank: i32, world: i32) i32;
@@ -171,6 +174,8 @@ pub extern fn zh_sumcheck_prove_interactive(ctx: *Ctx, poly: Mle, challenges: [*
 pub extern fn zh_sumcheck_proof_to_bytes(num_vars: u32, round_polys: [*c]const u64, final_point: [*c]const u64, final_eval: u64, out: [*c]u8) usize;
 pub extern fn zh_prodcheck_prove(ctx: *Ctx, polys: [*c]const Mle, d: u32, round_polys: [*c]u64, final_point: [*c]u64, final_evals: [*c]u64, claimed_sum: [*c]u64) i32;
 pub extern fn zh_prodcheck_prove_consume(ctx: *Ctx, polys: [*c]const Mle, d: u32, round_polys: [*c]u64, final_point: [*c]u64, final_evals: [*c]u64, claimed_sum: [*c]u64) i32;
+pub extern fn zh_time_sumcheck_prove(ctx: *Ctx, poly: Mle, reps: u32, us_per_prove: [*c]f64) i32;
+pub extern fn zh_eqcheck_prove(ctx: *Ctx, tau: [*c]const u64, num_vars: u32, polys: [*c]const Mle, d: u32, round_polys: [*c]u64, final_point: [*c]u64, final_evals: [*c]u64, claimed_sum: [*c]u64) i32;
 pub extern fn zh_commit(ctx: *Ctx, poly: Mle, tree: [*c]Tree, root: *[32]u8, num_vars: [*c]u32) i32;
 pub extern fn zh_batch_commit(ctx: *Ctx, polys: [*c]const Mle, count: u32, trees: [*c]Tree, roots: [*c]u8) i32;
 pub extern fn zh_commit_sharded(ctx: *Ctx, local_poly: Mle, tree: [*c]Tree, local_root: *[32]u8, root: *[32]u8) i32;

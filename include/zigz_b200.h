@@ -146,6 +146,9 @@ int32_t zb_mle_partial_eval(zb_ctx *ctx, zb_mle m, uint64_t r, zb_mle *out, uint
 int32_t zb_mle_fold_inplace(zb_ctx *ctx, zb_mle m, uint64_t r, uint64_t next_s0_s1[2]);
 /* eval :110-144 — LSB-first: point[k] <-> index bit k. O(N) fold instead of the reference's O(N*v) loop; same value */
 int32_t zb_mle_eval(zb_ctx *ctx, zb_mle m, const uint64_t *point, uint32_t npoint, uint64_t *out);
+/* eval for `count` polynomials of equal length at one point each (points: count x npoint, row-major) with ONE read-back:
+ * Prover.generateCommitments knows all 43 opening points before it needs any value (prover.zig:420-443) */
+int32_t zb_mle_eval_batch(zb_ctx *ctx, const zb_mle *polys, uint32_t count, const uint64_t *points, uint32_t npoint, uint64_t *out);
 /* add :235-250 / scalarMul :253-264 */
 int32_t zb_mle_add(zb_ctx *ctx, zb_mle a, zb_mle b, zb_mle *out);
 int32_t zb_mle_scalar_mul(zb_ctx *ctx, zb_mle a, uint64_t scalar, zb_mle *out);
@@ -159,6 +162,11 @@ int32_t zb_prod_round_coeffs(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint6
 int32_t zb_prod_fold_inplace(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, uint64_t *next_coeffs);
 /* the same fold out of place (partialEval semantics for all d polynomials): `out` receives d NEW handles */
 int32_t zb_prod_partial_eval(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t r, zb_mle *out, uint64_t *next_coeffs);
+
+/* eq(tau, .) as a table — EXTENSION (no reference behaviour), the weight table of an eq-weighted sumcheck:
+ * E[i] = prod_k (bit_k(i) ? tau[k] : 1 - tau[k]), index bit k <-> tau[k] as in Multilinear.eval (multilinear.zig:128-141), hence
+ * sum_i E[i] * A[i] == A.eval(tau). One product per entry from two half tables built on the host. */
+int32_t zb_mle_eq(zb_ctx *ctx, const uint64_t *tau, uint32_t num_vars, zb_mle *out);
 
 /* ---- two sumcheck rounds per pass over the data ----
  * With the top two index bits as variables (X, Y), G(X, Y) = sum_i prod_k B_k,i(X, Y) (B bilinear through the four quarter
@@ -198,6 +206,10 @@ int32_t zb_merkle_build_values(zb_ctx *ctx, const uint64_t *values, uint64_t n, 
 int32_t zb_merkle_info(zb_ctx *ctx, zb_tree t, uint64_t *n_values, uint32_t *height, uint8_t root[32]);
 /* open :324-360 — siblings: height*32 bytes leaf->root, dirs[l] = (index >> l) & 1, leaf_value = values[index] */
 int32_t zb_merkle_open(zb_ctx *ctx, zb_tree t, uint64_t index, uint8_t *siblings, uint8_t *dirs, uint64_t *leaf_value);
+/* open for `count` trees of equal shape, one leaf index each, in one launch and one read-back: siblings count x height x 32 bytes,
+ * dirs count x height, leaf_values count */
+int32_t zb_merkle_open_batch(zb_ctx *ctx, const zb_tree *trees, uint32_t count, const uint64_t *indices, uint8_t *siblings,
+                             uint8_t *dirs, uint64_t *leaf_values);
 /* leaf_hashes copy-out (tests): padded*32 bytes */
 int32_t zb_merkle_leaf_hashes(zb_ctx *ctx, zb_tree t, uint8_t *out, uint64_t n_digests);
 int32_t zb_merkle_free(zb_ctx *ctx, zb_tree t);

@@ -69,6 +69,20 @@ int32_t zh_prodcheck_prove(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_
 int32_t zh_prodcheck_prove_consume(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *round_polys,
                                    uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum);
 
+/* measurement helper: `reps` zh_sumcheck_prove calls in a row, wall-clock microseconds per prove (no binding overhead) */
+int32_t zh_time_sumcheck_prove(zb_ctx *ctx, zb_mle poly, uint32_t reps, double *us_per_prove);
+
+/* EXTENSION, clearly outside the reference (SURVEY.md §8 f4 "real degree-d sumcheck"): eq-weighted product sumcheck
+ *     sum_x eq(tau, x) * prod_{k<d} A_k(x),  d = 1 or 2,
+ * the form constraint-satisfaction and zero-check arguments use. Proved as the product sumcheck of the d + 1 tables
+ * (eq(tau, .), A_0, .., A_{d-1}) in the conventions of zh_prodcheck_prove: round polynomials of degree d + 1 in
+ * coefficient form (round_polys: v * (d + 2)), MSB-first binding, same transcript. final_evals: d + 1 values, eq first
+ * (== eq(tau, challenges in index-bit order)). tau[k] <-> index bit k as in Multilinear.eval, so for d == 1 the claimed
+ * sum is A_0.eval(tau) (multilinear.zig:110-144). The inputs are left untouched. Lasso's grand-product / memory-checking
+ * arguments are NOT built: the reference has no such code to be bit-exact with (lasso_prover.zig:147-158 are comments). */
+int32_t zh_eqcheck_prove(zb_ctx *ctx, const uint64_t *tau, uint32_t num_vars, const zb_mle *polys, uint32_t d, uint64_t *round_polys,
+                         uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum);
+
 /* ---- CommitmentScheme(BabyBear, SHA3Hasher): src/commitments/polynomial_commit.zig ---- */
 /* commit :69-83 */
 int32_t zh_commit(zb_ctx *ctx, zb_mle poly, zb_tree *tree, uint8_t root[32], uint32_t *num_vars);

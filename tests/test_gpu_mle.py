@@ -161,3 +161,45 @@ def test_u32_upload_and_clone(zlib, ctx):
     with pytest.raises(zlib.ZigzError) as err:
         zlib.Multilinear.init_u32(ctx, np.array([1, 2, 3, BB + 5], np.uint32))
     assert err.value.name == "NotCanonical"
+
+
+@pytest.mark.parametrize("lg,count", [(0, 3), (1, 2), (3, 5), (4, 1), (9, 43), (12, 4), (13, 3), (17, 2), (20, 3), (21, 2), (23, 2)])
+def test_eval_batch_matches_single_evaluations(zlib, ctx, po, lg, count):
+    """zb_mle_eval_batch (all opening points of Prover.generateCommitments at once, prover.zig:420-443) == count x eval."""
+    import ctypes as C
+    polys = [zlib.Multilinear.synthetic(ctx, 3000 + 17 * lg + i, 1 << lg) for i in range(count)]
+    pts = np.ascontiguousarray(po.fill_synthetic(BB, 77 + lg, 0, max(count * lg, 1))[: count * lg].reshape(count, lg))
+    hs = (C.c_uint64 * count)(*[p.handle for p in polys])
+    out = np.zeros(count, np.uint64)
+    ctx.check(zlib.lib().zb_mle_eval_batch(ctx.handle, hs, count, pts.ctypes.data_as(zlib.api.P64) if lg else None, lg,
+                                           out.ctypes.data_as(zlib.api.P64)))
+    for i, p in enumerate(polys):
+        assert int(out[i]) == p.eval(pts[i]), (lg, i)
+        if lg <= 12:
+            assert int(out[i]) == po.mle_eval(BB, p.evaluations, pts[i])
+        p.deinit()
+
+
+def test_merkle_open_batch_matches_single_openings(zlib, ctx, po):
+    import ctypes as C
+    for lg, count in ((0, 2), (1, 3), (6, 43), (11, 5)):
+        polys = [zlib.Multilinear.synthetic(ctx, 5000 + i, 1 << lg) for i in range(count)]
+        coms, trees = zlib.CommitmentScheme.batch_commit(polys)
+        idx = np.array([(i * 2654435761) % (1 << lg) for i in range(count)], np.uint64)
+        hs = (C.c_uint64 * count)(*[t.handle for t in trees])
+        h = max(lg, 1)
+        sib, dirs, vals = np.zeros((count, h, 32), np.uint8), np.zeros((count, h), np.uint8), np.zeros(count, np.uint64)
+        ctx.check(zlib.lib().zb_merkle_open_batch(ctx.handle, hs, count, idx.ctypes.data_as(zlib.api.P64), sib.ctypes.data_as(zlib.api.P8),
+                                                  dirs.ctypes.data_as(zlib.api.P8), vals.ctypes.data_as(zlib.api.P64)))
+        sib, dirs = sib.reshape(-1)[: count * lg * 32].reshape(count, lg, 32), dirs.reshape(-1)[: count * lg].reshape(count, lg)
+        for i, t in enumerate(trees):
+            pr = t.open(int(idx[i]))
+            assert pr.value == int(vals[i])
+            assert np.array_equal(pr.path.siblings, sib[i]) and np.array_equal(pr.path.directions, dirs[i])
+        bad = idx.copy()
+        bad[-1] = 1 << lg
+        assert zlib.lib().zb_merkle_open_batch(ctx.handle, hs, count, bad.ctypes.data_as(zlib.api.P64), None, None, None) == -6  # IndexOutOfBounds
+        for t in trees:
+            t.deinit()
+        for p in polys:
+            p.deinit()

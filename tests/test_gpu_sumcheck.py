@@ -384,3 +384,50 @@ def test_block_sums_and_fold_multi_entry_points(zlib, ctx, po):
     buf = np.zeros(32, np.uint64)
     assert L.zb_mle_block_sums(ctx.handle, small.handle, 2, buf.ctypes.data_as(zlib.api.P64)) == -22  # n < 4 * 2^k: BadArgument
     assert L.zb_mle_fold_multi(ctx.handle, small.handle, 1, buf.ctypes.data_as(zlib.api.P64), None, 1, buf.ctypes.data_as(zlib.api.P64)) == -22
+
+
+# ---------------------------------------------------------------- extension: eq-weighted product sumcheck
+def _eq_table(tau):
+    """E[i] = prod_k (bit_k(i) ? tau[k] : 1 - tau[k]) — independent numpy/Python-int construction."""
+    e = [1]
+    for t in tau:  # bit k is added as the new TOP bit of the indices built so far
+        t = int(t)
+        e = [x * (1 - t) % BB for x in e] + [x * t % BB for x in e]
+    return np.array(e, np.uint64)
+
+
+@pytest.mark.parametrize("d", [1, 2])
+@pytest.mark.parametrize("lg", [1, 2, 3, 6, 11, 16, 18])
+def test_eq_weighted_sumcheck_vs_oracle(zlib, ctx, po, d, lg):
+    """sum_x eq(tau, x) prod_k A_k(x) proved as the product sumcheck of (eq(tau, .), A_0, ..): same round polynomials as the
+    oracle's product prover on the explicitly built eq table; for d = 1 the claimed sum is Multilinear.eval(tau); the final
+    eq value is eq(tau, r) with the challenges in index-bit order."""
+    n = 1 << lg
+    tau = po.fill_synthetic(BB, 31337 + lg, 0, lg)
+    es = [po.fill_synthetic(BB, 600 + 3 * lg + k, 0, n) for k in range(d)]
+    polys = [zlib.Multilinear.init(ctx, e) for e in es]
+    E = _eq_table(tau)
+    import ctypes as C
+    h = C.c_uint64(0)
+    ctx.check(zlib.lib().zb_mle_eq(ctx.handle, tau.ctypes.data_as(zlib.api.P64), lg, C.byref(h)))
+    eqp = zlib.Multilinear(ctx, h.value)
+    assert np.array_equal(eqp.evaluations, E)
+    eqp.deinit()
+    want = po.prodcheck_prove(BB, [E] + es)
+    pr = zlib.EqProductSumcheckProver.prove(tau, polys)
+    assert pr.claimed_sum == want.claimed_sum
+    assert pr.round_polynomials.tolist() == want.round_polys.tolist()
+    assert pr.final_point.tolist() == want.final_point.tolist()
+    assert pr.final_evals == want.final_evals
+    if d == 1:
+        assert pr.claimed_sum == polys[0].eval(tau) == po.mle_eval(BB, es[0], tau)
+    r_by_bit = [int(x) for x in pr.final_point][::-1]  # round j binds index bit lg-1-j
+    eq_at_r = 1
+    for t, r in zip((int(x) for x in tau), r_by_bit):
+        eq_at_r = eq_at_r * ((t * r + (1 - t) * (1 - r)) % BB) % BB
+    assert pr.final_evals[0] == eq_at_r
+    ok, final_claim = po.sumcheck_verify_rounds(BB, pr.round_polynomials, pr.claimed_sum)
+    assert ok and final_claim == pr.final_eval
+    assert np.array_equal(polys[0].evaluations, es[0])  # inputs untouched
+    with pytest.raises(zlib.ZigzError):
+        zlib.EqProductSumcheckProver.prove(tau[:-1] if lg > 1 else np.zeros(3, np.uint64), polys)

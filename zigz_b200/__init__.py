@@ -8,6 +8,6 @@ back to a CPU path: creating a `Context` without a CUDA device raises `ZigzError
 from ._cabi import LIB_PATH, ZigzError, build, declared_prototypes, lib  # noqa: F401
 from .api import (  # noqa: F401
     BABYBEAR_P, TABLE_ADD, TABLE_AND, TABLE_XOR, CommitmentScheme, Context, FiatShamirTranscript, LassoProof, LassoProver,
-    MerkleOpeningProof, MerklePath, MerkleTree, Multilinear, OpeningProof, PolynomialCommitment, ProductSumcheckProver, SimpleMerkleTree,
+    MerkleOpeningProof, MerklePath, MerkleTree, Multilinear, OpeningProof, PolynomialCommitment, ProductSumcheckProver, EqProductSumcheckProver, SimpleMerkleTree,
     SumcheckProof, SumcheckProver, CommitmentOpenings, WITNESS_COLUMNS, generate_commitments, witness_pack, prove_from_trace, verify_proof, build_add_table, build_and_table, build_xor_table, eval_univariate_coeffs, sha3_256,
 )

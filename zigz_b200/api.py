@@ -394,6 +394,25 @@ class SumcheckProver:
         return SumcheckProof(v, rp, fp, fe.value)
 
 
+class EqProductSumcheckProver:
+    """EXTENSION (no reference behaviour): eq-weighted product sumcheck sum_x eq(tau, x) prod_k A_k(x), d = 1, 2."""
+
+    @staticmethod
+    def prove(tau, polys: Sequence["Multilinear"]) -> "SumcheckProof":
+        ctx = polys[0].ctx
+        d = len(polys)
+        v = max(polys[0].num_vars, 1)
+        t = _a64(tau)
+        hs = (u64 * d)(*[p.handle for p in polys])
+        rp, fp, fes = np.zeros((v, d + 2), np.uint64), np.zeros(v, np.uint64), np.zeros(d + 1, np.uint64)
+        cs = u64(0)
+        ctx.check(lib().zh_eqcheck_prove(ctx.handle, _p64(t) if t.size else None, t.size, hs, d, _p64(rp), _p64(fp), _p64(fes), C.byref(cs)))
+        fe = 1
+        for x in fes:
+            fe = fe * int(x) % BABYBEAR_P
+        return SumcheckProof(v, rp, fp, fe, cs.value, tuple(int(x) for x in fes))
+
+
 class ProductSumcheckProver:
     """Product of d (1..3) multilinears — extension in the reference's conventions."""
 

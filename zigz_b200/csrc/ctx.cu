@@ -1421,6 +1421,124 @@ int32_t zb_mle_eval(zb_ctx *ctx, zb_mle h, const uint64_t *point, uint32_t npoin
     return ZB_OK;
 }
 
+// Multilinear.eval for `count` polynomials of equal length, one point each, in one launch set and ONE read-back
+// (Prover.generateCommitments derives all 43 opening points before it absorbs any value, prover.zig:420-443).
+int32_t zb_mle_eval_batch(zb_ctx *ctx, const zb_mle *polys, uint32_t count, const uint64_t *points, uint32_t npoint, uint64_t *out) {
+    tail_quiesce(ctx);
+    if (!polys || !out || count == 0 || count > (DUMP_BYTES / sizeof(unsigned long long)) || (npoint && !points)) return ZB_ERR_BAD_ARGUMENT;
+    std::vector<const uint32_t *> ptrs(count);
+    uint64_t n = 0;
+    for (uint32_t i = 0; i < count; i++) {
+        Mle *m = get_mle(ctx, polys[i]);
+        if (!m) return ZB_ERR_BAD_HANDLE;
+        if (i == 0) n = m->n;
+        else if (m->n != n) return ZB_ERR_DIFFERENT_NUM_VARS;
+        ptrs[i] = m->d();
+    }
+    const uint32_t v = (uint32_t)__builtin_ctzll(n);
+    if (npoint != v) return ZB_ERR_WRONG_NUM_VARS; // multilinear.zig:112
+    for (uint64_t i = 0; i < (uint64_t)count * v; i++)
+        if (points[i] >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    // one parameter blob: [count table pointers][count x (v challenges, v Shoup companions)]
+    const uint32_t vv = v ? v : 1;
+    const size_t blob_bytes = (size_t)count * 8 + (size_t)count * 2 * vv * 4;
+    uint8_t *h_blob = nullptr;
+    int32_t rc = zb_host_scratch(ctx, blob_bytes, (void **)&h_blob);
+    if (rc) return rc;
+    memcpy(h_blob, ptrs.data(), (size_t)count * 8);
+    uint32_t *hp = (uint32_t *)(h_blob + (size_t)count * 8);
+    for (uint32_t i = 0; i < count; i++)
+        for (uint32_t k = 0; k < v; k++) {
+            const uint32_t r = (uint32_t)points[(size_t)i * v + k];
+            hp[(size_t)i * 2 * vv + k] = r;
+            hp[(size_t)i * 2 * vv + vv + k] = bb::shoup_pre(r);
+        }
+    BufRef d_blob, scratch[2];
+    rc = dev_alloc(ctx, blob_bytes, &d_blob);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d_blob->ptr, h_blob, blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t *const *d_ptrs = (const uint32_t *const *)d_blob->ptr;
+    const uint32_t *d_pts = (const uint32_t *)((uint8_t *)d_blob->ptr + (size_t)count * 8);
+    unsigned long long *d_dump = (unsigned long long *)((uint8_t *)ctx->d_mail + DUMP_OFFSET);
+    Mailbox mb = ctx->mailbox();
+    uint64_t cur_n = n;
+    uint32_t done = 0;
+    int which = 0;
+    const uint32_t *rows = nullptr; // after the first stage the partial results of all polynomials are rows of one buffer
+    for (;;) {
+        const bool big = cur_n >= (1ull << 20);
+        const int nv = big ? 10 : (int)(v - done < 12 ? v - done : 12);
+        const uint64_t n_out = cur_n >> nv;
+        const bool last = done + nv == v;
+        rc = dev_alloc(ctx, (size_t)count * (n_out < 32 ? 32 : n_out) * sizeof(uint32_t), &scratch[which]);
+        if (rc) return rc;
+        {
+            ProfScope _ps(ctx, big ? "eval_warp10_batch" : "eval_stage_batch", (uint64_t)count * (cur_n + n_out) * 4);
+            if (big && rows == nullptr)
+                launch_eval_warp10_batch(d_ptrs, cur_n, count, d_pts, vv, done, (uint32_t *)scratch[which]->ptr, ctx->sm_count, ctx->stream);
+            else
+                launch_eval_stage_batch(rows ? nullptr : d_ptrs, rows, cur_n, count, nv, d_pts, vv, done, (uint32_t *)scratch[which]->ptr,
+                                        last ? d_dump : nullptr, mb, ctx->stream);
+        }
+        LAUNCHED("eval_batch");
+        rows = (const uint32_t *)scratch[which]->ptr;
+        cur_n = n_out;
+        done += nv;
+        which ^= 1;
+        if (last) break;
+    }
+    rc = wait_mail(ctx, mb.seq);
+    if (rc) return rc;
+    const unsigned long long *res = (const unsigned long long *)((uint8_t *)ctx->h_mail + DUMP_OFFSET);
+    for (uint32_t i = 0; i < count; i++) out[i] = res[i];
+    return ZB_OK;
+}
+
+// eq(tau, .) as a table (extension: weights of an eq-weighted sumcheck). E[i] = prod_k (bit_k(i) ? tau[k] : 1 - tau[k]) — index bit
+// k <-> tau[k], the convention of Multilinear.eval (multilinear.zig:128-141), so sum_i E[i] A[i] == A.eval(tau).
+int32_t zb_mle_eq(zb_ctx *ctx, const uint64_t *tau, uint32_t v, zb_mle *out) {
+    tail_quiesce(ctx);
+    if (!out || v > 40 || (v && !tau)) return ZB_ERR_BAD_ARGUMENT;
+    for (uint32_t k = 0; k < v; k++)
+        if (tau[k] >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    const uint32_t s = v / 2, t = v - s; // low s variables / high t variables (t <= 20)
+    auto half = [&](uint32_t k0, uint32_t cnt, bool mont) {
+        std::vector<uint32_t> e(1ull << cnt);
+        e[0] = mont ? bb::R_MOD_P : 1u;
+        for (uint32_t j = 0; j < cnt; j++) { // after step j: entries for the bits 0..j of this half
+            const uint32_t r = (uint32_t)tau[k0 + j], nr = bb::sub(1u, r);
+            for (uint64_t i = 0; i < (1ull << j); i++) {
+                const uint32_t base = e[i];
+                e[i] = bb::mul(base, nr);
+                e[i + (1ull << j)] = bb::mul(base, r);
+            }
+        }
+        return e;
+    };
+    const std::vector<uint32_t> lo = half(0, s, false), hi = half(s, t, true);
+    BufRef dlo, dhi;
+    int32_t rc = dev_alloc(ctx, lo.size() * 4, &dlo);
+    if (rc == ZB_OK) rc = dev_alloc(ctx, hi.size() * 4, &dhi);
+    if (rc) return rc;
+    Mle *m = nullptr;
+    rc = new_mle(ctx, 1ull << v, out, &m);
+    if (rc) return rc;
+    cudaError_t ce = cudaMemcpyAsync(dlo->ptr, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(dhi->ptr, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess) {
+        ProfScope _ps(ctx, "eq_table", 4ull << v);
+        launch_eq_table((const uint32_t *)dlo->ptr, (const uint32_t *)dhi->ptr, (int)s, 1ull << v, m->d(), ctx->stream);
+    }
+    rc = ce == cudaSuccess ? check_launch(ctx, "eq_table") : cuda_fail(ctx, ce, "cudaMemcpyAsync(eq halves)");
+    if (rc == ZB_OK) rc = zb_sync(ctx); // lo / hi are stack-owned host vectors
+    else cudaStreamSynchronize(ctx->stream);
+    if (rc) {
+        ctx->mles.erase(*out);
+        *out = 0;
+    }
+    return rc;
+}
+
 int32_t zb_mle_add(zb_ctx *ctx, zb_mle a, zb_mle b, zb_mle *out) {
     tail_quiesce(ctx);
     Mle *ma = get_mle(ctx, a), *mb_ = get_mle(ctx, b);
@@ -1939,8 +2057,10 @@ int32_t zb_mle_fold_multi(zb_ctx *ctx, zb_mle h, uint32_t k_fold, const uint64_t
         return rc;
     }
     if (!out) get_mle(ctx, h)->n = mm;
-    if (dump) memcpy(sums, (uint8_t *)ctx->h_mail + DUMP_OFFSET, mm * sizeof(uint64_t));
-    else
+    if (dump) {
+        const uint32_t *t = (const uint32_t *)((uint8_t *)ctx->h_mail + DUMP_OFFSET);
+        for (uint64_t i = 0; i < mm; i++) sums[i] = t[i];
+    } else
         for (uint32_t b = 0; b < (1u << k_next); b++) sums[b] = ctx->h_mail[b];
     return ZB_OK;
 }
@@ -2141,6 +2261,57 @@ int32_t zb_merkle_open(zb_ctx *ctx, zb_tree h, uint64_t index, uint8_t *siblings
         uint32_t v;
         memcpy(&v, ctx->h_bulk() + 64 * 32, sizeof(v));
         *leaf_value = v;
+    }
+    return ZB_OK;
+}
+
+// open for `count` trees of equal shape, one leaf each, in one launch and one read-back
+int32_t zb_merkle_open_batch(zb_ctx *ctx, const zb_tree *trees, uint32_t count, const uint64_t *indices, uint8_t *siblings,
+                             uint8_t *dirs, uint64_t *leaf_values) {
+    tail_quiesce(ctx);
+    if (!trees || !indices || count == 0 || count > 65535) return ZB_ERR_BAD_ARGUMENT;
+    uint64_t padded = 0;
+    uint32_t height = 0;
+    std::vector<uint64_t> blob(3 * (size_t)count);
+    for (uint32_t i = 0; i < count; i++) {
+        Tree *t = get_tree(ctx, trees[i]);
+        if (!t) return ZB_ERR_BAD_HANDLE;
+        if (indices[i] >= t->n_values) return ZB_ERR_INDEX_OUT_OF_BOUNDS; // merkle_tree.zig:325
+        if (i == 0) padded = t->padded, height = t->height;
+        else if (t->padded != padded) return ZB_ERR_DIFFERENT_NUM_VARS;
+        blob[i] = (uint64_t)(uintptr_t)t->store->ptr;
+        blob[count + i] = (uint64_t)(uintptr_t)t->values->ptr;
+        blob[2 * (size_t)count + i] = indices[i];
+    }
+    if (height > 64) return ZB_ERR_BAD_ARGUMENT;
+    const size_t path_bytes = (size_t)count * height * 32, out_bytes = path_bytes + (size_t)count * 4, blob_bytes = blob.size() * 8;
+    uint8_t *h = nullptr;
+    int32_t rc = zb_host_scratch(ctx, blob_bytes + out_bytes, (void **)&h);
+    if (rc) return rc;
+    memcpy(h, blob.data(), blob_bytes);
+    BufRef d_blob, d_out;
+    rc = dev_alloc(ctx, blob_bytes, &d_blob);
+    if (rc == ZB_OK) rc = dev_alloc(ctx, out_bytes + 64, &d_out);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d_blob->ptr, h, blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t *db = (const uint64_t *)d_blob->ptr;
+    {
+        ProfScope _ps(ctx, "merkle_path_batch", 64ull * height * count);
+        launch_merkle_path_batch((const uint8_t *const *)db, (const uint32_t *const *)(db + count), db + 2 * (size_t)count, count, padded,
+                                 height, (uint8_t *)d_out->ptr, (uint32_t *)((uint8_t *)d_out->ptr + path_bytes), ctx->stream);
+    }
+    LAUNCHED("merkle_path_batch");
+    CK(cudaMemcpyAsync(h + blob_bytes, d_out->ptr, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (siblings && height) memcpy(siblings, h + blob_bytes, path_bytes);
+    for (uint32_t i = 0; i < count; i++) {
+        if (dirs)
+            for (uint32_t l = 0; l < height; l++) dirs[(size_t)i * height + l] = (uint8_t)((indices[i] >> l) & 1); // :341-345
+        if (leaf_values) {
+            uint32_t val;
+            memcpy(&val, h + blob_bytes + path_bytes + 4 * (size_t)i, 4);
+            leaf_values[i] = val;
+        }
     }
     return ZB_OK;
 }

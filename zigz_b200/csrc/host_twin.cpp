@@ -5,6 +5,7 @@
 #include "sha3_host.hpp"
 
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <immintrin.h>
@@ -481,6 +482,22 @@ int32_t group_prove(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool consume, 
 }
 } // namespace
 
+// measurement helper (like zb_int_pipe_peak / zb_h2d_rate): `reps` proves of `poly` in a row through this very ABI, wall-clock
+// microseconds per prove — the Python mirror's per-call overhead (~10 us) would otherwise be part of a 50 us measurement
+int32_t zh_time_sumcheck_prove(zb_ctx *ctx, zb_mle poly, uint32_t reps, double *us_per_prove) {
+    uint64_t n = 0;
+    uint32_t v = 0;
+    int32_t rc = zb_mle_len(ctx, poly, &n, &v);
+    if (rc || !us_per_prove || reps == 0) return rc ? rc : ZB_ERR_BAD_ARGUMENT;
+    std::vector<uint64_t> rp(2 * (size_t)(v ? v : 1)), fp(v ? v : 1);
+    uint64_t fe = 0, cs = 0;
+    for (int i = 0; i < 3 && rc == ZB_OK; i++) rc = zh_sumcheck_prove(ctx, poly, rp.data(), fp.data(), &fe, &cs);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t i = 0; i < reps && rc == ZB_OK; i++) rc = zh_sumcheck_prove(ctx, poly, rp.data(), fp.data(), &fe, &cs);
+    *us_per_prove = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
+    return rc;
+}
+
 int32_t zh_set_grid_min_log2(int32_t v) {
     const int32_t old = grid_min_log2();
     g_grid_min_log2.store(v < 0 ? 0 : v, std::memory_order_relaxed);
@@ -530,6 +547,24 @@ int32_t zh_prodcheck_prove_consume(zb_ctx *ctx, const zb_mle *polys, uint32_t d,
                                    uint64_t *final_evals, uint64_t *claimed_sum) {
     if (on_group(ctx, polys)) return group_prove(ctx, polys, d, true, nullptr, round_polys, final_point, final_evals, claimed_sum);
     return prove_rounds(ctx, polys, d, true, nullptr, round_polys, final_point, final_evals, claimed_sum);
+}
+
+int32_t zh_eqcheck_prove(zb_ctx *ctx, const uint64_t *tau, uint32_t num_vars, const zb_mle *polys, uint32_t d, uint64_t *round_polys,
+                         uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum) {
+    if (d < 1 || d > 2 || !polys || (num_vars && !tau)) return ZB_ERR_BAD_ARGUMENT;
+    if (zb_group_size(ctx) > 1 && (polys[0] >> 63)) return ZB_ERR_BAD_ARGUMENT; // sharded tables: not built for this extension
+    uint64_t n = 0;
+    uint32_t v = 0;
+    int32_t rc = zb_mle_len(ctx, polys[0], &n, &v);
+    if (rc) return rc;
+    if (v != num_vars) return ZB_ERR_WRONG_NUM_VARS;
+    if (v == 0) return ZB_ERR_NO_VARIABLES;
+    zb_mle all[3] = {0, polys[0], d > 1 ? polys[1] : 0};
+    rc = zb_mle_eq(ctx, tau, v, &all[0]);
+    if (rc) return rc;
+    rc = prove_rounds(ctx, all, d + 1, false, nullptr, round_polys, final_point, final_evals, claimed_sum);
+    zb_mle_free(ctx, all[0]);
+    return rc;
 }
 
 /* ------------------------------------------------------------------ commitment scheme */
@@ -632,12 +667,20 @@ int32_t zh_generate_commitments(zb_ctx *ctx, zh_transcript *tr, const zb_mle *po
     if (rc) return rc;
     zh_transcript_append_bytes(tr, "POLY_COMMITMENTS", 16); // PHASE 2 (:413-416)
     for (uint32_t i = 0; i < count; i++) zh_transcript_append_bytes(tr, roots + 32 * (size_t)i, 32);
-    for (uint32_t i = 0; i < count && rc == ZB_OK; i++) { // PHASE 3 (:420-443)
-        uint64_t *pt = points + (size_t)i * v;
-        for (uint32_t j = 0; j < v; j++) pt[j] = zh_transcript_challenge(tr);
+    // PHASE 3 (:420-443). The loop only draws challenges from the transcript (nothing is absorbed before PHASE 4), so
+    // all opening points exist before the first value is needed: the `count` evaluations are one batched launch set and
+    // the `count` Merkle paths one gather, two read-backs in total instead of 2 * count.
+    for (uint32_t i = 0; i < count; i++)
+        for (uint32_t j = 0; j < v; j++) points[(size_t)i * v + j] = zh_transcript_challenge(tr);
+    if (zb_group_size(ctx) > 1 && (polys[0] >> 63)) { // sharded tables of a multi-device context: one opening at a time
+        for (uint32_t i = 0; i < count && rc == ZB_OK; i++)
+            rc = zh_commit_open(ctx, polys[i], trees[i], points + (size_t)i * v, v, &values[i], &leaf_indices[i], &leaf_values[i],
+                                siblings + (size_t)i * v * 32, dirs + (size_t)i * v);
+    } else {
         // :427 and Scheme.open :431 evaluate the same polynomial at the same point twice; once is enough
-        rc = zh_commit_open(ctx, polys[i], trees[i], pt, v, &values[i], &leaf_indices[i], &leaf_values[i],
-                            siblings + (size_t)i * v * 32, dirs + (size_t)i * v);
+        rc = zb_mle_eval_batch(ctx, polys, count, points, v, values);
+        for (uint32_t i = 0; i < count; i++) leaf_indices[i] = zh_point_to_index(points + (size_t)i * v, v); // :102
+        if (rc == ZB_OK) rc = zb_merkle_open_batch(ctx, trees.data(), count, leaf_indices, siblings, dirs, leaf_values);
     }
     for (uint32_t i = 0; i < count; i++) zb_merkle_free(ctx, trees[i]); // :446-448
     if (rc) return rc;

@@ -128,7 +128,21 @@ __device__ __forceinline__ void round(uint32_t (&al)[25], uint32_t (&ah)[25], ui
 // UNROLL = rounds per loop iteration (24 = fully unrolled, constants folded)
 template <int UNROLL, uint32_t FMAMASK = 0>
 __device__ __forceinline__ void f1600(uint32_t (&al)[25], uint32_t (&ah)[25]) {
-    if constexpr (UNROLL >= 24) {
+    if constexpr (UNROLL > 100) {
+        // PEELED form, UNROLL = 100 + rounds per iteration of the middle loop (2 or 11): round 0 and round 23 stand outside the
+        // loop as straight-line code, so the compiler folds the constant lanes of the padded input block into round 0 (17 of
+        // the 25 lanes of a node block, 24 of a leaf block) and strips round 23 down to the four output lanes (chi of row 0
+        // only: 5 of the 25 rho/pi lanes) — neither is possible inside a rolled loop.
+        constexpr int UR = UNROLL - 100;
+        static_assert(22 % UR == 0, "the middle 22 rounds must split evenly");
+        round<FMAMASK>(al, ah, RC_LO[0], RC_HI[0]);
+#pragma unroll 1
+        for (int r = 1; r < 23; r += UR) {
+#pragma unroll
+            for (int k = 0; k < UR; k++) round<FMAMASK>(al, ah, RC_LO[r + k], RC_HI[r + k]);
+        }
+        round<FMAMASK>(al, ah, RC_LO[23], RC_HI[23]);
+    } else if constexpr (UNROLL >= 24) {
 #pragma unroll
         for (int r = 0; r < 24; r++) round<FMAMASK>(al, ah, RC_LO[r], RC_HI[r]);
     } else {

@@ -114,7 +114,7 @@ struct FoldWeights {
 void launch_block_sums(const uint32_t *src, uint64_t n, int k, const Mailbox &mb, int sm_count, cudaStream_t st);
 // dst[i] = sum_t w[t] src[t m + i] (m = n >> k, i < m; dst may equal src). k_next >= 0 with m >> k_next >= 4: payload =
 // 2^k_next block sums of dst. dump != nullptr (needs m <= 2^LIN_DUMP_MAX_LOG2, m % 4 == 0): the folded values themselves go to
-// dump[0..m) as u64 (host-mapped) instead, and the payload is empty.
+// dump[0..m) as canonical u32 (host-mapped, 16-byte aligned) instead, and the payload is empty.
 void launch_foldk_sums(const uint32_t *src, uint32_t *dst, uint64_t n, int k, const FoldWeights &w, int k_next,
                        unsigned long long *dump, const Mailbox &mb, int sm_count, cudaStream_t st);
 
@@ -135,6 +135,18 @@ void launch_eval_stage(const uint32_t *src, uint64_t n, int nvars, const EvalPoi
 void launch_eval_finish(const uint32_t *src, uint64_t n, int nv, const EvalPoint &pt, uint32_t *out, int nv2, const EvalPoint &pt2,
                         const Mailbox &mb, int sm_count, cudaStream_t st);
 
+// Batched Multilinear.eval (count polynomials of n entries, one point each): one stage folds tiles of 2^nv (nv <= 12) entries of
+// every polynomial: out[p][tile]. srcs: device array of count table pointers, or nullptr when the tables are the rows of
+// `src_rows` (row stride n). pts: device array [count][2][v] = (challenge, Shoup companion) per variable; this stage uses the
+// variables var0 .. var0 + nv. publish != nullptr (n == 2^nv): the count results also go to publish[p] (host-mapped u64) and the
+// last CTA raises mb.seq.
+void launch_eval_stage_batch(const uint32_t *const *srcs, const uint32_t *src_rows, uint64_t n, uint32_t count, int nv,
+                             const uint32_t *pts, uint32_t v, uint32_t var0, uint32_t *out, unsigned long long *publish,
+                             const Mailbox &mb, cudaStream_t st);
+// the 10-variable warp stage for large tables (n a multiple of 1024), batched the same way
+void launch_eval_warp10_batch(const uint32_t *const *srcs, uint64_t n, uint32_t count, const uint32_t *pts, uint32_t v, uint32_t var0,
+                              uint32_t *out, int sm_count, cudaStream_t st);
+
 // Large stage: folds the 10 low variables of `src` (n a multiple of 1024): out[j] = fold of src[1024 j ..). pt.r[0..10).
 void launch_eval_warp10(const uint32_t *src, uint64_t n, const EvalPoint &pt, uint32_t *out, int sm_count, cudaStream_t st);
 
@@ -145,6 +157,8 @@ void launch_widen_u32(const uint32_t *src, uint64_t *dst, uint64_t n, cudaStream
 void launch_fill(uint32_t *dst, uint64_t n, uint32_t value, cudaStream_t st);
 void launch_synthetic(uint32_t *dst, uint64_t n, uint64_t seed, uint64_t start, uint64_t stride, cudaStream_t st);
 void launch_add(const uint32_t *a, const uint32_t *b, uint32_t *out, uint64_t n, cudaStream_t st);
+// out[i] = lo[i & (2^s - 1)] * hi_mont[i >> s] * 2^-32 mod p
+void launch_eq_table(const uint32_t *lo, const uint32_t *hi_mont, int s, uint64_t n, uint32_t *out, cudaStream_t st);
 void launch_scalar_mul(const uint32_t *a, uint32_t s, uint32_t *out, uint64_t n, cudaStream_t st);
 
 // Witness packing (witness.zig:29-270): see k_witness_pack. n_cols <= 64.
@@ -178,6 +192,10 @@ constexpr uint64_t MERKLE_TOP_WIDTH = 1024;
 // publishes mb.seq
 void launch_merkle_path(const uint8_t *tree, uint64_t padded, uint32_t height, uint64_t index, uint8_t *out, const Mailbox &mb,
                         cudaStream_t st);
+// `count` (<= 65535) openings in one launch: paths to out[t][height][32], leaf values to vals[t]; trees / values / idx are
+// device arrays of `count` entries
+void launch_merkle_path_batch(const uint8_t *const *trees, const uint32_t *const *values, const uint64_t *idx, uint32_t count,
+                              uint64_t padded, uint32_t height, uint8_t *out, uint32_t *vals, cudaStream_t st);
 // copies the root of every tree of the batch to `out` (host-mapped bulk area), then publishes mb.seq
 void launch_merkle_roots(const MerkleBatch &b, uint64_t padded, uint8_t *out, const Mailbox &mb, cudaStream_t st);
 

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(KT) k_merkle_top(MerkleBatch b, uint64_t padde
         const uint8_t *in = tree + (2 * padded - (2 * padded >> level)) * 32;
         uint8_t *out = tree + (2 * padded - (2 * padded >> (level + 1))) * 32;
         const uint64_t width_out = width / 2;
-        for (uint64_t i = threadIdx.x; i < width_out; i += KT) hash_pair<0, 8>(in + i * 64, out + i * 32);
+        for (uint64_t i = threadIdx.x; i < width_out; i += KT) hash_pair<0, 102>(in + i * 64, out + i * 32);
         __syncthreads(); // global writes of this CTA are visible to the CTA after the barrier
         width = width_out;
         level++;
@@ -143,6 +143,25 @@ __global__ void k_merkle_roots(MerkleBatch b, uint64_t padded, uint8_t *out, Mai
     publish_seq(mb);
 }
 
+// `count` openings in one launch (Prover.generateCommitments opens 43 trees, prover.zig:420-443): CTA t gathers the path of
+// leaf idx[t] of tree t into out + t * (height * 32), and the leaf value into vals[t]
+__global__ void k_merkle_path_batch(const uint8_t *const *trees, const uint32_t *const *values, const uint64_t *idx, uint64_t padded,
+                                    uint32_t height, uint8_t *out, uint32_t *vals) {
+    const uint32_t t = blockIdx.x, l = threadIdx.x >> 1, half = threadIdx.x & 1;
+    const uint64_t index = idx[t];
+    if (l < height) {
+        const uint64_t sib = (index >> l) ^ 1ull;
+        const uint64_t off = (2 * padded - (2 * padded >> l)) + sib;
+        const uint4 *p = reinterpret_cast<const uint4 *>(trees[t] + off * 32);
+        reinterpret_cast<uint4 *>(out + ((uint64_t)t * height + l) * 32)[half] = p[half];
+    }
+    if (threadIdx.x == 0) vals[t] = values[t][index];
+}
+void launch_merkle_path_batch(const uint8_t *const *trees, const uint32_t *const *values, const uint64_t *idx, uint32_t count,
+                              uint64_t padded, uint32_t height, uint8_t *out, uint32_t *vals, cudaStream_t st) {
+    k_merkle_path_batch<<<count, 2 * 64, 0, st>>>(trees, values, idx, padded, height, out, vals);
+}
+
 static inline unsigned hash_grid(uint64_t items) {
     uint64_t g = (items + KT - 1) / KT;
     const uint64_t cap = 148ull * 64; // grid-stride beyond this
@@ -161,6 +180,8 @@ void launch_merkle_leaves(const MerkleBatch &b, uint64_t padded, cudaStream_t st
 #endif
     default:
         switch (keccak_unroll(true)) {
+        case 102: k_merkle_leaves<0, 102><<<grid, KT, 0, st>>>(b, padded); break;
+        case 111: k_merkle_leaves<0, 111><<<grid, KT, 0, st>>>(b, padded); break;
         case 12: k_merkle_leaves<0, 12><<<grid, KT, 0, st>>>(b, padded); break;
         case 8: k_merkle_leaves<0, 8><<<grid, KT, 0, st>>>(b, padded); break;
         case 6: k_merkle_leaves<0, 6><<<grid, KT, 0, st>>>(b, padded); break;
@@ -185,6 +206,8 @@ void launch_merkle_level(const MerkleBatch &b, uint64_t padded, uint32_t level, 
 #endif
     default:
         switch (keccak_unroll(false)) {
+        case 102: k_merkle_level<0, 102><<<grid, KT, 0, st>>>(b, io, oo, width_out); break;
+        case 111: k_merkle_level<0, 111><<<grid, KT, 0, st>>>(b, io, oo, width_out); break;
         case 12: k_merkle_level<0, 12><<<grid, KT, 0, st>>>(b, io, oo, width_out); break;
         case 8: k_merkle_level<0, 8><<<grid, KT, 0, st>>>(b, io, oo, width_out); break;
         case 6: k_merkle_level<0, 6><<<grid, KT, 0, st>>>(b, io, oo, width_out); break;

@@ -1349,9 +1349,10 @@ __global__ void __launch_bounds__(TPB, MINB) k_foldk_sums(const uint32_t *src, u
                 for (int q = 0; q < 4; q++) r[q] = NT == 4 ? (uint32_t)a[q] : reduce_small(a[q]);
             }
             o[i4] = make_uint4(r[0], r[1], r[2], r[3]);
-            if (dump != nullptr) {
-                volatile unsigned long long *d = (volatile unsigned long long *)dump + 4 * i4;
-                d[0] = r[0], d[1] = r[1], d[2] = r[2], d[3] = r[3];
+            if (dump != nullptr) { // published table: canonical u32, one 16-byte store per thread (a quarter of the PCIe writes of u64)
+                asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<uint4 *>(dump) + i4), "r"(r[0]), "r"(r[1]),
+                             "r"(r[2]), "r"(r[3])
+                             : "memory");
             } else {
                 s += (unsigned long long)(r[0] + r[1]) + (unsigned long long)(r[2] + r[3]);
             }
@@ -1564,6 +1565,96 @@ void launch_eval_finish(const uint32_t *src, uint64_t n, int nv, const EvalPoint
     k_eval_finish<<<(int)(n_tiles < cap ? n_tiles : cap), THREADS, 0, st>>>(src, n_tiles, nv, pt, out, nv2, pt2, mb);
 }
 
+// ---- batched evaluation (count polynomials, one point each; blockIdx.y = polynomial) ----
+__device__ __forceinline__ void load_point(const uint32_t *pts, uint32_t poly, uint32_t v, uint32_t var0, int nv, EvalPoint &pt) {
+    const uint32_t *r = pts + (size_t)poly * 2 * v + var0, *rp = r + v;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        pt.r[k] = k < nv ? r[k] : 0;
+        pt.rp[k] = k < nv ? rp[k] : 0;
+    }
+}
+__global__ void __launch_bounds__(THREADS) k_eval_stage_batch(const uint32_t *const *srcs, const uint32_t *src_rows, uint64_t n, int nv,
+                                                              const uint32_t *pts, uint32_t v, uint32_t var0, uint32_t *out,
+                                                              unsigned long long *publish, Mailbox mb) {
+    __shared__ uint32_t sm[THREADS / 32];
+    __shared__ bool is_last;
+    const uint32_t poly = blockIdx.y;
+    EvalPoint pt;
+    load_point(pts, poly, v, var0, nv, pt);
+    const uint32_t *src = srcs ? srcs[poly] : src_rows + (size_t)poly * n;
+    const uint64_t tile_elems = 1ull << nv, n_tiles = n >> nv;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t x = cta_fold_tile(src + tile * tile_elems, tile_elems, nv, pt, sm);
+        if (threadIdx.x == 0) {
+            out[(size_t)poly * n_tiles + tile] = x;
+            if (publish) ((volatile unsigned long long *)publish)[poly] = x;
+        }
+    }
+    if (publish == nullptr) return;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        is_last = (atomicAdd(mb.ticket, 1u) == gridDim.x * gridDim.y - 1);
+        if (is_last) {
+            *mb.ticket = 0u;
+            __threadfence_system();
+            ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
+        }
+    }
+}
+void launch_eval_stage_batch(const uint32_t *const *srcs, const uint32_t *src_rows, uint64_t n, uint32_t count, int nv,
+                             const uint32_t *pts, uint32_t v, uint32_t var0, uint32_t *out, unsigned long long *publish,
+                             const Mailbox &mb, cudaStream_t st) {
+    const uint64_t n_tiles = n >> nv;
+    dim3 grid((unsigned)(n_tiles < 1024 ? n_tiles : 1024), count);
+    k_eval_stage_batch<<<grid, THREADS, 0, st>>>(srcs, src_rows, n, nv, pts, v, var0, out, publish, mb);
+}
+
+__global__ void __launch_bounds__(THREADS) k_eval_warp10_batch(const uint32_t *const *srcs, uint64_t n_tiles, const uint32_t *pts, uint32_t v,
+                                                               uint32_t var0, uint32_t *out) {
+    const uint32_t poly = blockIdx.y;
+    EvalPoint pt;
+    load_point(pts, poly, v, var0, 10, pt);
+    const uint32_t *__restrict__ src = srcs[poly];
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * THREADS) >> 5;
+    for (uint64_t t = warp; t < n_tiles; t += n_warps) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(src + t * 1024) + lane;
+        uint4 q[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) q[j] = __ldg(p + 32 * j);
+        uint32_t e[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t a = bb::lerp(q[j].x, q[j].y, pt.r[0], pt.rp[0]);
+            const uint32_t b = bb::lerp(q[j].z, q[j].w, pt.r[0], pt.rp[0]);
+            e[j] = bb::lerp(a, b, pt.r[1], pt.rp[1]);
+        }
+#pragma unroll
+        for (int lv = 0; lv < 3; lv++) {
+#pragma unroll
+            for (int j = 0; j < (4 >> lv); j++) e[j] = bb::lerp(e[2 * j], e[2 * j + 1], pt.r[7 + lv], pt.rp[7 + lv]);
+        }
+        uint32_t x = e[0];
+#pragma unroll
+        for (int step = 0; step < 5; step++) {
+            uint32_t other = __shfl_down_sync(0xffffffffu, x, 1 << step);
+            x = bb::lerp(x, other, pt.r[2 + step], pt.rp[2 + step]);
+        }
+        if (lane == 0) out[(size_t)poly * n_tiles + t] = x;
+    }
+}
+void launch_eval_warp10_batch(const uint32_t *const *srcs, uint64_t n, uint32_t count, const uint32_t *pts, uint32_t v, uint32_t var0,
+                              uint32_t *out, int sm, cudaStream_t st) {
+    const uint64_t n_tiles = n >> 10;
+    uint64_t ctas = (n_tiles + THREADS / 32 - 1) / (THREADS / 32), cap = ((uint64_t)sm * 4 + count - 1) / count;
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    dim3 grid((unsigned)ctas, count);
+    k_eval_warp10_batch<<<grid, THREADS, 0, st>>>(srcs, n_tiles, pts, v, var0, out);
+}
+
 // Big stages: one WARP folds a tile of 1024 consecutive elements (10 variables) with fully coalesced 512-byte
 // loads and no block barrier. The multilinear extension is symmetric in the order variables are bound (exact
 // arithmetic), so the kernel binds them in the order the data arrives: bits 0,1 (inside a uint4), bits 7,8,9 (the
@@ -1747,6 +1838,13 @@ __global__ void k_synthetic(uint32_t *dst, uint64_t n, uint64_t seed, uint64_t s
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         dst[i] = (uint32_t)(splitmix64(seed + start + i * step) % bb::P);
 }
+// eq table of a point from two half tables: out[i] = lo[i & (2^s - 1)] * hi[i >> s], hi in Montgomery form (one product per entry;
+// the halves have <= 2^16 entries and stay in L1/L2)
+__global__ void k_eq_table(const uint32_t *__restrict__ lo, const uint32_t *__restrict__ hi_mont, int s, uint64_t n, uint32_t *out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, mask = (1ull << s) - 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = bb::mont_mul(__ldg(lo + (i & mask)), __ldg(hi_mont + (i >> s)));
+}
 __global__ void k_add(const uint32_t *a, const uint32_t *b, uint32_t *o, uint64_t n) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) o[i] = bb::add(a[i], b[i]);
@@ -1801,6 +1899,9 @@ void launch_widen_u32(const uint32_t *src, uint64_t *dst, uint64_t n, cudaStream
 void launch_fill(uint32_t *dst, uint64_t n, uint32_t v, cudaStream_t st) { k_fill<<<ew_grid(n), 256, 0, st>>>(dst, n, v); }
 void launch_synthetic(uint32_t *dst, uint64_t n, uint64_t seed, uint64_t start, uint64_t step, cudaStream_t st) {
     k_synthetic<<<ew_grid(n), 256, 0, st>>>(dst, n, seed, start, step);
+}
+void launch_eq_table(const uint32_t *lo, const uint32_t *hi_mont, int s, uint64_t n, uint32_t *out, cudaStream_t st) {
+    k_eq_table<<<ew_grid(n), 256, 0, st>>>(lo, hi_mont, s, n, out);
 }
 void launch_add(const uint32_t *a, const uint32_t *b, uint32_t *o, uint64_t n, cudaStream_t st) {
     k_add<<<ew_grid(n), 256, 0, st>>>(a, b, o, n);
