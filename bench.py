@@ -28,7 +28,10 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 SEED = 0x5A49475A
-MERKLE_ALU_OPS = 4308.0  # ALU-pipe instructions per Keccak-f[1600] + SHA3 framing in k_merkle_*: 24 x (122 LOP3 + 58 SHF) - folded constants
+# ALU-pipe (LOP3 + SHF) instructions per hash in k_merkle_* with the peeled Keccak (keccak.cuh, UNROLL 102), counted in the SASS
+# (cuobjdump): 11 iterations x 360 in the two-round loop + 220 (node) / 176 (leaf) in the folded first and stripped last round;
+# a tree has as many nodes as leaves, so the mean is 4158 (4308 with the rolled loops of round 1)
+MERKLE_ALU_OPS = 4158.0
 METRIC = "babybear_sumcheck_melem_per_s"
 UNIT = "Melem/s"
 
@@ -284,14 +287,14 @@ def run_ours(args):
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else 0.0
     kernel_ms = sum(v[1] for v in prof.values())
     # DRAM traffic of the dominant kernel: ncu's dram bytes / algorithmic bytes of the committed capture of this very
-    # configuration (profiles/r01_traffic.json), applied to this run's per-launch algorithmic bytes
+    # configuration (profiles/r02_traffic.json), applied to this run's per-launch algorithmic bytes
     traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         if dom_name in tj.get("families", {}) and dom_cnt:
             ratio = tj["families"][dom_name]["ratio"]
             traffic = ratio * dom_bytes / dom_cnt
-            traffic_src = ("ncu dram__bytes_read+write / algorithmic = %.4f (profiles/r01_traffic.json) x this run's algorithmic "
+            traffic_src = ("ncu dram__bytes_read+write / algorithmic = %.4f (profiles/r02_traffic.json) x this run's algorithmic "
                            "bytes per launch" % ratio)
     except Exception:  # noqa: BLE001
         pass

@@ -33,17 +33,19 @@ constexpr uint32_t FMA_MASKS[5] = {0u, 0x1FEu, 0x1FFFEu, 0x1FFFFFEu, 0x3FFFFFFEu
 #ifndef ZB_KECCAK_DEFAULT_VARIANT
 #define ZB_KECCAK_DEFAULT_VARIANT 0
 #endif
-// Rounds per loop iteration, measured at 2^24 leaves (profiles/r01_keccak_unroll.txt): the leaf kernel is fastest fully
-// unrolled (the mostly-zero initial state folds away), the node kernel with 8 rounds per iteration (23 KB of code fits
-// the 32 KB L1.5 instruction cache; fully unrolled it is 69 KB and 6 % slower).
+// Rounds per loop iteration. Round 1 (profiles/r01_keccak_unroll.txt): leaves fully unrolled (24), nodes 8 per iteration
+// (fully unrolled the code is 69 KB, more than the 32 KB L1.5 instruction cache). Round 2 (profiles/r02_sweep4.txt, 2^26
+// leaves): the PEELED form 102 — round 0 and round 23 as straight-line code around a loop of 11 x 2 rounds (keccak.cuh) —
+// gets the constant folding of the first round and the dead-lane elimination of the last one in ~12 KB of code:
+// node levels 15.96 -> 15.37 ms, leaves 16.51 -> 15.12 ms, commit 32.71 -> 30.75 ms.
 static int keccak_unroll(bool leaves) {
     static const int v_leaf = [] {
         const char *e = getenv("ZB_KECCAK_UNROLL_LEAF");
-        return e && *e ? atoi(e) : 24;
+        return e && *e ? atoi(e) : 102;
     }();
     static const int v_node = [] {
         const char *e = getenv("ZB_KECCAK_UNROLL");
-        return e && *e ? atoi(e) : 8;
+        return e && *e ? atoi(e) : 102;
     }();
     return leaves ? v_leaf : v_node;
 }
