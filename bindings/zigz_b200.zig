@@ -147,6 +147,7 @@ pub extern fn zb_mle_fold_multi(ctx: *Ctx, m: Mle, k_fold: u32, r: [*c]const u64
 pub extern fn zb_mle_collapse(ctx: *Ctx, m: Mle, value: u64) i32;
 pub extern fn zb_merkle_open_batch(ctx: *Ctx, trees: [*c]const Tree, count: u32, indices: [*c]const u64, siblings: [*c]u8, dirs: [*c]u8, leaf_values: [*c]u64) i32;
 pub extern fn zb_merkle_leaf_hashes(ctx: *Ctx, t: Tree, out: [*c]u8, n_digests: u64) i32;
+pub extern fn zb_witness_pack_commit(ctx: *Ctx, cols: [*c]const u64, num_steps: u64, n_cols: u32, n_hold: u32, out: [*c]Mle, num_vars: [*c]u32, trees: [*c]Tree, roots: [*c]u8) i32;
 pub extern fn zb_comm_unique_id(nccl_path: [*:0]const u8, out: *[128]u8) i32;
 pub extern fn zb_comm_init(ctx: *Ctx, nccl_path: [*:0]const u8, unique_id: *const [128]u8, rank: i32, world: i32) i32;
 pub extern fn zb_comm_info(ctx: *Ctx, rank: [*c]i32, world: [*c]i32) i32;

@@ -240,6 +240,11 @@ int32_t zb_table_mle(zb_ctx *ctx, int32_t op, uint32_t bits, zb_mle *out);
 int32_t zb_witness_pack(zb_ctx *ctx, const uint64_t *cols, uint64_t num_steps, uint32_t n_cols, uint32_t n_hold, zb_mle *out,
                         uint32_t *num_vars);
 
+/* zb_witness_pack and the commit of the n_cols (<= 64) resulting polynomials (zb_merkle_build) as ONE pipeline: while column c
+ * crosses PCIe, the GPU packs and leaf-hashes column c-1. Same polynomials, same trees and roots as the two calls in a row. */
+int32_t zb_witness_pack_commit(zb_ctx *ctx, const uint64_t *cols, uint64_t num_steps, uint32_t n_cols, uint32_t n_hold, zb_mle *out,
+                               uint32_t *num_vars, zb_tree *trees, uint8_t *roots);
+
 /* ---- multi-GPU: one context per process and GPU; NCCL over NVLink/NVSwitch carries the per-round exchange ----
  * The hypercube is sharded CYCLICALLY (rank = low log2(world) index bits) so that every MSB-first pair (i, i + n/2)
  * of partialEval / roundPolynomial is local to one GPU; per round only the d+1 partial coefficients cross GPUs.

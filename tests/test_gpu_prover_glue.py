@@ -105,3 +105,36 @@ def test_prove_from_trace_larger_trace_vs_oracle(zlib, ctx, po):
     bad = bytearray(proof)
     bad[len(bad) // 2] ^= 0x10
     assert zlib.verify_proof(bytes(bad), inp["program"]) == po.verify_proof(BB, bytes(bad), inp["program"])
+
+
+@pytest.mark.parametrize("steps", [1, 2, 5, 64, 1000, 4097, (1 << 17) + 3])
+def test_witness_pack_commit_pipeline_equals_the_two_calls(zlib, ctx, po, steps):
+    """zb_witness_pack_commit (trace upload overlapped with leaf hashing) == zb_witness_pack followed by zb_merkle_build:
+    same polynomials (witness.zig:29-270), same roots and openings (merkle_tree.zig:283-360); the large case crosses the
+    pinned-staging threshold of the upload path."""
+    if steps > 100000:
+        rng = np.random.default_rng(steps)
+        cols = rng.integers(0, 1 << 64, size=(43, steps), dtype=np.uint64)
+    else:
+        cols = witness_cols(steps)
+    polys, coms, trees = zlib.witness_pack_commit(ctx, cols)
+    ref = zlib.witness_pack(ctx, cols)
+    rcoms, rtrees = zlib.CommitmentScheme.batch_commit(ref)
+    assert len(polys) == 43
+    for i in (0, 1, 32, 33, 42) if steps > 100000 else range(43):
+        assert np.array_equal(polys[i].evaluations, ref[i].evaluations), i
+    for a, b in zip(coms, rcoms):
+        assert a.commitment == b.commitment and a.num_vars == b.num_vars
+    if steps <= 1000:
+        want = po.witness_pack(BB, cols, 33)
+        for i in (0, 7, 33, 42):
+            assert coms[i].commitment == po.merkle_build(want[i]).root
+    padded = len(polys[0])
+    for i in (0, 42):
+        for idx in {0, padded - 1, padded // 2}:
+            pa, pb = trees[i].open(idx), rtrees[i].open(idx)
+            assert pa.value == pb.value and np.array_equal(pa.path.siblings, pb.path.siblings)
+    for x in polys + ref:
+        x.deinit()
+    for t in trees + rtrees:
+        t.deinit()

@@ -9,5 +9,5 @@ from ._cabi import LIB_PATH, ZigzError, build, declared_prototypes, lib  # noqa:
 from .api import (  # noqa: F401
     BABYBEAR_P, TABLE_ADD, TABLE_AND, TABLE_XOR, CommitmentScheme, Context, FiatShamirTranscript, LassoProof, LassoProver,
     MerkleOpeningProof, MerklePath, MerkleTree, Multilinear, OpeningProof, PolynomialCommitment, ProductSumcheckProver, EqProductSumcheckProver, SimpleMerkleTree,
-    SumcheckProof, SumcheckProver, CommitmentOpenings, WITNESS_COLUMNS, generate_commitments, witness_pack, prove_from_trace, verify_proof, build_add_table, build_and_table, build_xor_table, eval_univariate_coeffs, sha3_256,
+    SumcheckProof, SumcheckProver, CommitmentOpenings, WITNESS_COLUMNS, generate_commitments, witness_pack, witness_pack_commit, prove_from_trace, verify_proof, build_add_table, build_and_table, build_xor_table, eval_univariate_coeffs, sha3_256,
 )

@@ -649,6 +649,20 @@ def witness_pack(ctx: Context, cols, n_hold: int = 33) -> List[Multilinear]:
 VERDICTS = {0: "Accept", 1: "RejectInvalidSumcheck", 2: "RejectInvalidLookup", 3: "RejectInvalidCommitment"}
 
 
+def witness_pack_commit(ctx: Context, cols, n_hold: int = 33):
+    """witness_pack + CommitmentScheme.batch_commit as one pipeline (zb_witness_pack_commit: the trace upload overlaps the
+    leaf hashing). Returns (polynomials, commitments, trees) — same values as the two calls in a row."""
+    c = _a64(cols)
+    n_cols, steps = c.shape
+    out, trees = (u64 * n_cols)(), (u64 * n_cols)()
+    roots = np.zeros((n_cols, 32), np.uint8)
+    nv = u32(0)
+    ctx.check(lib().zb_witness_pack_commit(ctx.handle, _p64(c.reshape(-1)), steps, n_cols, n_hold, out, C.byref(nv), trees, _p8(roots)))
+    polys = [Multilinear(ctx, out[i]) for i in range(n_cols)]
+    return (polys, [PolynomialCommitment(roots[i].tobytes(), nv.value) for i in range(n_cols)],
+            [SimpleMerkleTree(ctx, trees[i], roots[i].tobytes()) for i in range(n_cols)])
+
+
 def prove_from_trace(ctx: Context, program: bytes, entry_pc: int, initial_regs, cols, final_pc: int, final_regs, outputs,
                      compat_buffer: bool = False) -> bytes:
     """Everything `zigz prove` does after the VM has produced the trace (src/prover/prover.zig:91-226) + the "ZIGZ" v1

@@ -75,6 +75,8 @@ struct zb_ctx {
     unsigned long long seq = 0;
     uint64_t launches = 0;
     uint64_t h2d_bytes = 0; // bytes handed to host->device copies by the upload paths (bench.py: pcie_frac)
+    cudaStream_t copy_stream = nullptr; // second stream for copies that overlap kernels (zb_witness_pack_commit), made on demand
+    cudaEvent_t pipe_up[3] = {nullptr, nullptr, nullptr}, pipe_used[3] = {nullptr, nullptr, nullptr};
     // allocator cache
     std::multimap<size_t, void *> free_blocks;
     size_t cached_bytes = 0;
@@ -518,12 +520,13 @@ int32_t ensure_pack(zb_ctx *ctx) {
 // Plain H2D copy of `bytes` bytes that does not depend on the source being page-locked: pageable sources are copied by
 // the pool threads into the rotating pinned staging buffers while the previous piece is in flight (the driver's own
 // pageable path manages ~11 GB/s on these hosts), pinned sources go straight to the DMA engine.
-int32_t staged_h2d(zb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+int32_t staged_h2d(zb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st = nullptr) {
+    if (!st) st = ctx->stream;
     cudaPointerAttributes attr{};
     const bool pinned = cudaPointerGetAttributes(&attr, h_src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (pinned || bytes < (1u << 20)) {
-        CK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
         ctx->h2d_bytes += bytes;
         return ZB_OK;
     }
@@ -543,9 +546,9 @@ int32_t staged_h2d(zb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
             const size_t lo = per * tid < m ? per * tid : m, hi = lo + per < m ? lo + per : m;
             if (hi > lo) memcpy(stage + lo, src + lo, hi - lo);
         });
-        CK(cudaMemcpyAsync((char *)d_dst + off, stage, m, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync((char *)d_dst + off, stage, m, cudaMemcpyHostToDevice, st));
         ctx->h2d_bytes += m;
-        CK(cudaEventRecord(ctx->pack_done[buf], ctx->stream));
+        CK(cudaEventRecord(ctx->pack_done[buf], st));
     }
     return ZB_OK;
 }
@@ -813,6 +816,11 @@ void zb_ctx_destroy(zb_ctx *ctx) {
     for (int b = 0; b < 3; b++) {
         if (ctx->pack_buf[b]) cudaFreeHost(ctx->pack_buf[b]);
         if (ctx->pack_done[b]) cudaEventDestroy(ctx->pack_done[b]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int b = 0; b < 3; b++) {
+        if (ctx->pipe_up[b]) cudaEventDestroy(ctx->pipe_up[b]);
+        if (ctx->pipe_used[b]) cudaEventDestroy(ctx->pipe_used[b]);
     }
     if (ctx->h_chal) cudaFreeHost(ctx->h_chal);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
@@ -2081,7 +2089,7 @@ int32_t zb_mle_collapse(zb_ctx *ctx, zb_mle h, uint64_t value) {
 
 /* ------------------------------------------------------------------ Merkle */
 
-static int32_t build_batch(zb_ctx *ctx, Tree **ts, uint32_t count, uint8_t *roots) {
+static int32_t build_batch(zb_ctx *ctx, Tree **ts, uint32_t count, uint8_t *roots, bool with_leaves = true) {
     const uint64_t padded = ts[0]->padded;
     const uint32_t height = ts[0]->height;
     MerkleBatch b{};
@@ -2091,11 +2099,13 @@ static int32_t build_batch(zb_ctx *ctx, Tree **ts, uint32_t count, uint8_t *root
         b.n_values[t] = ts[t]->n_values;
         b.tree[t] = (uint8_t *)ts[t]->store->ptr;
     }
-    {
-        ProfScope _ps(ctx, "merkle_leaves", padded * 36 * count);
-        launch_merkle_leaves(b, padded, ctx->stream);
+    if (with_leaves) {
+        {
+            ProfScope _ps(ctx, "merkle_leaves", padded * 36 * count);
+            launch_merkle_leaves(b, padded, ctx->stream);
+        }
+        LAUNCHED("merkle_leaves");
     }
-    LAUNCHED("merkle_leaves");
     uint32_t level = 0;
     while ((padded >> level) > MERKLE_TOP_WIDTH) {
         {
@@ -2487,6 +2497,98 @@ int32_t zb_witness_pack(zb_ctx *ctx, const uint64_t *cols, uint64_t num_steps, u
     }
     rc = zb_sync(ctx);
     return rc ? fail(rc) : ZB_OK;
+}
+
+// WitnessGenerator.generate + the commit phase of Prover.generateCommitments (prover.zig:405-410) as ONE pipeline: column c
+// goes up on a copy stream while the SMs pack and leaf-hash column c-1, so the 8-byte-per-value trace upload (PCIe) and the
+// leaf hashing (integer pipe) overlap instead of adding up; the upper levels of all trees follow as one batched build.
+int32_t zb_witness_pack_commit(zb_ctx *ctx, const uint64_t *cols, uint64_t num_steps, uint32_t n_cols, uint32_t n_hold, zb_mle *out,
+                               uint32_t *num_vars, zb_tree *trees, uint8_t *roots) {
+    tail_quiesce(ctx);
+    if (n_cols == 0 || n_cols > (uint32_t)MAX_BATCH || n_hold > n_cols || !out || !trees || !cols || num_steps == 0)
+        return ZB_ERR_BAD_ARGUMENT;
+    uint32_t v = 0;
+    while ((1ull << v) < num_steps) v++;
+    const uint64_t padded = 1ull << v;
+    if (num_vars) *num_vars = v;
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 3; b++) {
+            CK(cudaEventCreateWithFlags(&ctx->pipe_up[b], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->pipe_used[b], cudaEventDisableTiming));
+        }
+    }
+    uint32_t made = 0, made_trees = 0;
+    auto fail = [&](int32_t rc) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        for (uint32_t c = 0; c < made; c++) ctx->mles.erase(out[c]);
+        for (uint32_t c = 0; c < made_trees; c++) ctx->trees.erase(trees[c]);
+        return rc;
+    };
+    uint32_t *ptrs[MAX_BATCH];
+    for (uint32_t c = 0; c < n_cols; c++, made++) {
+        Mle *m = nullptr;
+        const int32_t rc = new_mle(ctx, padded, &out[c], &m);
+        if (rc) return fail(rc);
+        ptrs[c] = m->d();
+    }
+    Tree *ts[MAX_BATCH];
+    for (uint32_t c = 0; c < n_cols; c++, made_trees++) {
+        BufRef vals; // the tree's own copy of the values (merkle_tree.zig:291)
+        int32_t rc = dev_alloc(ctx, padded * sizeof(uint32_t), &vals);
+        Tree *tp = nullptr;
+        if (rc == ZB_OK) rc = new_tree(ctx, vals, padded, &trees[c], &tp);
+        if (rc) return fail(rc);
+    }
+    for (uint32_t c = 0; c < n_cols; c++) ts[c] = get_tree(ctx, trees[c]); // the table no longer grows
+    uint32_t h_last[MAX_BATCH] = {0};
+    for (uint32_t c = 0; c < n_hold; c++) h_last[c] = (uint32_t)(cols[(size_t)c * num_steps + num_steps - 1] % bb::P);
+    BufRef d_last, slots;
+    int32_t rc = dev_alloc(ctx, sizeof(h_last), &d_last);
+    if (rc == ZB_OK) rc = dev_alloc(ctx, 3 * num_steps * sizeof(uint64_t), &slots);
+    if (rc) return fail(rc);
+    cudaError_t ce = cudaMemcpyAsync(d_last->ptr, h_last, sizeof(h_last), cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream); // h_last is a stack buffer
+    if (ce != cudaSuccess) return fail(cuda_fail(ctx, ce, "witness_pack_commit: padding values"));
+    for (uint32_t c = 0; c < n_cols; c++) {
+        const int slot = (int)(c % 3);
+        uint64_t *stage = (uint64_t *)slots->ptr + (size_t)slot * num_steps;
+        if (c >= 3) ce = cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_used[slot], 0); // the pack kernel has drained the slot
+        if (ce != cudaSuccess) return fail(cuda_fail(ctx, ce, "cudaStreamWaitEvent"));
+        rc = staged_h2d(ctx, stage, cols + (size_t)c * num_steps, num_steps * sizeof(uint64_t), ctx->copy_stream);
+        if (rc) return fail(rc);
+        ce = cudaEventRecord(ctx->pipe_up[slot], ctx->copy_stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream, ctx->pipe_up[slot], 0);
+        if (ce != cudaSuccess) return fail(cuda_fail(ctx, ce, "cudaEventRecord"));
+        {
+            ProfScope _ps(ctx, "witness_pack", num_steps * 8 + padded * 4);
+            launch_witness_pack(stage, padded, 0, num_steps, padded, 1, c < n_hold ? 1u : 0u, (const uint32_t *)d_last->ptr + c, &ptrs[c],
+                                ctx->stream);
+        }
+        rc = check_launch(ctx, "witness_pack");
+        if (rc) return fail(rc);
+        ce = cudaEventRecord(ctx->pipe_used[slot], ctx->stream);
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(ts[c]->values->ptr, ptrs[c], padded * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (ce != cudaSuccess) return fail(cuda_fail(ctx, ce, "witness_pack_commit: tree values"));
+        MerkleBatch one{};
+        one.count = 1;
+        one.values[0] = (const uint32_t *)ts[c]->values->ptr;
+        one.n_values[0] = padded;
+        one.tree[0] = (uint8_t *)ts[c]->store->ptr;
+        {
+            ProfScope _ps(ctx, "merkle_leaves", padded * 36);
+            launch_merkle_leaves(one, padded, ctx->stream);
+        }
+        rc = check_launch(ctx, "merkle_leaves");
+        if (rc) return fail(rc);
+    }
+    rc = build_batch(ctx, ts, n_cols, roots, /*with_leaves=*/false);
+    if (rc) return fail(rc);
+    ce = cudaStreamSynchronize(ctx->copy_stream);
+    if (ce != cudaSuccess) return fail(cuda_fail(ctx, ce, "copy stream"));
+    return ZB_OK;
 }
 
 /* ------------------------------------------------------------------ multi-GPU (NCCL, dlopen'ed) */

@@ -652,19 +652,34 @@ int32_t zh_commit_verify(const uint8_t root[32], uint64_t leaf_value, const uint
     return zh_merkle_verify(root, leaf_value, siblings, dirs, height);
 }
 
+static int32_t commitments_after_build(zb_ctx *ctx, zh_transcript *tr, const zb_mle *polys, std::vector<zb_tree> &trees, uint32_t count,
+                                       uint8_t *roots, uint64_t *points, uint64_t *values, uint64_t *leaf_indices, uint64_t *leaf_values,
+                                       uint8_t *siblings, uint8_t *dirs);
+
 int32_t zh_generate_commitments(zb_ctx *ctx, zh_transcript *tr, const zb_mle *polys, uint32_t count, uint8_t *roots,
                                 uint64_t *points, uint64_t *values, uint64_t *leaf_indices, uint64_t *leaf_values,
                                 uint8_t *siblings, uint8_t *dirs) {
     // Prover.generateCommitments, src/prover/prover.zig:366-467. Same transcript traffic, same outputs; the 43 commits
     // are ONE batched device build (trees retained), each opening is an O(N) evaluation + a gather.
     if (!tr || !polys || count == 0) return ZB_ERR_BAD_ARGUMENT;
+    std::vector<zb_tree> trees(count, 0);
+    const int32_t rc = zb_merkle_build(ctx, polys, count, trees.data(), roots); // PHASE 1 (:405-410)
+    if (rc) return rc;
+    return commitments_after_build(ctx, tr, polys, trees, count, roots, points, values, leaf_indices, leaf_values, siblings, dirs);
+}
+
+// PHASES 2-4 of Prover.generateCommitments on trees that exist already (built by zb_merkle_build, or by the pipelined
+// zb_witness_pack_commit of zh_prove_from_trace); the trees are released on return (:446-448)
+static int32_t commitments_after_build(zb_ctx *ctx, zh_transcript *tr, const zb_mle *polys, std::vector<zb_tree> &trees, uint32_t count,
+                                       uint8_t *roots, uint64_t *points, uint64_t *values, uint64_t *leaf_indices, uint64_t *leaf_values,
+                                       uint8_t *siblings, uint8_t *dirs) {
     uint64_t n;
     uint32_t v;
     int32_t rc = zb_mle_len(ctx, polys[0], &n, &v);
-    if (rc) return rc;
-    std::vector<zb_tree> trees(count, 0);
-    rc = zb_merkle_build(ctx, polys, count, trees.data(), roots); // PHASE 1 (:405-410)
-    if (rc) return rc;
+    if (rc) {
+        for (uint32_t i = 0; i < count; i++) zb_merkle_free(ctx, trees[i]);
+        return rc;
+    }
     zh_transcript_append_bytes(tr, "POLY_COMMITMENTS", 16); // PHASE 2 (:413-416)
     for (uint32_t i = 0; i < count; i++) zh_transcript_append_bytes(tr, roots + 32 * (size_t)i, 32);
     // PHASE 3 (:420-443). The loop only draws challenges from the transcript (nothing is absorbed before PHASE 4), so
@@ -798,9 +813,23 @@ int32_t zh_prove_from_trace(zb_ctx *ctx, const uint8_t *program, size_t program_
     zh_transcript_append_field(&tr, entry_pc % P); // :103
     for (uint32_t i = 0; i < n_init; i++) zh_transcript_append_field(&tr, initial_regs[i] % P); // :106-110
     // witness polynomials straight into HBM (witness.zig:29-270)
+    // ... and their commitments in the same pipeline (the trace upload overlaps the leaf hashing): PHASE 1 of
+    // Prover.generateCommitments (prover.zig:405-410) needs nothing from the transcript, only the polynomials
     zb_mle polys[43] = {0};
+    std::vector<zb_tree> trees(43, 0);
+    std::vector<uint8_t> roots(43 * 32);
     uint32_t nv = 0;
-    int32_t rc = zb_witness_pack(ctx, cols, num_steps, 43, 33, polys, &nv);
+    int32_t rc;
+    if (num_steps >= (1u << 15)) {
+        rc = zb_witness_pack_commit(ctx, cols, num_steps, 43, 33, polys, &nv, trees.data(), roots.data());
+    } else { // short traces: 3 x 43 tiny launches cost more than the overlap saves (1.9 vs 1.45 ms at 2^12 steps)
+        rc = zb_witness_pack(ctx, cols, num_steps, 43, 33, polys, &nv);
+        if (rc == ZB_OK) {
+            rc = zb_merkle_build(ctx, polys, 43, trees.data(), roots.data());
+            if (rc)
+                for (int i = 0; i < 43; i++) zb_mle_free(ctx, polys[i]);
+        }
+    }
     if (rc) return rc;
     ByteWriter w{out, out + exact};
     w.bytes("ZIGZ", 4); // header, serialization.zig:175-182
@@ -837,9 +866,10 @@ int32_t zh_prove_from_trace(zb_ctx *ctx, const uint8_t *program, size_t program_
     }
     // commitments + openings on the device (prover.zig:366-467)
     const size_t vv = v ? v : 1;
-    std::vector<uint8_t> roots(43 * 32), sib(43 * vv * 32), dirs(43 * vv);
+    std::vector<uint8_t> sib(43 * vv * 32), dirs(43 * vv);
     std::vector<uint64_t> pts(43 * vv), vals(43), li(43), lv(43);
-    rc = zh_generate_commitments(ctx, &tr, polys, 43, roots.data(), pts.data(), vals.data(), li.data(), lv.data(), sib.data(), dirs.data());
+    rc = commitments_after_build(ctx, &tr, polys, trees, 43, roots.data(), pts.data(), vals.data(), li.data(), lv.data(), sib.data(),
+                                 dirs.data());
     for (int i = 0; i < 43; i++) zb_mle_free(ctx, polys[i]);
     if (rc) return rc;
     for (int i = 0; i < 43; i++) { // serialization.zig:374-429

@@ -898,9 +898,13 @@ static void fold_grid_t(int nfold, const PolySet &ps, uint64_t m, uint32_t r1, u
     static const int ASYNC = tune("ZB_GRID_ASYNC", 1);
     static const int ASYNC_MIN = tune("ZB_GRID_ASYNC_MIN_LOG2", 16);
     // bulk-copy ring (cp.async.bulk + mbarrier): default for two folded variables, where the per-thread LDGSTS ring spends
-    // 48 copy instructions per thread and iteration (ZB_GRID_BULK: bit 0 = nfold 0, bit 1 = nfold 1, bit 2 = nfold 2)
+    // 48 copy instructions per thread and iteration (ZB_GRID_BULK: bit 0 = nfold 0, bit 1 = nfold 1, bit 2 = nfold 2).
+    // Measured (profiles/r02_sweep1.txt, r02_sweep5.txt, r02_ncu_full_2p30_summary.txt): at 2^29 entries the bulk ring needs
+    // 13 % fewer warp-instructions and runs at 6.58 TB/s under ncu (LDGSTS ring 6.43), but in the bench loop the whole chain is
+    // within 1 % either way (DRAM-bound), and for tiles counts below ~50 per CTA its 96 KB stages fill and drain too slowly:
+    // bulk from 2^26 folded entries up, the per-thread ring below.
     static const int BULK = tune("ZB_GRID_BULK", 4);
-    static const int BULK_MIN = tune("ZB_GRID_BULK_MIN_LOG2", 18);
+    static const int BULK_MIN = tune("ZB_GRID_BULK_MIN_LOG2", 26);
     if (((BULK >> nfold) & 1) && m >= (1ull << BULK_MIN) && (m / 8) % 256 == 0) {
         if (nfold == 0) fold_grid_bulk_launch<D, 0>(ps, m, r1, r2, mb, sm, st);
         else if (nfold == 1) fold_grid_bulk_launch<D, 1>(ps, m, r1, r2, mb, sm, st);
