@@ -550,6 +550,24 @@ def run_extras(args, z, ctx, peak):
                                                    "sample": "the same 2^20-entry table"},
                                   "note": "several rounds per pass through linearity: block sums, 5-variable folds, last <= 10 rounds from a published table"}
     p20.deinit()
+    # A/B of the two latency mechanisms on this very box (wall clock per prove, 2^20 entries): the d = 1 schedule with several
+    # rounds per pass vs one round per kernel + persistent tail, and the persistent tail kernel of the product prover on / off
+    ab = {}
+    p20b = z.Multilinear.synthetic(ctx, SEED, 1 << 20)
+    for lin in (1, 0):
+        ctx.set_option("linear_d1", lin)
+        ctx.check(z.lib().zh_time_sumcheck_prove(ctx.handle, p20b.handle, 100, C.byref(us)))
+        ab["d1_2^20_us_" + ("several_rounds_per_pass" if lin else "one_round_per_kernel_and_tail")] = us.value
+    ctx.set_option("linear_d1", 1)
+    p3 = [z.Multilinear.synthetic(ctx, SEED + k, 1 << 20) for k in range(3)]
+    old_tail = ctx.get_option("tail_log2")
+    for tl in (old_tail, 0):
+        ctx.set_option("tail_log2", tl)
+        ab[f"d3_2^20_us_tail_log2_{tl}"] = wall(lambda: z.ProductSumcheckProver.prove(p3), 50, warm=5) * 1e6
+    ctx.set_option("tail_log2", old_tail)
+    for p in p3 + [p20b]:
+        p.deinit()
+    out["latency_mechanisms_ab"] = ab
     # d=1 sumcheck over 2^28: HBM-bound regime of the reference's own prover
     lg = min(28, args.log2n)
     pb = z.Multilinear.synthetic(ctx, SEED, 1 << lg)
