@@ -167,9 +167,11 @@ struct zb_ctx {
         m.acc = d_acc;
         m.ticket = d_ticket;
         m.mail = d_mail;
-        m.seq = ++seq;
+        if (((++seq) & 0xffffffffull) == 0) ++seq; // tag 0 is what a cleared mailbox word carries
+        m.seq = seq;
         m.xchg = nullptr;
         m.xseq = 0;
+        m.tagged = true; // payload words validate themselves (kernels.h); kernels that publish other things ignore it
         return m;
     }
     uint8_t *h_bulk() { return (uint8_t *)h_mail + BULK_OFFSET; }
@@ -297,22 +299,34 @@ namespace {
 
 void rearm(zb_ctx *c);
 
-// Wait for the mailbox sequence number published by the last CTA of the most recent launch.
-int32_t wait_mail_raw(zb_ctx *ctx, unsigned long long seq);
-int32_t wait_mail(zb_ctx *ctx, unsigned long long seq) {
-    const int32_t rc = wait_mail_raw(ctx, seq);
+// Has the launch with sequence number `seq` published? tagged_words > 0: the kernel wrote that many self-validating payload
+// words (Mailbox::tagged) and no fence — every one of them must carry the tag; 0: payload, fence, then the sequence number.
+inline bool mail_ready(const zb_ctx *ctx, unsigned long long seq, int tagged_words) {
+    volatile const unsigned long long *m = ctx->h_mail;
+    if (tagged_words <= 0) return m[MAIL_WORDS] == seq;
+    const unsigned long long tag = seq & 0xffffffffull;
+    for (int k = 0; k < tagged_words; k++)
+        if ((m[k] >> 32) != tag) return false;
+    return true;
+}
+// payload word k of a tagged (or plain 32-bit) mailbox
+inline uint64_t mail_word(const zb_ctx *ctx, int k) { return ctx->h_mail[k] & 0xffffffffull; }
+
+// Wait for the mailbox of the most recent launch (published by its last CTA).
+int32_t wait_mail_raw(zb_ctx *ctx, unsigned long long seq, int tagged_words);
+int32_t wait_mail(zb_ctx *ctx, unsigned long long seq, int tagged_words = 0) {
+    const int32_t rc = wait_mail_raw(ctx, seq, tagged_words);
     if (rc) rearm(ctx);
     return rc;
 }
-int32_t wait_mail_raw(zb_ctx *ctx, unsigned long long seq) {
-    volatile unsigned long long *flag = ctx->h_mail + MAIL_WORDS;
+int32_t wait_mail_raw(zb_ctx *ctx, unsigned long long seq, int tagged_words) {
     auto t0 = std::chrono::steady_clock::now();
     uint64_t spins = 0;
-    while (*flag != seq) {
+    while (!mail_ready(ctx, seq, tagged_words)) {
         if ((++spins & 0xFFFF) == 0) {
             cudaError_t q = cudaStreamQuery(ctx->stream);
             if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(ctx, q, "kernel");
-            if (q == cudaSuccess && *flag != seq) {
+            if (q == cudaSuccess && !mail_ready(ctx, seq, tagged_words)) {
                 // stream drained but flag missing: give the PCIe write a moment, then report
                 if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) {
                     ctx->last_error = "mailbox sequence not published";
@@ -343,6 +357,7 @@ inline bool reduce_p2p(const zb_ctx *c) { return c->comm_reduce == 2 && c->d_xch
 inline Mailbox round_mailbox(zb_ctx *c, bool reduce) {
     Mailbox m = c->mailbox();
     if (reduce) {
+        m.tagged = false; // plain words: they are summed over the ranks before they reach the host
         if (reduce_p2p(c)) {
             m.xchg = c->d_xchg_view; // the kernel itself sums over the ranks and publishes
             m.xseq = ++c->xchg_seq;
@@ -1286,9 +1301,9 @@ int32_t zb_mle_sum(zb_ctx *ctx, zb_mle h, uint64_t *out) {
         launch_sum(m->d(), m->n, mb, ctx->sm_count, ctx->stream);
     }
     LAUNCHED("sum");
-    int32_t rc = wait_mail(ctx, mb.seq);
+    int32_t rc = wait_mail(ctx, mb.seq, 1);
     if (rc) return rc;
-    *out = ctx->h_mail[0];
+    *out = mail_word(ctx, 0);
     return ZB_OK;
 }
 
@@ -1305,10 +1320,10 @@ int32_t zb_mle_round_sums(zb_ctx *ctx, zb_mle h, uint64_t out[2]) {
         launch_round_sums(1, ps, m->n, mb, ctx->sm_count, ctx->stream);
     }
     LAUNCHED("round_sums");
-    int32_t rc = wait_mail(ctx, mb.seq);
+    int32_t rc = wait_mail(ctx, mb.seq, 2);
     if (rc) return rc;
-    out[0] = ctx->h_mail[0];
-    out[1] = ctx->h_mail[1];
+    out[0] = mail_word(ctx, 0);
+    out[1] = mail_word(ctx, 1);
     return ZB_OK;
 }
 
@@ -1323,11 +1338,11 @@ static int32_t fold_common(zb_ctx *ctx, const uint32_t *src, uint32_t *dst, uint
         launch_fold_sums(1, ps, n, (uint32_t)r, mb, ctx->sm_count, ctx->stream);
     }
     LAUNCHED("fold_sums");
-    int32_t rc = wait_mail(ctx, mb.seq);
+    int32_t rc = wait_mail(ctx, mb.seq, n == 2 ? 1 : 2);
     if (rc) return rc;
     if (next) {
-        next[0] = ctx->h_mail[0];
-        next[1] = n == 2 ? 0 : ctx->h_mail[1];
+        next[0] = mail_word(ctx, 0);
+        next[1] = n == 2 ? 0 : mail_word(ctx, 1);
     }
     return ZB_OK;
 }
@@ -1423,9 +1438,9 @@ int32_t zb_mle_eval(zb_ctx *ctx, zb_mle h, const uint64_t *point, uint32_t npoin
         done += nv;
         which ^= 1;
     } while (done < v);
-    int32_t rc = wait_mail(ctx, mb.seq);
+    int32_t rc = wait_mail(ctx, mb.seq, 1);
     if (rc) return rc;
-    *out = ctx->h_mail[0];
+    *out = mail_word(ctx, 0);
     return ZB_OK;
 }
 
@@ -1640,7 +1655,7 @@ int32_t zb_prod_round_coeffs(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint6
         rc = comm_publish(ctx, mb.seq, d == 1 ? 2 : (int)d + 1);
         if (rc) return rc;
     }
-    rc = wait_mail(ctx, mb.seq);
+    rc = wait_mail(ctx, mb.seq, mb.tagged ? (d == 1 ? 2 : (int)d + 1) : 0);
     if (rc) return rc;
     evals_to_coeffs(d, ctx->h_mail, out);
     return ZB_OK;
@@ -1649,12 +1664,11 @@ int32_t zb_prod_round_coeffs(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint6
 // Waits for mailbox sequence `seq` of a kernel that polls the host for its challenge (tail session or pre-launched
 // fold). *gone = true when the kernel has left instead (starvation exit: launches serialised by a profiler, or the host
 // thread lost the CPU): the tables are untouched for this round and the caller redoes it with a plain launch.
-static int32_t wait_polling_kernel(zb_ctx *ctx, unsigned long long seq, bool *gone) {
-    volatile unsigned long long *flag = ctx->h_mail + MAIL_WORDS;
+static int32_t wait_polling_kernel(zb_ctx *ctx, unsigned long long seq, int tagged_words, bool *gone) {
     auto t0 = std::chrono::steady_clock::now();
     uint64_t spins = 0;
     *gone = false;
-    while (*flag != seq) {
+    while (!mail_ready(ctx, seq, tagged_words)) {
         if ((++spins & 0x3FFF) == 0) {
             cudaError_t q = cudaStreamQuery(ctx->stream);
             if (q != cudaSuccess && q != cudaErrorNotReady) {
@@ -1664,9 +1678,9 @@ static int32_t wait_polling_kernel(zb_ctx *ctx, unsigned long long seq, bool *go
             }
             if (q == cudaSuccess) { // drained: give the mapped write 2 ms to land, then decide
                 auto t1 = std::chrono::steady_clock::now();
-                while (*flag != seq && std::chrono::steady_clock::now() - t1 < std::chrono::milliseconds(2)) {
+                while (!mail_ready(ctx, seq, tagged_words) && std::chrono::steady_clock::now() - t1 < std::chrono::milliseconds(2)) {
                 }
-                if (*flag != seq) *gone = true;
+                if (!mail_ready(ctx, seq, tagged_words)) *gone = true;
                 break;
             }
             if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
@@ -1824,9 +1838,10 @@ static int32_t fold_inplace_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, u
         rc = prelaunch_next(ctx, polys, d, ms, n / 2);
         if (rc) return rc;
     }
+    const int nw = n == 2 ? (int)d : (d == 1 ? 2 : (int)d + 1); // payload words of this round's kernel
     if (polling) {
         bool gone = false;
-        rc = wait_polling_kernel(ctx, mb.seq, &gone);
+        rc = wait_polling_kernel(ctx, mb.seq, mb.tagged ? nw : 0, &gone);
         if (rc) return rc;
         if (gone) {
             // redo the round with a plain launch (same exchange round number) and stop using polling kernels here
@@ -1839,6 +1854,7 @@ static int32_t fold_inplace_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, u
             Mailbox mb2 = ctx->mailbox();
             mb2.xchg = mb.xchg;
             mb2.xseq = mb.xseq;
+            mb2.tagged = !red;
             if (red && !mb2.xchg) mb2.mail = ctx->d_comm;
             {
                 ProfScope _ps(ctx, name, n * 6 * d);
@@ -1850,18 +1866,18 @@ static int32_t fold_inplace_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, u
                 rc = comm_publish(ctx, mb2.seq, d == 1 ? 2 : (int)d + 1);
                 if (rc) return rc;
             }
-            rc = wait_mail(ctx, mb2.seq);
+            rc = wait_mail(ctx, mb2.seq, mb2.tagged ? nw : 0);
             if (rc) return rc;
         } else if (in_tail) {
             ctx->tail.n = n / 2;
             if (n == 2) ctx->tail.active = false; // the kernel returns after the last round
         }
     } else {
-        rc = wait_mail(ctx, mb.seq);
+        rc = wait_mail(ctx, mb.seq, mb.tagged ? nw : 0);
         if (rc) return rc;
     }
     for (uint32_t k = 0; k < d; k++) ms[k]->n = n / 2;
-    for (int k = 0; k < 4; k++) payload[k] = ctx->h_mail[k];
+    for (int k = 0; k < 4; k++) payload[k] = mail_word(ctx, k);
     return ZB_OK;
 }
 
@@ -1916,7 +1932,7 @@ int32_t zb_prod_partial_eval(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint6
         for (uint32_t k = 0; k < d; k++) mo[k] = get_mle(ctx, out[k]);
         rc = prelaunch_next(ctx, out, d, mo, n / 2);
     }
-    if (rc == ZB_OK) rc = wait_mail(ctx, mb.seq);
+    if (rc == ZB_OK) rc = wait_mail(ctx, mb.seq, mb.tagged ? (n == 2 ? (int)d : (d == 1 ? 2 : (int)d + 1)) : 0);
     if (rc) {
         tail_quiesce(ctx); // a pre-launched kernel may reference the tables that are dropped here
         for (uint32_t k = 0; k < d; k++) ctx->mles.erase(out[k]);
@@ -1924,7 +1940,7 @@ int32_t zb_prod_partial_eval(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint6
     }
     if (next) {
         if (n == 2)
-            for (uint32_t k = 0; k < d; k++) next[k] = ctx->h_mail[k];
+            for (uint32_t k = 0; k < d; k++) next[k] = mail_word(ctx, (int)k);
         else
             evals_to_coeffs(d, ctx->h_mail, next);
     }
@@ -1973,7 +1989,7 @@ static int32_t fold_grid_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint
     }
     rc = check_launch(ctx, "fold_grid");
     if (rc == ZB_OK && red) rc = comm_publish(ctx, mb.seq, ns);
-    if (rc == ZB_OK) rc = wait_mail(ctx, mb.seq);
+    if (rc == ZB_OK) rc = wait_mail(ctx, mb.seq, mb.tagged ? ns : 0);
     if (rc) {
         if (out && nfold)
             for (uint32_t k = 0; k < d; k++) ctx->mles.erase(out[k]);
@@ -1984,7 +2000,7 @@ static int32_t fold_grid_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint
         gather_polys(ctx, polys, d, mm); // the handle table may have been rehashed by new_mle: look the tables up again
         for (uint32_t k = 0; k < d; k++) mm[k]->n = m;
     }
-    for (int k = 0; k < ns; k++) grid[k] = ctx->h_mail[k];
+    for (int k = 0; k < ns; k++) grid[k] = mail_word(ctx, k);
     return ZB_OK;
 }
 
@@ -2011,9 +2027,9 @@ int32_t zb_mle_block_sums(zb_ctx *ctx, zb_mle h, uint32_t k, uint64_t *sums) {
         launch_block_sums(m->d(), m->n, (int)k, mb, ctx->sm_count, ctx->stream);
     }
     LAUNCHED("block_sums");
-    int32_t rc = wait_mail(ctx, mb.seq);
+    int32_t rc = wait_mail(ctx, mb.seq, 1 << k);
     if (rc) return rc;
-    for (uint32_t b = 0; b < (1u << k); b++) sums[b] = ctx->h_mail[b];
+    for (uint32_t b = 0; b < (1u << k); b++) sums[b] = mail_word(ctx, (int)b);
     return ZB_OK;
 }
 
@@ -2056,7 +2072,7 @@ int32_t zb_mle_fold_multi(zb_ctx *ctx, zb_mle h, uint32_t k_fold, const uint64_t
         launch_foldk_sums(src, dst, n, (int)k_fold, fw, (int)k_next, d_dump, mb, ctx->sm_count, ctx->stream);
     }
     int32_t rc = check_launch(ctx, "foldk_sums");
-    if (rc == ZB_OK) rc = wait_mail(ctx, mb.seq);
+    if (rc == ZB_OK) rc = wait_mail(ctx, mb.seq, dump ? 0 : 1 << k_next); // a published table: fence + sequence number
     if (rc) {
         if (out) {
             ctx->mles.erase(*out);
@@ -2069,7 +2085,7 @@ int32_t zb_mle_fold_multi(zb_ctx *ctx, zb_mle h, uint32_t k_fold, const uint64_t
         const uint32_t *t = (const uint32_t *)((uint8_t *)ctx->h_mail + DUMP_OFFSET);
         for (uint64_t i = 0; i < mm; i++) sums[i] = t[i];
     } else
-        for (uint32_t b = 0; b < (1u << k_next); b++) sums[b] = ctx->h_mail[b];
+        for (uint32_t b = 0; b < (1u << k_next); b++) sums[b] = mail_word(ctx, (int)b);
     return ZB_OK;
 }
 

@@ -32,7 +32,16 @@ struct Mailbox {
     unsigned long long seq;     // sequence value this launch must publish
     const XchgView *xchg;       // non-null: sum the payload over all ranks through peer memory before publishing
     unsigned long long xseq;    // exchange round number: counts exchanged rounds only, identical on every rank
+    // tagged payload: every payload word is written as (low 32 bits of seq) << 32 | value (all payload values are canonical
+    // field elements < 2^31), so each word validates itself and NO system-scope fence is needed between the payload and the
+    // sequence number — the host waits until every word it expects carries the tag. Saves ~1.5 us per host round trip
+    // (profiles/r02_sweep7_*.txt). false: plain words, fence, then the sequence number (payloads that are not 32-bit values:
+    // digests, published tables; and mailboxes that are reduced over ranks first).
+    bool tagged;
 };
+__host__ __device__ inline unsigned long long mail_tagged(unsigned long long seq, unsigned long long v) {
+    return ((seq & 0xffffffffull) << 32) | (v & 0xffffffffull);
+}
 
 struct PolySet {
     const uint32_t *src[MAX_POLYS];

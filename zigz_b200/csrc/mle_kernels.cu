@@ -142,9 +142,14 @@ __device__ __forceinline__ void publish_sums(unsigned long long (&s)[NS], const 
             *mb.ticket = 0u;
             fin(tot);
             if (mb.xchg == nullptr) {
+                if (mb.tagged) { // self-validating words: no fence
 #pragma unroll
-                for (int k = 0; k < NS; k++) ((volatile unsigned long long *)mb.mail)[k] = tot[k];
-                __threadfence_system();
+                    for (int k = 0; k < NS; k++) ((volatile unsigned long long *)mb.mail)[k] = mail_tagged(mb.seq, tot[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NS; k++) ((volatile unsigned long long *)mb.mail)[k] = tot[k];
+                    __threadfence_system();
+                }
                 ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
             } else {
 #pragma unroll
@@ -416,9 +421,9 @@ __global__ void k_fold_last(PolySet ps, uint32_t r, uint32_t rp, Mailbox mb) {
         for (int k = 0; k < D; k++) {
             uint32_t v = bb::lerp(ps.src[k][0], ps.src[k][1], r, rp);
             ps.dst[k][0] = v;
-            ((volatile unsigned long long *)mb.mail)[k] = v;
+            ((volatile unsigned long long *)mb.mail)[k] = mb.tagged ? mail_tagged(mb.seq, v) : v;
         }
-        __threadfence_system();
+        if (!mb.tagged) __threadfence_system();
         ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
     }
 }
@@ -983,9 +988,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_rounds(PolySet ps, uint64
                 for (int k = 0; k < D; k++) {
                     uint32_t v = bb::lerp(ps.src[k][0], ps.src[k][1], r, rp);
                     ps.dst[k][0] = v;
-                    mail[k] = v;
+                    mail[k] = mb.tagged ? mail_tagged(mb.seq + round, v) : v;
                 }
-                __threadfence_system();
+                if (!mb.tagged) __threadfence_system();
                 mail[MAIL_WORDS] = mb.seq + round;
             }
             return;
@@ -1055,8 +1060,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_rounds(PolySet ps, uint64
             if (lane == 0) {
                 Finish<D>()(tot);
 #pragma unroll
-                for (int k = 0; k < NS; k++) mail[k] = tot[k];
-                __threadfence_system();
+                for (int k = 0; k < NS; k++) mail[k] = mb.tagged ? mail_tagged(mb.seq + round, tot[k]) : tot[k];
+                if (!mb.tagged) __threadfence_system();
                 mail[MAIL_WORDS] = mb.seq + round;
             }
         }
@@ -1253,9 +1258,12 @@ struct BlockAcc {
             __threadfence();
             const int lane = threadIdx.x;
             volatile unsigned long long *mail = (volatile unsigned long long *)mb.mail;
-            if (lane < nb) mail[lane] = atomicExch(&mb.acc[lane], 0ull) % bb::P; // read + re-arm
+            if (lane < nb) {
+                const unsigned long long v = atomicExch(&mb.acc[lane], 0ull) % bb::P; // read + re-arm
+                mail[lane] = mb.tagged ? mail_tagged(mb.seq, v) : v;
+            }
             if (lane == 0) *mb.ticket = 0u;
-            __threadfence_system(); // one fence: payload (all lanes) before the sequence number
+            if (!mb.tagged || nb == 0) __threadfence_system(); // plain words / a published table: payload before the sequence number
             __syncwarp();
             if (lane == 0) mail[MAIL_WORDS] = mb.seq;
         }
@@ -1464,8 +1472,8 @@ __global__ void __launch_bounds__(THREADS) k_eval_stage(const uint32_t *src, uin
             }
             out[tile] = w[0];
             if (publish) {
-                ((volatile unsigned long long *)mb.mail)[0] = w[0];
-                __threadfence_system();
+                ((volatile unsigned long long *)mb.mail)[0] = mb.tagged ? mail_tagged(mb.seq, w[0]) : w[0];
+                if (!mb.tagged) __threadfence_system();
                 ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
             }
         }
@@ -1556,8 +1564,8 @@ __global__ void __launch_bounds__(THREADS) k_eval_finish(const uint32_t *src, ui
     const uint32_t v = cta_fold_tile(out, n_tiles, nv2, pt2, sm);
     if (threadIdx.x == 0) {
         *mb.ticket = 0u;
-        ((volatile unsigned long long *)mb.mail)[0] = v;
-        __threadfence_system();
+        ((volatile unsigned long long *)mb.mail)[0] = mb.tagged ? mail_tagged(mb.seq, v) : v;
+        if (!mb.tagged) __threadfence_system();
         ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
     }
 }
@@ -1800,7 +1808,7 @@ void launch_eval_stage(const uint32_t *src, uint64_t n, int nvars, const EvalPoi
     uint64_t n_tiles = n >> nvars;
     uint64_t cap = (uint64_t)sm * 8;
     int grid = (int)(n_tiles < cap ? n_tiles : cap);
-    Mailbox m = mb ? *mb : Mailbox{nullptr, nullptr, nullptr, 0, nullptr, 0};
+    Mailbox m = mb ? *mb : Mailbox{nullptr, nullptr, nullptr, 0, nullptr, 0, false};
     k_eval_stage<<<grid, THREADS, 0, st>>>(src, n_tiles, nvars, pt, out, m, mb != nullptr);
 }
 
