@@ -142,6 +142,8 @@ pub extern fn zb_mle_download_u32(ctx: *Ctx, m: Mle, offset: u64, out: [*c]u32, 
 pub extern fn zb_host_scratch(ctx: *Ctx, bytes: usize, out: [*c]?*anyopaque) i32;
 pub extern fn zb_mle_eval_batch(ctx: *Ctx, polys: [*c]const Mle, count: u32, points: [*c]const u64, npoint: u32, out: [*c]u64) i32;
 pub extern fn zb_mle_eq(ctx: *Ctx, tau: [*c]const u64, num_vars: u32, out: [*c]Mle) i32;
+pub extern fn zb_prod_fold_dump(ctx: *Ctx, polys: [*c]const Mle, d: u32, nfold: u32, r: [*c]const u64, tables: [*c]u32) i32;
+pub extern fn zb_prod_collapse(ctx: *Ctx, polys: [*c]const Mle, d: u32, values: [*c]const u64) i32;
 pub extern fn zb_mle_block_sums(ctx: *Ctx, m: Mle, k: u32, sums: [*c]u64) i32;
 pub extern fn zb_mle_fold_multi(ctx: *Ctx, m: Mle, k_fold: u32, r: [*c]const u64, out: [*c]Mle, k_next: u32, sums: [*c]u64) i32;
 pub extern fn zb_mle_collapse(ctx: *Ctx, m: Mle, value: u64) i32;
@@ -175,6 +177,7 @@ pub extern fn zh_sumcheck_prove_interactive(ctx: *Ctx, poly: Mle, challenges: [*
 pub extern fn zh_sumcheck_proof_to_bytes(num_vars: u32, round_polys: [*c]const u64, final_point: [*c]const u64, final_eval: u64, out: [*c]u8) usize;
 pub extern fn zh_prodcheck_prove(ctx: *Ctx, polys: [*c]const Mle, d: u32, round_polys: [*c]u64, final_point: [*c]u64, final_evals: [*c]u64, claimed_sum: [*c]u64) i32;
 pub extern fn zh_prodcheck_prove_consume(ctx: *Ctx, polys: [*c]const Mle, d: u32, round_polys: [*c]u64, final_point: [*c]u64, final_evals: [*c]u64, claimed_sum: [*c]u64) i32;
+pub extern fn zh_prodcheck_finish_small(d: u32, tables: [*c]u32, m: u64, round: u32, tr: *Transcript, fixed_challenges: [*c]const u64, round_polys: [*c]u64, final_point: [*c]u64, final_evals: [*c]u64) i32;
 pub extern fn zh_time_sumcheck_prove(ctx: *Ctx, poly: Mle, reps: u32, us_per_prove: [*c]f64) i32;
 pub extern fn zh_eqcheck_prove(ctx: *Ctx, tau: [*c]const u64, num_vars: u32, polys: [*c]const Mle, d: u32, round_polys: [*c]u64, final_point: [*c]u64, final_evals: [*c]u64, claimed_sum: [*c]u64) i32;
 pub extern fn zh_commit(ctx: *Ctx, poly: Mle, tree: [*c]Tree, root: *[32]u8, num_vars: [*c]u32) i32;

@@ -181,6 +181,16 @@ int32_t zb_prod_grid(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *gri
 int32_t zb_prod_fold_grid(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint32_t nfold, const uint64_t *r, zb_mle *out,
                           uint64_t *grid);
 
+/* ---- small product tables leave the device (the last rounds of SumcheckProver.prove, sumcheck_prover.zig:50-77, are latency) ----
+ * zb_prod_fold_dump: bind `nfold` (0..2) top variables with r[0] (, r[1]) — partialEval applied nfold times — and return the
+ * FOLDED tables to the host: tables[k * m + i], k < d, i < m = n >> nfold, canonical u32; m <= 2^12. The device tables are not
+ * modified. The host twin finishes the remaining log2(m) rounds itself: a host round trip per round (~8 us) would cost more
+ * than the few hundred field multiplications the round is.
+ * zb_prod_collapse: every table becomes the single value values[k] (length 1) — how a consuming prove leaves its tables when
+ * the last rounds ran on the host. Stream-ordered, returns without waiting. */
+int32_t zb_prod_fold_dump(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint32_t nfold, const uint64_t *r, uint32_t *tables);
+int32_t zb_prod_collapse(zb_ctx *ctx, const zb_mle *polys, uint32_t d, const uint64_t *values);
+
 /* ---- several rounds per pass for ONE polynomial (d = 1, SumcheckProver.prove sumcheck_prover.zig:50-77) ----
  * roundPolynomial (multilinear.zig:205-232) is linear in the table, so the 2^k sums over the blocks selected by the top k
  * index bits hold the next k round polynomials (the host folds the 2^k sums with each challenge exactly as partialEval

@@ -43,7 +43,8 @@ uint64_t zh_eval_univariate(const uint64_t *coeffs, uint32_t n, uint64_t x);
 /* ---- SumcheckProver(BabyBear): src/proofs/sumcheck_prover.zig ---- */
 /* Tuning: tables of at least 2^v entries are proved two rounds per pass over the data (zb_prod_grid / zb_prod_fold_grid:
  * ~10.7 instead of 16 bytes of HBM traffic per element and polynomial, half the host round trips); smaller ones one round per
- * kernel. 0 disables the two-round path. Default 15 (env ZB_GRID_MIN_LOG2). Returns the previous value. Process-wide. */
+ * kernel. 0 disables the two-round path; -1 selects the default (env ZB_GRID_MIN_LOG2, else 5 while small product tables finish
+ * on the host — zb option "prod_host_tail_log2" > 0 — and 15 otherwise). Returns the previous setting. Process-wide. */
 int32_t zh_set_grid_min_log2(int32_t v);
 /* prove :26-91. `poly` is left untouched (the reference copies it, :47). round_polys: v*2 coefficients [s0, s1-s0],
  * final_point: v challenges, final_eval: current_poly.evaluations[0], claimed_sum: sumOverHypercube (:40).
@@ -68,6 +69,15 @@ int32_t zh_prodcheck_prove(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_
 /* same, consuming the inputs (folded in place: no extra device memory; handles end with length 1) */
 int32_t zh_prodcheck_prove_consume(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint64_t *round_polys,
                                    uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum);
+
+/* The host's share of a product prove: the LAST rounds, once the tables are small. tables[k * m + i] (k < d, i < m, m a power of
+ * two <= 4096, canonical u32 — what zb_prod_fold_dump returns) are the current tables before round `round`; the function runs
+ * rounds round .. round + log2(m) - 1 exactly as the provers above do (roundPolynomial over MSB-first pairs, transcript `tr`
+ * or fixed challenges, partialEval; sumcheck_prover.zig:50-77) and writes round_polys[(round + t) * (d + 1) ..], final_point[round + t],
+ * final_evals[0..d). `tables` is scratch (folded in place). The provers call this once their tables have <= 2^"prod_host_tail_log2"
+ * entries: a device round trip per round (~8 us) costs more than the few hundred multiplications the round is. */
+int32_t zh_prodcheck_finish_small(uint32_t d, uint32_t *tables, uint64_t m, uint32_t round, zh_transcript *tr,
+                                  const uint64_t *fixed_challenges, uint64_t *round_polys, uint64_t *final_point, uint64_t *final_evals);
 
 /* measurement helper: `reps` zh_sumcheck_prove calls in a row, wall-clock microseconds per prove (no binding overhead) */
 int32_t zh_time_sumcheck_prove(zb_ctx *ctx, zb_mle poly, uint32_t reps, double *us_per_prove);

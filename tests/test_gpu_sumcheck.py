@@ -228,6 +228,7 @@ def test_tail_kernel_starvation_falls_back_to_launches(zlib, po):
         c2.set_option("tail_log2", 14)  # the default, unless ZB_TAIL_LOG2 overrides it
         c2.set_option("prelaunch", 1)
         c2.set_option("linear_d1", 0)  # the one-round-per-kernel prover is the one with polling kernels
+        c2.set_option("prod_host_tail_log2", 0)  # ... and it only runs when small tables do not finish on the host
         for lg in (12, 18):  # 2^12: the tail kernel starves; 2^18: a pre-launched fold kernel starves
             e = po.fill_synthetic(BB, 4242, 0, 1 << lg)
             poly = zlib.Multilinear.init(c2, e)
@@ -246,10 +247,14 @@ def test_tail_kernel_starvation_falls_back_to_launches(zlib, po):
 
 
 # ---------------------------------------------------------------- two rounds per pass (zb_prod_grid / zb_prod_fold_grid)
-@pytest.mark.parametrize("grid_min", [3, 5, 8, 0])
-def test_two_rounds_per_pass_gives_identical_proofs(zlib, ctx, po, grid_min):
-    """Force the bivariate-grid path down to tiny tables (and switch it off): proofs must not change by a bit."""
+@pytest.mark.parametrize("host_tail", [0, 9])
+@pytest.mark.parametrize("grid_min", [3, 5, 8, 0, -1])
+def test_two_rounds_per_pass_gives_identical_proofs(zlib, ctx, po, grid_min, host_tail):
+    """Force the bivariate-grid path down to tiny tables (and switch it off), with and without the host finishing the small
+    tables: proofs must not change by a bit."""
     old = zlib.lib().zh_set_grid_min_log2(grid_min)
+    old_ht = ctx.get_option("prod_host_tail_log2")
+    ctx.set_option("prod_host_tail_log2", host_tail)
     try:
         for d, lg in ((1, 5), (1, 6), (1, 9), (1, 14), (2, 5), (2, 8), (2, 11), (3, 5), (3, 6), (3, 7), (3, 10), (3, 13), (3, 16)):
             es = [po.fill_synthetic(BB, 1234 + k, 0, 1 << lg) for k in range(d)]
@@ -269,6 +274,72 @@ def test_two_rounds_per_pass_gives_identical_proofs(zlib, ctx, po, grid_min):
         assert pi.round_polynomials.tolist() == wi.round_polys.tolist() and pi.final_eval == wi.final_eval
     finally:
         zlib.lib().zh_set_grid_min_log2(old)
+        ctx.set_option("prod_host_tail_log2", old_ht)
+
+
+@pytest.mark.parametrize("host_tail", [1, 2, 4, 7, 10, 12])
+def test_small_tables_finish_on_the_host(zlib, ctx, po, host_tail):
+    """zb_prod_fold_dump + the host twin's own rounds (tables of <= 2^host_tail entries leave the device): every threshold, table
+    sizes on both sides of it, all degrees, consuming and not — proofs equal the oracle's bit for bit, a consumed table ends as
+    its final evaluation, an untouched one stays untouched."""
+    old_ht = ctx.get_option("prod_host_tail_log2")
+    ctx.set_option("prod_host_tail_log2", host_tail)
+    try:
+        for d in (1, 2, 3):
+            for lg in sorted({1, 2, host_tail, host_tail + 1, host_tail + 2, host_tail + 3, 12, 15}):
+                es = [po.fill_synthetic(BB, 4321 + 7 * k + lg, 0, 1 << lg) for k in range(d)]
+                want = po.prodcheck_prove(BB, es)
+                for consume in (False, True):
+                    polys = [zlib.Multilinear.init(ctx, e) for e in es]
+                    pr = zlib.ProductSumcheckProver.prove(polys, consume=consume)
+                    assert pr.claimed_sum == want.claimed_sum, (d, lg)
+                    assert pr.round_polynomials.tolist() == want.round_polys.tolist(), (d, lg, consume)
+                    assert pr.final_point.tolist() == want.final_point.tolist() and pr.final_evals == want.final_evals
+                    for k in range(d):
+                        if consume:
+                            assert polys[k].evaluations.tolist() == [want.final_evals[k]], (d, lg, k)
+                        else:
+                            assert np.array_equal(polys[k].evaluations, es[k])
+                        polys[k].deinit()
+        e = po.fill_synthetic(BB, 77, 0, 1 << 11)
+        ch = po.fill_synthetic(BB, 78, 0, 11)
+        ctx.set_option("linear_d1", 0)  # proveInteractive through the product path (d = 1) with fixed challenges
+        pi = zlib.SumcheckProver.prove_interactive(zlib.Multilinear.init(ctx, e), ch)
+        wi = po.sumcheck_prove_interactive(BB, e, ch)
+        assert pi.round_polynomials.tolist() == wi.round_polys.tolist() and pi.final_eval == wi.final_eval
+    finally:
+        ctx.set_option("linear_d1", 1)
+        ctx.set_option("prod_host_tail_log2", old_ht)
+
+
+def test_fold_dump_entry_directly(zlib, ctx, po):
+    """zb_prod_fold_dump against partialEval applied nfold times (multilinear.zig:154-180); error behaviour."""
+    import ctypes as C
+    L = zlib.lib()
+    for d in (1, 2, 3):
+        for lg, nfold in ((0, 0), (1, 1), (2, 2), (5, 0), (9, 1), (12, 2), (10, 0), (11, 1), (12, 0), (13, 1), (14, 2)):
+            es = [po.fill_synthetic(BB, 900 + k + lg, 0, 1 << lg) for k in range(d)]
+            polys = [zlib.Multilinear.init(ctx, e) for e in es]
+            hs = (C.c_uint64 * d)(*[p.handle for p in polys])
+            r = [int(x) for x in po.fill_synthetic(BB, 55 + lg, 0, 2)]
+            rr = (C.c_uint64 * 2)(*r)
+            m = (1 << lg) >> nfold
+            out = (C.c_uint32 * (d * m))()
+            ctx.check(L.zb_prod_fold_dump(ctx.handle, hs, d, nfold, rr, out))
+            got = np.frombuffer(out, dtype=np.uint32).reshape(d, m)
+            for k in range(d):
+                w = np.array(es[k], dtype=np.uint64)
+                for t in range(nfold):
+                    w = po.mle_partial_eval(BB, w, r[t])
+                assert got[k].tolist() == [int(x) for x in w], (d, lg, nfold, k)
+                assert np.array_equal(polys[k].evaluations, es[k])  # the device tables are not modified
+    big = [zlib.Multilinear.init(ctx, po.fill_synthetic(BB, 1, 0, 1 << 14))]
+    hs = (C.c_uint64 * 1)(big[0].handle)
+    out = (C.c_uint32 * 8192)()
+    rr = (C.c_uint64 * 2)(1, BB)
+    assert L.zb_prod_fold_dump(ctx.handle, hs, 1, 1, rr, out) == -22  # BadArgument: 2^13 folded entries are too many
+    assert L.zb_prod_fold_dump(ctx.handle, hs, 1, 2, rr, out) == -20  # NotCanonical
+    assert L.zb_prod_fold_dump(ctx.handle, hs, 1, 3, rr, out) == -22
 
 
 def test_grid_entry_points_directly(zlib, ctx, po):

@@ -183,3 +183,42 @@ def test_host_pool_and_narrowing_cpp():
                     os.path.join(root, "zigz_b200", "csrc", "hostpack.cpp"), "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "hostpool ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_prodcheck_finish_small_is_a_whole_small_prove(zlib, po):
+    """zh_prodcheck_finish_small (the rounds the provers run on the host once their tables are small, four lanes wide from 8
+    entries up) from round 0 with a fresh transcript IS a product prove of the small tables: bit-equal to the oracle for every
+    degree and size, including edge values (0, p - 1) that exercise the conditional corrections."""
+    import ctypes as C
+    L = zlib.lib()
+    rng = np.random.default_rng(11)
+    for d in (1, 2, 3):
+        for lg in range(1, 13):  # (a 1-entry table has no rounds: error.NoVariables, sumcheck_prover.zig:30-32)
+            m = 1 << lg
+            for trial in range(3 if lg < 8 else 1):
+                if trial == 0:
+                    es = [po.fill_synthetic(BB, 50 + 3 * k + lg, 0, m) for k in range(d)]
+                elif trial == 1:
+                    es = [rng.choice(np.array([0, 1, BB - 1, BB - 2, (BB + 1) // 2], dtype=np.uint64), size=m) for _ in range(d)]
+                else:
+                    es = [rng.integers(0, BB, size=m, dtype=np.uint64) for _ in range(d)]
+                want = po.prodcheck_prove(BB, es)
+                tables = np.ascontiguousarray(np.concatenate(es).astype(np.uint32))
+                rp = np.zeros((max(lg, 1), d + 1), np.uint64)
+                fp = np.zeros(max(lg, 1), np.uint64)
+                fe = np.zeros(3, np.uint64)
+                t = zlib.FiatShamirTranscript()
+                rc = L.zh_prodcheck_finish_small(d, tables.ctypes.data_as(C.POINTER(C.c_uint32)), m, 0, t._t, None,
+                                                 rp.ctypes.data_as(C.POINTER(C.c_uint64)), fp.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                 fe.ctypes.data_as(C.POINTER(C.c_uint64)))
+                assert rc == 0
+                assert rp[:lg].tolist() == want.round_polys.tolist(), (d, lg, trial)
+                assert fp[:lg].tolist() == want.final_point.tolist()
+                assert tuple(int(x) for x in fe[:d]) == want.final_evals
+    bad = np.array([BB, 0], dtype=np.uint32)
+    out = np.zeros(8, np.uint64)
+    p64 = out.ctypes.data_as(C.POINTER(C.c_uint64))
+    t = zlib.FiatShamirTranscript()
+    assert L.zh_prodcheck_finish_small(1, bad.ctypes.data_as(C.POINTER(C.c_uint32)), 2, 0, t._t, None, p64, p64, p64) == -20
+    assert L.zh_prodcheck_finish_small(1, bad.ctypes.data_as(C.POINTER(C.c_uint32)), 3, 0, t._t, None, p64, p64, p64) == -22
+    assert L.zh_prodcheck_finish_small(4, bad.ctypes.data_as(C.POINTER(C.c_uint32)), 2, 0, t._t, None, p64, p64, p64) == -22

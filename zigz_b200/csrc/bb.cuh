@@ -11,6 +11,8 @@ constexpr uint32_t P = 2013265921u;        // 0x78000001
 constexpr uint32_t P_NEG_INV = 2013265919u; // -P^{-1} mod 2^32  (P * 0x88000001 == 1 mod 2^32)
 constexpr uint32_t R_MOD_P = 268435454u;   // 2^32 mod P
 constexpr uint32_t R2_MOD_P = 1172168163u; // 2^64 mod P
+constexpr uint32_t R3_MOD_P = 317946875u; // 2^96 mod P
+constexpr uint32_t R4_MOD_P = 663890614u; // 2^128 mod P
 
 __host__ __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
     uint32_t s = a + b;
@@ -51,6 +53,18 @@ __device__ __forceinline__ uint32_t mont_mul_lazy(uint32_t a, uint32_t b) {
     const uint64_t t = (uint64_t)a * b;
     const uint32_t m = (uint32_t)t * 0x88000001u; // P^{-1} mod 2^32
     return (uint32_t)(t >> 32) + P - __umulhi(m, P);
+}
+
+// t * R^E mod P for ANY 64-bit t (E = 0, 1, 2), canonical, without a 64-bit division: t = hi 2^32 + lo, and a Montgomery product
+// with the constant R^(E+2) resp. R^(E+1) turns each half into its share (mont_mul divides by R once). This is how the raw
+// u64 accumulators of the round kernels become canonical field elements; ~12 instructions where `t % P` (software division)
+// followed by a modular product costs a few hundred — it runs on ONE thread per kernel (the publishing one), 16 times for a
+// round grid, on the critical path of every host round trip.
+template <int E>
+__device__ __forceinline__ uint32_t reduce64_scaled(unsigned long long t) {
+    constexpr uint32_t CH = E == 0 ? R2_MOD_P : (E == 1 ? R3_MOD_P : R4_MOD_P);
+    constexpr uint32_t CL = E == 0 ? R_MOD_P : (E == 1 ? R2_MOD_P : R3_MOD_P);
+    return add(mont_mul((uint32_t)(t >> 32), CH), mont_mul((uint32_t)t, CL));
 }
 
 // plain a*b mod P via two Montgomery steps is wasteful; for a one-off product use this

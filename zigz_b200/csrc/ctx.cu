@@ -56,7 +56,9 @@ struct Tree {
 constexpr size_t BULK_OFFSET = 512;          // bytes into the mapped mailbox page (payload words + sequence number come first)
 constexpr size_t BULK_BYTES = 64 * 32 * 2;   // 64 digests for paths / roots (x2 slack)
 constexpr size_t DUMP_OFFSET = BULK_OFFSET + BULK_BYTES; // published tables of zb_mle_fold_multi (u64 per value)
-constexpr size_t DUMP_BYTES = sizeof(unsigned long long) << LIN_DUMP_MAX_LOG2;
+constexpr size_t DUMP_BYTES_LIN = sizeof(unsigned long long) << LIN_DUMP_MAX_LOG2;
+constexpr size_t DUMP_BYTES_PROD = (MAX_POLYS * sizeof(uint32_t)) << PROD_DUMP_MAX_LOG2; // zb_prod_fold_dump: d tables of u32
+constexpr size_t DUMP_BYTES = DUMP_BYTES_LIN > DUMP_BYTES_PROD ? DUMP_BYTES_LIN : DUMP_BYTES_PROD;
 static_assert((MAIL_WORDS + 1) * sizeof(unsigned long long) <= BULK_OFFSET, "mailbox payload overlaps the bulk area");
 constexpr size_t STAGE_ELEMS = 32ull << 20;  // upload staging chunk (u64 elements)
 
@@ -133,6 +135,8 @@ struct zb_ctx {
     // table has <= 2^host_tail_log2 entries it is published whole and the host finishes the (latency-bound) last rounds
     bool linear_d1 = true;
     int host_tail_log2 = LIN_DUMP_MAX_LOG2;
+    // product provers (d <= 3): tables of <= 2^this entries are handed to the host twin, which finishes the rounds (0: never)
+    int prod_host_tail_log2 = 10;
     int linear_k = LIN_MAX_K; // variables bound per pass
     void *scratch = nullptr; // zb_host_scratch
     size_t scratch_bytes = 0;
@@ -784,6 +788,10 @@ int32_t zb_ctx_create(int32_t device, zb_ctx **out) {
         const int x = atoi(t);
         ctx->host_tail_log2 = x < 2 ? 2 : (x > LIN_DUMP_MAX_LOG2 ? LIN_DUMP_MAX_LOG2 : x);
     }
+    if (const char *t = getenv("ZB_PROD_HOST_TAIL_LOG2")) {
+        const int x = atoi(t);
+        ctx->prod_host_tail_log2 = x < 0 ? 0 : (x > PROD_DUMP_MAX_LOG2 ? PROD_DUMP_MAX_LOG2 : x);
+    }
     if ((e = cudaMalloc(&ctx->d_bcast, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
     ctx->d_claim = (unsigned int *)(ctx->d_bcast + 1);
     cudaMemsetAsync(ctx->d_bcast, 0, 2 * sizeof(unsigned long long), ctx->stream);
@@ -907,6 +915,11 @@ int32_t zb_set_option(zb_ctx *ctx, const char *key, int64_t value) {
         ctx->host_tail_log2 = (int)value;
         return ZB_OK;
     }
+    if (key && !strcmp(key, "prod_host_tail_log2")) {
+        if (value < 0 || value > PROD_DUMP_MAX_LOG2) return ZB_ERR_BAD_ARGUMENT;
+        ctx->prod_host_tail_log2 = (int)value;
+        return ZB_OK;
+    }
     if (key && !strcmp(key, "linear_k")) {
         if (value < 1 || value > LIN_MAX_K) return ZB_ERR_BAD_ARGUMENT;
         ctx->linear_k = (int)value;
@@ -939,6 +952,10 @@ int32_t zb_get_option(zb_ctx *ctx, const char *key, int64_t *value) {
     }
     if (key && value && !strcmp(key, "linear_d1")) {
         *value = ctx->linear_d1 ? 1 : 0;
+        return ZB_OK;
+    }
+    if (key && value && !strcmp(key, "prod_host_tail_log2")) {
+        *value = ctx->prod_host_tail_log2;
         return ZB_OK;
     }
     if (key && value && !strcmp(key, "host_tail_log2")) {
@@ -2012,6 +2029,53 @@ int32_t zb_prod_fold_grid(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint32_t
                           uint64_t *grid) {
     if (nfold < 1) return ZB_ERR_BAD_ARGUMENT;
     return fold_grid_impl(ctx, polys, d, nfold, r, out, grid);
+}
+
+int32_t zb_prod_fold_dump(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint32_t nfold, const uint64_t *r, uint32_t *tables) {
+    if (d < 1 || d > (uint32_t)MAX_POLYS || !polys || !tables || nfold > 2 || (nfold && !r)) return ZB_ERR_BAD_ARGUMENT;
+    tail_quiesce(ctx);
+    Mle *ms[MAX_POLYS];
+    int32_t rc = gather_polys(ctx, polys, d, ms);
+    if (rc) return rc;
+    const uint64_t n = ms[0]->n, m = n >> nfold;
+    if (m < 1 || (m << nfold) != n || m > (1ull << PROD_DUMP_MAX_LOG2)) return ZB_ERR_BAD_ARGUMENT;
+    for (uint32_t t = 0; t < nfold; t++)
+        if (r[t] >= bb::P) return ZB_ERR_NOT_CANONICAL;
+    PolySet ps{};
+    for (uint32_t k = 0; k < d; k++) ps.src[k] = ps.dst[k] = ms[k]->d();
+    Mailbox mb = ctx->mailbox();
+    {
+        ProfScope _ps(ctx, d == 1 ? "fold_dump_d1" : d == 2 ? "fold_dump_d2" : "fold_dump_d3", (uint64_t)d * 4 * (n + m));
+        launch_fold_dump((int)d, (int)nfold, ps, m, nfold ? (uint32_t)r[0] : 0, nfold > 1 ? (uint32_t)r[1] : 0,
+                         (uint32_t *)((uint8_t *)ctx->d_mail + DUMP_OFFSET), mb, ctx->stream);
+    }
+    rc = check_launch(ctx, "fold_dump");
+    if (rc == ZB_OK) rc = wait_mail(ctx, mb.seq, 0); // a published table: fence + sequence number
+    if (rc) return rc;
+    memcpy(tables, (const uint8_t *)ctx->h_mail + DUMP_OFFSET, (size_t)d * m * sizeof(uint32_t));
+    return ZB_OK;
+}
+
+int32_t zb_prod_collapse(zb_ctx *ctx, const zb_mle *polys, uint32_t d, const uint64_t *values) {
+    if (d < 1 || d > (uint32_t)MAX_POLYS || !polys || !values) return ZB_ERR_BAD_ARGUMENT;
+    tail_quiesce(ctx);
+    Mle *ms[MAX_POLYS];
+    int32_t rc = gather_polys(ctx, polys, d, ms);
+    if (rc) return rc;
+    uint32_t v[MAX_POLYS] = {0, 0, 0};
+    PolySet ps{};
+    for (uint32_t k = 0; k < d; k++) {
+        if (values[k] >= bb::P) return ZB_ERR_NOT_CANONICAL;
+        v[k] = (uint32_t)values[k];
+        ps.src[k] = ps.dst[k] = ms[k]->d();
+    }
+    {
+        ProfScope _ps(ctx, "fill", 4 * d);
+        launch_fill_heads(ps, (int)d, v, ctx->stream);
+    }
+    LAUNCHED("fill_heads");
+    for (uint32_t k = 0; k < d; k++) ms[k]->n = 1;
+    return ZB_OK; // stream-ordered: every later call on the context sees the collapsed tables
 }
 
 /* ------------------------------------------------------------------ d = 1: several rounds per pass (linearity) */

@@ -126,16 +126,18 @@ static void grid_round_b(uint32_t d, const uint64_t *grid, uint64_t r, uint64_t 
 
 // process-wide tuning knob (test hook zh_set_grid_min_log2): atomic, so that host threads driving different contexts
 // (one per GPU of a device-mask context) can read it while a test thread sets it
-static std::atomic<int> g_grid_min_log2{-1};
-static int grid_min_log2() { // tables below 2^this use one kernel per round (and the persistent tail); 0 disables the grid path
-    int v = g_grid_min_log2.load(std::memory_order_relaxed);
-    if (v < 0) {
+static std::atomic<int> g_grid_min_log2{-1}; // -1: the default below
+// folded tables below 2^this are bound one round per kernel (and by the persistent tail); 0 disables the grid path. Default: 5
+// when small tables finish on the host anyway ("prod_host_tail_log2" > 0: every device pass then serves two rounds), else 15
+// (below that the persistent single-round tail is the cheaper way down)
+static int grid_min_log2(bool host_tail_on) {
+    const int v = g_grid_min_log2.load(std::memory_order_relaxed);
+    if (v >= 0) return v;
+    static const int env = [] {
         const char *e = getenv("ZB_GRID_MIN_LOG2");
-        int x = e && *e ? atoi(e) : 15;
-        v = x < 0 ? 0 : x;
-        g_grid_min_log2.store(v, std::memory_order_relaxed);
-    }
-    return v;
+        return e && *e ? (atoi(e) < 0 ? 0 : atoi(e)) : -1;
+    }();
+    return env >= 0 ? env : (host_tail_on ? 5 : 15);
 }
 
 static int gather_log2() {
@@ -215,6 +217,132 @@ static int32_t prove_linear(zb_ctx *ctx, zb_mle poly, uint32_t v, bool consume, 
     return rc;
 }
 
+// ---- the last rounds of a product sumcheck on the host ----
+// Four field elements per AVX2 register (one per 64-bit lane, values < 2^32). Montgomery product a b 2^-32 mod p in the
+// subtractive form the kernels use (bb.cuh: mont_mul_lazy): with m = lo(t) p^-1 mod 2^32 the difference t - m p is an exact
+// multiple of 2^32, so the result is hi(t) - hi(m p) in (-p, p), made canonical with one conditional addition. Needs a b < 2^32 p.
+namespace hv {
+const uint64_t R1 = (1ull << 32) % P;  // 2^32 mod p
+const uint64_t R2 = (R1 * R1) % P;     // 2^64 mod p
+const uint64_t R3 = (R2 * R1) % P;     // 2^96 mod p
+inline __m256i bcast(uint64_t x) { return _mm256_set1_epi64x((long long)x); }
+inline __m256i load4(const uint32_t *p) { return _mm256_cvtepu32_epi64(_mm_loadu_si128((const __m128i *)p)); }
+inline void store4(uint32_t *p, __m256i v) { // low 32 bits of every lane
+    const __m256i q = _mm256_permutevar8x32_epi32(v, _mm256_setr_epi32(0, 2, 4, 6, 0, 0, 0, 0));
+    _mm_storeu_si128((__m128i *)p, _mm256_castsi256_si128(q));
+}
+inline __m256i mont(__m256i a, __m256i b) {
+    const __m256i t = _mm256_mul_epu32(a, b);
+    const __m256i m = _mm256_mul_epu32(t, bcast(0x88000001u)); // low halves: lo(t) * p^-1 (only the low 32 bits are used next)
+    const __m256i mp = _mm256_mul_epu32(m, bcast(P));
+    const __m256i u = _mm256_sub_epi64(_mm256_srli_epi64(t, 32), _mm256_srli_epi64(mp, 32));
+    return _mm256_add_epi64(u, _mm256_and_si256(_mm256_cmpgt_epi64(_mm256_setzero_si256(), u), bcast(P)));
+}
+inline __m256i sub(__m256i a, __m256i b) { // canonical a - b mod p
+    const __m256i u = _mm256_sub_epi64(a, b);
+    return _mm256_add_epi64(u, _mm256_and_si256(_mm256_cmpgt_epi64(_mm256_setzero_si256(), u), bcast(P)));
+}
+inline __m256i add(__m256i a, __m256i b) { // canonical a + b mod p
+    const __m256i s = _mm256_add_epi64(a, b);
+    return _mm256_sub_epi64(s, _mm256_andnot_si256(_mm256_cmpgt_epi64(bcast(P), s), bcast(P)));
+}
+inline uint64_t hsum(__m256i v) { // lanes hold sums of < 2^12 canonical terms: no overflow
+    alignas(32) uint64_t x[4];
+    _mm256_store_si256((__m256i *)x, v);
+    return x[0] + x[1] + x[2] + x[3];
+}
+} // namespace hv
+
+// T[k][0 .. m) are the d current tables (canonical u32, as published by zb_prod_fold_dump). Each round is roundPolynomial over
+// MSB-first pairs — the same point sets as the kernels: {s0, s1} (d = 1), {g(0), g(1), g(inf)} (d = 2), {g(0), g(1), g(-1),
+// g(inf)} (d = 3), exact field arithmetic, so the coefficients equal the device path's bit for bit — then the transcript, then
+// partialEval (sumcheck_prover.zig:50-77, multilinear.zig:166-173). Halves of >= 4 pairs run four lanes wide.
+static void finish_rounds_on_host(uint32_t d, uint32_t *T, uint64_t m, uint32_t round, zh_transcript *tr, const uint64_t *fixed_challenges,
+                                  uint64_t *round_polys, uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum) {
+    const uint32_t nc = d + 1;
+    uint32_t *t0 = T, *t1 = T + m, *t2 = T + 2 * m;
+    for (uint64_t len = m; len >= 2; len /= 2, round++) {
+        const uint64_t h = len / 2;
+        uint64_t e[4] = {0, 0, 0, 0}; // u64 sums of canonical terms (< 2^31 each, <= 2^11 of them): exact
+        if (d == 1) {
+            for (uint64_t i = 0; i < h; i++) {
+                e[0] += t0[i];
+                e[1] += t0[i + h];
+            }
+        } else if (h >= 4) {
+            // products come out scaled by 2^-32 per Montgomery step: the sums are rescaled once (R^(d-1)) after the loop
+            __m256i s0 = _mm256_setzero_si256(), s1 = s0, s2 = s0, s3 = s0;
+            if (d == 2) {
+                for (uint64_t i = 0; i < h; i += 4) {
+                    const __m256i a0 = hv::load4(t0 + i), b0 = hv::load4(t0 + i + h), a1 = hv::load4(t1 + i), b1 = hv::load4(t1 + i + h);
+                    s0 = _mm256_add_epi64(s0, hv::mont(a0, a1));
+                    s1 = _mm256_add_epi64(s1, hv::mont(b0, b1));
+                    s2 = _mm256_add_epi64(s2, hv::mont(hv::sub(b0, a0), hv::sub(b1, a1)));
+                }
+                e[0] = f_mul(hv::hsum(s0) % P, hv::R1);
+                e[1] = f_mul(hv::hsum(s1) % P, hv::R1);
+                e[2] = f_mul(hv::hsum(s2) % P, hv::R1);
+            } else {
+                for (uint64_t i = 0; i < h; i += 4) {
+                    const __m256i a0 = hv::load4(t0 + i), b0 = hv::load4(t0 + i + h), a1 = hv::load4(t1 + i), b1 = hv::load4(t1 + i + h),
+                                  a2 = hv::load4(t2 + i), b2 = hv::load4(t2 + i + h);
+                    const __m256i d0 = hv::sub(b0, a0), d1 = hv::sub(b1, a1), d2 = hv::sub(b2, a2); // slope = value at infinity
+                    s0 = _mm256_add_epi64(s0, hv::mont(hv::mont(a0, a1), a2));
+                    s1 = _mm256_add_epi64(s1, hv::mont(hv::mont(b0, b1), b2));
+                    s2 = _mm256_add_epi64(s2, hv::mont(hv::mont(hv::sub(a0, d0), hv::sub(a1, d1)), hv::sub(a2, d2))); // X = -1
+                    s3 = _mm256_add_epi64(s3, hv::mont(hv::mont(d0, d1), d2));
+                }
+                e[0] = f_mul(hv::hsum(s0) % P, hv::R2);
+                e[1] = f_mul(hv::hsum(s1) % P, hv::R2);
+                e[2] = f_mul(hv::hsum(s2) % P, hv::R2);
+                e[3] = f_mul(hv::hsum(s3) % P, hv::R2);
+            }
+        } else if (d == 2) {
+            for (uint64_t i = 0; i < h; i++) {
+                const uint64_t a0 = t0[i], b0 = t0[i + h], a1 = t1[i], b1 = t1[i + h];
+                e[0] += f_mul(a0, a1);
+                e[1] += f_mul(b0, b1);
+                e[2] += f_mul(f_sub(b0, a0), f_sub(b1, a1));
+            }
+        } else {
+            for (uint64_t i = 0; i < h; i++) {
+                const uint64_t a0 = t0[i], b0 = t0[i + h], a1 = t1[i], b1 = t1[i + h], a2 = t2[i], b2 = t2[i + h];
+                const uint64_t d0 = f_sub(b0, a0), d1 = f_sub(b1, a1), d2 = f_sub(b2, a2);
+                e[0] += f_mul(f_mul(a0, a1), a2);
+                e[1] += f_mul(f_mul(b0, b1), b2);
+                e[2] += f_mul(f_mul(f_sub(a0, d0), f_sub(a1, d1)), f_sub(a2, d2)); // X = -1: a - (b - a)
+                e[3] += f_mul(f_mul(d0, d1), d2);
+            }
+        }
+        for (uint32_t k = 0; k < 4; k++) e[k] %= P;
+        uint64_t c[4];
+        evals_to_coeffs(d, e, c);
+        for (uint32_t k = 0; k < nc; k++) round_polys[(size_t)round * nc + k] = c[k];
+        if (round == 0 && claimed_sum) *claimed_sum = f_add(e[0], e[1]); // g(0) + g(1) (sumOverHypercube for d == 1, :40)
+        uint64_t r;
+        if (fixed_challenges) {
+            r = fixed_challenges[round]; // proveInteractive :127
+        } else {
+            zh_transcript_append_fields(tr, c, nc); // generateChallenge, sumcheck_protocol.zig:176-184
+            r = zh_transcript_challenge(tr);
+        }
+        final_point[round] = r;
+        const __m256i rR = hv::bcast(f_mul(r, hv::R1)); // r in Montgomery form: mont(rR, x) = r x
+        for (uint32_t k = 0; k < d; k++) { // partialEval :166-173
+            uint32_t *t = T + (size_t)k * m;
+            if (h >= 4) {
+                for (uint64_t i = 0; i < h; i += 4) {
+                    const __m256i lo = hv::load4(t + i), hi = hv::load4(t + i + h);
+                    hv::store4(t + i, hv::add(lo, hv::mont(hv::sub(hi, lo), rR)));
+                }
+            } else {
+                for (uint64_t i = 0; i < h; i++) t[i] = (uint32_t)f_add(t[i], f_mul(r, f_sub(t[i + h], t[i])));
+            }
+        }
+    }
+    for (uint32_t k = 0; k < d; k++) final_evals[k] = T[(size_t)k * m]; // current_poly.evaluations[0] (:88)
+}
+
 static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool consume, const uint64_t *fixed_challenges,
                             uint64_t *round_polys, uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum) {
     if (d < 1 || d > 3 || !polys) return ZB_ERR_BAD_ARGUMENT;
@@ -236,9 +364,10 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
     const uint32_t nc = d + 1;
     bool sharded = world > 1;
     // while sharded: device-side reduction on, persistent tail off (the per-round collective needs the stream)
-    int64_t tail_log2 = 0, comm_reduce = 0;
+    int64_t tail_log2 = 0, comm_reduce = 0, host_tail = 0;
     zb_get_option(ctx, "tail_log2", &tail_log2);
     zb_get_option(ctx, "comm_reduce", &comm_reduce);
+    zb_get_option(ctx, "prod_host_tail_log2", &host_tail);
     struct Restore {
         zb_ctx *c;
         int64_t tail, red;
@@ -261,24 +390,32 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
     zh_transcript tr; // State.init -> FiatShamirTranscript.init (sumcheck_protocol.zig:149-164)
     uint64_t coeffs[4];
     uint64_t grid[16];
-    // large tables: two rounds per pass over the data (phase 1 below); the first pass then already yields the grid
-    const int gmin = grid_min_log2();
-    uint64_t grid_min_n = gmin ? (1ull << gmin) : ~0ull;
-    if (sharded && gmin) { // stay above the point where the sharded regime is left
-        const uint64_t g2 = 2ull << gather_log2();
-        if (grid_min_n < g2) grid_min_n = g2;
+    alignas(32) uint32_t host_tables[3u << 12]; // tables of <= 2^12 entries finish on the host (zb_prod_fold_dump)
+    // tables that are small and whole (not sharded) leave the device: the host finishes their rounds
+    auto host_finishes = [&](uint64_t len) { return !sharded && host_tail > 0 && len <= (1ull << host_tail); };
+    auto collapse_consumed = [&]() { return consume ? zb_prod_collapse(ctx, polys, d, final_evals) : ZB_OK; };
+    if (host_finishes(n)) {
+        rc = zb_prod_fold_dump(ctx, polys, d, 0, nullptr, host_tables);
+        if (rc) return rc;
+        finish_rounds_on_host(d, host_tables, n, 0, &tr, fixed_challenges, round_polys, final_point, final_evals, claimed_sum);
+        return collapse_consumed();
     }
-    const bool grid_phase = gmin && n >= grid_min_n && n >= 64 && v_local >= 3;
-    // first pass of the grid phase: "grid" = G of the raw tables (no fold; arithmetic-heavy for d = 3), or "sums" = the plain
-    // round-0 sums, after which the first fold already produces the grid of rounds 1 and 2
+    // two rounds per pass over the data (zb_prod_grid / zb_prod_fold_grid) while the folded tables keep >= 2^gmin entries
+    const int gmin = grid_min_log2(host_tail > 0);
+    const uint64_t grid_min_n = gmin ? (1ull << gmin) : ~0ull;
+    auto grid_serves = [&](uint64_t folded_len) { return gmin && folded_len >= grid_min_n && folded_len >= 32; };
+    // first pass: "grid" = G of the raw tables (no fold; arithmetic-heavy for d = 3), or "sums" = the plain round-0 sums, after
+    // which the first fold already produces the grid of rounds 1 and 2
     static const bool first_is_grid = [] {
         const char *e = getenv("ZB_GRID_FIRST");
         return e && !strcmp(e, "grid");
     }();
-    if (grid_phase && first_is_grid) {
+    bool have_grid = false; // `grid` holds G of the current tables: this round's AND the next round's polynomial
+    if (first_is_grid && gmin && n >= 64) {
         rc = zb_prod_grid(ctx, polys, d, grid);
         if (rc) return rc;
         grid_round_a(d, grid, coeffs);
+        have_grid = true;
     } else {
         rc = zb_prod_round_coeffs(ctx, polys, d, coeffs);
         if (rc) return rc;
@@ -290,7 +427,7 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
         *claimed_sum = s;
     }
     zb_mle cur[3] = {polys[0], d > 1 ? polys[1] : 0, d > 2 ? polys[2] : 0};
-    bool owned = false;
+    bool owned = false; // `cur` are tables of ours (the caller's stay intact unless `consume`)
     uint64_t n_cur = n; // current (local) table length
     auto cleanup = [&]() {
         if (owned)
@@ -298,94 +435,13 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
                 if (cur[k]) zb_mle_free(ctx, cur[k]);
         owned = false;
     };
+    // Invariant at the top of the loop: `coeffs` is the polynomial of round `round` over the current tables; with have_grid,
+    // `grid` also determines round + 1 once this round's challenge is known. Each pass binds one or two variables.
     uint32_t round = 0;
-    // ---- phase 1: two rounds per pass over the data while the tables are large (zb_prod_grid / zb_prod_fold_grid) ----
-    {
-        const uint64_t min_n = grid_min_n;
-        if (grid_phase && !first_is_grid) {
-            // round 0 from the plain sums; its fold yields the grid of rounds 1 and 2
-            for (uint32_t k = 0; k < nc; k++) round_polys[k] = coeffs[k];
-            uint64_t r0;
-            if (fixed_challenges) {
-                r0 = fixed_challenges[0];
-            } else {
-                zh_transcript_append_fields(&tr, coeffs, nc);
-                r0 = zh_transcript_challenge(&tr);
-            }
-            final_point[0] = r0;
-            round = 1;
-            const bool fresh = !consume;
-            zb_mle next[3] = {0, 0, 0};
-            const uint64_t rr0[2] = {r0, 0};
-            rc = zb_prod_fold_grid(ctx, cur, d, 1, rr0, fresh ? next : nullptr, grid);
-            if (rc) return rc;
-            if (fresh) {
-                for (uint32_t k = 0; k < d; k++) cur[k] = next[k];
-                owned = true;
-            }
-            n_cur /= 2;
-            grid_round_a(d, grid, coeffs);
-        }
-        if (grid_phase) {
-            for (;;) {
-                uint64_t rr[2];
-                for (int t = 0; t < 2; t++) {
-                    if (t == 1) grid_round_b(d, grid, rr[0], coeffs);
-                    for (uint32_t k = 0; k < nc; k++) round_polys[(size_t)(round + t) * nc + k] = coeffs[k];
-                    if (fixed_challenges) {
-                        rr[t] = fixed_challenges[round + t];
-                    } else {
-                        zh_transcript_append_fields(&tr, coeffs, nc);
-                        rr[t] = zh_transcript_challenge(&tr);
-                    }
-                    final_point[round + t] = rr[t];
-                }
-                round += 2;
-                const uint64_t n_after = n_cur / 4;
-                const bool more = n_after >= min_n && n_after >= 32;
-                const bool fresh = !owned && !consume; // the caller's tables must stay intact: fold into new ones
-                if (more) {
-                    zb_mle next[3] = {0, 0, 0};
-                    rc = zb_prod_fold_grid(ctx, cur, d, 2, rr, fresh ? next : nullptr, grid);
-                    if (rc) {
-                        cleanup();
-                        return rc;
-                    }
-                    if (fresh) {
-                        for (uint32_t k = 0; k < d; k++) cur[k] = next[k];
-                        owned = true;
-                    }
-                    n_cur = n_after;
-                    grid_round_a(d, grid, coeffs);
-                    continue;
-                }
-                // last pair of this phase: bind the two variables with the single-round kernels; the second one
-                // returns the coefficients of the round after them (or the final evaluations)
-                if (fresh) {
-                    zb_mle next[3] = {0, 0, 0};
-                    rc = zb_prod_partial_eval(ctx, cur, d, rr[0], next, coeffs);
-                    if (rc) return rc;
-                    for (uint32_t k = 0; k < d; k++) cur[k] = next[k];
-                    owned = true;
-                } else {
-                    rc = zb_prod_fold_inplace(ctx, cur, d, rr[0], coeffs);
-                }
-                if (rc == ZB_OK) rc = zb_prod_fold_inplace(ctx, cur, d, rr[1], coeffs);
-                if (rc) {
-                    cleanup();
-                    return rc;
-                }
-                n_cur = n_after;
-                consume = true; // `cur` is ours from here on (or the caller allowed consumption)
-                break;
-            }
-        }
-    }
-    // ---- phase 2: one round per kernel (persistent tail for small tables) ----
-    for (; round < v; round++) {
+    while (round < v) {
         if (sharded && n_cur <= (1ull << gather_log2())) {
-            // leave the sharded regime: all-gather the shards into the global order; `coeffs` already hold the
-            // (global) coefficients of this round, so nothing is recomputed
+            // leave the sharded regime: all-gather the shards into the global order; what is in hand (`coeffs`, `grid`) are
+            // global sums already, so nothing is recomputed
             zb_mle full[3] = {0, 0, 0};
             for (uint32_t k = 0; k < d && rc == ZB_OK; k++) rc = zb_comm_allgather_cyclic(ctx, cur[k], &full[k]);
             if (rc) {
@@ -397,38 +453,73 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
             cleanup();
             for (uint32_t k = 0; k < d; k++) cur[k] = full[k];
             owned = true;
-            consume = true; // the gathered tables are ours
             sharded = false;
             n_cur *= (uint64_t)world;
             restore.now();
         }
-        for (uint32_t k = 0; k < nc; k++) round_polys[(size_t)round * nc + k] = coeffs[k];
-        uint64_t r;
-        if (fixed_challenges) {
-            r = fixed_challenges[round]; // proveInteractive :127
-        } else {
-            zh_transcript_append_fields(&tr, coeffs, nc); // generateChallenge, sumcheck_protocol.zig:176-184
-            r = zh_transcript_challenge(&tr);
+        const uint32_t nf = have_grid ? 2 : 1;
+        uint64_t rr[2] = {0, 0};
+        for (uint32_t t = 0; t < nf; t++) {
+            if (t == 1) grid_round_b(d, grid, rr[0], coeffs);
+            for (uint32_t k = 0; k < nc; k++) round_polys[(size_t)(round + t) * nc + k] = coeffs[k];
+            if (fixed_challenges) {
+                rr[t] = fixed_challenges[round + t]; // proveInteractive :127
+            } else {
+                zh_transcript_append_fields(&tr, coeffs, nc); // generateChallenge, sumcheck_protocol.zig:176-184
+                rr[t] = zh_transcript_challenge(&tr);
+            }
+            final_point[round + t] = rr[t];
+            // (the reference also evaluates the round polynomial at r to advance its claim, :63-70; the value never
+            //  reaches the proof, so it is not computed here)
         }
-        final_point[round] = r;
-        // (the reference also evaluates the round polynomial at r to advance its claim, :63-70; the value never
-        //  reaches the proof, so it is not computed here)
-        if (round == 0 && !consume) {
-            zb_mle next[3];
-            rc = zb_prod_partial_eval(ctx, polys, d, r, next, coeffs);
+        round += nf;
+        const uint64_t n_after = n_cur >> nf;
+        have_grid = false;
+        if (host_finishes(n_after)) {
+            // the folded tables go to the host, which finishes the proof (the device tables are left as they are)
+            rc = zb_prod_fold_dump(ctx, cur, d, nf, rr, host_tables);
+            if (rc == ZB_OK)
+                finish_rounds_on_host(d, host_tables, n_after, round, &tr, fixed_challenges, round_polys, final_point, final_evals, nullptr);
+            const bool callers = !owned;
+            cleanup();
+            if (rc == ZB_OK && callers) rc = collapse_consumed();
+            return rc;
+        }
+        const bool fresh = !owned && !consume; // the caller's tables must stay intact: fold into new ones
+        if (grid_serves(n_after)) {
+            zb_mle next[3] = {0, 0, 0};
+            rc = zb_prod_fold_grid(ctx, cur, d, nf, rr, fresh ? next : nullptr, grid);
+            if (rc) {
+                cleanup();
+                return rc;
+            }
+            if (fresh) {
+                for (uint32_t k = 0; k < d; k++) cur[k] = next[k];
+                owned = true;
+            }
+            n_cur = n_after;
+            grid_round_a(d, grid, coeffs);
+            have_grid = true;
+            continue;
+        }
+        // one round per kernel (the persistent tail serves small tables); the last call returns the coefficients of the round
+        // after them — or, after the last fold, the d final evaluations (current_poly.evaluations[0], :88)
+        if (fresh) {
+            zb_mle next[3] = {0, 0, 0};
+            rc = zb_prod_partial_eval(ctx, cur, d, rr[0], next, coeffs);
             if (rc) return rc;
             for (uint32_t k = 0; k < d; k++) cur[k] = next[k];
             owned = true;
         } else {
-            rc = zb_prod_fold_inplace(ctx, cur, d, r, coeffs);
+            rc = zb_prod_fold_inplace(ctx, cur, d, rr[0], coeffs);
         }
+        if (rc == ZB_OK && nf == 2) rc = zb_prod_fold_inplace(ctx, cur, d, rr[1], coeffs);
         if (rc) {
             cleanup();
             return rc;
         }
-        n_cur /= 2;
+        n_cur = n_after;
     }
-    // after the last fold `coeffs` holds the d final evaluations (current_poly.evaluations[0], :88)
     for (uint32_t k = 0; k < d; k++) final_evals[k] = coeffs[k];
     cleanup();
     return ZB_OK;
@@ -498,10 +589,18 @@ int32_t zh_time_sumcheck_prove(zb_ctx *ctx, zb_mle poly, uint32_t reps, double *
     return rc;
 }
 
+int32_t zh_prodcheck_finish_small(uint32_t d, uint32_t *tables, uint64_t m, uint32_t round, zh_transcript *tr,
+                                  const uint64_t *fixed_challenges, uint64_t *round_polys, uint64_t *final_point, uint64_t *final_evals) {
+    if (d < 1 || d > 3 || !tables || m < 1 || m > 4096 || (m & (m - 1)) || (!tr && !fixed_challenges) || !final_evals) return ZB_ERR_BAD_ARGUMENT;
+    if (m > 1 && (!round_polys || !final_point)) return ZB_ERR_BAD_ARGUMENT;
+    for (uint64_t i = 0; i < (uint64_t)d * m; i++)
+        if (tables[i] >= P) return ZB_ERR_NOT_CANONICAL;
+    finish_rounds_on_host(d, tables, m, round, tr, fixed_challenges, round_polys, final_point, final_evals, nullptr);
+    return ZB_OK;
+}
+
 int32_t zh_set_grid_min_log2(int32_t v) {
-    const int32_t old = grid_min_log2();
-    g_grid_min_log2.store(v < 0 ? 0 : v, std::memory_order_relaxed);
-    return old;
+    return g_grid_min_log2.exchange(v < 0 ? -1 : v, std::memory_order_relaxed); // -1 = back to the default
 }
 
 int32_t zh_sumcheck_prove(zb_ctx *ctx, zb_mle poly, uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval,

@@ -80,6 +80,15 @@ inline bool fold_sums_is_vector(uint64_t n) { return n >= 16 && ((n / 4) % 4) ==
 void launch_tail_rounds(int d, const PolySet &ps, uint64_t n, const Mailbox &mb, const unsigned long long *chal,
                         unsigned int chal_seq0, unsigned int *status, cudaStream_t st);
 
+// Small product tables leave the device: bind nfold (0..2) top variables with r1 (, r2) and write the m = n >> nfold folded values
+// of each of the d tables, canonical u32, to dump[k * m + i] (host-mapped); then fence + mb.seq (no payload words). One CTA;
+// m <= 2^PROD_DUMP_MAX_LOG2. The device tables are not modified.
+constexpr int PROD_DUMP_MAX_LOG2 = 12;
+void launch_fold_dump(int d, int nfold, const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, uint32_t *dump, const Mailbox &mb,
+                      cudaStream_t st);
+// dst[k][0] = vals[k], k < d
+void launch_fill_heads(const PolySet &ps, int d, const uint32_t *vals, cudaStream_t st);
+
 // multi-GPU: src[0..n) (NCCL-summed canonical payload words) -> mailbox payload mod p + sequence number
 void launch_publish_reduced(const unsigned long long *src, int n, unsigned long long *mail, unsigned long long seq, cudaStream_t st);
 // multi-GPU: all-gathered cyclic shards [rank][j] -> global order out[rank + world * j]

@@ -103,7 +103,7 @@ __device__ __forceinline__ bool xchg_allreduce(unsigned long long (&tot)[NS], co
         unsigned long long x = v[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        tot[k] = x % bb::P; // sums of <= 16 canonical words: exact
+        tot[k] = bb::reduce64_scaled<0>(x); // sums of <= 16 canonical words: exact
     }
     return __all_sync(0xffffffffu, ok);
 }
@@ -210,12 +210,7 @@ template <int D>
 struct Finish {
     __device__ void operator()(unsigned long long (&t)[NSums<D>::value]) const {
 #pragma unroll
-        for (int k = 0; k < NSums<D>::value; k++) {
-            uint32_t v = (uint32_t)(t[k] % bb::P);
-            if constexpr (D == 2) v = bb::mul(v, bb::R_MOD_P);
-            if constexpr (D == 3) v = bb::mul(v, bb::R2_MOD_P);
-            t[k] = v;
-        }
+        for (int k = 0; k < NSums<D>::value; k++) t[k] = bb::reduce64_scaled<D - 1>(t[k]);
     }
 };
 
@@ -453,12 +448,7 @@ template <int D, int NS>
 struct FinishGrid {
     __device__ void operator()(unsigned long long (&t)[NS]) const {
 #pragma unroll
-        for (int k = 0; k < NS; k++) {
-            uint32_t v = (uint32_t)(t[k] % bb::P);
-            if constexpr (D == 2) v = bb::mul(v, bb::R_MOD_P);
-            if constexpr (D == 3) v = bb::mul(v, bb::R2_MOD_P);
-            t[k] = v;
-        }
+        for (int k = 0; k < NS; k++) t[k] = bb::reduce64_scaled<D - 1>(t[k]);
     }
 };
 
@@ -1069,6 +1059,52 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_rounds(PolySet ps, uint64
     }
 }
 
+// Small tables leave the device: bind `nfold` (0..2) top variables of the D tables (n = m << nfold entries each, the same dot
+// products as the grid kernels) and write the m folded values of every table, canonical u32, table after table, to `dump`
+// (host-mapped) — the host twin finishes the last <= 10 rounds of a product sumcheck itself instead of paying a host round
+// trip (~8 us) per round for a few hundred multiplications. One CTA: m <= 2^PROD_DUMP_MAX_LOG2. The device tables stay as they are.
+template <int D>
+__global__ void __launch_bounds__(TAIL_THREADS) k_fold_dump(PolySet ps, uint64_t m, int nfold, bb::BilinearWeights bw, uint32_t *dump,
+                                                            Mailbox mb) {
+    const uint32_t w0 = bw.w[0], w1 = bw.w[1], w2 = bw.w[2], w3 = bw.w[3];
+    for (uint64_t i = threadIdx.x; i < m; i += TAIL_THREADS) {
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const uint32_t *p = ps.src[k];
+            uint32_t v;
+            if (nfold == 0) v = p[i];
+            else if (nfold == 1) v = bb::dot2(p[i], p[i + m], w0, w1);
+            else v = bb::dot4(p[i], p[i + m], p[i + 2 * m], p[i + 3 * m], w0, w1, w2, w3);
+            asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(dump + (uint64_t)k * m + i), "r"(v) : "memory");
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) ((volatile unsigned long long *)mb.mail)[MAIL_WORDS] = mb.seq;
+}
+
+void launch_fold_dump(int d, int nfold, const PolySet &ps, uint64_t m, uint32_t r1, uint32_t r2, uint32_t *dump, const Mailbox &mb,
+                      cudaStream_t st) {
+    bb::BilinearWeights bw{};
+    if (nfold == 1) {
+        bw.w[0] = bb::mul(bb::sub(1u, r1), bb::R_MOD_P);
+        bw.w[1] = bb::mul(r1, bb::R_MOD_P);
+    } else if (nfold == 2) {
+        bw = bb::bilinear_weights(r1, r2);
+    }
+    if (d == 1) k_fold_dump<1><<<1, TAIL_THREADS, 0, st>>>(ps, m, nfold, bw, dump, mb);
+    else if (d == 2) k_fold_dump<2><<<1, TAIL_THREADS, 0, st>>>(ps, m, nfold, bw, dump, mb);
+    else k_fold_dump<3><<<1, TAIL_THREADS, 0, st>>>(ps, m, nfold, bw, dump, mb);
+}
+
+// the tables of a consumed product prove end as their final evaluations (what v in-place folds would have left in slot 0)
+__global__ void k_fill_heads(PolySet ps, int d, uint32_t v0, uint32_t v1, uint32_t v2) {
+    if (threadIdx.x < d) ps.dst[threadIdx.x][0] = threadIdx.x == 0 ? v0 : (threadIdx.x == 1 ? v1 : v2);
+}
+void launch_fill_heads(const PolySet &ps, int d, const uint32_t *vals, cudaStream_t st) {
+    k_fill_heads<<<1, 32, 0, st>>>(ps, d, vals[0], d > 1 ? vals[1] : 0, d > 2 ? vals[2] : 0);
+}
+
 void launch_tail_rounds(int d, const PolySet &ps, uint64_t n, const Mailbox &mb, const unsigned long long *chal,
                         unsigned int chal_seq0, unsigned int *status, cudaStream_t st) {
     if (d == 1) k_tail_rounds<1><<<1, TAIL_THREADS, 0, st>>>(ps, n, mb, chal, chal_seq0, status);
@@ -1192,7 +1228,7 @@ void launch_fold_sums(int d, const PolySet &ps, uint64_t n, uint32_t r, const Ma
 // plain sum (sumOverHypercube)
 // ---------------------------------------------------------------------------------------------
 struct FinishSum {
-    __device__ void operator()(unsigned long long (&t)[1]) const { t[0] = t[0] % bb::P; }
+    __device__ void operator()(unsigned long long (&t)[1]) const { t[0] = bb::reduce64_scaled<0>(t[0]); }
 };
 
 __global__ void __launch_bounds__(THREADS) k_sum(const uint32_t *src, uint64_t n, Mailbox mb) {
@@ -1259,7 +1295,7 @@ struct BlockAcc {
             const int lane = threadIdx.x;
             volatile unsigned long long *mail = (volatile unsigned long long *)mb.mail;
             if (lane < nb) {
-                const unsigned long long v = atomicExch(&mb.acc[lane], 0ull) % bb::P; // read + re-arm
+                const unsigned long long v = bb::reduce64_scaled<0>(atomicExch(&mb.acc[lane], 0ull)); // read + re-arm
                 mail[lane] = mb.tagged ? mail_tagged(mb.seq, v) : v;
             }
             if (lane == 0) *mb.ticket = 0u;
@@ -1848,7 +1884,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 __global__ void k_synthetic(uint32_t *dst, uint64_t n, uint64_t seed, uint64_t start, uint64_t step) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        dst[i] = (uint32_t)(splitmix64(seed + start + i * step) % bb::P);
+        dst[i] = bb::reduce64_scaled<0>(splitmix64(seed + start + i * step));
 }
 // eq table of a point from two half tables: out[i] = lo[i & (2^s - 1)] * hi[i >> s], hi in Montgomery form (one product per entry;
 // the halves have <= 2^16 entries and stay in L1/L2)
@@ -1882,7 +1918,7 @@ __global__ void k_witness_pack(const uint64_t *cols, uint64_t chunk, uint64_t st
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < chunk; j += stride) {
         const uint64_t i = step0 + j;
         if (i >= padded) break;
-        o[i] = i < num_steps ? (uint32_t)(cols[c * chunk + j] % bb::P) : fill;
+        o[i] = i < num_steps ? bb::reduce64_scaled<0>(cols[c * chunk + j]) : fill; // F.init: any u64 mod p
     }
 }
 void launch_witness_pack(const uint64_t *cols, uint64_t chunk, uint64_t step0, uint64_t num_steps, uint64_t padded,
@@ -1941,7 +1977,7 @@ __device__ __forceinline__ uint32_t hash_row3(uint64_t a, uint64_t b, uint64_t c
     uint64_t h = xxh3_8(a);
     h = xxh3_8(h ^ b);
     h = xxh3_8(h ^ c);
-    return (uint32_t)(h % bb::P);
+    return bb::reduce64_scaled<0>(h);
 }
 
 __global__ void k_xxh3_rows(const uint32_t *rows, uint64_t n_rows, uint32_t arity, uint64_t n_padded, uint32_t *out) {
@@ -1951,7 +1987,7 @@ __global__ void k_xxh3_rows(const uint32_t *rows, uint64_t n_rows, uint32_t arit
         if (i < n_rows) {
             uint64_t h = 0;
             for (uint32_t k = 0; k < arity; k++) h = xxh3_8(h ^ (uint64_t)rows[i * arity + k]);
-            v = (uint32_t)(h % bb::P);
+            v = bb::reduce64_scaled<0>(h);
         }
         out[i] = v;
     }
