@@ -560,12 +560,20 @@ def run_extras(args, z, ctx, peak):
         ab["d1_2^20_us_" + ("several_rounds_per_pass" if lin else "one_round_per_kernel_and_tail")] = us.value
     ctx.set_option("linear_d1", 1)
     p3 = [z.Multilinear.synthetic(ctx, SEED + k, 1 << 20) for k in range(3)]
-    old_tail = ctx.get_option("tail_log2")
-    for tl in (old_tail, 0):
-        ctx.set_option("tail_log2", tl)
-        ab[f"d3_2^20_us_tail_log2_{tl}"] = wall(lambda: z.ProductSumcheckProver.prove(p3), 50, warm=5) * 1e6
-    ctx.set_option("tail_log2", old_tail)
-    for p in p3 + [p20b]:
+    # product prover: small tables finish on the host (zb_prod_fold_dump + zh_prodcheck_finish_small, two rounds per device pass
+    # down to the hand-over) vs one host round trip per round below 2^15 entries (persistent tail kernel on / off)
+    old_tail, old_ht = ctx.get_option("tail_log2"), ctx.get_option("prod_host_tail_log2")
+    p3s = [z.Multilinear.synthetic(ctx, SEED + k, 1 << 12) for k in range(3)]
+    for name, polys3 in (("2^20", p3), ("2^12", p3s)):
+        ctx.set_option("prod_host_tail_log2", old_ht)
+        ab[f"d3_{name}_us_host_finishes_2^{old_ht}"] = wall(lambda: z.ProductSumcheckProver.prove(polys3), 100, warm=5) * 1e6
+        ctx.set_option("prod_host_tail_log2", 0)
+        for tl in (old_tail, 0):
+            ctx.set_option("tail_log2", tl)
+            ab[f"d3_{name}_us_round_trip_per_round_tail_log2_{tl}"] = wall(lambda: z.ProductSumcheckProver.prove(polys3), 50, warm=5) * 1e6
+        ctx.set_option("tail_log2", old_tail)
+    ctx.set_option("prod_host_tail_log2", old_ht)
+    for p in p3 + p3s + [p20b]:
         p.deinit()
     out["latency_mechanisms_ab"] = ab
     # d=1 sumcheck over 2^28: HBM-bound regime of the reference's own prover

@@ -157,6 +157,7 @@ pub extern fn zb_comm_allreduce_u64(ctx: *Ctx, vals: [*c]u64, n: u32) i32;
 pub extern fn zb_comm_p2p_handle(ctx: *Ctx, out: *[64]u8) i32;
 pub extern fn zb_comm_p2p_attach(ctx: *Ctx, handles: [*c]const u8) i32;
 pub extern fn zb_comm_allgather_cyclic(ctx: *Ctx, local: Mle, out: [*c]Mle) i32;
+pub extern fn zb_comm_allgather_cyclic_batch(ctx: *Ctx, locals: [*c]const Mle, count: u32, outs: [*c]Mle) i32;
 pub extern fn zb_comm_destroy(ctx: *Ctx) i32;
 pub extern fn zh_transcript_new() *Transcript;
 pub extern fn zh_transcript_clone(t: *const Transcript) *Transcript;

@@ -274,6 +274,8 @@ int32_t zb_comm_p2p_attach(zb_ctx *ctx, const uint8_t *handles);
 /* all-gather of cyclic shards: out[rank + world*j] = shard_rank[j] (a NEW polynomial of world * n_local entries,
  * identical on every rank) — used to leave the sharded regime once the tables are small */
 int32_t zb_comm_allgather_cyclic(zb_ctx *ctx, zb_mle local, zb_mle *out);
+/* the same for `count` (1..3) shards of equal length with ONE rendezvous and one stream synchronisation */
+int32_t zb_comm_allgather_cyclic_batch(zb_ctx *ctx, const zb_mle *locals, uint32_t count, zb_mle *outs);
 int32_t zb_comm_destroy(zb_ctx *ctx);
 
 #ifdef __cplusplus

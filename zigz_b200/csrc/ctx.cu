@@ -188,6 +188,7 @@ struct LocalComm {
     std::atomic<int> count{0};
     std::atomic<int> sense{0};
     const void *ptr[XCHG_MAX_RANKS] = {nullptr};
+    const void *ptrs[MAX_POLYS][XCHG_MAX_RANKS] = {{nullptr}}; // batched all-gather: [table][rank]
     // sense-reversing barrier between the ranks' host threads (every rank calls it the same number of times)
     void barrier() {
         const int s = sense.load(std::memory_order_acquire);
@@ -363,7 +364,8 @@ inline Mailbox round_mailbox(zb_ctx *c, bool reduce) {
     if (reduce) {
         m.tagged = false; // plain words: they are summed over the ranks before they reach the host
         if (reduce_p2p(c)) {
-            m.xchg = c->d_xchg_view; // the kernel itself sums over the ranks and publishes
+            m.tagged = true; // ... by the kernel itself, which then publishes the totals as tagged words
+            m.xchg = c->d_xchg_view;
             m.xseq = ++c->xchg_seq;
         } else {
             m.mail = c->d_comm; // the kernel writes the exchange buffer, comm_publish() does the rest
@@ -515,7 +517,12 @@ int32_t read_err_flag(zb_ctx *ctx) {
 //    staging buffers (canonical check included) while the previous chunk's H2D copy is in flight: 4 bytes per
 //    element cross PCIe instead of 8;
 //  direct mode: the u64 data is copied as is and narrowed by a kernel (k_narrow).
-constexpr uint64_t PACK_CHUNK = 8ull << 20; // elements per staging buffer (32 MiB narrowed)
+// elements per staging buffer (default 2^23: 32 MiB narrowed; ZB_PACK_CHUNK_LOG2 = 16..24 for experiments)
+static const uint64_t PACK_CHUNK = [] {
+    const char *e = getenv("ZB_PACK_CHUNK_LOG2");
+    const int x = e && *e ? atoi(e) : 23;
+    return 1ull << (x < 16 ? 16 : (x > 24 ? 24 : x));
+}();
 constexpr int PACK_BUFS = 3;
 
 int upload_threads(zb_ctx *ctx) {
@@ -2735,51 +2742,89 @@ int32_t comm_publish(zb_ctx *ctx, unsigned long long seq, int nwords) {
 } // namespace
 } // extern "C++"
 
-int32_t zb_comm_allgather_cyclic(zb_ctx *ctx, zb_mle local, zb_mle *out) {
+int32_t zb_comm_allgather_cyclic_batch(zb_ctx *ctx, const zb_mle *locals, uint32_t count, zb_mle *outs) {
     tail_quiesce(ctx);
-    Mle *m = get_mle(ctx, local);
-    if (!m || !out) return m ? ZB_ERR_BAD_ARGUMENT : ZB_ERR_BAD_HANDLE;
-    if (ctx->world == 1) return zb_mle_clone(ctx, local, out);
-    if (ctx->local) { // same process: every rank reads the peers' shards directly over NVLink
-        const uint64_t n = m->n;
-        const uint32_t *mine = m->d();
-        BufRef keep = m->buf;
-        Mle *o = nullptr;
-        int32_t rc = new_mle(ctx, n * ctx->world, out, &o);
-        ctx->local->ptr[ctx->rank] = mine;
-        ctx->local->barrier();
-        if (rc == ZB_OK) {
-            PeerSrc ps{};
-            for (int q = 0; q < ctx->world; q++) ps.p[q] = (const uint32_t *)ctx->local->ptr[q];
-            launch_interleave_peers(ps, o->d(), n, (uint32_t)ctx->world, ctx->sm_count, ctx->stream);
-            rc = check_launch(ctx, "interleave_peers");
-            if (rc == ZB_OK) rc = zb_sync(ctx);
-        }
-        ctx->local->barrier(); // the peers have finished reading this rank's shard
-        if (rc && *out) {
-            ctx->mles.erase(*out);
-            *out = 0;
-        }
+    if (!locals || !outs || count < 1 || count > (uint32_t)MAX_POLYS) return ZB_ERR_BAD_ARGUMENT;
+    uint64_t n = 0;
+    BufRef src[MAX_POLYS];
+    for (uint32_t k = 0; k < count; k++) {
+        Mle *m = get_mle(ctx, locals[k]);
+        if (!m) return ZB_ERR_BAD_HANDLE;
+        if (k && m->n != n) return ZB_ERR_DIFFERENT_NUM_VARS;
+        n = m->n;
+        src[k] = m->buf;
+        outs[k] = 0;
+    }
+    auto drop = [&]() {
+        for (uint32_t k = 0; k < count; k++)
+            if (outs[k]) {
+                ctx->mles.erase(outs[k]);
+                outs[k] = 0;
+            }
+    };
+    if (ctx->world == 1) {
+        int32_t rc = ZB_OK;
+        for (uint32_t k = 0; k < count && rc == ZB_OK; k++) rc = zb_mle_clone(ctx, locals[k], &outs[k]);
+        if (rc) drop();
         return rc;
     }
-    if (!ctx->nccl_comm) return ZB_ERR_BAD_ARGUMENT;
-    const uint64_t n = m->n;
-    BufRef src = m->buf, tmp;
-    int32_t rc = dev_alloc(ctx, n * ctx->world * sizeof(uint32_t), &tmp);
-    if (rc) return rc;
-    Mle *o = nullptr;
-    rc = new_mle(ctx, n * ctx->world, out, &o);
-    if (rc) return rc;
-    int r = g_nccl.AllGather(src->ptr, tmp->ptr, (size_t)n, NCCL_UINT32, ctx->nccl_comm, ctx->stream);
-    if (r) {
-        ctx->mles.erase(*out);
-        return nccl_fail(ctx, r, "ncclAllGather");
+    uint32_t *dst[MAX_POLYS] = {nullptr, nullptr, nullptr};
+    int32_t rc = ZB_OK;
+    for (uint32_t k = 0; k < count && rc == ZB_OK; k++) {
+        Mle *o = nullptr;
+        rc = new_mle(ctx, n * ctx->world, &outs[k], &o);
+        if (rc == ZB_OK) dst[k] = o->d();
     }
-    launch_interleave((const uint32_t *)tmp->ptr, o->d(), n, (uint32_t)ctx->world, ctx->stream);
-    rc = check_launch(ctx, "interleave");
+    if (ctx->local) { // same process: every rank reads the peers' shards directly over NVLink; one rendezvous for all tables
+        for (uint32_t k = 0; k < count; k++) ctx->local->ptrs[k][ctx->rank] = src[k]->ptr;
+        ctx->local->barrier();
+        for (uint32_t k = 0; k < count && rc == ZB_OK; k++) {
+            PeerSrc ps{};
+            for (int q = 0; q < ctx->world; q++) ps.p[q] = (const uint32_t *)ctx->local->ptrs[k][q];
+            launch_interleave_peers(ps, dst[k], n, (uint32_t)ctx->world, ctx->sm_count, ctx->stream);
+            rc = check_launch(ctx, "interleave_peers");
+        }
+        if (rc == ZB_OK) rc = zb_sync(ctx);
+        else cudaStreamSynchronize(ctx->stream);
+        ctx->local->barrier(); // the peers have finished reading this rank's shards
+        if (rc) drop();
+        return rc;
+    }
+    if (rc) {
+        drop();
+        return rc;
+    }
+    if (!ctx->nccl_comm) {
+        drop();
+        return ZB_ERR_BAD_ARGUMENT;
+    }
+    BufRef tmp;
+    rc = dev_alloc(ctx, (size_t)count * n * ctx->world * sizeof(uint32_t), &tmp);
+    if (rc) {
+        drop();
+        return rc;
+    }
+    for (uint32_t k = 0; k < count; k++) {
+        uint32_t *t = (uint32_t *)tmp->ptr + (size_t)k * n * ctx->world;
+        const int r = g_nccl.AllGather(src[k]->ptr, t, (size_t)n, NCCL_UINT32, ctx->nccl_comm, ctx->stream);
+        if (r) {
+            cudaStreamSynchronize(ctx->stream);
+            drop();
+            return nccl_fail(ctx, r, "ncclAllGather");
+        }
+        launch_interleave(t, dst[k], n, (uint32_t)ctx->world, ctx->stream);
+        rc = check_launch(ctx, "interleave");
+        if (rc) break;
+    }
     if (rc == ZB_OK) rc = zb_sync(ctx);
-    if (rc) ctx->mles.erase(*out);
+    else cudaStreamSynchronize(ctx->stream);
+    if (rc) drop();
     return rc;
+}
+
+int32_t zb_comm_allgather_cyclic(zb_ctx *ctx, zb_mle local, zb_mle *out) {
+    if (!out) return ZB_ERR_BAD_ARGUMENT;
+    return zb_comm_allgather_cyclic_batch(ctx, &local, 1, out);
 }
 
 int32_t zb_comm_p2p_handle(zb_ctx *ctx, uint8_t out[64]) {

@@ -443,10 +443,8 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
             // leave the sharded regime: all-gather the shards into the global order; what is in hand (`coeffs`, `grid`) are
             // global sums already, so nothing is recomputed
             zb_mle full[3] = {0, 0, 0};
-            for (uint32_t k = 0; k < d && rc == ZB_OK; k++) rc = zb_comm_allgather_cyclic(ctx, cur[k], &full[k]);
+            rc = zb_comm_allgather_cyclic_batch(ctx, cur, d, full);
             if (rc) {
-                for (uint32_t k = 0; k < d; k++)
-                    if (full[k]) zb_mle_free(ctx, full[k]);
                 cleanup();
                 return rc;
             }

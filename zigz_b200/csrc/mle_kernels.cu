@@ -62,12 +62,13 @@ __device__ __forceinline__ bool xchg_allreduce(unsigned long long (&tot)[NS], co
     const int lane = threadIdx.x & 31;
     const int world = xv->world, rank = xv->rank;
     const unsigned long long set = (seq & 1ull) * XCHG_SET_WORDS;
+    // Self-validating words (the payload values are canonical field elements < 2^31): (low 32 bits of seq) << 32 | value. No
+    // system-scope fence between payload and flag, no flag at all: a row has arrived when every one of its words carries the
+    // tag. An 8-byte peer store is atomic, and the alternating sets keep round seq - 1 apart from round seq.
     if (lane < world) {
         volatile unsigned long long *dst = xv->peer[lane] + set;
 #pragma unroll
-        for (int k = 0; k < NS; k++) dst[rank * XCHG_ROW + k] = tot[k];
-        __threadfence_system();
-        dst[XCHG_MAX_RANKS * XCHG_ROW + rank] = seq;
+        for (int k = 0; k < NS; k++) dst[rank * XCHG_ROW + k] = mail_tagged(seq, tot[k]);
     }
     bool ok = true;
     unsigned long long v[NS];
@@ -76,15 +77,21 @@ __device__ __forceinline__ bool xchg_allreduce(unsigned long long (&tot)[NS], co
     if (lane < world) {
         volatile unsigned long long *mine = xv->peer[rank] + set;
         const long long t0 = clock64(), patience = xv->patience;
-        while (mine[XCHG_MAX_RANKS * XCHG_ROW + lane] != seq) {
+        const unsigned long long tag = seq & 0xffffffffull;
+        for (;;) {
+            bool all = true;
+#pragma unroll
+            for (int k = 0; k < NS; k++) {
+                const unsigned long long w = mine[lane * XCHG_ROW + k];
+                all = all && (w >> 32) == tag;
+                v[k] = w & 0xffffffffull;
+            }
+            if (all) break;
             if (clock64() - t0 > patience) {
                 ok = false;
                 break;
             }
         }
-        __threadfence_system();
-#pragma unroll
-        for (int k = 0; k < NS; k++) v[k] = mine[lane * XCHG_ROW + k];
         if (xv->stats != nullptr) { // the slowest peer's row sets this rank's wait
             long long waited = clock64() - t0;
 #pragma unroll
@@ -166,10 +173,13 @@ __device__ __forceinline__ void publish_sums(unsigned long long (&s)[NS], const 
             const bool ok = xchg_allreduce<NS>(tot, mb.xchg, mb.xseq);
             if (lane == 0) {
                 volatile unsigned long long *mail = (volatile unsigned long long *)mb.mail;
+                if (!ok) { // status word: 1 = a peer never arrived (the host clears it); ordered before the payload it qualifies
+                    mail[MAIL_WORDS - 1] = 1ull;
+                    __threadfence_system();
+                }
+                // tagged payload (mb.tagged is set for these mailboxes): the host waits for the tags, no fence on the way
 #pragma unroll
-                for (int k = 0; k < NS; k++) mail[k] = tot[k];
-                mail[MAIL_WORDS - 1] = ok ? 0ull : 1ull; // status word: 1 = a peer never arrived
-                __threadfence_system();
+                for (int k = 0; k < NS; k++) mail[k] = mail_tagged(mb.seq, tot[k]);
                 mail[MAIL_WORDS] = mb.seq;
             }
         }
