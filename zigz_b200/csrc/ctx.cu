@@ -158,6 +158,7 @@ struct zb_ctx {
     unsigned long long *d_xchg = nullptr;
     void *xchg_peer[16] = {nullptr};
     XchgView *d_xchg_view = nullptr;
+    unsigned long long gather_seq = 0; // rounds of the in-kernel all-gather (identical on every rank)
     unsigned long long *d_xchg_stats = nullptr; // {wait cycles, exchanged rounds}
     // single-process multi-GPU (zb_ctx_create_mask): the contexts of one process that form a communicator without NCCL
     // or CUDA IPC share a LocalComm (host barrier + pointer exchange for the peer-memory collectives); the FRONT context
@@ -2775,6 +2776,23 @@ int32_t zb_comm_allgather_cyclic_batch(zb_ctx *ctx, const zb_mle *locals, uint32
         rc = new_mle(ctx, n * ctx->world, &outs[k], &o);
         if (rc == ZB_OK) dst[k] = o->d();
     }
+    static const bool xchg_gather = [] {
+        const char *e = getenv("ZB_GATHER_XCHG"); // 0: NCCL / host-rendezvous all-gather (the fallback paths below)
+        return !(e && *e == '0');
+    }();
+    if (rc == ZB_OK && xchg_gather && ctx->d_xchg_view && n <= (1ull << XCHG_GATHER_MAX_LOG2)) {
+        // peers attached (CUDA IPC or one process): ONE kernel stages, signals, waits and pulls — no rendezvous, no sync; what
+        // follows on the stream sees the gathered tables, and the shards may be dropped right away (stream order)
+        PolySet sh{}, os{};
+        for (uint32_t k = 0; k < count; k++) {
+            sh.src[k] = (const uint32_t *)src[k]->ptr;
+            os.dst[k] = dst[k];
+        }
+        launch_gather_xchg(ctx->d_xchg_view, ctx->world, sh, os, (int)count, n, ++ctx->gather_seq, ctx->d_ticket, ctx->d_mail, ctx->stream);
+        rc = check_launch(ctx, "gather_xchg");
+        if (rc) drop();
+        return rc;
+    }
     if (ctx->local) { // same process: every rank reads the peers' shards directly over NVLink; one rendezvous for all tables
         for (uint32_t k = 0; k < count; k++) ctx->local->ptrs[k][ctx->rank] = src[k]->ptr;
         ctx->local->barrier();
@@ -2832,7 +2850,7 @@ int32_t zb_comm_p2p_handle(zb_ctx *ctx, uint8_t out[64]) {
     if (!out) return ZB_ERR_BAD_ARGUMENT;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
     if (!ctx->d_xchg) {
-        const size_t bytes = 2 * XCHG_SET_WORDS * sizeof(unsigned long long);
+        const size_t bytes = XCHG_BUFFER_BYTES; // payload sets + the staging area of the in-kernel all-gather
         CK(cudaMalloc(&ctx->d_xchg, bytes));
         CK(cudaMemset(ctx->d_xchg, 0, bytes));
     }
@@ -3321,7 +3339,7 @@ int32_t zb_ctx_create_mask(uint32_t device_mask, zb_ctx **out) {
     }
     auto lc = std::make_shared<LocalComm>();
     lc->world = world;
-    const size_t xbytes = 2 * XCHG_SET_WORDS * sizeof(unsigned long long);
+    const size_t xbytes = XCHG_BUFFER_BYTES;
     for (int r = 0; r < world; r++) {
         cudaSetDevice(devs[r]);
         c[r]->local = lc;

@@ -18,6 +18,13 @@ constexpr int MAIL_WORDS = 40;  // u64 payload words per mailbox (16-word round 
 constexpr int XCHG_MAX_RANKS = 16;
 constexpr int XCHG_ROW = 16;
 constexpr int XCHG_SET_WORDS = XCHG_MAX_RANKS * XCHG_ROW + XCHG_MAX_RANKS;
+// Behind the two payload sets the same buffer carries the staging area of the in-kernel all-gather that ends the sharded regime
+// (launch_gather_xchg): per set XCHG_MAX_RANKS arrival words, then per set MAX_POLYS shards of up to 2^XCHG_GATHER_MAX_LOG2 u32.
+constexpr int XCHG_GATHER_MAX_LOG2 = 16;
+constexpr size_t XCHG_GATHER_FLAGS_OFF = 2 * (size_t)XCHG_SET_WORDS;                    // in u64 words
+constexpr size_t XCHG_GATHER_DATA_OFF = XCHG_GATHER_FLAGS_OFF + 2 * XCHG_MAX_RANKS;     // in u64 words
+constexpr size_t XCHG_GATHER_SET_ELEMS = (size_t)3 << XCHG_GATHER_MAX_LOG2;            // u32 per set (3 = MAX_POLYS)
+constexpr size_t XCHG_BUFFER_BYTES = XCHG_GATHER_DATA_OFF * 8 + 2 * XCHG_GATHER_SET_ELEMS * 4;
 struct XchgView {
     unsigned long long *peer[XCHG_MAX_RANKS]; // peer[q] = rank q's exchange buffer as seen from this GPU (peer[rank] = own)
     int rank, world;
@@ -91,6 +98,13 @@ void launch_fill_heads(const PolySet &ps, int d, const uint32_t *vals, cudaStrea
 
 // multi-GPU: src[0..n) (NCCL-summed canonical payload words) -> mailbox payload mod p + sequence number
 void launch_publish_reduced(const unsigned long long *src, int n, unsigned long long *mail, unsigned long long seq, cudaStream_t st);
+// multi-GPU all-gather of `count` cyclic shards (n_local <= 2^XCHG_GATHER_MAX_LOG2 entries each) in ONE kernel over peer memory:
+// every rank copies its shards into its own exchange buffer, raises its arrival word in every peer's buffer, waits for the
+// peers' words and pulls their shards into the global order outs.dst[k][q + world * j] = shard_q,k[j]. gseq: gather round
+// number, identical on all ranks, alternating between the two staging sets. A peer that never arrives sets the mailbox status
+// word (mail[MAIL_WORDS - 1] = 1), which the next wait on the mailbox reports. No host rendezvous, no stream synchronisation.
+void launch_gather_xchg(const XchgView *xv, int world, const PolySet &shards, const PolySet &outs, int count, uint64_t n_local,
+                        unsigned long long gseq, unsigned int *ticket, unsigned long long *mail, cudaStream_t st);
 // multi-GPU: all-gathered cyclic shards [rank][j] -> global order out[rank + world * j]
 void launch_interleave(const uint32_t *gathered, uint32_t *out, uint64_t n_local, uint32_t world, cudaStream_t st);
 

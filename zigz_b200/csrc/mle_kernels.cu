@@ -1167,6 +1167,79 @@ void launch_interleave_peers(const PeerSrc &ps, uint32_t *out, uint64_t n_local,
     uint64_t g = (n_local + PEER_J - 1) / PEER_J, cap = (uint64_t)sm * 8;
     k_interleave_peers<<<(int)(g < cap ? (g ? g : 1) : cap), PEER_J, PEER_J * world * sizeof(uint32_t), st>>>(ps, out, n_local, world);
 }
+// The all-gather that ends the sharded regime, without NCCL, host rendezvous or stream synchronisation (launch_gather_xchg in
+// kernels.h). Phase 1: the grid copies this rank's shards into its own staging set; the last CTA to finish (atomic ticket)
+// raises this rank's arrival word in every peer's buffer (after a system-scope fence). Phase 2: every CTA waits for all
+// arrival words in the LOCAL buffer, then pulls the peers' staged shards — coalesced remote reads, interleave in shared memory,
+// coalesced local writes, as k_interleave_peers. The grid is small enough to be co-resident (the wait cannot starve phase 1).
+constexpr int GATHER_CTAS = 64;
+__global__ void __launch_bounds__(PEER_J) k_gather_xchg(const XchgView *xv, PolySet shards, PolySet outs, int count, uint64_t n_local,
+                                                        unsigned long long gseq, unsigned int *ticket, unsigned long long *mail) {
+    extern __shared__ uint32_t sm_peer[]; // [PEER_J * world]
+    __shared__ int s_ok;
+    const int world = xv->world, rank = xv->rank;
+    const size_t set = (size_t)(gseq & 1ull);
+    unsigned long long *mine = xv->peer[rank];
+    uint32_t *stage = reinterpret_cast<uint32_t *>(mine + XCHG_GATHER_DATA_OFF) + set * XCHG_GATHER_SET_ELEMS;
+    const uint64_t gtid = (uint64_t)blockIdx.x * PEER_J + threadIdx.x, gstride = (uint64_t)gridDim.x * PEER_J;
+    for (int k = 0; k < count; k++)
+        for (uint64_t i = gtid; i < n_local; i += gstride) stage[((size_t)k << XCHG_GATHER_MAX_LOG2) + i] = shards.src[k][i];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) { // every CTA's copies are in place
+            *ticket = 0u;
+            __threadfence_system();
+            for (int q = 0; q < world; q++)
+                ((volatile unsigned long long *)xv->peer[q])[XCHG_GATHER_FLAGS_OFF + set * XCHG_MAX_RANKS + rank] = gseq;
+        }
+    }
+    if (threadIdx.x < 32) {
+        bool ok = true;
+        if ((int)threadIdx.x < world) {
+            volatile unsigned long long *flag = mine + XCHG_GATHER_FLAGS_OFF + set * XCHG_MAX_RANKS + threadIdx.x;
+            const long long t0 = clock64(), patience = xv->patience;
+            while (*flag != gseq)
+                if (clock64() - t0 > patience) {
+                    ok = false;
+                    break;
+                }
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        if (threadIdx.x == 0) {
+            s_ok = ok ? 1 : 0;
+            if (!ok) { // reported by the next wait on the mailbox ("a rank never arrived")
+                ((volatile unsigned long long *)mail)[MAIL_WORDS - 1] = 1ull;
+                __threadfence_system();
+            }
+        }
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    __threadfence_system();
+    for (int k = 0; k < count; k++) {
+        uint32_t *out = outs.dst[k];
+        for (uint64_t j0 = (uint64_t)blockIdx.x * PEER_J; j0 < n_local; j0 += (uint64_t)gridDim.x * PEER_J) {
+            const uint64_t j = j0 + threadIdx.x;
+            for (int q = 0; q < world; q++) {
+                const volatile uint32_t *src = reinterpret_cast<const volatile uint32_t *>(xv->peer[q] + XCHG_GATHER_DATA_OFF) +
+                                               set * XCHG_GATHER_SET_ELEMS + ((size_t)k << XCHG_GATHER_MAX_LOG2);
+                sm_peer[threadIdx.x * world + q] = j < n_local ? src[j] : 0u;
+            }
+            __syncthreads();
+            const uint64_t cnt = (n_local - j0 < PEER_J ? n_local - j0 : PEER_J) * world;
+            for (uint64_t t = threadIdx.x; t < cnt; t += PEER_J) out[j0 * world + t] = sm_peer[t];
+            __syncthreads();
+        }
+    }
+}
+void launch_gather_xchg(const XchgView *xv, int world, const PolySet &shards, const PolySet &outs, int count, uint64_t n_local,
+                        unsigned long long gseq, unsigned int *ticket, unsigned long long *mail, cudaStream_t st) {
+    const uint64_t g = (n_local + PEER_J - 1) / PEER_J;
+    const int grid = (int)(g < (uint64_t)GATHER_CTAS ? (g ? g : 1) : (uint64_t)GATHER_CTAS);
+    k_gather_xchg<<<grid, PEER_J, PEER_J * world * sizeof(uint32_t), st>>>(xv, shards, outs, count, n_local, gseq, ticket, mail);
+}
 // push: dst_q[j] = src[j * world + q] (j < n_out): coalesced local reads, 128-byte coalesced stores into every peer.
 // Serves the host-order (contiguous block per GPU) -> cyclic-shard deal after an upload.
 __global__ void __launch_bounds__(PEER_J) k_deal_peers(const uint32_t *src, PeerDst pd, uint64_t n_out, uint32_t world) {
