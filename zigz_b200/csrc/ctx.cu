@@ -2788,7 +2788,10 @@ int32_t zb_comm_allgather_cyclic_batch(zb_ctx *ctx, const zb_mle *locals, uint32
             sh.src[k] = (const uint32_t *)src[k]->ptr;
             os.dst[k] = dst[k];
         }
-        launch_gather_xchg(ctx->d_xchg_view, ctx->world, sh, os, (int)count, n, ++ctx->gather_seq, ctx->d_ticket, ctx->d_mail, ctx->stream);
+        {
+            ProfScope _ps(ctx, "gather_xchg", (uint64_t)count * n * ctx->world * sizeof(uint32_t));
+            launch_gather_xchg(ctx->d_xchg_view, ctx->world, sh, os, (int)count, n, ++ctx->gather_seq, ctx->d_ticket, ctx->d_mail, ctx->stream);
+        }
         rc = check_launch(ctx, "gather_xchg");
         if (rc) drop();
         return rc;

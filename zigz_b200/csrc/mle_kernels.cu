@@ -1172,18 +1172,62 @@ void launch_interleave_peers(const PeerSrc &ps, uint32_t *out, uint64_t n_local,
 // raises this rank's arrival word in every peer's buffer (after a system-scope fence). Phase 2: every CTA waits for all
 // arrival words in the LOCAL buffer, then pulls the peers' staged shards — coalesced remote reads, interleave in shared memory,
 // coalesced local writes, as k_interleave_peers. The grid is small enough to be co-resident (the wait cannot starve phase 1).
-constexpr int GATHER_CTAS = 64;
+constexpr int GATHER_CTAS = 148; // one per SM at most: the whole grid must be resident while it waits for the peers
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint32_t *p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// pull for shard lengths that are multiples of 4: one 16-byte load per peer (all W of them in flight), then the W x 4 values a
+// thread holds are 4 W CONSECUTIVE output words (rows j .. j + 3 of W entries each): 16-byte stores, no shared memory
+template <int W>
+__device__ __forceinline__ void gather_pull_v4(const XchgView *xv, size_t set, int count, const PolySet &outs, uint64_t n4) {
+    const uint64_t items = (uint64_t)count * n4, stride = (uint64_t)gridDim.x * PEER_J;
+    for (uint64_t it = (uint64_t)blockIdx.x * PEER_J + threadIdx.x; it < items; it += stride) {
+        const int k = (int)(it / n4);
+        const uint64_t j4 = it - (uint64_t)k * n4;
+        uint32_t v[W][4];
+#pragma unroll
+        for (int q = 0; q < W; q++) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(xv->peer[q] + XCHG_GATHER_DATA_OFF) + set * XCHG_GATHER_SET_ELEMS +
+                                  ((size_t)k << XCHG_GATHER_MAX_LOG2);
+            const uint4 x = ld_volatile_v4(src + 4 * j4);
+            v[q][0] = x.x, v[q][1] = x.y, v[q][2] = x.z, v[q][3] = x.w;
+        }
+        uint4 *o = reinterpret_cast<uint4 *>(outs.dst[k] + 4 * j4 * W);
+        if constexpr (W == 2) {
+            o[0] = make_uint4(v[0][0], v[1][0], v[0][1], v[1][1]);
+            o[1] = make_uint4(v[0][2], v[1][2], v[0][3], v[1][3]);
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+                for (int q = 0; q < W; q += 4) o[(jj * W + q) / 4] = make_uint4(v[q][jj], v[q + 1][jj], v[q + 2][jj], v[q + 3][jj]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(PEER_J) k_gather_xchg(const XchgView *xv, PolySet shards, PolySet outs, int count, uint64_t n_local,
                                                         unsigned long long gseq, unsigned int *ticket, unsigned long long *mail) {
-    extern __shared__ uint32_t sm_peer[]; // [PEER_J * world]
+    extern __shared__ uint32_t sm_peer[]; // [PEER_J * world] (scalar path only)
     __shared__ int s_ok;
     const int world = xv->world, rank = xv->rank;
     const size_t set = (size_t)(gseq & 1ull);
     unsigned long long *mine = xv->peer[rank];
     uint32_t *stage = reinterpret_cast<uint32_t *>(mine + XCHG_GATHER_DATA_OFF) + set * XCHG_GATHER_SET_ELEMS;
     const uint64_t gtid = (uint64_t)blockIdx.x * PEER_J + threadIdx.x, gstride = (uint64_t)gridDim.x * PEER_J;
-    for (int k = 0; k < count; k++)
-        for (uint64_t i = gtid; i < n_local; i += gstride) stage[((size_t)k << XCHG_GATHER_MAX_LOG2) + i] = shards.src[k][i];
+    const bool vec = (n_local % 4) == 0 && (world == 2 || world == 4 || world == 8 || world == 16);
+    if (vec) {
+        const uint64_t n4 = n_local / 4;
+        for (uint64_t it = gtid; it < (uint64_t)count * n4; it += gstride) {
+            const int k = (int)(it / n4);
+            const uint64_t j4 = it - (uint64_t)k * n4;
+            reinterpret_cast<uint4 *>(stage + ((size_t)k << XCHG_GATHER_MAX_LOG2))[j4] = reinterpret_cast<const uint4 *>(shards.src[k])[j4];
+        }
+    } else {
+        for (int k = 0; k < count; k++)
+            for (uint64_t i = gtid; i < n_local; i += gstride) stage[((size_t)k << XCHG_GATHER_MAX_LOG2) + i] = shards.src[k][i];
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1218,6 +1262,14 @@ __global__ void __launch_bounds__(PEER_J) k_gather_xchg(const XchgView *xv, Poly
     __syncthreads();
     if (!s_ok) return;
     __threadfence_system();
+    if (vec) {
+        const uint64_t n4 = n_local / 4;
+        if (world == 2) gather_pull_v4<2>(xv, set, count, outs, n4);
+        else if (world == 4) gather_pull_v4<4>(xv, set, count, outs, n4);
+        else if (world == 8) gather_pull_v4<8>(xv, set, count, outs, n4);
+        else gather_pull_v4<16>(xv, set, count, outs, n4);
+        return;
+    }
     for (int k = 0; k < count; k++) {
         uint32_t *out = outs.dst[k];
         for (uint64_t j0 = (uint64_t)blockIdx.x * PEER_J; j0 < n_local; j0 += (uint64_t)gridDim.x * PEER_J) {
@@ -1236,7 +1288,8 @@ __global__ void __launch_bounds__(PEER_J) k_gather_xchg(const XchgView *xv, Poly
 }
 void launch_gather_xchg(const XchgView *xv, int world, const PolySet &shards, const PolySet &outs, int count, uint64_t n_local,
                         unsigned long long gseq, unsigned int *ticket, unsigned long long *mail, cudaStream_t st) {
-    const uint64_t g = (n_local + PEER_J - 1) / PEER_J;
+    // vector path: count * n_local / 4 items; scalar path: tiles of PEER_J entries
+    const uint64_t g = (n_local % 4) == 0 ? ((uint64_t)count * (n_local / 4) + PEER_J - 1) / PEER_J : (n_local + PEER_J - 1) / PEER_J;
     const int grid = (int)(g < (uint64_t)GATHER_CTAS ? (g ? g : 1) : (uint64_t)GATHER_CTAS);
     k_gather_xchg<<<grid, PEER_J, PEER_J * world * sizeof(uint32_t), st>>>(xv, shards, outs, count, n_local, gseq, ticket, mail);
 }
