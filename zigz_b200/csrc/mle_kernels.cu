@@ -131,22 +131,32 @@ __device__ __forceinline__ void publish_sums(unsigned long long (&s)[NS], const 
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        unsigned long long tot[NS];
 #pragma unroll
         for (int k = 0; k < NS; k++) {
             unsigned long long v = 0;
 #pragma unroll
             for (int w = 0; w < TPB / 32; w++) v += sm[k][w];
-            atomicAdd(&mb.acc[k], v);
+            tot[k] = v;
         }
-        __threadfence();
-        unsigned int t = atomicAdd(mb.ticket, 1u);
-        is_last = (t == gridDim.x - 1);
-        if (is_last) {
-            __threadfence();
-            unsigned long long tot[NS];
+        if (gridDim.x == 1) {
+            // a single CTA already holds the totals: no accumulators, no ticket, no device-scope fences (small tables are
+            // pure latency: ~3 us of dependent global atomics per launch)
+            is_last = true;
+        } else {
 #pragma unroll
-            for (int k = 0; k < NS; k++) tot[k] = atomicExch(&mb.acc[k], 0ull); // read + re-arm
-            *mb.ticket = 0u;
+            for (int k = 0; k < NS; k++) atomicAdd(&mb.acc[k], tot[k]);
+            __threadfence();
+            unsigned int t = atomicAdd(mb.ticket, 1u);
+            is_last = (t == gridDim.x - 1);
+            if (is_last) {
+                __threadfence();
+#pragma unroll
+                for (int k = 0; k < NS; k++) tot[k] = atomicExch(&mb.acc[k], 0ull); // read + re-arm
+                *mb.ticket = 0u;
+            }
+        }
+        if (is_last) {
             fin(tot);
             if (mb.xchg == nullptr) {
                 if (mb.tagged) { // self-validating words: no fence
