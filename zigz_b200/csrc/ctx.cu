@@ -599,6 +599,11 @@ int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32
         const char *e = getenv("ZB_UPLOAD_PCIE_GBS"); // H2D rate the queue model assumes
         return (e && *e ? atof(e) : 53.0) * 1e9;
     }();
+    static const int raw_cap = [] {
+        const char *e = getenv("ZB_UPLOAD_RAW_CAP"); // adaptive rule: at most one raw chunk in this many (0: no cap)
+        return e && *e ? atoi(e) : 6;
+    }();
+    uint64_t raw_count = 0;
     const int raw_every = pinned ? raw_every_cfg : 0;
     BufRef raw_stage;
     if (raw_every != 0 && n > PACK_CHUNK * 4) {
@@ -623,9 +628,13 @@ int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32
         bool raw = false;
         if (raw_stage && raw_every > 0) raw = (chunk_idx % raw_every) == (uint64_t)(raw_every - 1);
         else if (raw_stage) {
+            // ... and at most one chunk in raw_cap goes raw: a raw chunk takes twice the link time and twice the DMA reads of
+            // host DRAM of a packed one, and on hosts where DRAM rather than the cores limits the packing the uncapped rule
+            // sent 40 % raw and LOST 15 % against packing everything (profiles/r02_upload_policy_boxes.txt)
             const double est = pack_s > 0 ? pack_s : (double)m * 8 / (4.0e9 * T);
-            raw = dma_free_at - now_s() < est;
+            raw = dma_free_at - now_s() < est && (raw_cap <= 0 || (raw_count + 1) * (uint64_t)raw_cap <= chunk_idx + 1);
         }
+        if (raw) raw_count++;
         if (raw) {
             CK(cudaMemcpyAsync(raw_stage->ptr, host + off, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
             ctx->h2d_bytes += m * sizeof(uint64_t);
