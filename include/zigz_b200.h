@@ -196,11 +196,14 @@ int32_t zb_prod_collapse(zb_ctx *ctx, const zb_mle *polys, uint32_t d, const uin
  * index bits hold the next k round polynomials (the host folds the 2^k sums with each challenge exactly as partialEval
  * folds the table), and the k partialEval steps (:154-180) that follow collapse into one pass:
  *   new[i] = sum_b w_b e[b m + i],  w_b = prod_j (b_j ? r_j : 1 - r_j),  m = n / 2^k  — the same canonical values.
- * zb_mle_block_sums: sums[b], b < 2^k (1 <= k <= 5, n >= 2^(k+2)).
- * zb_mle_fold_multi: binds the top k_fold (1..5) variables with r[0..k_fold) (r[0] = the top bit, as partialEval would), in
+ * zb_mle_block_sums: sums[b], b < 2^k (1 <= k <= 8, n >= 2^(k+2)); more than 32 blocks are meant for small tables (one CTA
+ * per block).
+ * zb_mle_fold_multi: binds the top k_fold variables with r[0..k_fold) (r[0] = the top bit, as partialEval would), in
  * place when out == NULL (the handle shrinks to m entries) or into a NEW table, and returns 2^k_next sums over the blocks of
- * the folded table. k_next == log2(m) (allowed up to 10) returns the folded table itself — the host can then finish
- * the remaining <= 10 rounds without another device round trip. Otherwise k_next <= 5 and m >= 2^(k_next+2). */
+ * the folded table. k_next == log2(m) (allowed up to 12) returns the folded table itself — the host can then finish
+ * the remaining <= 12 rounds without another device round trip; k_fold may then be 1..8 (a 2^20-entry prove is two device
+ * calls: 256 block sums, then one fold of 8 variables that publishes 2^12 entries). Otherwise k_fold <= 5, k_next <= 5 and
+ * m >= 2^(k_next+2). */
 int32_t zb_mle_block_sums(zb_ctx *ctx, zb_mle m, uint32_t k, uint64_t *sums);
 int32_t zb_mle_fold_multi(zb_ctx *ctx, zb_mle m, uint32_t k_fold, const uint64_t *r, zb_mle *out, uint32_t k_next, uint64_t *sums);
 /* replaces the table by the single value `value` (length 1): how a consuming prove leaves its polynomial when the last

@@ -398,12 +398,13 @@ def test_grid_entry_points_directly(zlib, ctx, po):
 
 
 # ---------------------------------------------------------------- d = 1: several rounds per pass (zb_mle_block_sums / zb_mle_fold_multi)
-@pytest.mark.parametrize("lg", [11, 12, 13, 15, 16, 17, 19, 21, 22])
-@pytest.mark.parametrize("host_tail", [10, 7, 2])
+@pytest.mark.parametrize("lg", [11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22])
+@pytest.mark.parametrize("host_tail", [12, 10, 7, 2])
 def test_linear_prover_matches_one_round_per_kernel_and_oracle(zlib, ctx, po, lg, host_tail):
     """SumcheckProver.prove (sumcheck_prover.zig:26-91) through block sums + multi-variable folds: every pass shape
-    (first pass of 5, folds of 5, published tables of 2^2..2^10 entries, left-over variable counts) against the oracle,
-    the interactive variant, and the consuming variant (the polynomial ends as its final evaluation)."""
+    (small tables: ONE block-sum pass of up to 2^8 blocks + ONE fold of up to 8 variables; large ones: passes of 5; published
+    tables of 2^2..2^12 entries, left-over variable counts) against the oracle, the interactive variant, and the consuming
+    variant (the polynomial ends as its final evaluation)."""
     e = po.fill_synthetic(BB, 0xC0FFEE + lg, 0, 1 << lg)
     want = po.sumcheck_prove(BB, e)
     ctx.set_option("host_tail_log2", host_tail)
@@ -419,7 +420,7 @@ def test_linear_prover_matches_one_round_per_kernel_and_oracle(zlib, ctx, po, lg
         assert pc.round_polynomials.tolist() == want.round_polys.tolist() and pc.final_evals[0] == want.final_eval
         assert len(poly) == 1 and int(poly.evaluations[0]) == want.final_eval
     finally:
-        ctx.set_option("host_tail_log2", 10)
+        ctx.set_option("host_tail_log2", 12)
 
 
 def test_block_sums_and_fold_multi_entry_points(zlib, ctx, po):
@@ -427,10 +428,12 @@ def test_block_sums_and_fold_multi_entry_points(zlib, ctx, po):
     import ctypes as C
     L = zlib.lib()
     rng = np.random.default_rng(11)
-    for lg, k, k_next in ((7, 1, 2), (9, 2, 5), (12, 3, 4), (13, 5, 5), (14, 4, 10), (12, 5, 7), (16, 5, 1), (8, 5, 3)):
+    # (k_next == log2 of the folded length: the folded table itself comes back — the wide kernel, k up to 8)
+    for lg, k, k_next in ((7, 1, 2), (9, 2, 5), (12, 3, 4), (13, 5, 5), (14, 4, 10), (12, 5, 7), (16, 5, 1), (8, 5, 3), (3, 1, 2), (10, 6, 4),
+                          (14, 7, 7), (20, 8, 12), (16, 8, 8), (13, 1, 12), (10, 8, 2)):
         e = po.fill_synthetic(BB, 7000 + lg, 0, 1 << lg)
         poly = zlib.Multilinear.init(ctx, e)
-        kk = min(k, 5)
+        kk = k
         sums = np.zeros(1 << kk, np.uint64)
         ctx.check(L.zb_mle_block_sums(ctx.handle, poly.handle, kk, sums.ctypes.data_as(zlib.api.P64)))
         blocks = e.reshape(1 << kk, -1)

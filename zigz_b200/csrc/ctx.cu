@@ -354,6 +354,37 @@ int32_t wait_mail_raw(zb_ctx *ctx, unsigned long long seq, int tagged_words) {
     return ZB_OK;
 }
 
+// Wait until `count` self-validating words (written by many CTAs, in any order) all carry the tag of `seq`.
+int32_t wait_tagged_words(zb_ctx *ctx, const volatile unsigned long long *w, unsigned long long seq, uint64_t count) {
+    const unsigned long long tag = seq & 0xffffffffull;
+    auto t0 = std::chrono::steady_clock::now();
+    uint64_t spins = 0, k = 0;
+    while (k < count) {
+        if ((w[k] >> 32) == tag) {
+            k++;
+            continue;
+        }
+        if ((++spins & 0xFFFF) == 0) {
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            int32_t rc = ZB_OK;
+            if (q != cudaSuccess && q != cudaErrorNotReady) rc = cuda_fail(ctx, q, "kernel");
+            else if (q == cudaSuccess && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2) && (w[k] >> 32) != tag) {
+                ctx->last_error = "published words never arrived";
+                rc = ZB_ERR_TIMEOUT;
+            } else if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
+                ctx->last_error = "timeout waiting for kernel";
+                rc = ZB_ERR_TIMEOUT;
+            }
+            if (rc) {
+                rearm(ctx);
+                return rc;
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return ZB_OK;
+}
+
 int32_t comm_publish(zb_ctx *ctx, unsigned long long seq, int nwords); // defined with the NCCL layer
 
 // Mailbox for a kernel whose payload must be summed over the ranks: the kernel writes into the device exchange
@@ -2101,7 +2132,21 @@ int32_t zb_mle_block_sums(zb_ctx *ctx, zb_mle h, uint32_t k, uint64_t *sums) {
     tail_quiesce(ctx);
     Mle *m = get_mle(ctx, h);
     if (!m) return ZB_ERR_BAD_HANDLE;
-    if (!sums || k < 1 || k > (uint32_t)LIN_MAX_K || m->n < (4ull << k)) return ZB_ERR_BAD_ARGUMENT;
+    if (!sums || k < 1 || k > (uint32_t)LIN_WIDE_MAX_K || m->n < (4ull << k)) return ZB_ERR_BAD_ARGUMENT;
+    if (k > (uint32_t)LIN_MAX_K) { // more than 32 blocks: one CTA per block, one self-validating word each (small tables)
+        const Mailbox wmb = ctx->mailbox(); // takes a sequence number
+        unsigned long long *d_words = (unsigned long long *)((uint8_t *)ctx->d_mail + DUMP_OFFSET);
+        {
+            ProfScope _ps(ctx, "block_sums_d1", m->n * 4);
+            launch_block_sums_wide(m->d(), m->n, (int)k, d_words, wmb.seq, ctx->stream);
+        }
+        LAUNCHED("block_sums_wide");
+        const volatile unsigned long long *w = (const volatile unsigned long long *)((uint8_t *)ctx->h_mail + DUMP_OFFSET);
+        const int32_t rcw = wait_tagged_words(ctx, w, wmb.seq, 1ull << k);
+        if (rcw) return rcw;
+        for (uint32_t b = 0; b < (1u << k); b++) sums[b] = w[b] & 0xffffffffull;
+        return ZB_OK;
+    }
     Mailbox mb = ctx->mailbox();
     {
         ProfScope _ps(ctx, "block_sums_d1", m->n * 4);
@@ -2118,10 +2163,58 @@ int32_t zb_mle_fold_multi(zb_ctx *ctx, zb_mle h, uint32_t k_fold, const uint64_t
     tail_quiesce(ctx);
     Mle *m = get_mle(ctx, h);
     if (!m) return ZB_ERR_BAD_HANDLE;
-    if (!r || !sums || k_fold < 1 || k_fold > (uint32_t)LIN_MAX_K) return ZB_ERR_BAD_ARGUMENT;
+    if (!r || !sums || k_fold < 1 || k_fold > (uint32_t)LIN_WIDE_MAX_K) return ZB_ERR_BAD_ARGUMENT;
     const uint64_t n = m->n, mm = n >> k_fold;
     if (mm < 4 || (mm << k_fold) != n) return ZB_ERR_BAD_ARGUMENT;
     const bool dump = (1ull << k_next) == mm;
+    if (k_fold > (uint32_t)LIN_MAX_K && !dump) return ZB_ERR_BAD_ARGUMENT; // more than 5 variables only when the folded table is published
+    static const bool wide_on = [] {
+        const char *e = getenv("ZB_LIN_WIDE"); // 0: published tables through the streaming kernel (k_fold <= 5 only)
+        return !(e && *e == '0');
+    }();
+    if (dump && k_next <= (uint32_t)LIN_DUMP_MAX_LOG2 && (wide_on || k_fold > (uint32_t)LIN_MAX_K)) {
+        // small table, published whole: the wide kernel (all rows of a column in one CTA, self-validating words, no ticket)
+        for (uint32_t j = 0; j < k_fold; j++)
+            if (r[j] >= bb::P) return ZB_ERR_NOT_CANONICAL;
+        WideWeights ww{};
+        ww.w[0] = bb::R_MOD_P;
+        for (uint32_t j = 0; j < k_fold; j++) {
+            const uint32_t rj = (uint32_t)r[j], nj = bb::sub(1u, rj);
+            for (int t = (1 << j) - 1; t >= 0; t--) {
+                const uint32_t base = ww.w[t];
+                ww.w[2 * t] = bb::mul(base, nj);
+                ww.w[2 * t + 1] = bb::mul(base, rj);
+            }
+        }
+        const uint32_t *wsrc = m->d();
+        uint32_t *wdst = m->d();
+        BufRef wkeep = m->buf;
+        if (out) {
+            Mle *o = nullptr;
+            int32_t rc0 = new_mle(ctx, mm, out, &o);
+            if (rc0) return rc0;
+            wdst = o->d();
+        }
+        const Mailbox wmb = ctx->mailbox();
+        unsigned long long *d_words = (unsigned long long *)((uint8_t *)ctx->d_mail + DUMP_OFFSET);
+        {
+            ProfScope _ps(ctx, "foldk_d1", (n + mm) * 4);
+            launch_foldk_wide(wsrc, wdst, n, (int)k_fold, ww, d_words, wmb.seq, ctx->stream);
+        }
+        int32_t rcw = check_launch(ctx, "foldk_wide");
+        const volatile unsigned long long *w = (const volatile unsigned long long *)((uint8_t *)ctx->h_mail + DUMP_OFFSET);
+        if (rcw == ZB_OK) rcw = wait_tagged_words(ctx, w, wmb.seq, mm);
+        if (rcw) {
+            if (out) {
+                ctx->mles.erase(*out);
+                *out = 0;
+            }
+            return rcw;
+        }
+        if (!out) get_mle(ctx, h)->n = mm;
+        for (uint64_t i = 0; i < mm; i++) sums[i] = w[i] & 0xffffffffull;
+        return ZB_OK;
+    }
     if (dump ? k_next > (uint32_t)LIN_DUMP_MAX_LOG2 : (k_next < 1 || k_next > (uint32_t)LIN_MAX_K || mm < (4ull << k_next)))
         return ZB_ERR_BAD_ARGUMENT;
     for (uint32_t j = 0; j < k_fold; j++)

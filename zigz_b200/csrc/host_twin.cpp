@@ -154,69 +154,6 @@ static int gather_log2() {
 // rounds of the big table (roundPolynomial is linear, multilinear.zig:205-232), so the host runs those rounds on S exactly as
 // sumcheck_prover.zig:50-77 does — roundPolynomial, transcript, partialEval — while the device only sees one launch per k
 // rounds. When the folded table is small enough to be published whole, S is the table itself and the host finishes the proof.
-static int32_t prove_linear(zb_ctx *ctx, zb_mle poly, uint32_t v, bool consume, const uint64_t *fixed_challenges,
-                            uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint64_t *claimed_sum) {
-    int64_t dump_log2 = 10, kk = 5;
-    zb_get_option(ctx, "host_tail_log2", &dump_log2);
-    zb_get_option(ctx, "linear_k", &kk);
-    const uint32_t K = (uint32_t)kk;    // variables per device pass
-    uint64_t S[1u << 10];
-    uint64_t rs[10];
-    uint32_t u = v;                     // log2 of the current device table
-    uint32_t have = u - 2 < K ? u - 2 : K; // S holds 2^have block sums (blocks of >= 4 entries)
-    int32_t rc = zb_mle_block_sums(ctx, poly, have, S);
-    if (rc) return rc;
-    zh_transcript tr; // State.init -> FiatShamirTranscript.init (sumcheck_protocol.zig:149-164)
-    zb_mle cur = poly;
-    bool owned = false;
-    uint32_t round = 0;
-    for (;;) {
-        uint64_t len = 1ull << have;
-        for (uint32_t t = 0; t < have; t++, round++) {
-            const uint64_t h = len / 2;
-            uint64_t s0 = 0, s1 = 0; // roundPolynomial :216-224 on the block sums
-            for (uint64_t i = 0; i < h; i++) {
-                s0 = f_add(s0, S[i]);
-                s1 = f_add(s1, S[i + h]);
-            }
-            const uint64_t c[2] = {s0, f_sub(s1, s0)}; // :229
-            round_polys[2 * (size_t)round] = c[0];
-            round_polys[2 * (size_t)round + 1] = c[1];
-            if (round == 0 && claimed_sum) *claimed_sum = f_add(s0, s1); // sumOverHypercube, sumcheck_prover.zig:40
-            uint64_t r;
-            if (fixed_challenges) {
-                r = fixed_challenges[round]; // proveInteractive :127
-            } else {
-                zh_transcript_append_fields(&tr, c, 2); // generateChallenge, sumcheck_protocol.zig:176-184
-                r = zh_transcript_challenge(&tr);
-            }
-            final_point[round] = r;
-            rs[t < 10 ? t : 9] = r;
-            for (uint64_t i = 0; i < h; i++) S[i] = f_add(S[i], f_mul(r, f_sub(S[i + h], S[i]))); // partialEval :166-173
-            len = h;
-        }
-        if (u == have) break; // S was the (published) table itself: S[0] is current_poly.evaluations[0] (:88)
-        // the device binds the same `have` variables in one pass and returns the sums for the next rounds
-        const uint32_t u_next = u - have;
-        const uint32_t k_next = u_next <= (uint32_t)dump_log2 ? u_next : (u_next - 2 < K ? u_next - 2 : K);
-        zb_mle next = 0;
-        rc = zb_mle_fold_multi(ctx, cur, have, rs, (consume || owned) ? nullptr : &next, k_next, S);
-        if (rc) break;
-        if (next) {
-            cur = next;
-            owned = true;
-        }
-        u = u_next;
-        have = k_next;
-    }
-    if (rc == ZB_OK) {
-        *final_eval = S[0];
-        if (consume) rc = zb_mle_collapse(ctx, poly, S[0]); // the caller's table ends as its final evaluation, as after v folds
-    }
-    if (owned) zb_mle_free(ctx, cur);
-    return rc;
-}
-
 // ---- the last rounds of a product sumcheck on the host ----
 // Four field elements per AVX2 register (one per 64-bit lane, values < 2^32). Montgomery product a b 2^-32 mod p in the
 // subtractive form the kernels use (bb.cuh: mont_mul_lazy): with m = lo(t) p^-1 mod 2^32 the difference t - m p is an exact
@@ -343,6 +280,76 @@ static void finish_rounds_on_host(uint32_t d, uint32_t *T, uint64_t m, uint32_t 
     for (uint32_t k = 0; k < d; k++) final_evals[k] = T[(size_t)k * m]; // current_poly.evaluations[0] (:88)
 }
 
+static int32_t prove_linear(zb_ctx *ctx, zb_mle poly, uint32_t v, bool consume, const uint64_t *fixed_challenges,
+                            uint64_t *round_polys, uint64_t *final_point, uint64_t *final_eval, uint64_t *claimed_sum) {
+    int64_t dump_log2 = 12, kk = 5;
+    zb_get_option(ctx, "host_tail_log2", &dump_log2);
+    zb_get_option(ctx, "linear_k", &kk);
+    const uint32_t K = (uint32_t)kk;    // variables per device pass (large tables)
+    alignas(32) uint64_t S[1u << 12];
+    alignas(32) uint32_t T[1u << 12];
+    uint64_t rs[10];
+    uint32_t u = v;                     // log2 of the current device table
+    // Small tables (at most 8 variables above the published size): ONE block-sum pass with 2^(v - dump) blocks, then ONE fold
+    // that binds all of them and publishes the table — two device round trips for a 2^20-entry prove. Otherwise K per pass.
+    uint32_t have = (v > (uint32_t)dump_log2 && v - (uint32_t)dump_log2 <= 8) ? v - (uint32_t)dump_log2 : (u - 2 < K ? u - 2 : K);
+    int32_t rc = zb_mle_block_sums(ctx, poly, have, S); // S holds 2^have block sums (blocks of >= 4 entries)
+    if (rc) return rc;
+    zh_transcript tr; // State.init -> FiatShamirTranscript.init (sumcheck_protocol.zig:149-164)
+    zb_mle cur = poly;
+    bool owned = false;
+    uint32_t round = 0;
+    for (;;) {
+        uint64_t len = 1ull << have;
+        for (uint32_t t = 0; t < have; t++, round++) {
+            const uint64_t h = len / 2;
+            uint64_t s0 = 0, s1 = 0; // roundPolynomial :216-224 on the block sums
+            for (uint64_t i = 0; i < h; i++) {
+                s0 = f_add(s0, S[i]);
+                s1 = f_add(s1, S[i + h]);
+            }
+            const uint64_t c[2] = {s0, f_sub(s1, s0)}; // :229
+            round_polys[2 * (size_t)round] = c[0];
+            round_polys[2 * (size_t)round + 1] = c[1];
+            if (round == 0 && claimed_sum) *claimed_sum = f_add(s0, s1); // sumOverHypercube, sumcheck_prover.zig:40
+            uint64_t r;
+            if (fixed_challenges) {
+                r = fixed_challenges[round]; // proveInteractive :127
+            } else {
+                zh_transcript_append_fields(&tr, c, 2); // generateChallenge, sumcheck_protocol.zig:176-184
+                r = zh_transcript_challenge(&tr);
+            }
+            final_point[round] = r;
+            rs[t < 10 ? t : 9] = r;
+            for (uint64_t i = 0; i < h; i++) S[i] = f_add(S[i], f_mul(r, f_sub(S[i + h], S[i]))); // partialEval :166-173
+            len = h;
+        }
+        // the device binds the same `have` variables in one pass and returns the sums for the next rounds — or the folded
+        // table itself once it is small, on which the host runs the remaining rounds (four lanes wide)
+        const uint32_t u_next = u - have;
+        const bool publish = u_next <= (uint32_t)dump_log2;
+        const uint32_t k_next = publish ? u_next : (u_next - 2 < K ? u_next - 2 : K);
+        zb_mle next = 0;
+        rc = zb_mle_fold_multi(ctx, cur, have, rs, (consume || owned) ? nullptr : &next, k_next, S);
+        if (rc) break;
+        if (next) {
+            cur = next;
+            owned = true;
+        }
+        u = u_next;
+        have = k_next;
+        if (publish) {
+            const uint64_t m = 1ull << u;
+            for (uint64_t i = 0; i < m; i++) T[i] = (uint32_t)S[i];
+            finish_rounds_on_host(1, T, m, round, &tr, fixed_challenges, round_polys, final_point, final_eval, nullptr);
+            break;
+        }
+    }
+    if (rc == ZB_OK && consume) rc = zb_mle_collapse(ctx, poly, *final_eval); // the caller's table ends as its final evaluation, as after v folds
+    if (owned) zb_mle_free(ctx, cur);
+    return rc;
+}
+
 static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool consume, const uint64_t *fixed_challenges,
                             uint64_t *round_polys, uint64_t *final_point, uint64_t *final_evals, uint64_t *claimed_sum) {
     if (d < 1 || d > 3 || !polys) return ZB_ERR_BAD_ARGUMENT;
@@ -352,7 +359,9 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
     if (rc) return rc;
     int32_t rank = 0, world = 1;
     zb_comm_info(ctx, &rank, &world);
-    if (d == 1 && world == 1 && v_local > 10) {
+    int64_t lin_dump = 12;
+    zb_get_option(ctx, "host_tail_log2", &lin_dump);
+    if (d == 1 && world == 1 && v_local > (uint32_t)lin_dump && v_local > 10) {
         int64_t lin = 0;
         zb_get_option(ctx, "linear_d1", &lin);
         if (lin) return prove_linear(ctx, polys[0], v_local, consume, fixed_challenges, round_polys, final_point, final_evals, claimed_sum);
@@ -368,6 +377,7 @@ static int32_t prove_rounds(zb_ctx *ctx, const zb_mle *polys, uint32_t d, bool c
     zb_get_option(ctx, "tail_log2", &tail_log2);
     zb_get_option(ctx, "comm_reduce", &comm_reduce);
     zb_get_option(ctx, "prod_host_tail_log2", &host_tail);
+    if (d == 1 && host_tail > 0 && lin_dump > host_tail) host_tail = lin_dump; // one table: its rounds are cheaper still on the host
     struct Restore {
         zb_ctx *c;
         int64_t tail, red;

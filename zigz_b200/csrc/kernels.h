@@ -138,7 +138,8 @@ inline bool fold_grid_ok(uint64_t m) { return m >= 8 && (m % 8) == 0; }
 // w_b = prod_j (b_j ? r_j : 1 - r_j) — exactly partialEval applied k times (exact field arithmetic) — emitting the next
 // block sums on the way: 2^28 entries take 5 passes (8.3 B per element) instead of 28 rounds (13.3-16 B per element).
 constexpr int LIN_MAX_K = 5;          // variables per pass (32 block sums / 32-term dot product)
-constexpr int LIN_DUMP_MAX_LOG2 = 10; // a folded table of <= 2^10 entries is published whole (block length 1)
+constexpr int LIN_DUMP_MAX_LOG2 = 12; // a folded table of <= 2^12 entries is published whole (block length 1)
+constexpr int LIN_WIDE_MAX_K = 8;     // small tables: up to 8 variables per pass (launch_block_sums_wide / launch_foldk_wide)
 struct FoldWeights {
     uint32_t w[1 << LIN_MAX_K]; // Montgomery form (w R mod p), index = the K top index bits (first-bound variable = MSB)
 };
@@ -149,6 +150,18 @@ void launch_block_sums(const uint32_t *src, uint64_t n, int k, const Mailbox &mb
 // dump[0..m) as canonical u32 (host-mapped, 16-byte aligned) instead, and the payload is empty.
 void launch_foldk_sums(const uint32_t *src, uint32_t *dst, uint64_t n, int k, const FoldWeights &w, int k_next,
                        unsigned long long *dump, const Mailbox &mb, int sm_count, cudaStream_t st);
+
+// The same two steps for SMALL tables (latency-bound: fewer, wider passes), k up to LIN_WIDE_MAX_K. Results go to `words`
+// (host-mapped u64) as self-validating words (low 32 bits of seq) << 32 | value — no ticket, no fence, no sequence word: the host
+// waits until every word carries the tag.
+//   block sums: words[b] = sum of src over block b of 2^k equal blocks (n % (4 * 2^k) == 0), one CTA per block
+//   fold:       dst[i] = sum_b w[b] src[b m + i] (m = n >> k <= 2^LIN_DUMP_MAX_LOG2, m % 4 == 0; dst may equal src) and words[i] = dst[i]
+struct WideWeights {
+    uint32_t w[1 << LIN_WIDE_MAX_K]; // Montgomery form, index as in FoldWeights
+};
+void launch_block_sums_wide(const uint32_t *src, uint64_t n, int k, unsigned long long *words, unsigned long long seq, cudaStream_t st);
+void launch_foldk_wide(const uint32_t *src, uint32_t *dst, uint64_t n, int k, const WideWeights &w, unsigned long long *words,
+                       unsigned long long seq, cudaStream_t st);
 
 // Plain sum of all n evaluations: payload {sum mod p}
 void launch_sum(const uint32_t *src, uint64_t n, const Mailbox &mb, int sm_count, cudaStream_t st);

@@ -1586,6 +1586,101 @@ void launch_foldk_sums(const uint32_t *src, uint32_t *dst, uint64_t n, int k, co
     }
 }
 
+// ---- the same two steps for small (L2-resident, latency-bound) tables: up to 8 variables per pass ----
+// Block sums: CTA b owns block b; its canonical sum goes out as ONE self-validating word. No accumulators, no ticket.
+__global__ void __launch_bounds__(LIN_TPB) k_block_sums_wide(const uint32_t *__restrict__ src, uint64_t len4, unsigned long long *words,
+                                                             unsigned long long seq) {
+    __shared__ unsigned long long sm[LIN_TPB / 32];
+    const uint4 *p = reinterpret_cast<const uint4 *>(src) + (uint64_t)blockIdx.x * len4;
+    unsigned long long s = 0;
+#pragma unroll 4
+    for (uint64_t i = threadIdx.x; i < len4; i += LIN_TPB) {
+        const uint4 v = p[i];
+        s += (unsigned long long)(v.x + v.y) + (unsigned long long)(v.z + v.w); // each pair < 2^32
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < LIN_TPB / 32; w++) t += sm[w];
+        ((volatile unsigned long long *)words)[blockIdx.x] = mail_tagged(seq, bb::reduce64_scaled<0>(t));
+    }
+}
+void launch_block_sums_wide(const uint32_t *src, uint64_t n, int k, unsigned long long *words, unsigned long long seq, cudaStream_t st) {
+    k_block_sums_wide<<<1 << k, LIN_TPB, 0, st>>>(src, (n >> k) / 4, words, seq);
+}
+
+// Fold: a CTA owns 16 vector columns (64 outputs) and ALL 2^K rows, split over G row groups of RPG rows (RPG loads per thread,
+// all in flight; dot products in groups of four, bb::dot4); the groups meet in shared memory. In place is safe: a column is
+// read and written by one CTA only, and the writes follow the barrier.
+template <int K>
+__global__ void __launch_bounds__(LIN_TPB) k_foldk_wide(const uint32_t *src, uint32_t *dst, uint64_t m4, WideWeights ww,
+                                                        unsigned long long *words, unsigned long long seq) {
+    constexpr int NB = 1 << K;
+    constexpr int RPG = NB >= 64 ? NB / 16 : (NB >= 4 ? 4 : NB); // rows per group: 2, 4, 4, 4, 4, 4, 8, 16
+    constexpr int G = NB / RPG;                                   // groups:         1, 1, 2, 4, 8, 16, 16, 16
+    __shared__ unsigned long long part[G][16][4];
+    const int o = threadIdx.x & 15, g = threadIdx.x >> 4;
+    const uint64_t col = (uint64_t)blockIdx.x * 16 + o;
+    if (g < G) {
+        unsigned long long a[4] = {0, 0, 0, 0};
+        if (col < m4) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(src);
+            uint4 v[RPG];
+#pragma unroll
+            for (int r = 0; r < RPG; r++) v[r] = p[(uint64_t)(g * RPG + r) * m4 + col];
+            if constexpr (RPG == 2) {
+                const uint32_t w0 = ww.w[0], w1 = ww.w[1];
+                a[0] = bb::dot2(v[0].x, v[1].x, w0, w1);
+                a[1] = bb::dot2(v[0].y, v[1].y, w0, w1);
+                a[2] = bb::dot2(v[0].z, v[1].z, w0, w1);
+                a[3] = bb::dot2(v[0].w, v[1].w, w0, w1);
+            } else {
+#pragma unroll
+                for (int r = 0; r < RPG; r += 4) {
+                    const uint32_t w0 = ww.w[g * RPG + r], w1 = ww.w[g * RPG + r + 1], w2 = ww.w[g * RPG + r + 2], w3 = ww.w[g * RPG + r + 3];
+                    a[0] += bb::dot4(v[r].x, v[r + 1].x, v[r + 2].x, v[r + 3].x, w0, w1, w2, w3);
+                    a[1] += bb::dot4(v[r].y, v[r + 1].y, v[r + 2].y, v[r + 3].y, w0, w1, w2, w3);
+                    a[2] += bb::dot4(v[r].z, v[r + 1].z, v[r + 2].z, v[r + 3].z, w0, w1, w2, w3);
+                    a[3] += bb::dot4(v[r].w, v[r + 1].w, v[r + 2].w, v[r + 3].w, w0, w1, w2, w3);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) part[g][o][c] = a[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) { // thread = (column o2, lane c)
+        const int o2 = threadIdx.x >> 2, c = threadIdx.x & 3;
+        const uint64_t col2 = (uint64_t)blockIdx.x * 16 + o2;
+        if (col2 < m4) {
+            unsigned long long t = 0;
+#pragma unroll
+            for (int gg = 0; gg < G; gg++) t += part[gg][o2][c]; // <= 64 canonical values
+            const uint32_t val = bb::reduce64_scaled<0>(t);
+            dst[col2 * 4 + c] = val;
+            ((volatile unsigned long long *)words)[col2 * 4 + c] = mail_tagged(seq, val);
+        }
+    }
+}
+void launch_foldk_wide(const uint32_t *src, uint32_t *dst, uint64_t n, int k, const WideWeights &w, unsigned long long *words,
+                       unsigned long long seq, cudaStream_t st) {
+    const uint64_t m4 = (n >> k) / 4;
+    const int grid = (int)((m4 + 15) / 16);
+    switch (k) {
+    case 1: k_foldk_wide<1><<<grid, LIN_TPB, 0, st>>>(src, dst, m4, w, words, seq); break;
+    case 2: k_foldk_wide<2><<<grid, LIN_TPB, 0, st>>>(src, dst, m4, w, words, seq); break;
+    case 3: k_foldk_wide<3><<<grid, LIN_TPB, 0, st>>>(src, dst, m4, w, words, seq); break;
+    case 4: k_foldk_wide<4><<<grid, LIN_TPB, 0, st>>>(src, dst, m4, w, words, seq); break;
+    case 5: k_foldk_wide<5><<<grid, LIN_TPB, 0, st>>>(src, dst, m4, w, words, seq); break;
+    case 6: k_foldk_wide<6><<<grid, LIN_TPB, 0, st>>>(src, dst, m4, w, words, seq); break;
+    case 7: k_foldk_wide<7><<<grid, LIN_TPB, 0, st>>>(src, dst, m4, w, words, seq); break;
+    default: k_foldk_wide<8><<<grid, LIN_TPB, 0, st>>>(src, dst, m4, w, words, seq); break;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Multilinear.eval, LSB-first. One stage folds NV <= 12 variables: a CTA folds a tile of 2^NV consecutive
 // elements to one value: 16 elements per thread in registers (4 variables), 5 variables by warp shuffle,
