@@ -548,7 +548,7 @@ def run_extras(args, z, ctx, peak):
                                   "bound": "latency (one host round trip per pass; the table is L2-resident)",
                                   "cpu_baseline": {"ms": cdt * 1e3, "melem_per_s": (1 << 20) / cdt / 1e6, "cores": 1, "kind": "port",
                                                    "sample": "the same 2^20-entry table"},
-                                  "note": "several rounds per pass through linearity: block sums, 5-variable folds, last <= 10 rounds from a published table"}
+                                  "note": "several rounds per pass through linearity: 256 block sums, one 8-variable fold, last 12 rounds from a published table"}
     p20.deinit()
     # A/B of the two latency mechanisms on this very box (wall clock per prove, 2^20 entries): the d = 1 schedule with several
     # rounds per pass vs one round per kernel + persistent tail, and the persistent tail kernel of the product prover on / off
