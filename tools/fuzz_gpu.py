@@ -33,10 +33,13 @@ with z.Context(0) as ctx:
     while time.time() < t_end:
         ctx.set_option("tail_log2", int(rng.choice([0, 2, 5, 10, 14, 16])))
         ctx.set_option("prelaunch", int(rng.integers(0, 2)))
-        L.zh_set_grid_min_log2(int(rng.choice([0, 3, 6, 10, 18])))
+        L.zh_set_grid_min_log2(int(rng.choice([-1, 0, 3, 6, 10, 18])))
+        ctx.set_option("prod_host_tail_log2", int(rng.choice([0, 1, 3, 7, 10, 12])))  # small product tables finish on the host
+        ctx.set_option("host_tail_log2", int(rng.choice([2, 5, 10, 12])))            # d = 1: published-table size
+        ctx.set_option("linear_d1", int(rng.integers(0, 2)))
         op = rng.integers(0, 6)
         if op == 0:  # full proofs
-            d, lg = int(rng.integers(1, 4)), int(rng.integers(1, 17))
+            d, lg = int(rng.integers(1, 4)), int(rng.integers(1, 19))
             es = [rand_table(1 << lg) for _ in range(d)]
             polys = [z.Multilinear.init(ctx, e) for e in es]
             want = po.prodcheck_prove(BB, es)
