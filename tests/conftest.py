@@ -42,3 +42,19 @@ def ctx(zlib):
     c = zlib.Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture(params=["default", "device_rounds"])
+def rounds_mode(request, ctx):
+    """Runs a GPU test twice: with the default schedule (small tables are handed to the host twin, which finishes the last
+    rounds; d = 1 goes through block sums + multi-variable folds) and with EVERY round on the device (`linear_d1 = 0`,
+    `prod_host_tail_log2 = 0`: round kernels, scalar and last-fold kernels, the persistent tail) — so the small-size and
+    golden-vector cases keep exercising the CUDA kernels themselves, not only the host part of the default schedule."""
+    keys = ("linear_d1", "prod_host_tail_log2")
+    old = {k: ctx.get_option(k) for k in keys}
+    if request.param == "device_rounds":
+        ctx.set_option("linear_d1", 0)
+        ctx.set_option("prod_host_tail_log2", 0)
+    yield request.param
+    for k, v in old.items():
+        ctx.set_option(k, v)

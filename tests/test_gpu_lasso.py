@@ -4,7 +4,7 @@ import pytest
 
 from _cases import BB, assert_sumcheck_equal, lasso_queries
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("rounds_mode")]
 
 
 def _same(pr, want):

@@ -6,7 +6,7 @@ import pytest
 
 from _cases import BB, assert_sumcheck_equal, sumcheck_case_evals, synthetic
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("rounds_mode")]
 
 
 def test_golden_sumcheck(zlib, ctx, golden):
