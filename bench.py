@@ -94,6 +94,9 @@ class ClockSampler:
                 "sm_max_mhz": float(self.max_sm), "reasons": reasons, "samples": len(sm), "source": "nvml, 2 ms polling inside the timed region"}
 
 
+HOST_AFFINITY = None  # what bind_near_gpu did on rank 0 (multi-rank runs)
+
+
 def dist_setup(n_gpus):
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
@@ -101,6 +104,11 @@ def dist_setup(n_gpus):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if os.environ.get("ZB_BENCH_BIND", "1") != "0":
+            # every rank next to its own GPU (host buffers, packing threads): the ranks' uploads share the host
+            from zigz_b200 import sharded
+            global HOST_AFFINITY
+            HOST_AFFINITY = sharded.bind_near_gpu(local)
         return rank, world, local, dist
     return 0, 1, 0, None
 
@@ -389,7 +397,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32 (canonical BabyBear in registers; u64 accumulators)", "data": "synthetic",
-                "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "host_affinity": HOST_AFFINITY,
                 "roofline": roofline, "kernels": by_kernel}
         if e2e_pageable is not None:
             line["e2e_pageable"] = e2e_pageable

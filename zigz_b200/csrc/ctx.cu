@@ -630,10 +630,15 @@ int32_t upload_narrow_host(zb_ctx *ctx, const uint64_t *host, uint64_t n, uint32
         const char *e = getenv("ZB_UPLOAD_PCIE_GBS"); // H2D rate the queue model assumes
         return (e && *e ? atof(e) : 53.0) * 1e9;
     }();
-    static const int raw_cap = [] {
+    static const int raw_cap_cfg = [] {
         const char *e = getenv("ZB_UPLOAD_RAW_CAP"); // adaptive rule: at most one raw chunk in this many (0: no cap)
-        return e && *e ? atoi(e) : 6;
+        return e && *e ? atoi(e) : -1;
     }();
+    // default: capped with a full complement of packing threads (>= 16: the threads nearly keep the link busy on their own, and
+    // raw chunks then mostly take DRAM bandwidth away from them); uncapped with fewer threads per GPU (several ranks share the
+    // host: 12 threads per rank on the 2-GPU box — the link has headroom, the cores do not: 426 ms per step uncapped against
+    // 540 ms with one raw chunk in six, profiles/r02_upload_policy_boxes.txt)
+    const int raw_cap = raw_cap_cfg >= 0 ? raw_cap_cfg : (ctx->pool->size() >= 16 ? 6 : 0);
     uint64_t raw_count = 0;
     const int raw_every = pinned ? raw_every_cfg : 0;
     BufRef raw_stage;

@@ -21,6 +21,47 @@ def nccl_library_path() -> str | None:
         return None
 
 
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_near_gpu(index: int) -> dict:
+    """Best effort, multi-rank hosts: pin this process — and the threads it starts later, i.e. the upload packing pool — to the
+    CPUs of the NUMA node GPU `index` hangs off (sysfs `local_cpulist` of its PCI device), so that the rank's pinned host
+    buffers are first-touched next to its own PCIe root. A host that exposes no NUMA topology (numa_node = -1, or a CPU list
+    that covers everything) is left alone. Returns what it found and did; never raises."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        if isinstance(bus, bytes):
+            bus = bus.decode()
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}"
+        with open(path + "/numa_node") as f:
+            node = int(f.read())
+        with open(path + "/local_cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        target = cpus & allowed
+        info.update(numa_node=node, local_cpus=len(cpus), allowed_cpus=len(allowed))
+        if node >= 0 and target and len(target) < len(allowed):
+            os.sched_setaffinity(0, target)
+            info.update(bound=True, cpus=len(target))
+    except Exception as e:  # noqa: BLE001 - plumbing only: report, never fail the caller
+        info["error"] = repr(e)[:200]
+    return info
+
+
 class Comm:
     """Attaches an NCCL communicator to `ctx`; rank 0's unique id travels through torch.distributed."""
 
