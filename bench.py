@@ -108,7 +108,7 @@ def dist_setup(n_gpus):
             # every rank next to its own GPU (host buffers, packing threads): the ranks' uploads share the host
             from zigz_b200 import sharded
             global HOST_AFFINITY
-            HOST_AFFINITY = sharded.bind_near_gpu(local)
+            HOST_AFFINITY = sharded.bind_near_gpu(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
         return rank, world, local, dist
     return 0, 1, 0, None
 

@@ -31,11 +31,12 @@ def _parse_cpulist(text: str) -> set:
     return cpus
 
 
-def bind_near_gpu(index: int) -> dict:
+def bind_near_gpu(index: int, local_world: int = 1) -> dict:
     """Best effort, multi-rank hosts: pin this process — and the threads it starts later, i.e. the upload packing pool — to the
     CPUs of the NUMA node GPU `index` hangs off (sysfs `local_cpulist` of its PCI device), so that the rank's pinned host
     buffers are first-touched next to its own PCIe root. A host that exposes no NUMA topology (numa_node = -1, or a CPU list
-    that covers everything) is left alone. Returns what it found and did; never raises."""
+    that covers everything) is left alone. `local_world`: ranks on this host (sizes the packing pool among the ranks that share
+    the node). Returns what it found and did; never raises."""
     info = {"bound": False}
     try:
         import pynvml
@@ -57,6 +58,21 @@ def bind_near_gpu(index: int) -> dict:
         if node >= 0 and target and len(target) < len(allowed):
             os.sched_setaffinity(0, target)
             info.update(bound=True, cpus=len(target))
+            # the library sizes its packing pool as (CPUs it may run on) / (ranks): after binding, the CPUs of this node are
+            # shared by the ranks whose GPUs hang off the same node only
+            sharing = 0
+            for other in range(max(local_world, 1)):
+                try:
+                    ob = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(other)).busId
+                    ob = ob.decode() if isinstance(ob, bytes) else ob
+                    od, orest = ob.split(":", 1)
+                    with open(f"/sys/bus/pci/devices/{od[-4:].lower()}:{orest.lower()}/numa_node") as f:
+                        sharing += int(f.read()) == node
+                except Exception:  # noqa: BLE001
+                    pass
+            threads = max(1, len(target) // max(sharing, 1))
+            os.environ.setdefault("ZB_UPLOAD_THREADS", str(threads))
+            info.update(ranks_on_node=sharing, upload_threads=int(os.environ["ZB_UPLOAD_THREADS"]))
     except Exception as e:  # noqa: BLE001 - plumbing only: report, never fail the caller
         info["error"] = repr(e)[:200]
     return info
