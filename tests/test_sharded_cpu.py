@@ -91,3 +91,18 @@ def test_shard_maps():
             b = sharded.block_shard(e, r, world)
             assert b[0] == r * n // world and len(b) == n // world
     assert sharded.combine_round_coeffs([[BB - 1, 5], [3, BB - 2]]) == [2, 3]
+
+
+def test_bind_near_gpu_is_best_effort():
+    """Host plumbing of the multi-rank bench: CPU-list parsing, and no exception (nor any change of affinity) on a host without
+    NVML / NUMA information."""
+    import os
+
+    from zigz_b200 import sharded
+    assert sharded._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert sharded._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    info = sharded.bind_near_gpu(0, 8)
+    assert isinstance(info, dict) and "bound" in info
+    if not info["bound"]:
+        assert os.sched_getaffinity(0) == before
