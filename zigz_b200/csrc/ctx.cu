@@ -2052,8 +2052,12 @@ static int32_t fold_grid_impl(zb_ctx *ctx, const zb_mle *polys, uint32_t d, uint
     static const char *names[3][3] = {{"grid_d1", "fold1_grid_d1", "fold2_grid_d1"},
                                       {"grid_d2", "fold1_grid_d2", "fold2_grid_d2"},
                                       {"grid_d3", "fold1_grid_d3", "fold2_grid_d3"}};
+    // two-variable folds below 2^24 entries are latency-bound launches (>= 10 % of their duration is fixed cost): reported as a
+    // family of their own, so that the bandwidth-bound launches' rate is not averaged with theirs
+    static const char *small2[3] = {"fold2_grid_small_d1", "fold2_grid_small_d2", "fold2_grid_small_d3"};
+    const char *scope = (nfold == 2 && n < (1ull << 24)) ? small2[d - 1] : names[d - 1][nfold];
     {
-        ProfScope _ps(ctx, names[d - 1][nfold], (uint64_t)d * 4 * (n + (nfold ? m : 0)));
+        ProfScope _ps(ctx, scope, (uint64_t)d * 4 * (n + (nfold ? m : 0)));
         launch_fold_grid((int)d, (int)nfold, ps, m, nfold ? (uint32_t)r[0] : 0, nfold > 1 ? (uint32_t)r[1] : 0, mb, ctx->sm_count,
                          ctx->stream);
     }
