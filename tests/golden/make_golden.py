@@ -289,7 +289,9 @@ def main():
     sc["bb_1to8"] = {"p": BABYBEAR, "evals": list(range(1, 9)), **sumcheck_prove(BABYBEAR, list(range(1, 9)))}
     e = [i + 1 for i in range(256)]  # examples/sumcheck_scalability.zig:44-46 pattern
     sc["bb_iplus1_256"] = {"p": BABYBEAR, "pattern": "i+1", "n": 256, **sumcheck_prove(BABYBEAR, e)}
-    for lg in (1, 2, 5, 12):
+    # 2^14 / 2^16: sizes at which the GPU prover's own passes do the work (block sums + a multi-variable fold; the host twin only
+    # finishes the last <= 12 rounds)
+    for lg in (1, 2, 5, 12, 14, 16):
         e = synthetic(BABYBEAR, 0x5A49475A, 1 << lg)
         sc[f"bb_synth_2^{lg}"] = {"p": BABYBEAR, "seed": 0x5A49475A, "n": 1 << lg, **sumcheck_prove(BABYBEAR, e)}
     e = synthetic(BABYBEAR, 7, 64)
@@ -299,7 +301,7 @@ def main():
 
     pc = {}
     for d in (1, 2, 3):
-        for lg in (1, 3, 8):
+        for lg in (1, 3, 8, 11, 13):  # 2^11 / 2^13: above the size at which the GPU prover hands its tables to the host
             polys = [synthetic(BABYBEAR, 0x5A49475A + k, 1 << lg) for k in range(d)]
             pc[f"d{d}_2^{lg}"] = {"d": d, "seed": 0x5A49475A, "n": 1 << lg, **prodcheck_prove(BABYBEAR, polys)}
     g["prodcheck"] = pc

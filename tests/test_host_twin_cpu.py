@@ -222,3 +222,26 @@ def test_prodcheck_finish_small_is_a_whole_small_prove(zlib, po):
     assert L.zh_prodcheck_finish_small(1, bad.ctypes.data_as(C.POINTER(C.c_uint32)), 2, 0, t._t, None, p64, p64, p64) == -20
     assert L.zh_prodcheck_finish_small(1, bad.ctypes.data_as(C.POINTER(C.c_uint32)), 3, 0, t._t, None, p64, p64, p64) == -22
     assert L.zh_prodcheck_finish_small(4, bad.ctypes.data_as(C.POINTER(C.c_uint32)), 2, 0, t._t, None, p64, p64, p64) == -22
+
+
+def test_prodcheck_finish_small_vs_golden(zlib, golden):
+    """The same host rounds against the independent pure-Python restatement (tests/golden/make_golden.py)."""
+    import ctypes as C
+
+    from _cases import synthetic
+    L = zlib.lib()
+    seen = 0
+    for name, case in golden["prodcheck"].items():
+        d, n = case["d"], case["n"]
+        if n > 4096 or n < 2:
+            continue
+        lg = n.bit_length() - 1
+        tables = np.ascontiguousarray(np.concatenate([synthetic(case["seed"] + k, n) for k in range(d)]).astype(np.uint32))
+        rp, fp, fe = np.zeros((lg, d + 1), np.uint64), np.zeros(lg, np.uint64), np.zeros(3, np.uint64)
+        t = zlib.FiatShamirTranscript()
+        p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint64))
+        assert L.zh_prodcheck_finish_small(d, tables.ctypes.data_as(C.POINTER(C.c_uint32)), n, 0, t._t, None, p64(rp), p64(fp), p64(fe)) == 0
+        assert rp.tolist() == [list(r) for r in case["round_polys"]], name
+        assert fp.tolist() == list(case["final_point"]), name
+        seen += 1
+    assert seen >= 9
